@@ -1,0 +1,169 @@
+/* mamg.h -- C-ABI of the B200-native metric-AMG apply path.
+ *
+ * Drop-in boundary for ONE path of anabudisa/metric-amg-examples: building and
+ * applying the HAZmath metric-AMG preconditioner inside the cbc.block Krylov
+ * solve.  The reference crosses Python -> C through the `haznics` SWIG module;
+ * every entry point below names the reference-side call it replaces
+ * (paths are relative to the reference checkout).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; the caller owns every array it passes in,
+ *     the library copies what it keeps; outputs are caller-allocated.
+ *   - every function returns 0 on success and a negative code on failure and
+ *     never throws across the ABI; mamg_last_error() gives the message
+ *     (mirrors cbc.block's RuntimeError when the C setup returns NULL).
+ *   - a handle is not thread-safe; distinct handles are independent.
+ *   - fp64 values, int32 indices (same widths as the reference's
+ *     PETSc -> dCSRmat conversion, src/utils.py:108).
+ */
+#ifndef MAMG_H
+#define MAMG_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Integer values of the haznics macros used by src/amg_parameters.py:5-16,42
+ * and src/input_metric.dat:68-99 (symbolic use only). */
+enum {
+  MAMG_UA_AMG = 1, MAMG_SA_AMG = 2,
+  MAMG_V_CYCLE = 1, MAMG_W_CYCLE = 2, MAMG_AMLI_CYCLE = 3, MAMG_NL_AMLI_CYCLE = 4, MAMG_ADD_CYCLE = 5,
+  MAMG_SMOOTHER_JACOBI = 1, MAMG_SMOOTHER_GS = 2, MAMG_SMOOTHER_SGS = 3,
+  MAMG_SMOOTHER_SOR = 5, MAMG_SMOOTHER_SSOR = 6, MAMG_SMOOTHER_L1DIAG = 10,
+  MAMG_VMB = 1, MAMG_MIS = 2, MAMG_MWM = 3, MAMG_HEC = 4, MAMG_HEM = 5,
+  MAMG_SCHWARZ_FORWARD = 1, MAMG_SCHWARZ_BACKWARD = 2, MAMG_SCHWARZ_SYMMETRIC = 3,
+  MAMG_SOLVER_UMFPACK = 32,
+  MAMG_OFF = 0, MAMG_ON = 1
+};
+
+/* The parameter dict of src/amg_parameters.py:3-89 as a struct; field names are
+ * the dict keys (what haznics.param_amg_set_dict consumes upstream). */
+typedef struct mamg_params {
+  int32_t AMG_type;          /* UA_AMG | SA_AMG */
+  int32_t cycle_type;        /* V_CYCLE | W_CYCLE */
+  int32_t max_levels;
+  int32_t maxit;             /* cycles per apply */
+  int32_t smoother;          /* SMOOTHER_* */
+  double  relaxation;        /* SOR/SSOR weight, Jacobi damping */
+  int32_t presmooth_iter;
+  int32_t postsmooth_iter;
+  int32_t coarse_dof;
+  int32_t coarse_solver;     /* 32 = direct */
+  int32_t coarse_scaling;    /* ON | OFF */
+  int32_t aggregation_type;  /* VMB | HEM | HEC */
+  double  strong_coupled;
+  int32_t max_aggregation;
+  int32_t amli_degree;
+  int32_t Schwarz_levels;
+  int32_t Schwarz_mmsize;
+  int32_t Schwarz_maxlvl;
+  int32_t Schwarz_type;      /* SCHWARZ_FORWARD | BACKWARD | SYMMETRIC */
+  int32_t Schwarz_blksolver; /* 32 = direct */
+  int32_t print_level;
+  int32_t reserved[8];
+} mamg_params;
+
+typedef struct mamg_handle_s* mamg_handle;
+
+/* error text of the last failing call in this thread */
+const char* mamg_last_error(void);
+/* library build tag, e.g. "mamg 0.1 sm_100a" */
+const char* mamg_version(void);
+
+/* haznics.AMG_param() defaults == src/utils.py:60-82 (the inline dict used when
+ * the reference passes no parameters). */
+int mamg_params_default(mamg_params* p);
+
+/* ---- setup: replaces block.algebraic.hazmath.metricAMG(A, W, idofs=, parameters=)
+ *      (src/utils.py:86,88) and AMG(A, parameters=) (src/utils.py:40).
+ *      A is the monolithic CSR that PETSc_to_dCSRmat(A) hands to HAZmath
+ *      (src/utils.py:108); idofs are 0-based monolithic indices
+ *      (src/bidomain_2d.py:192, src/emi_2d.py:205, src/emi_3d.py:134-138);
+ *      n_idofs = 0 means "no interface dofs" (plain AMG).  Host only: needs no GPU. */
+int mamg_setup(const mamg_params* p, int32_t n, const int32_t* indptr, const int32_t* indices,
+               const double* data, int32_t n_idofs, const int32_t* idofs, mamg_handle* out);
+int mamg_destroy(mamg_handle h);
+
+/* ---- hierarchy introspection / export (natural ordering) so that the CPU oracle
+ *      applies the cycle on the identical hierarchy (north_star) */
+int mamg_num_levels(mamg_handle h, int32_t* nlevels);
+/* info[0]=rows info[1]=nnz info[2]=n_aggregates info[3]=n_colors info[4]=n_patches
+ * info[5]=n_patch_entries info[6]=n_patch_colors info[7]=max_patch_size */
+int mamg_level_info(mamg_handle h, int32_t level, int64_t info[8]);
+int mamg_level_export(mamg_handle h, int32_t level, int32_t* indptr, int32_t* indices, double* data,
+                      int32_t* agg, int32_t* color, uint8_t* gs_skip);
+int mamg_schwarz_export(mamg_handle h, int32_t level, int32_t* patch_ptr, int32_t* patch_dofs,
+                        int32_t* patch_seed, int32_t* patch_color);
+/* dense row-major inverse of the coarsest operator, n_c*n_c doubles */
+int mamg_coarse_export(mamg_handle h, double* inv);
+int mamg_setup_seconds(mamg_handle h, double* seconds);
+
+/* ---- device: upload the hierarchy (colour-permuted CSR per level) to one B200.
+ *      stream = a cudaStream_t cast to void* the library launches on (NULL: the
+ *      library creates its own non-blocking stream). Fails if no CUDA device. */
+int mamg_to_device(mamg_handle h, int32_t device, void* stream);
+int mamg_set_stream(mamg_handle h, void* stream);
+int mamg_device_bytes(mamg_handle h, int64_t* bytes);
+
+/* ---- apply: replaces haznics.apply_precond(b_np, x_np, precond) that cbc.block's
+ *      Precond.matvec runs for every B*r inside ConjGrad (src/bidomain_2d.py:205-206).
+ *      z = B r, one cycle (params.maxit cycles) from a zero initial guess.
+ *      on_device = 0: r, z are host arrays (copied inside the call, synchronous);
+ *      on_device = 1: r, z are device pointers in the caller's (natural) dof order,
+ *      the call is asynchronous on the handle's stream. */
+int mamg_apply(mamg_handle h, const double* r, double* z, int32_t on_device);
+
+/* y = A_level x on the device copy of the hierarchy (natural order, host or device
+ * arrays as for mamg_apply); what dolfin's A*x (PETSc MatMult) does in the Krylov
+ * loop (src/bidomain_2d.py:206) for level 0. */
+int mamg_spmv(mamg_handle h, int32_t level, const double* x, double* y, int32_t on_device);
+/* one pre-smoothing application (params.presmooth_iter sweeps of params.smoother, and
+ * Schwarz where configured) on level `level`: x <- S(x, b). For kernel parity tests. */
+int mamg_smooth(mamg_handle h, int32_t level, const double* b, double* x, int32_t post,
+                int32_t on_device);
+
+/* ---- Krylov: replaces block.iterative.ConjGrad(A, precond=B, tolerance=, maxiter=,
+ *      relativeconv=) followed by x = AAinv * b (src/bidomain_2d.py:205-206,
+ *      src/emi_2d.py:211-212).  A is level 0 of the hierarchy.  Stopping rule of
+ *      cbc.block: sqrt(r.Br) <= tolerance (absolute) or <= tolerance*sqrt(r0.Br0)
+ *      (relative != 0).  residuals has room for maxiter+1 entries, alphas/betas for
+ *      maxiter (may be NULL).  x holds the initial guess on entry when
+ *      use_initial_guess != 0, else it is ignored. */
+int mamg_pcg(mamg_handle h, const double* b, double* x, double tolerance, int32_t relative,
+             int32_t maxiter, int32_t use_initial_guess, int32_t on_device, int32_t* niters,
+             double* residuals, double* alphas, double* betas);
+/* preconditioned MINRES / restarted right-preconditioned GMRES with the same surface
+ * (block.iterative.MinRes / LGMRES share ConjGrad's constructor upstream). */
+int mamg_minres(mamg_handle h, const double* b, double* x, double tolerance, int32_t relative,
+                int32_t maxiter, int32_t on_device, int32_t* niters, double* residuals);
+int mamg_gmres(mamg_handle h, const double* b, double* x, double tolerance, int32_t relative,
+               int32_t maxiter, int32_t restart, int32_t on_device, int32_t* niters,
+               double* residuals);
+
+/* ---- measurement helpers (bench.py): kernel launches issued on the handle's stream
+ *      since the last reset, and algorithmic bytes (SURVEY 8d model) of one cycle. */
+int mamg_launch_count(mamg_handle h, int64_t* launches, int32_t reset);
+int mamg_cycle_bytes(mamg_handle h, int64_t* bytes);
+
+/* ---- synthetic systems of BASELINE.json's configs: P1 on UnitSquare/UnitCube
+ *      (right-diagonal / 6-tet Kuhn split, lexicographic dofs), the matrices the
+ *      reference assembles with FEniCS_ii and flattens with ii_convert
+ *      (src/bidomain_2d.py:64-68,96-97,178; src/emi_2d.py:90-94,125-126).
+ *      indptr == NULL: only nrows/nnz are returned.  Otherwise *nnz is the capacity of
+ *      indices/data on entry (rows * 2 * 3^dim always suffices) and the actual nnz on return. */
+int mamg_assemble_scalar(int32_t dim, const int32_t* ncell, const double* h, double cK, double cM,
+                         int64_t* nrows, int64_t* nnz, int32_t* indptr, int32_t* indices,
+                         double* data);
+int mamg_assemble_bidomain(int32_t dim, int32_t ncell, double kappa1, double kappa2, double gamma,
+                           int64_t* nrows, int64_t* nnz, int32_t* indptr, int32_t* indices,
+                           double* data);
+int mamg_assemble_emi(int32_t dim, int32_t ncell, double kappa1, double kappa2, double gamma,
+                      int64_t* nrows, int64_t* nnz, int32_t* indptr, int32_t* indices,
+                      double* data);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAMG_H */

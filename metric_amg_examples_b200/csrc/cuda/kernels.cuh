@@ -1,0 +1,311 @@
+// Hand-written sm_100a kernels of the metric-AMG cycle and the Krylov loop (fp64, int32).
+//
+// Every kernel here is HBM-bound (SpMV: 2 flop per 12 B), so the rules that matter are
+// coalescing, enough loads in flight and no re-reads; tensor cores are not used because no
+// step is a dense contraction (BASELINE.json north_star).
+//
+// Matrix layout: CSR whose rows are permuted so that every Gauss-Seidel colour is one
+// contiguous row range (stable inside a colour, so the banded x-locality of the
+// lexicographic mesh ordering survives inside each colour block).  A sub-warp of LANES
+// threads owns one row: its val/col loads are contiguous and the x-gathers of neighbouring
+// rows fall in the same cache lines.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace mamg {
+
+constexpr int kBlock = 256;
+
+// Sum over the LANES threads of one sub-warp (all of them hold the same row, so the whole
+// sub-warp is converged here even when neighbouring sub-warps have exited); lane 0 gets the sum.
+template <int LANES>
+__device__ __forceinline__ double subwarp_sum(double v) {
+  const unsigned int full = LANES == 32 ? 0xffffffffu : ((1u << LANES) - 1u);
+  const unsigned int mask = full << ((threadIdx.x & 31) / LANES * LANES);
+#pragma unroll
+  for (int o = LANES / 2; o > 0; o >>= 1) v += __shfl_down_sync(mask, v, o, LANES);
+  return v;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Row dot product a_i . x by one sub-warp; the full sum is valid in lane 0 of the sub-warp.
+template <int LANES>
+__device__ __forceinline__ double row_dot(const int* __restrict__ ja, const double* __restrict__ a,
+                                          const double* x, int p0, int p1, int lane) {
+  double s = 0.0;
+  for (int p = p0 + lane; p < p1; p += LANES) s += a[p] * x[ja[p]];
+  return subwarp_sum<LANES>(s);
+}
+
+// ---------------------------------------------------------------------------------------
+// K1  y = A x   |   y = b - A x          (HAZmath dcsr_mxv / dcsr_aAxpy; PETSc MatMult)
+// ---------------------------------------------------------------------------------------
+template <int LANES, bool RESID>
+__global__ void __launch_bounds__(kBlock)
+spmv_kernel(int n, const int* __restrict__ ia, const int* __restrict__ ja,
+            const double* __restrict__ a, const double* __restrict__ x,
+            const double* __restrict__ b, double* __restrict__ y) {
+  const int lane = threadIdx.x % LANES;
+  const int row = (blockIdx.x * kBlock + threadIdx.x) / LANES;
+  if (row >= n) return;
+  double s = row_dot<LANES>(ja, a, x, ia[row], ia[row + 1], lane);
+  if (lane == 0) y[row] = RESID ? b[row] - s : s;
+}
+
+// Deterministic two-stage reduction: every block writes its partial sums, the block that
+// arrives last adds them in index order (fixed order => run-to-run and rank-count
+// independent rounding) and stores the NV results in out[0..NV).
+template <int NV>
+__device__ __forceinline__ bool block_reduce_finish(double (&v)[NV], double* partial,
+                                                    unsigned int* ticket, double* out) {
+  __shared__ double sm[NV][kBlock / 32];
+  __shared__ bool is_last;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double w = warp_sum(v[k]);
+    if (lane == 0) sm[k][warp] = w;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      double s = 0.0;
+      for (int w = 0; w < kBlock / 32; ++w) s += sm[k][w];
+      partial[(size_t)k * gridDim.x + blockIdx.x] = s;
+    }
+    __threadfence();
+    unsigned int t = atomicInc(ticket, gridDim.x - 1);  // wraps to 0 after the last block
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return false;
+  __threadfence();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += kBlock)
+      s += ((volatile double*)partial)[(size_t)k * gridDim.x + i];
+    // fixed-shape tree over the block: identical for every run
+    double w = warp_sum(s);
+    __syncthreads();
+    if (lane == 0) sm[k][warp] = w;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int q = 0; q < kBlock / 32; ++q) t += sm[k][q];
+      out[k] = t;
+    }
+  }
+  return true;  // thread 0 of this block has written out[0..NV) and may post-process it
+}
+
+// PCG scalars live on the device: sc[0]=rz, sc[1]=d.q, sc[2]=alpha, sc[3]=rz_new, sc[4]=beta
+// q = A d  with the dot product d.q in the epilogue; the finishing block sets
+// sc[1] = d.q and alpha = sc[2] = rz / d.q                       (K1 + K10 fused)
+template <int LANES>
+__global__ void __launch_bounds__(kBlock)
+spmv_dot_kernel(int n, const int* __restrict__ ia, const int* __restrict__ ja,
+                const double* __restrict__ a, const double* __restrict__ d, double* __restrict__ q,
+                double* partial, unsigned int* ticket, double* sc) {
+  const int lane = threadIdx.x % LANES;
+  const int nsub = gridDim.x * (kBlock / LANES);  // fixed grid, rows strided: few tickets, fixed partial count
+  double v[1] = {0.0};
+  for (int row = (blockIdx.x * kBlock + threadIdx.x) / LANES; row < n; row += nsub) {
+    double s = row_dot<LANES>(ja, a, d, ia[row], ia[row + 1], lane);
+    if (lane == 0) { q[row] = s; v[0] += s * d[row]; }
+  }
+  if (block_reduce_finish<1>(v, partial, ticket, sc + 1) && threadIdx.x == 0) sc[2] = sc[0] / sc[1];
+}
+
+// ---------------------------------------------------------------------------------------
+// K6  one colour of a Gauss-Seidel / SOR sweep on rows [r0, r1)   (HAZmath smoother_dcsr_gs /
+//     _sgs / _sor in natural order; here in the multicolour order the oracle shares)
+//       x_i <- x_i + w (b_i - sum_j a_ij x_j) / a_ii
+//     Rows of one colour do not couple, so the in-place update equals the sequential sweep.
+// ---------------------------------------------------------------------------------------
+template <int LANES>
+__global__ void __launch_bounds__(kBlock)
+gs_color_kernel(int r0, int r1, const int* __restrict__ ia, const int* __restrict__ ja,
+                const double* __restrict__ a, const double* __restrict__ invd,
+                const uint8_t* __restrict__ skip, const double* __restrict__ b, double* x,
+                double omega) {
+  const int lane = threadIdx.x % LANES;
+  const int row = r0 + (blockIdx.x * kBlock + threadIdx.x) / LANES;
+  if (row >= r1) return;
+  if (skip != nullptr && skip[row]) return;
+  double s = row_dot<LANES>(ja, a, x, ia[row], ia[row + 1], lane);
+  if (lane == 0) x[row] += omega * (b[row] - s) * invd[row];
+}
+
+// damped Jacobi, out of place: xn = x + w D^-1 (b - A x)
+template <int LANES>
+__global__ void __launch_bounds__(kBlock)
+jacobi_kernel(int n, const int* __restrict__ ia, const int* __restrict__ ja,
+              const double* __restrict__ a, const double* __restrict__ invd,
+              const uint8_t* __restrict__ skip, const double* __restrict__ b,
+              const double* __restrict__ x, double* __restrict__ xn, double omega) {
+  const int lane = threadIdx.x % LANES;
+  const int row = (blockIdx.x * kBlock + threadIdx.x) / LANES;
+  if (row >= n) return;
+  double s = row_dot<LANES>(ja, a, x, ia[row], ia[row + 1], lane);
+  if (lane == 0) {
+    bool sk = skip != nullptr && skip[row];
+    xn[row] = sk ? x[row] : x[row] + omega * (b[row] - s) * invd[row];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K3  fused residual + unsmoothed-aggregation restriction (HAZmath dcsr_aAxpy + dcsr_mxv_agg):
+//       bc[I] = sum_{i in aggregate I} (b_i - a_i . x),   xc[I] = 0
+//     One sub-warp per coarse row walks the fine rows of its aggregate, so every fine row is
+//     read exactly once and the fine residual is never stored.
+// ---------------------------------------------------------------------------------------
+template <int LANES>
+__global__ void __launch_bounds__(kBlock)
+resid_restrict_kernel(int nc, const int* __restrict__ cptr, const int* __restrict__ cidx,
+                      const int* __restrict__ ia, const int* __restrict__ ja,
+                      const double* __restrict__ a, const double* __restrict__ x,
+                      const double* __restrict__ b, double* __restrict__ bc,
+                      double* __restrict__ xc) {
+  const int lane = threadIdx.x % LANES;
+  const int I = (blockIdx.x * kBlock + threadIdx.x) / LANES;
+  if (I >= nc) return;
+  double acc = 0.0;
+  for (int q = cptr[I]; q < cptr[I + 1]; ++q) {
+    const int i = cidx[q];
+    double s = row_dot<LANES>(ja, a, x, ia[i], ia[i + 1], lane);
+    acc += b[i] - s;
+  }
+  if (lane == 0) { bc[I] = acc; xc[I] = 0.0; }
+}
+
+// ---------------------------------------------------------------------------------------
+// coarse scaling (src/amg_parameters.py:58 "coarse_scaling": ON):
+//   alpha = (e . r) / (e . A e), clipped to <= 1 as in the FASP-lineage cycle; NaN -> 1.
+//   out[0] = e.r, out[1] = e.Ae, out[2] = alpha
+// ---------------------------------------------------------------------------------------
+template <int LANES>
+__global__ void __launch_bounds__(kBlock)
+scale_dots_kernel(int n, const int* __restrict__ ia, const int* __restrict__ ja,
+                  const double* __restrict__ a, const double* __restrict__ e,
+                  const double* __restrict__ r, double* partial, unsigned int* ticket, double* out) {
+  const int lane = threadIdx.x % LANES;
+  const int nsub = gridDim.x * (kBlock / LANES);
+  double v[2] = {0.0, 0.0};
+  for (int row = (blockIdx.x * kBlock + threadIdx.x) / LANES; row < n; row += nsub) {
+    double s = row_dot<LANES>(ja, a, e, ia[row], ia[row + 1], lane);
+    if (lane == 0) { double ei = e[row]; v[0] += ei * r[row]; v[1] += ei * s; }
+  }
+  if (block_reduce_finish<2>(v, partial, ticket, out) && threadIdx.x == 0) {
+    double al = out[0] / out[1];
+    out[2] = (al < 1.0) ? al : 1.0;
+  }
+}
+
+// K4  x_i += alpha * e[agg(i)]      (HAZmath dcsr_aAxpy_agg)
+__global__ void __launch_bounds__(kBlock)
+prolong_kernel(int n, const int* __restrict__ agg, const double* __restrict__ e,
+               const double* __restrict__ alpha, double* __restrict__ x) {
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  const int I = agg[i];
+  if (I >= 0) x[i] += (alpha ? *alpha : 1.0) * e[I];
+}
+
+// K8  coarsest solve x = Ainv b with the precomputed dense inverse, one warp per row
+__global__ void __launch_bounds__(kBlock)
+dense_gemv_kernel(int n, const double* __restrict__ M, const double* __restrict__ b,
+                  double* __restrict__ x) {
+  const int row = (blockIdx.x * kBlock + threadIdx.x) / 32, lane = threadIdx.x % 32;
+  if (row >= n) return;
+  double s = 0.0;
+  for (int j = lane; j < n; j += 32) s += M[(size_t)row * n + j] * b[j];
+  s = warp_sum(s);
+  if (lane == 0) x[row] = s;
+}
+
+// ---------------------------------------------------------------------------------------
+// vector kernels
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) fill_kernel(int n, double* x, double v) {
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  if (i < n) x[i] = v;
+}
+// out[i] = in[map[i]]
+__global__ void __launch_bounds__(kBlock)
+gather_kernel(int n, const int* __restrict__ map, const double* __restrict__ in, double* __restrict__ out) {
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  if (i < n) out[i] = in[map[i]];
+}
+__global__ void __launch_bounds__(kBlock)
+copy_kernel(int n, const double* __restrict__ in, double* __restrict__ out) {
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  if (i < n) out[i] = in[i];
+}
+
+// out[0] = u.v     (K10 dots, fixed-order reduction)
+__global__ void __launch_bounds__(kBlock)
+dot_kernel(int n, const double* __restrict__ u, const double* __restrict__ v, double* partial,
+           unsigned int* ticket, double* out) {
+  double acc[1] = {0.0};
+  for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) acc[0] += u[i] * v[i];
+  block_reduce_finish<1>(acc, partial, ticket, out);
+}
+// out[0] = u.v, out[1] = u.w
+__global__ void __launch_bounds__(kBlock)
+dot2_kernel(int n, const double* __restrict__ u, const double* __restrict__ v,
+            const double* __restrict__ w, double* partial, unsigned int* ticket, double* out) {
+  double acc[2] = {0.0, 0.0};
+  for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+    double ui = u[i];
+    acc[0] += ui * v[i];
+    acc[1] += ui * w[i];
+  }
+  block_reduce_finish<2>(acc, partial, ticket, out);
+}
+
+// rz_new = r.z; the finishing block sets sc[3] = rz_new, beta = sc[4] = rz_new / rz, sc[0] = rz_new
+// (first == 1: only sc[0] = r.z, the initial residual)
+__global__ void __launch_bounds__(kBlock)
+pcg_rz_kernel(int n, const double* __restrict__ r, const double* __restrict__ z, double* partial,
+              unsigned int* ticket, double* sc, int first) {
+  double acc[1] = {0.0};
+  for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) acc[0] += r[i] * z[i];
+  if (block_reduce_finish<1>(acc, partial, ticket, sc + 3) && threadIdx.x == 0) {
+    if (!first) sc[4] = sc[3] / sc[0];
+    sc[0] = sc[3];
+  }
+}
+
+// x += alpha d ; r -= alpha q
+__global__ void __launch_bounds__(kBlock)
+pcg_update_kernel(int n, const double* __restrict__ sc, const double* __restrict__ d,
+                  const double* __restrict__ q, double* __restrict__ x, double* __restrict__ r) {
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  const double al = sc[2];
+  x[i] += al * d[i];
+  r[i] -= al * q[i];
+}
+// d = z + beta d
+__global__ void __launch_bounds__(kBlock)
+pcg_dir_kernel(int n, const double* __restrict__ sc, const double* __restrict__ z, double* __restrict__ d) {
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  d[i] = z[i] + sc[4] * d[i];
+}
+// y = a x + b y (host scalars), used by MINRES/GMRES
+__global__ void __launch_bounds__(kBlock)
+axpby_kernel(int n, double a, const double* __restrict__ x, double b, double* __restrict__ y) {
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  if (i < n) y[i] = a * x[i] + b * y[i];
+}
+
+}  // namespace mamg

@@ -1,0 +1,231 @@
+// Host half of the C-ABI declared in include/mamg.h (setup, export, synthetic systems).
+// The device half (mamg_to_device, mamg_apply, mamg_pcg, ...) is in csrc/cuda/device.cu.
+#include <cstring>
+#include <exception>
+#include <string>
+
+#include "handle.h"
+
+namespace mamg {
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+}  // namespace mamg
+
+using namespace mamg;
+
+#define MAMG_TRY try {
+#define MAMG_CATCH                                                   \
+  }                                                                  \
+  catch (const std::exception& e) { set_error(e.what()); return -2; } \
+  catch (...) { set_error("unknown C++ exception"); return -2; }
+
+extern "C" {
+
+const char* mamg_last_error(void) { return g_err.c_str(); }
+const char* mamg_version(void) { return "mamg 0.1 sm_100a"; }
+
+int mamg_params_default(mamg_params* p) {
+  if (!p) { set_error("params: NULL"); return -1; }
+  std::memset(p, 0, sizeof(*p));
+  // src/utils.py:60-82
+  p->AMG_type = MAMG_UA_AMG;
+  p->cycle_type = MAMG_W_CYCLE;
+  p->max_levels = 20;
+  p->maxit = 1;
+  p->smoother = MAMG_SMOOTHER_SGS;
+  p->relaxation = 1.2;
+  p->presmooth_iter = 1;
+  p->postsmooth_iter = 1;
+  p->coarse_dof = 100;
+  p->coarse_solver = MAMG_SOLVER_UMFPACK;
+  p->coarse_scaling = MAMG_ON;
+  p->aggregation_type = MAMG_HEM;
+  p->strong_coupled = 0.1;
+  p->max_aggregation = 100;
+  p->amli_degree = 3;
+  p->Schwarz_levels = 1;
+  p->Schwarz_mmsize = 100;
+  p->Schwarz_maxlvl = 2;
+  p->Schwarz_type = MAMG_SCHWARZ_SYMMETRIC;
+  p->Schwarz_blksolver = MAMG_SOLVER_UMFPACK;
+  p->print_level = 0;
+  return 0;
+}
+
+int mamg_setup(const mamg_params* p, int32_t n, const int32_t* indptr, const int32_t* indices,
+               const double* data, int32_t n_idofs, const int32_t* idofs, mamg_handle* out) {
+  MAMG_TRY
+  if (!p || !indptr || !indices || !data || !out) { set_error("setup: NULL argument"); return -1; }
+  if (n <= 0) { set_error("setup: matrix has no rows"); return -1; }
+  if (indptr[0] != 0) { set_error("setup: indptr[0] != 0"); return -1; }
+  for (int i = 0; i < n; ++i)
+    if (indptr[i + 1] < indptr[i]) { set_error("setup: indptr not monotone"); return -1; }
+  const int nnz = indptr[n];
+  for (int q = 0; q < n_idofs; ++q)
+    if (idofs[q] < 0 || idofs[q] >= n) { set_error("setup: interface dof out of range"); return -1; }
+  Csr A;
+  A.n = A.m = n;
+  A.ia.assign(indptr, indptr + n + 1);
+  A.ja.assign(indices, indices + nnz);
+  A.a.assign(data, data + nnz);
+  for (int i = 0; i < n; ++i) {
+    bool has_diag = false;
+    for (int q = A.ia[i]; q < A.ia[i + 1]; ++q) {
+      if (A.ja[q] < 0 || A.ja[q] >= n) { set_error("setup: column index out of range"); return -1; }
+      if (A.ja[q] == i && A.a[q] != 0.0) has_diag = true;
+    }
+    if (!has_diag) { set_error("setup: row " + std::to_string(i) + " has no nonzero diagonal"); return -1; }
+  }
+  mamg_handle h = new mamg_handle_s();
+  std::string err;
+  if (!build_hierarchy(*p, std::move(A), idofs, n_idofs, h->H, err)) {
+    delete h;
+    set_error("AMG levels failed to set up: " + err);
+    return -3;
+  }
+  *out = h;
+  return 0;
+  MAMG_CATCH
+}
+
+int mamg_destroy(mamg_handle h) {
+  if (!h) return 0;
+  if (h->dev) device_state_free(h->dev);
+  delete h;
+  return 0;
+}
+
+int mamg_num_levels(mamg_handle h, int32_t* nlevels) {
+  if (!h || !nlevels) { set_error("num_levels: NULL"); return -1; }
+  *nlevels = (int32_t)h->H.lv.size();
+  return 0;
+}
+
+static const Level* get_level(mamg_handle h, int level) {
+  if (!h) { set_error("NULL handle"); return nullptr; }
+  if (level < 0 || level >= (int)h->H.lv.size()) { set_error("level out of range"); return nullptr; }
+  return &h->H.lv[level];
+}
+
+int mamg_level_info(mamg_handle h, int32_t level, int64_t info[8]) {
+  const Level* L = get_level(h, level);
+  if (!L) return -1;
+  info[0] = L->A.n;
+  info[1] = L->A.nnz();
+  info[2] = L->nc;
+  info[3] = L->ncolors;
+  info[4] = L->sw.npatch();
+  info[5] = (int64_t)L->sw.dofs.size();
+  info[6] = L->sw.ncolors;
+  info[7] = L->sw.max_size;
+  return 0;
+}
+
+int mamg_level_export(mamg_handle h, int32_t level, int32_t* indptr, int32_t* indices, double* data,
+                      int32_t* agg, int32_t* color, uint8_t* gs_skip) {
+  const Level* L = get_level(h, level);
+  if (!L) return -1;
+  const int n = L->A.n;
+  if (indptr) std::memcpy(indptr, L->A.ia.data(), sizeof(int) * (n + 1));
+  if (indices) std::memcpy(indices, L->A.ja.data(), sizeof(int) * L->A.ja.size());
+  if (data) std::memcpy(data, L->A.a.data(), sizeof(double) * L->A.a.size());
+  if (agg) {
+    if (L->agg.empty()) for (int i = 0; i < n; ++i) agg[i] = -1;
+    else std::memcpy(agg, L->agg.data(), sizeof(int) * n);
+  }
+  if (color) {
+    if (L->color.empty()) for (int i = 0; i < n; ++i) color[i] = 0;
+    else std::memcpy(color, L->color.data(), sizeof(int) * n);
+  }
+  if (gs_skip) {
+    if (L->gs_skip.empty()) std::memset(gs_skip, 0, n);
+    else std::memcpy(gs_skip, L->gs_skip.data(), n);
+  }
+  return 0;
+}
+
+int mamg_schwarz_export(mamg_handle h, int32_t level, int32_t* patch_ptr, int32_t* patch_dofs,
+                        int32_t* patch_seed, int32_t* patch_color) {
+  const Level* L = get_level(h, level);
+  if (!L) return -1;
+  const SchwarzPatches& s = L->sw;
+  if (patch_ptr && !s.ptr.empty()) std::memcpy(patch_ptr, s.ptr.data(), sizeof(int) * s.ptr.size());
+  if (patch_dofs && !s.dofs.empty()) std::memcpy(patch_dofs, s.dofs.data(), sizeof(int) * s.dofs.size());
+  if (patch_seed && !s.seed.empty()) std::memcpy(patch_seed, s.seed.data(), sizeof(int) * s.seed.size());
+  if (patch_color && !s.color.empty()) std::memcpy(patch_color, s.color.data(), sizeof(int) * s.color.size());
+  return 0;
+}
+
+int mamg_coarse_export(mamg_handle h, double* inv) {
+  if (!h || !inv) { set_error("coarse_export: NULL"); return -1; }
+  std::memcpy(inv, h->H.coarse_inv.data(), sizeof(double) * h->H.coarse_inv.size());
+  return 0;
+}
+
+int mamg_setup_seconds(mamg_handle h, double* seconds) {
+  if (!h || !seconds) { set_error("setup_seconds: NULL"); return -1; }
+  *seconds = h->H.setup_seconds;
+  return 0;
+}
+
+static int export_csr(const Csr& A, int64_t* nrows, int64_t* nnz, int32_t* indptr, int32_t* indices,
+                      double* data) {
+  const int64_t cap = (indptr && nnz) ? *nnz : 0;
+  if (nrows) *nrows = A.n;
+  if (nnz) *nnz = A.nnz();
+  if (indptr) {
+    if (cap < A.nnz()) { set_error("assemble: indices/data capacity (*nnz on entry) too small"); return -1; }
+    std::memcpy(indptr, A.ia.data(), sizeof(int) * (A.n + 1));
+    if (indices) std::memcpy(indices, A.ja.data(), sizeof(int) * A.ja.size());
+    if (data) std::memcpy(data, A.a.data(), sizeof(double) * A.a.size());
+  }
+  return 0;
+}
+
+// indptr == NULL: sizes only.  Otherwise *nnz holds the capacity of indices/data on entry (an
+// upper bound such as rows * 2 * 3^dim is enough) and the actual nnz on return.
+static int check_problem(int dim, int n, bool emi) {
+  if (dim != 2 && dim != 3) { set_error("assemble: dim must be 2 or 3"); return -1; }
+  if (n < 2) { set_error("assemble: need at least 2 cells per direction"); return -1; }
+  if (emi && (n < 4 || n % 2)) { set_error("assemble_emi: ncell must be even and >= 4 (src/utils.py:192)"); return -1; }
+  double nv = 1;
+  for (int a = 0; a < dim; ++a) nv *= (a == dim - 1 && emi) ? n / 2 + 1 : n + 1;
+  double nnz_est = 2 * nv * (dim == 2 ? 14 : 30);
+  if (2 * nv > 2.0e9 || nnz_est > 2.1e9) { set_error("assemble: system exceeds int32 indexing"); return -1; }
+  return 0;
+}
+
+int mamg_assemble_scalar(int32_t dim, const int32_t* ncell, const double* hh, double cK, double cM,
+                         int64_t* nrows, int64_t* nnz, int32_t* indptr, int32_t* indices,
+                         double* data) {
+  MAMG_TRY
+  if (dim < 1 || dim > 3 || !ncell || !hh) { set_error("assemble_scalar: bad arguments"); return -1; }
+  Csr A;
+  p1_scalar(dim, ncell, hh, cK, cM, A);
+  return export_csr(A, nrows, nnz, indptr, indices, data);
+  MAMG_CATCH
+}
+
+int mamg_assemble_bidomain(int32_t dim, int32_t ncell, double kappa1, double kappa2, double gamma,
+                           int64_t* nrows, int64_t* nnz, int32_t* indptr, int32_t* indices,
+                           double* data) {
+  MAMG_TRY
+  if (check_problem(dim, ncell, false)) return -1;
+  Csr A;
+  assemble_bidomain(dim, ncell, kappa1, kappa2, gamma, A);
+  return export_csr(A, nrows, nnz, indptr, indices, data);
+  MAMG_CATCH
+}
+
+int mamg_assemble_emi(int32_t dim, int32_t ncell, double kappa1, double kappa2, double gamma,
+                      int64_t* nrows, int64_t* nnz, int32_t* indptr, int32_t* indices,
+                      double* data) {
+  MAMG_TRY
+  if (check_problem(dim, ncell, true)) return -1;
+  Csr A;
+  assemble_emi(dim, ncell, kappa1, kappa2, gamma, A);
+  return export_csr(A, nrows, nnz, indptr, indices, data);
+  MAMG_CATCH
+}
+
+}  // extern "C"

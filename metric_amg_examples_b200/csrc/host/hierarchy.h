@@ -1,0 +1,77 @@
+// Host-side hierarchy of the metric-AMG preconditioner (natural ordering).
+//
+// What metricAMG(A, W, idofs=, parameters=) builds inside HAZmath when the
+// reference calls it (reference src/utils.py:86): level operators A_l,
+// unsmoothed-aggregation maps, Schwarz patches on the first Schwarz_levels
+// levels and the factorised coarsest matrix.  The reference keeps this on the
+// CPU; so do we (BASELINE.json north_star: "AMG setup ... may remain ... CPU
+// setup exported once per problem").  Everything the device path and the
+// oracle consume is exported from these structs, so both run on one hierarchy.
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../../include/mamg.h"
+
+namespace mamg {
+
+struct Csr {
+  int n = 0;     // rows
+  int m = 0;     // columns
+  std::vector<int> ia, ja;
+  std::vector<double> a;
+  int nnz() const { return ia.empty() ? 0 : ia[n]; }
+};
+
+struct SchwarzPatches {
+  // CSR-of-lists in natural numbering of the level (HAZmath iblock/jblock).
+  std::vector<int> ptr;    // npatch+1
+  std::vector<int> dofs;   // sorted ascending inside a patch
+  std::vector<int> seed;   // seed dof of every patch
+  std::vector<int> color;  // conflict colour of every patch
+  int ncolors = 0;
+  int max_size = 0;
+  int npatch() const { return ptr.empty() ? 0 : (int)ptr.size() - 1; }
+};
+
+struct Level {
+  Csr A;                       // natural ordering
+  std::vector<int> agg;        // size n; coarse index or -1 (row left out of every aggregate)
+  int nc = 0;                  // number of aggregates == rows of next level
+  std::vector<int> color;      // multicolour GS colour of every row
+  int ncolors = 0;
+  std::vector<uint8_t> gs_skip;  // 1: row is smoothed by Schwarz, not by GS (level < Schwarz_levels)
+  SchwarzPatches sw;           // empty unless level < Schwarz_levels
+  Csr P;                       // only for SA_AMG (smoothed prolongator), else empty
+};
+
+struct Hierarchy {
+  mamg_params prm;
+  std::vector<Level> lv;
+  std::vector<double> coarse_inv;  // dense row-major inverse of the coarsest A (n_c x n_c)
+  double setup_seconds = 0;
+};
+
+// ---- setup pieces (each file states the reference lines it restates) -------
+void aggregate_hem(const Csr& A, std::vector<int>& agg, int& nc);
+void aggregate_vmb(const Csr& A, double strong, int max_agg, std::vector<int>& agg, int& nc);
+void galerkin_ua(const Csr& A, const std::vector<int>& agg, int nc, Csr& Ac);
+void multicolor_greedy(const Csr& A, std::vector<int>& color, int& ncolors);
+void schwarz_patches(const Csr& A, const int* seeds, int nseeds, int maxlvl, int mmsize,
+                     SchwarzPatches& out);
+void schwarz_color(const Csr& A, SchwarzPatches& sw);
+bool dense_inverse(const Csr& A, std::vector<double>& inv);
+bool build_hierarchy(const mamg_params& prm, Csr&& A0, const int* idofs, int n_idofs,
+                     Hierarchy& H, std::string& err);
+
+// structured P1 problems (assemble.cpp)
+void p1_scalar(int dim, const int* ncell, const double* h, double cK, double cM, Csr& out);
+void assemble_bidomain(int dim, int n, double k1, double k2, double g, Csr& out);
+void assemble_emi(int dim, int n, double k1, double k2, double g, Csr& out);
+
+// error text shared by every C-ABI entry point (capi.cpp)
+void set_error(const std::string& msg);
+
+}  // namespace mamg

@@ -1,0 +1,408 @@
+// CPU setup of the unsmoothed-aggregation hierarchy that the cycle is applied on.
+//
+// The reference reaches this through metricAMG(A, W, idofs=, parameters=)
+// (src/utils.py:86) / AMG(A, parameters=) (src/utils.py:40); the arithmetic lives
+// in the un-vendored HAZmath C library, so the choices HAZmath's source would pin are
+// frozen here explicitly (SURVEY 8c, items v-vii) and shared with the oracle through
+// mamg_level_export:
+//   * rows whose off-diagonal entries are all zero (Dirichlet identity rows after the
+//     symmetric apply_bc, src/bidomain_2d.py:97) join no aggregate (empty P row);
+//   * HEM (src/amg_parameters.py:60): heavy-edge matching in natural row order, the
+//     partner is the unmatched neighbour with the largest |a_ij| (first one on ties);
+//     rows left without a free partner join the aggregate of their heaviest neighbour;
+//   * VMB (src/amg_parameters.py:16): Vanek-Mandel-Brezina greedy aggregation with the
+//     symmetric strength test a_ij^2 >= theta^2 |a_ii a_jj| and the max_aggregation cap;
+//   * tentative P is boolean, R = P', A_{l+1} = P' A_l P (Galerkin);
+//   * coarsening stops at coarse_dof rows or max_levels (src/amg_parameters.py:50,56);
+//   * the coarsest operator is inverted densely (coarse_solver 32 = direct).
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+#include <queue>
+
+#include "hierarchy.h"
+
+namespace mamg {
+
+static inline bool row_isolated(const Csr& A, int i) {
+  for (int p = A.ia[i]; p < A.ia[i + 1]; ++p)
+    if (A.ja[p] != i && A.a[p] != 0.0) return false;
+  return true;
+}
+
+void aggregate_hem(const Csr& A, std::vector<int>& agg, int& nc) {
+  const int n = A.n;
+  agg.assign(n, -2);
+  nc = 0;
+  std::vector<int> pending;
+  for (int i = 0; i < n; ++i) {
+    if (agg[i] != -2) continue;
+    if (row_isolated(A, i)) { agg[i] = -1; continue; }
+    int best = -1;
+    double bw = 0.0;
+    for (int p = A.ia[i]; p < A.ia[i + 1]; ++p) {
+      int j = A.ja[p];
+      if (j == i || agg[j] != -2) continue;
+      double w = std::fabs(A.a[p]);
+      if (w > bw) { bw = w; best = j; }
+    }
+    if (best >= 0 && !row_isolated(A, best)) {
+      agg[i] = agg[best] = nc++;
+    } else {
+      pending.push_back(i);
+    }
+  }
+  for (int i : pending) {
+    int best = -1;
+    double bw = 0.0;
+    for (int p = A.ia[i]; p < A.ia[i + 1]; ++p) {
+      int j = A.ja[p];
+      if (j == i || agg[j] < 0) continue;
+      double w = std::fabs(A.a[p]);
+      if (w > bw) { bw = w; best = j; }
+    }
+    agg[i] = best >= 0 ? agg[best] : nc++;
+  }
+}
+
+void aggregate_vmb(const Csr& A, double strong, int max_agg, std::vector<int>& agg, int& nc) {
+  const int n = A.n;
+  std::vector<double> diag(n, 0.0);
+  for (int i = 0; i < n; ++i)
+    for (int p = A.ia[i]; p < A.ia[i + 1]; ++p)
+      if (A.ja[p] == i) diag[i] = A.a[p];
+  const double s2 = strong * strong;
+  auto is_strong = [&](int i, int p) {
+    int j = A.ja[p];
+    if (j == i || A.a[p] == 0.0) return false;
+    return A.a[p] * A.a[p] >= s2 * std::fabs(diag[i] * diag[j]);
+  };
+  agg.assign(n, -2);
+  nc = 0;
+  if (max_agg < 2) max_agg = 2;
+  // rows without strong neighbours are left out
+  for (int i = 0; i < n; ++i) {
+    bool any = false;
+    for (int p = A.ia[i]; p < A.ia[i + 1] && !any; ++p) any = is_strong(i, p);
+    if (!any) agg[i] = -1;
+  }
+  // pass 1: seed aggregates whose whole strong neighbourhood is free
+  for (int i = 0; i < n; ++i) {
+    if (agg[i] != -2) continue;
+    bool free_nbhd = true;
+    for (int p = A.ia[i]; p < A.ia[i + 1] && free_nbhd; ++p)
+      if (is_strong(i, p) && agg[A.ja[p]] != -2 && agg[A.ja[p]] != -1) free_nbhd = false;
+    if (!free_nbhd) continue;
+    int cnt = 1;
+    agg[i] = nc;
+    for (int p = A.ia[i]; p < A.ia[i + 1] && cnt < max_agg; ++p)
+      if (is_strong(i, p) && agg[A.ja[p]] == -2) { agg[A.ja[p]] = nc; ++cnt; }
+    ++nc;
+  }
+  // pass 2: attach leftovers to the pass-1 aggregate they are most strongly tied to
+  std::vector<int> frozen(agg);
+  for (int i = 0; i < n; ++i) {
+    if (agg[i] != -2) continue;
+    int best = -1;
+    double bw = 0.0;
+    for (int p = A.ia[i]; p < A.ia[i + 1]; ++p) {
+      if (!is_strong(i, p) || frozen[A.ja[p]] < 0) continue;
+      double w = std::fabs(A.a[p]);
+      if (w > bw) { bw = w; best = A.ja[p]; }
+    }
+    if (best >= 0) agg[i] = frozen[best];
+  }
+  // pass 3: what is still free forms new aggregates with its free strong neighbours
+  for (int i = 0; i < n; ++i) {
+    if (agg[i] != -2) continue;
+    int cnt = 1;
+    agg[i] = nc;
+    for (int p = A.ia[i]; p < A.ia[i + 1] && cnt < max_agg; ++p)
+      if (is_strong(i, p) && agg[A.ja[p]] == -2) { agg[A.ja[p]] = nc; ++cnt; }
+    ++nc;
+  }
+}
+
+// A_c = P' A P for boolean P (aggregate-specialised RAP): coarse row I is the sum of the
+// fine rows of aggregate I with columns mapped through agg; columns sorted ascending.
+void galerkin_ua(const Csr& A, const std::vector<int>& agg, int nc, Csr& Ac) {
+  const int n = A.n;
+  std::vector<int> cptr(nc + 1, 0), cidx;
+  for (int i = 0; i < n; ++i)
+    if (agg[i] >= 0) ++cptr[agg[i] + 1];
+  for (int I = 0; I < nc; ++I) cptr[I + 1] += cptr[I];
+  cidx.resize(cptr[nc]);
+  {
+    std::vector<int> fill(cptr.begin(), cptr.end() - 1);
+    for (int i = 0; i < n; ++i)
+      if (agg[i] >= 0) cidx[fill[agg[i]]++] = i;
+  }
+  Ac.n = Ac.m = nc;
+  Ac.ia.assign(nc + 1, 0);
+#pragma omp parallel
+  {
+    std::vector<int> mark(nc, -1);
+#pragma omp for schedule(static)
+    for (int I = 0; I < nc; ++I) {
+      int cnt = 0;
+      for (int q = cptr[I]; q < cptr[I + 1]; ++q) {
+        int i = cidx[q];
+        for (int p = A.ia[i]; p < A.ia[i + 1]; ++p) {
+          int J = agg[A.ja[p]];
+          if (J < 0) continue;
+          if (mark[J] != I) { mark[J] = I; ++cnt; }
+        }
+      }
+      Ac.ia[I + 1] = cnt;
+    }
+  }
+  for (int I = 0; I < nc; ++I) Ac.ia[I + 1] += Ac.ia[I];
+  Ac.ja.resize(Ac.ia[nc]);
+  Ac.a.resize(Ac.ia[nc]);
+#pragma omp parallel
+  {
+    std::vector<int> pos(nc, -1);
+    std::vector<std::pair<int, double>> rowbuf;
+#pragma omp for schedule(static)
+    for (int I = 0; I < nc; ++I) {
+      const int base = Ac.ia[I];
+      int cnt = 0;
+      for (int q = cptr[I]; q < cptr[I + 1]; ++q) {
+        int i = cidx[q];
+        for (int p = A.ia[i]; p < A.ia[i + 1]; ++p) {
+          int J = agg[A.ja[p]];
+          if (J < 0) continue;
+          if (pos[J] < base) { pos[J] = base + cnt; Ac.ja[base + cnt] = J; Ac.a[base + cnt] = A.a[p]; ++cnt; }
+          else Ac.a[pos[J]] += A.a[p];
+        }
+      }
+      rowbuf.resize(cnt);
+      for (int k = 0; k < cnt; ++k) rowbuf[k] = {Ac.ja[base + k], Ac.a[base + k]};
+      std::sort(rowbuf.begin(), rowbuf.end(),
+                [](const std::pair<int, double>& x, const std::pair<int, double>& y) { return x.first < y.first; });
+      for (int k = 0; k < cnt; ++k) { Ac.ja[base + k] = rowbuf[k].first; Ac.a[base + k] = rowbuf[k].second; pos[rowbuf[k].first] = -1; }
+    }
+  }
+}
+
+// Greedy multicolouring in natural row order over the nonzero off-diagonal couplings:
+// the fixed ordering the Gauss-Seidel sweeps use on the device AND in the oracle
+// (north_star: "Gauss-Seidel via a fixed multicolour ordering applied identically in
+// the reference comparison").
+void multicolor_greedy(const Csr& A, std::vector<int>& color, int& ncolors) {
+  const int n = A.n;
+  color.assign(n, -1);
+  ncolors = 0;
+  std::vector<int> forbid;  // forbid[c] == i  <=> colour c taken by a neighbour of row i
+  for (int i = 0; i < n; ++i) {
+    for (int p = A.ia[i]; p < A.ia[i + 1]; ++p) {
+      int j = A.ja[p];
+      if (j == i || A.a[p] == 0.0 || color[j] < 0) continue;
+      if ((int)forbid.size() <= color[j]) forbid.resize(color[j] + 1, -1);
+      forbid[color[j]] = i;
+    }
+    int c = 0;
+    while (c < (int)forbid.size() && forbid[c] == i) ++c;
+    color[i] = c;
+    if (c + 1 > ncolors) ncolors = c + 1;
+    if ((int)forbid.size() < ncolors) forbid.resize(ncolors, -1);
+  }
+}
+
+// Schwarz blocks: seed + Schwarz_maxlvl graph rings (breadth first over nonzero couplings),
+// at most Schwarz_mmsize dofs (src/amg_parameters.py:83-85); dofs sorted ascending.
+void schwarz_patches(const Csr& A, const int* seeds, int nseeds, int maxlvl, int mmsize,
+                     SchwarzPatches& out) {
+  out.ptr.assign(1, 0);
+  out.dofs.clear();
+  out.seed.assign(seeds, seeds + nseeds);
+  out.max_size = 0;
+  if (mmsize < 1) mmsize = 1;
+  std::vector<int> mark(A.n, -1), cur, nxt, blk;
+  for (int s = 0; s < nseeds; ++s) {
+    const int seed = seeds[s];
+    blk.assign(1, seed);
+    mark[seed] = s;
+    cur.assign(1, seed);
+    for (int ring = 0; ring < maxlvl && (int)blk.size() < mmsize; ++ring) {
+      nxt.clear();
+      for (int i : cur) {
+        for (int p = A.ia[i]; p < A.ia[i + 1]; ++p) {
+          int j = A.ja[p];
+          if (A.a[p] == 0.0 || mark[j] == s) continue;
+          if ((int)blk.size() >= mmsize) break;
+          mark[j] = s;
+          blk.push_back(j);
+          nxt.push_back(j);
+        }
+      }
+      cur.swap(nxt);
+    }
+    std::sort(blk.begin(), blk.end());
+    out.dofs.insert(out.dofs.end(), blk.begin(), blk.end());
+    out.ptr.push_back((int)out.dofs.size());
+    out.max_size = std::max(out.max_size, (int)blk.size());
+  }
+}
+
+// Conflict colouring of the patches, greedy in patch order.  Two patches conflict when one
+// touches the other's dofs or their matrix neighbours (then their multiplicative updates do
+// not commute); patches of one colour can be solved concurrently with a result identical to
+// visiting them one after another.
+void schwarz_color(const Csr& A, SchwarzPatches& sw) {
+  const int np = sw.npatch();
+  sw.color.assign(np, 0);
+  sw.ncolors = 0;
+  if (np == 0) return;
+  int W = 4;  // 64-bit words per dof mask, grown on demand
+  std::vector<uint64_t> mask((size_t)A.n * W, 0), forb;
+  for (int p = 0; p < np; ++p) {
+    forb.assign(W, 0);
+    for (int q = sw.ptr[p]; q < sw.ptr[p + 1]; ++q) {
+      int i = sw.dofs[q];
+      const uint64_t* mi = &mask[(size_t)i * W];
+      for (int w = 0; w < W; ++w) forb[w] |= mi[w];
+      for (int e = A.ia[i]; e < A.ia[i + 1]; ++e) {
+        if (A.a[e] == 0.0) continue;
+        const uint64_t* mj = &mask[(size_t)A.ja[e] * W];
+        for (int w = 0; w < W; ++w) forb[w] |= mj[w];
+      }
+    }
+    int c = -1;
+    for (int w = 0; w < W && c < 0; ++w)
+      if (~forb[w]) c = w * 64 + __builtin_ctzll(~forb[w]);
+    if (c < 0) {  // all W*64 colours taken: widen the masks
+      const int W2 = W * 2;
+      std::vector<uint64_t> m2((size_t)A.n * W2, 0);
+      for (size_t i = 0; i < (size_t)A.n; ++i)
+        for (int w = 0; w < W; ++w) m2[i * W2 + w] = mask[i * W + w];
+      mask.swap(m2);
+      c = W * 64;
+      W = W2;
+    }
+    sw.color[p] = c;
+    sw.ncolors = std::max(sw.ncolors, c + 1);
+    for (int q = sw.ptr[p]; q < sw.ptr[p + 1]; ++q)
+      mask[(size_t)sw.dofs[q] * W + c / 64] |= 1ull << (c % 64);
+  }
+}
+
+// Dense inverse of the coarsest operator by Gauss-Jordan with partial pivoting in extended
+// precision (stands in for the UMFPACK factorisation, coarse_solver 32).
+bool dense_inverse(const Csr& A, std::vector<double>& inv) {
+  const int n = A.n;
+  std::vector<long double> M((size_t)n * 2 * n, 0.0L);
+  for (int i = 0; i < n; ++i) {
+    for (int p = A.ia[i]; p < A.ia[i + 1]; ++p) M[(size_t)i * 2 * n + A.ja[p]] += A.a[p];
+    M[(size_t)i * 2 * n + n + i] = 1.0L;
+  }
+  for (int c = 0; c < n; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < n; ++r)
+      if (fabsl(M[(size_t)r * 2 * n + c]) > fabsl(M[(size_t)piv * 2 * n + c])) piv = r;
+    if (M[(size_t)piv * 2 * n + c] == 0.0L) return false;
+    if (piv != c)
+      for (int k = 0; k < 2 * n; ++k) std::swap(M[(size_t)piv * 2 * n + k], M[(size_t)c * 2 * n + k]);
+    long double d = 1.0L / M[(size_t)c * 2 * n + c];
+    for (int k = 0; k < 2 * n; ++k) M[(size_t)c * 2 * n + k] *= d;
+    for (int r = 0; r < n; ++r) {
+      if (r == c) continue;
+      long double f = M[(size_t)r * 2 * n + c];
+      if (f == 0.0L) continue;
+      for (int k = c; k < 2 * n; ++k) M[(size_t)r * 2 * n + k] -= f * M[(size_t)c * 2 * n + k];
+    }
+  }
+  inv.resize((size_t)n * n);
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) inv[(size_t)i * n + j] = (double)M[(size_t)i * 2 * n + n + j];
+  return true;
+}
+
+static void greedy_mis(const Csr& A, std::vector<int>& seeds) {
+  std::vector<char> state(A.n, 0);  // 0 free, 1 in MIS, 2 excluded
+  seeds.clear();
+  for (int i = 0; i < A.n; ++i) {
+    if (state[i]) continue;
+    state[i] = 1;
+    seeds.push_back(i);
+    for (int p = A.ia[i]; p < A.ia[i + 1]; ++p)
+      if (A.a[p] != 0.0 && state[A.ja[p]] == 0) state[A.ja[p]] = 2;
+  }
+}
+
+bool build_hierarchy(const mamg_params& prm, Csr&& A0, const int* idofs, int n_idofs,
+                     Hierarchy& H, std::string& err) {
+  auto t0 = std::chrono::steady_clock::now();
+  H.prm = prm;
+  H.lv.clear();
+  H.lv.emplace_back();
+  H.lv[0].A = std::move(A0);
+  if (prm.AMG_type != MAMG_UA_AMG) { err = "AMG_type: only UA_AMG is implemented (SA_AMG pending)"; return false; }
+  if (prm.cycle_type != MAMG_V_CYCLE && prm.cycle_type != MAMG_W_CYCLE) {
+    err = "cycle_type: only V_CYCLE and W_CYCLE are implemented";
+    return false;
+  }
+  if (prm.aggregation_type != MAMG_HEM && prm.aggregation_type != MAMG_VMB) {
+    err = "aggregation_type: only HEM and VMB are implemented";
+    return false;
+  }
+  switch (prm.smoother) {
+    case MAMG_SMOOTHER_JACOBI: case MAMG_SMOOTHER_GS: case MAMG_SMOOTHER_SGS:
+    case MAMG_SMOOTHER_SOR: case MAMG_SMOOTHER_SSOR: break;
+    default: err = "smoother: only JACOBI, GS, SGS, SOR, SSOR are implemented"; return false;
+  }
+  if (prm.coarse_solver != MAMG_SOLVER_UMFPACK) { err = "coarse_solver: only 32 (direct) is implemented"; return false; }
+  if (prm.Schwarz_levels > 0 && prm.Schwarz_blksolver != MAMG_SOLVER_UMFPACK) {
+    err = "Schwarz_blksolver: only 32 (direct) is implemented";
+    return false;
+  }
+  const int max_levels = std::max(1, prm.max_levels);
+  std::vector<int> seeds(idofs, idofs + n_idofs);
+  const bool metric = n_idofs > 0;
+  int l = 0;
+  while (true) {
+    Level& L = H.lv[l];
+    const int n = L.A.n;
+    const bool last = !(n > prm.coarse_dof && l < max_levels - 1);
+    if (!last && l < prm.Schwarz_levels) {
+      if (!metric) greedy_mis(L.A, seeds);
+      schwarz_patches(L.A, seeds.data(), (int)seeds.size(), prm.Schwarz_maxlvl, prm.Schwarz_mmsize, L.sw);
+      schwarz_color(L.A, L.sw);
+      L.gs_skip.assign(n, metric ? 0 : 1);
+      if (metric) for (int s : seeds) L.gs_skip[s] = 1;
+    }
+    if (last) break;
+    if (prm.aggregation_type == MAMG_HEM) aggregate_hem(L.A, L.agg, L.nc);
+    else aggregate_vmb(L.A, prm.strong_coupled, prm.max_aggregation, L.agg, L.nc);
+    if (L.nc == 0 || L.nc >= n) {  // no coarsening possible: this level becomes the coarsest
+      L.agg.clear(); L.nc = 0; L.sw = SchwarzPatches(); L.gs_skip.clear();
+      break;
+    }
+    multicolor_greedy(L.A, L.color, L.ncolors);
+    H.lv.emplace_back();
+    galerkin_ua(H.lv[l].A, H.lv[l].agg, H.lv[l].nc, H.lv[l + 1].A);
+    if (metric && l + 1 < prm.Schwarz_levels) {  // carry the interface seeds to the next level
+      std::vector<int> nxt;
+      std::vector<char> seen(H.lv[l].nc, 0);
+      for (int s : seeds) {
+        int I = H.lv[l].agg[s];
+        if (I >= 0 && !seen[I]) { seen[I] = 1; nxt.push_back(I); }
+      }
+      std::sort(nxt.begin(), nxt.end());
+      seeds.swap(nxt);
+    }
+    ++l;
+  }
+  const Csr& Ac = H.lv.back().A;
+  if (Ac.n > 8192) {
+    err = "coarsest level has " + std::to_string(Ac.n) + " rows (> 8192): direct coarse solve refused";
+    return false;
+  }
+  if (!dense_inverse(Ac, H.coarse_inv)) { err = "coarsest operator is singular"; return false; }
+  H.setup_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return true;
+}
+
+}  // namespace mamg

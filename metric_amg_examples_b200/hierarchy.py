@@ -1,0 +1,209 @@
+"""Thin Python owner of a mamg_handle: setup, export (for the oracle), device calls."""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import as_f64, as_i32, check, lib, ptr
+from .params import to_struct
+
+
+def csr_arrays(A):
+    """(indptr i32, indices i32, data f64, n) from whatever the caller holds.
+
+    Accepted, in the reference's own order of preference: dolfin PETScMatrix / petsc4py Mat
+    (what PETSc_to_dCSRmat takes, src/utils.py:108) when those modules exist, scipy.sparse
+    matrices, torch sparse-CSR tensors, or a plain (indptr, indices, data[, shape]) tuple.
+    """
+    if hasattr(A, "mat") and callable(A.mat):  # dolfin PETScMatrix
+        A = A.mat()
+    if hasattr(A, "getValuesCSR"):  # petsc4py.PETSc.Mat
+        indptr, indices, data = A.getValuesCSR()
+        return as_i32(indptr), as_i32(indices), as_f64(data), len(indptr) - 1
+    if isinstance(A, (tuple, list)):
+        indptr, indices, data = A[:3]
+        return as_i32(indptr), as_i32(indices), as_f64(data), len(indptr) - 1
+    if hasattr(A, "crow_indices"):  # torch sparse CSR
+        return (as_i32(A.crow_indices().cpu().numpy()), as_i32(A.col_indices().cpu().numpy()),
+                as_f64(A.values().cpu().numpy()), A.shape[0])
+    if hasattr(A, "tocsr"):
+        A = A.tocsr()
+        if A.shape[0] != A.shape[1]:
+            raise ValueError("matrix must be square")
+        if not A.has_sorted_indices:
+            A = A.sorted_indices()
+        return as_i32(A.indptr), as_i32(A.indices), as_f64(A.data), A.shape[0]
+    raise TypeError(f"cannot interpret {type(A)} as a CSR matrix")
+
+
+class Hierarchy:
+    """Owns one metric-AMG hierarchy (host) and, after to_device(), its copy on one B200."""
+
+    def __init__(self, A, parameters=None, idofs=None):
+        indptr, indices, data, n = csr_arrays(A)
+        self.n = int(n)
+        self.params = to_struct(parameters)
+        idofs = as_i32(idofs) if idofs is not None else np.zeros(0, np.int32)
+        self.idofs = idofs
+        h = C.c_void_p()
+        check(lib.mamg_setup(C.byref(self.params), self.n, ptr(indptr), ptr(indices), ptr(data),
+                             len(idofs), ptr(idofs), C.byref(h)))
+        self._h = h
+        self.on_device = False
+        self.device = None
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            lib.mamg_destroy(h)
+            self._h = None
+
+    # ---- introspection -------------------------------------------------------------------
+    @property
+    def num_levels(self):
+        v = C.c_int32()
+        check(lib.mamg_num_levels(self._h, C.byref(v)))
+        return v.value
+
+    @property
+    def setup_seconds(self):
+        v = C.c_double()
+        check(lib.mamg_setup_seconds(self._h, C.byref(v)))
+        return v.value
+
+    def level_info(self, level):
+        info = (C.c_int64 * 8)()
+        check(lib.mamg_level_info(self._h, level, info))
+        keys = ["rows", "nnz", "n_aggregates", "n_colors", "n_patches", "n_patch_entries",
+                "n_patch_colors", "max_patch_size"]
+        return dict(zip(keys, [int(x) for x in info]))
+
+    def export_level(self, level):
+        """Natural-ordering arrays of one level (what the oracle consumes)."""
+        info = self.level_info(level)
+        n, nnz = info["rows"], info["nnz"]
+        out = {
+            "n": n, "indptr": np.empty(n + 1, np.int32), "indices": np.empty(nnz, np.int32),
+            "data": np.empty(nnz, np.float64), "agg": np.empty(n, np.int32),
+            "color": np.empty(n, np.int32), "gs_skip": np.empty(n, np.uint8),
+            "n_aggregates": info["n_aggregates"], "n_colors": info["n_colors"],
+        }
+        check(lib.mamg_level_export(self._h, level, ptr(out["indptr"]), ptr(out["indices"]),
+                                    ptr(out["data"]), ptr(out["agg"]), ptr(out["color"]),
+                                    ptr(out["gs_skip"])))
+        npatch = info["n_patches"]
+        out["patch_ptr"] = np.zeros(npatch + 1, np.int32)
+        out["patch_dofs"] = np.empty(info["n_patch_entries"], np.int32)
+        out["patch_seed"] = np.empty(npatch, np.int32)
+        out["patch_color"] = np.empty(npatch, np.int32)
+        out["n_patch_colors"] = info["n_patch_colors"]
+        if npatch:
+            check(lib.mamg_schwarz_export(self._h, level, ptr(out["patch_ptr"]), ptr(out["patch_dofs"]),
+                                          ptr(out["patch_seed"]), ptr(out["patch_color"])))
+        return out
+
+    def export(self):
+        levels = [self.export_level(l) for l in range(self.num_levels)]
+        nc = levels[-1]["n"]
+        inv = np.empty((nc, nc), np.float64)
+        check(lib.mamg_coarse_export(self._h, ptr(inv)))
+        from .params import struct_to_dict
+        return {"levels": levels, "coarse_inv": inv, "params": struct_to_dict(self.params)}
+
+    def cycle_bytes(self):
+        v = C.c_int64()
+        check(lib.mamg_cycle_bytes(self._h, C.byref(v)))
+        return v.value
+
+    # ---- device ------------------------------------------------------------------------------
+    def to_device(self, device=0, stream=None):
+        check(lib.mamg_to_device(self._h, int(device), C.c_void_p(stream) if stream else None))
+        self.on_device = True
+        self.device = int(device)
+        return self
+
+    def set_stream(self, stream):
+        check(lib.mamg_set_stream(self._h, C.c_void_p(stream) if stream else None))
+
+    def device_bytes(self):
+        v = C.c_int64()
+        check(lib.mamg_device_bytes(self._h, C.byref(v)))
+        return v.value
+
+    def launch_count(self, reset=False):
+        v = C.c_int64()
+        check(lib.mamg_launch_count(self._h, C.byref(v), int(reset)))
+        return v.value
+
+    def _require_device(self):
+        if not self.on_device:
+            self.to_device(0)
+
+    @staticmethod
+    def _is_torch_cuda(x):
+        return hasattr(x, "is_cuda") and x.is_cuda
+
+    def _vec_call(self, fn, ins, n_out, *scalars):
+        """Run fn(handle, in..., out, scalars..., on_device) for numpy or torch-CUDA vectors."""
+        self._require_device()
+        if self._is_torch_cuda(ins[0]):
+            import torch
+            ins = [v.contiguous() for v in ins]
+            for v in ins:
+                if v.dtype != torch.float64:
+                    raise TypeError("device vectors must be float64")
+            out = torch.empty(n_out, dtype=torch.float64, device=ins[0].device)
+            torch.cuda.current_stream(ins[0].device).synchronize()
+            check(fn(self._h, *[C.c_void_p(v.data_ptr()) for v in ins], C.c_void_p(out.data_ptr()), *scalars, 1))
+            return out
+        ins = [as_f64(v) for v in ins]
+        out = np.empty(n_out, np.float64)
+        check(fn(self._h, *[ptr(v) for v in ins], ptr(out), *scalars, 0))
+        return out
+
+    def apply(self, r):
+        """z = B r: one multigrid cycle (mamg_apply)."""
+        if r.shape[0] != self.n:
+            raise ValueError(f"vector has {r.shape[0]} entries, operator has {self.n}")
+        return self._vec_call(lib.mamg_apply, [r], self.n)
+
+    def spmv(self, x, level=0):
+        self._require_device()
+        n = self.level_info(level)["rows"]
+        x = as_f64(x)
+        y = np.empty(n, np.float64)
+        check(lib.mamg_spmv(self._h, level, ptr(x), ptr(y), 0))
+        return y
+
+    def smooth(self, b, x, level=0, post=False):
+        self._require_device()
+        b = as_f64(b)
+        x = as_f64(x).copy()
+        check(lib.mamg_smooth(self._h, level, ptr(b), ptr(x), int(post), 0))
+        return x
+
+    def pcg(self, b, x0=None, tolerance=1e-8, relative=False, maxiter=500):
+        """cbc.block ConjGrad on the device; returns (x, info)."""
+        self._require_device()
+        res = np.zeros(maxiter + 1, np.float64)
+        al = np.zeros(max(maxiter, 1), np.float64)
+        be = np.zeros(max(maxiter, 1), np.float64)
+        nit = C.c_int32()
+        if self._is_torch_cuda(b):
+            import torch
+            b = b.contiguous()
+            x = torch.zeros_like(b) if x0 is None else x0.clone().contiguous()
+            torch.cuda.current_stream(b.device).synchronize()
+            rc = lib.mamg_pcg(self._h, C.c_void_p(b.data_ptr()), C.c_void_p(x.data_ptr()), tolerance,
+                              int(relative), maxiter, int(x0 is not None), 1, C.byref(nit), ptr(res),
+                              ptr(al), ptr(be))
+        else:
+            b = as_f64(b)
+            x = np.zeros(self.n, np.float64) if x0 is None else as_f64(x0).copy()
+            rc = lib.mamg_pcg(self._h, ptr(b), ptr(x), tolerance, int(relative), maxiter,
+                              int(x0 is not None), 0, C.byref(nit), ptr(res), ptr(al), ptr(be))
+        check(rc, allow=(1,))
+        k = nit.value
+        info = {"niters": k, "residuals": res[:k + 1].tolist(), "alphas": al[:k].tolist(),
+                "betas": be[:k].tolist(), "breakdown": rc == 1}
+        return x, info

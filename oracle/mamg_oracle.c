@@ -1,0 +1,365 @@
+/* mamg_oracle.c -- CPU restatement of the metric-AMG apply path.  TEST INFRASTRUCTURE ONLY:
+ * it may be imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs, never by the product package.
+ *
+ * PARITY UNPINNED.  The reference repository (anabudisa/metric-amg-examples) contains no
+ * arithmetic of this path, no tests and no golden vectors; the algorithm lives in three
+ * un-vendored, un-pinned dependencies that are absent from this machine:
+ *   - HAZmath / haznics (github.com/HAZmathTeam/hazmath, branch unspecified, README.md:19-20):
+ *     precond_amg -> mgcycle, smoother_dcsr_{gs,sgs,sor,jacobi}, smoother_dcsr_Schwarz_*,
+ *     aggregate-specialised restriction/prolongation, UMFPACK coarse solve;
+ *   - cbc.block (bitbucket.org/fenics-apps/cbc.block master, README.md:19):
+ *     block.iterative.ConjGrad (precondconjgrad) and the hazmath Precond.matvec wrapper;
+ *   - FEniCS_ii (github.com/MiroK/fenics_ii): ii_convert / ReductionOperator (block flattening).
+ * What follows restates their published algorithms (FASP-lineage multigrid cycle, standard
+ * preconditioned CG) and is anchored on the reference's own call sites:
+ *   parameters      src/amg_parameters.py:47-89, src/utils.py:60-82
+ *   operator        src/utils.py:45-90 (metricAMG(A, W, idofs=, parameters=))
+ *   Krylov call     src/bidomain_2d.py:205-216, src/emi_2d.py:211, src/emi_3d.py:143
+ * Choices HAZmath's source would pin are frozen here and in DESIGN.md ("Frozen choices").
+ *
+ * Two smoother orderings are implemented:
+ *   ordering 0  natural row / patch order (the sequential order HAZmath uses)
+ *   ordering 1  the multicolour order the device uses ("a fixed multicolour ordering that is
+ *               applied identically in the reference comparison", BASELINE.json north_star)
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+enum { UA_AMG = 1, V_CYCLE = 1, W_CYCLE = 2, SM_JACOBI = 1, SM_GS = 2, SM_SGS = 3, SM_SOR = 5, SM_SSOR = 6,
+       SW_FORWARD = 1, SW_BACKWARD = 2, SW_SYMMETRIC = 3 };
+
+typedef struct {
+  int n, nnz, nc, ncolors, npatch, npcolors, maxpatch;
+  int *ia, *ja, *agg, *color, *pptr, *pdofs, *pcolor;
+  /* rows / patches grouped by colour (built once) */
+  int *crow_ptr, *crow, *cpat_ptr, *cpat;
+  unsigned char* skip;
+  double *a, *invd, *x, *b, *w;
+} orc_level;
+
+typedef struct {
+  int cycle_type, maxit, smoother, presmooth, postsmooth, coarse_scaling, schwarz_type;
+  double relaxation;
+  int nlevels, cap;
+  orc_level* lv;
+  double* coarse_inv;
+  double *Lm, *rhs; /* patch scratch */
+  int ordering;
+  long visits;      /* level visits of the last apply (for reporting) */
+} orc_hier;
+
+static void* xmalloc(size_t n) { void* p = malloc(n ? n : 1); if (!p) abort(); return p; }
+static void* xdup(const void* src, size_t n) { void* p = xmalloc(n); if (n) memcpy(p, src, n); return p; }
+
+orc_hier* orc_create(int cycle_type, int maxit, int smoother, double relaxation, int presmooth,
+                     int postsmooth, int coarse_scaling, int schwarz_type) {
+  orc_hier* h = (orc_hier*)calloc(1, sizeof(orc_hier));
+  h->cycle_type = cycle_type; h->maxit = maxit; h->smoother = smoother; h->relaxation = relaxation;
+  h->presmooth = presmooth; h->postsmooth = postsmooth; h->coarse_scaling = coarse_scaling;
+  h->schwarz_type = schwarz_type; h->ordering = 1;
+  return h;
+}
+
+int orc_add_level(orc_hier* h, int n, const int* ia, const int* ja, const double* a, const int* agg,
+                  int nc, const int* color, int ncolors, const unsigned char* skip, int npatch,
+                  const int* pptr, const int* pdofs, const int* pcolor, int npcolors) {
+  if (h->nlevels == h->cap) {
+    h->cap = h->cap ? 2 * h->cap : 8;
+    h->lv = (orc_level*)realloc(h->lv, sizeof(orc_level) * h->cap);
+  }
+  orc_level* L = &h->lv[h->nlevels++];
+  memset(L, 0, sizeof(*L));
+  L->n = n; L->nnz = ia[n]; L->nc = nc; L->ncolors = ncolors > 0 ? ncolors : 1;
+  L->ia = (int*)xdup(ia, sizeof(int) * (n + 1));
+  L->ja = (int*)xdup(ja, sizeof(int) * L->nnz);
+  L->a = (double*)xdup(a, sizeof(double) * L->nnz);
+  L->agg = (int*)xdup(agg, sizeof(int) * n);
+  L->color = (int*)xdup(color, sizeof(int) * n);
+  L->skip = (unsigned char*)xdup(skip, n);
+  L->invd = (double*)xmalloc(sizeof(double) * n);
+  for (int i = 0; i < n; ++i) {
+    L->invd[i] = 1.0;
+    for (int p = ia[i]; p < ia[i + 1]; ++p) if (ja[p] == i) L->invd[i] = 1.0 / a[p];
+  }
+  L->x = (double*)calloc(n ? n : 1, sizeof(double));
+  L->b = (double*)calloc(n ? n : 1, sizeof(double));
+  L->w = (double*)calloc(n ? n : 1, sizeof(double));
+  /* rows by colour, natural order inside a colour */
+  L->crow_ptr = (int*)calloc(L->ncolors + 1, sizeof(int));
+  L->crow = (int*)xmalloc(sizeof(int) * n);
+  for (int i = 0; i < n; ++i) L->crow_ptr[L->color[i] + 1]++;
+  for (int c = 0; c < L->ncolors; ++c) L->crow_ptr[c + 1] += L->crow_ptr[c];
+  {
+    int* fill = (int*)xdup(L->crow_ptr, sizeof(int) * (L->ncolors + 1));
+    for (int i = 0; i < n; ++i) L->crow[fill[L->color[i]]++] = i;
+    free(fill);
+  }
+  L->npatch = npatch; L->npcolors = npcolors;
+  if (npatch > 0) {
+    L->pptr = (int*)xdup(pptr, sizeof(int) * (npatch + 1));
+    L->pdofs = (int*)xdup(pdofs, sizeof(int) * pptr[npatch]);
+    L->pcolor = (int*)xdup(pcolor, sizeof(int) * npatch);
+    L->cpat_ptr = (int*)calloc(npcolors + 1, sizeof(int));
+    L->cpat = (int*)xmalloc(sizeof(int) * npatch);
+    for (int p = 0; p < npatch; ++p) {
+      L->cpat_ptr[pcolor[p] + 1]++;
+      int s = pptr[p + 1] - pptr[p];
+      if (s > L->maxpatch) L->maxpatch = s;
+    }
+    for (int c = 0; c < npcolors; ++c) L->cpat_ptr[c + 1] += L->cpat_ptr[c];
+    int* fill = (int*)xdup(L->cpat_ptr, sizeof(int) * (npcolors + 1));
+    for (int p = 0; p < npatch; ++p) L->cpat[fill[pcolor[p]]++] = p;
+    free(fill);
+    size_t m = (size_t)L->maxpatch;
+    h->Lm = (double*)realloc(h->Lm, sizeof(double) * m * m);
+    h->rhs = (double*)realloc(h->rhs, sizeof(double) * m);
+  }
+  return h->nlevels - 1;
+}
+
+void orc_set_coarse(orc_hier* h, const double* inv) {
+  int n = h->lv[h->nlevels - 1].n;
+  h->coarse_inv = (double*)xdup(inv, sizeof(double) * (size_t)n * n);
+}
+void orc_set_ordering(orc_hier* h, int ordering) { h->ordering = ordering; }
+void orc_set_cycle(orc_hier* h, int cycle_type) { h->cycle_type = cycle_type; }
+long orc_visits(orc_hier* h) { return h->visits; }
+
+void orc_destroy(orc_hier* h) {
+  if (!h) return;
+  for (int l = 0; l < h->nlevels; ++l) {
+    orc_level* L = &h->lv[l];
+    free(L->ia); free(L->ja); free(L->a); free(L->agg); free(L->color); free(L->skip); free(L->invd);
+    free(L->x); free(L->b); free(L->w); free(L->crow_ptr); free(L->crow);
+    free(L->pptr); free(L->pdofs); free(L->pcolor); free(L->cpat_ptr); free(L->cpat);
+  }
+  free(h->lv); free(h->coarse_inv); free(h->Lm); free(h->rhs); free(h);
+}
+
+/* ---- kernels ------------------------------------------------------------------------------ */
+static double row_dot(const orc_level* L, int i, const double* x) {
+  double s = 0.0;
+  for (int p = L->ia[i]; p < L->ia[i + 1]; ++p) s += L->a[p] * x[L->ja[p]];
+  return s;
+}
+
+void orc_spmv_level(const orc_level* L, const double* x, double* y) {
+  for (int i = 0; i < L->n; ++i) y[i] = row_dot(L, i, x);
+}
+
+/* x_i <- x_i + w (b_i - a_i . x) / a_ii  for one row */
+static void gs_row(const orc_level* L, int i, const double* b, double* x, double w) {
+  if (L->skip[i]) return;
+  x[i] += w * (b[i] - row_dot(L, i, x)) * L->invd[i];
+}
+
+/* one directional sweep. ordering 0: rows 0..n-1 (or reversed); ordering 1: colours ascending
+ * (descending), natural order inside a colour; skip_first_color drops the colour the previous
+ * sweep just finished (exact no-op for w = 1, mirrored from the device path). */
+static void gs_sweep(const orc_hier* h, const orc_level* L, const double* b, double* x, double w,
+                     int backward, int skip_first_color) {
+  if (h->ordering == 0) {
+    if (!backward) for (int i = 0; i < L->n; ++i) gs_row(L, i, b, x, w);
+    else for (int i = L->n - 1; i >= 0; --i) gs_row(L, i, b, x, w);
+    return;
+  }
+  for (int cc = skip_first_color; cc < L->ncolors; ++cc) {
+    int c = backward ? L->ncolors - 1 - cc : cc;
+    for (int q = L->crow_ptr[c]; q < L->crow_ptr[c + 1]; ++q) gs_row(L, L->crow[q], b, x, w);
+  }
+}
+
+static void jacobi(const orc_level* L, const double* b, double* x, double w) {
+  for (int i = 0; i < L->n; ++i)
+    L->w[i] = L->skip[i] ? x[i] : x[i] + w * (b[i] - row_dot(L, i, x)) * L->invd[i];
+  memcpy(x, L->w, sizeof(double) * L->n);
+}
+
+/* exact solve on one patch: x_B += A_BB^{-1} (b - A x)_B, dense Cholesky in patch order */
+static void patch_solve(orc_hier* h, const orc_level* L, int p, const double* b, double* x) {
+  const int q0 = L->pptr[p], s = L->pptr[p + 1] - q0;
+  const int* idx = L->pdofs + q0;
+  double* M = h->Lm;
+  double* r = h->rhs;
+  for (int k = 0; k < s; ++k) {
+    int i = idx[k];
+    r[k] = b[i] - row_dot(L, i, x);
+    for (int c = 0; c < s; ++c) M[k * s + c] = 0.0;
+    for (int e = L->ia[i]; e < L->ia[i + 1]; ++e) {
+      int j = L->ja[e];
+      /* idx is sorted ascending: binary search */
+      int lo = 0, hi = s - 1;
+      while (lo <= hi) {
+        int mid = (lo + hi) / 2;
+        if (idx[mid] == j) { M[k * s + mid] = L->a[e]; break; }
+        if (idx[mid] < j) lo = mid + 1; else hi = mid - 1;
+      }
+    }
+  }
+  for (int j = 0; j < s; ++j) {
+    double d = sqrt(M[j * s + j]);
+    M[j * s + j] = d;
+    r[j] /= d;
+    for (int i = j + 1; i < s; ++i) M[i * s + j] /= d;
+    for (int k = j + 1; k < s; ++k) {
+      double lkj = M[k * s + j];
+      for (int i = k; i < s; ++i) M[i * s + k] -= M[i * s + j] * lkj;
+    }
+    for (int i = j + 1; i < s; ++i) r[i] -= M[i * s + j] * r[j];
+  }
+  for (int j = s - 1; j >= 0; --j) {
+    r[j] /= M[j * s + j];
+    for (int i = 0; i < j; ++i) r[i] -= M[j * s + i] * r[j];
+  }
+  for (int k = 0; k < s; ++k) x[idx[k]] += r[k];
+}
+
+static void schwarz_sweep(orc_hier* h, const orc_level* L, const double* b, double* x, int backward) {
+  if (h->ordering == 0) {
+    if (!backward) for (int p = 0; p < L->npatch; ++p) patch_solve(h, L, p, b, x);
+    else for (int p = L->npatch - 1; p >= 0; --p) patch_solve(h, L, p, b, x);
+    return;
+  }
+  for (int cc = 0; cc < L->npcolors; ++cc) {
+    int c = backward ? L->npcolors - 1 - cc : cc;
+    for (int q = L->cpat_ptr[c]; q < L->cpat_ptr[c + 1]; ++q) patch_solve(h, L, L->cpat[q], b, x);
+  }
+}
+
+/* pre-smoothing: Schwarz on the interface patches, then the point smoother on the other rows
+ * (src/utils.py:84); post-smoothing: the adjoint order. */
+static void smooth(orc_hier* h, int lev, const double* b, double* x, int post) {
+  orc_level* L = &h->lv[lev];
+  const int iters = post ? h->postsmooth : h->presmooth;
+  const int mc = h->ordering == 1;
+  for (int phase = 0; phase < 2; ++phase) {
+    const int do_schwarz = post ? phase == 1 : phase == 0;
+    if (do_schwarz) {
+      if (L->npatch == 0) continue;
+      int fwd, bwd;
+      if (h->schwarz_type == SW_SYMMETRIC) fwd = bwd = 1;
+      else if (h->schwarz_type == SW_FORWARD) { fwd = !post; bwd = post; }
+      else { fwd = post; bwd = !post; }
+      if (fwd) schwarz_sweep(h, L, b, x, 0);
+      if (bwd) schwarz_sweep(h, L, b, x, 1);
+    } else {
+      for (int it = 0; it < iters; ++it) {
+        switch (h->smoother) {
+          case SM_JACOBI: jacobi(L, b, x, h->relaxation); break;
+          case SM_GS: gs_sweep(h, L, b, x, 1.0, post, 0); break;
+          case SM_SOR: gs_sweep(h, L, b, x, h->relaxation, post, 0); break;
+          case SM_SGS: gs_sweep(h, L, b, x, 1.0, 0, 0); gs_sweep(h, L, b, x, 1.0, 1, mc ? 1 : 0); break;
+          case SM_SSOR: gs_sweep(h, L, b, x, h->relaxation, 0, 0); gs_sweep(h, L, b, x, h->relaxation, 1, 0); break;
+        }
+      }
+    }
+  }
+}
+
+static void coarse_solve(orc_hier* h) {
+  orc_level* L = &h->lv[h->nlevels - 1];
+  const int n = L->n;
+  for (int i = 0; i < n; ++i) {
+    double s = 0.0;
+    for (int j = 0; j < n; ++j) s += h->coarse_inv[(size_t)i * n + j] * L->b[j];
+    L->x[i] = s;
+  }
+}
+
+/* FASP-lineage cycle: level l > 0 is visited cycle_type times per parent visit,
+ * re-entering with its current iterate. */
+static void cycle_level(orc_hier* h, int lev) {
+  if (lev == h->nlevels - 1) { coarse_solve(h); return; }
+  const int reps = (lev > 0 && h->cycle_type == W_CYCLE) ? 2 : 1;
+  orc_level* L = &h->lv[lev];
+  orc_level* C = &h->lv[lev + 1];
+  for (int rep = 0; rep < reps; ++rep) {
+    h->visits++;
+    smooth(h, lev, L->b, L->x, 0);
+    memset(C->b, 0, sizeof(double) * C->n);
+    for (int i = 0; i < L->n; ++i) {
+      int I = L->agg[i];
+      if (I >= 0) C->b[I] += L->b[i] - row_dot(L, i, L->x);
+    }
+    memset(C->x, 0, sizeof(double) * C->n);
+    cycle_level(h, lev + 1);
+    double alpha = 1.0;
+    if (h->coarse_scaling) {
+      double num = 0.0, den = 0.0;
+      for (int i = 0; i < C->n; ++i) { num += C->x[i] * C->b[i]; den += C->x[i] * row_dot(C, i, C->x); }
+      alpha = num / den;
+      alpha = (alpha < 1.0) ? alpha : 1.0;  /* MIN(alpha, 1.0); NaN -> 1 */
+    }
+    for (int i = 0; i < L->n; ++i) {
+      int I = L->agg[i];
+      if (I >= 0) L->x[i] += alpha * C->x[I];
+    }
+    smooth(h, lev, L->b, L->x, 1);
+  }
+}
+
+/* z = B r : haznics.apply_precond as called by cbc.block's Precond.matvec */
+void orc_apply(orc_hier* h, const double* r, double* z) {
+  orc_level* L0 = &h->lv[0];
+  h->visits = 0;
+  memcpy(L0->b, r, sizeof(double) * L0->n);
+  if (h->nlevels == 1) { coarse_solve(h); memcpy(z, L0->x, sizeof(double) * L0->n); return; }
+  memset(L0->x, 0, sizeof(double) * L0->n);
+  for (int it = 0; it < (h->maxit > 1 ? h->maxit : 1); ++it) cycle_level(h, 0);
+  memcpy(z, L0->x, sizeof(double) * L0->n);
+}
+
+void orc_spmv(orc_hier* h, int lev, const double* x, double* y) { orc_spmv_level(&h->lv[lev], x, y); }
+
+void orc_smooth(orc_hier* h, int lev, const double* b, double* x, int post) { smooth(h, lev, b, x, post); }
+
+/* cbc.block precondconjgrad.  Returns the iteration count;
+ * residuals[0..niters], alphas/betas[0..niters-1]. */
+int orc_pcg(orc_hier* h, const double* b, double* x, double tol, int relative, int maxiter,
+            int use_guess, double* residuals, double* alphas, double* betas) {
+  orc_level* L0 = &h->lv[0];
+  const int n = L0->n;
+  double* r = (double*)xmalloc(sizeof(double) * n);
+  double* z = (double*)xmalloc(sizeof(double) * n);
+  double* d = (double*)xmalloc(sizeof(double) * n);
+  double* q = (double*)xmalloc(sizeof(double) * n);
+  if (!use_guess) memset(x, 0, sizeof(double) * n);
+  for (int i = 0; i < n; ++i) r[i] = b[i] - (use_guess ? row_dot(L0, i, x) : 0.0);
+  orc_apply(h, r, z);
+  memcpy(d, z, sizeof(double) * n);
+  double rz = 0.0;
+  for (int i = 0; i < n; ++i) rz += r[i] * z[i];
+  double res = sqrt(rz);
+  residuals[0] = res;
+  const double target = relative ? tol * res : tol;
+  int it = 0;
+  while (res > target && it < maxiter) {
+    double dq = 0.0;
+    for (int i = 0; i < n; ++i) { q[i] = row_dot(L0, i, d); dq += d[i] * q[i]; }
+    double alpha = rz / dq;
+    for (int i = 0; i < n; ++i) { x[i] += alpha * d[i]; r[i] -= alpha * q[i]; }
+    orc_apply(h, r, z);
+    double rz2 = 0.0;
+    for (int i = 0; i < n; ++i) rz2 += r[i] * z[i];
+    double beta = rz2 / rz;
+    for (int i = 0; i < n; ++i) d[i] = z[i] + beta * d[i];
+    rz = rz2;
+    res = sqrt(rz);
+    if (alphas) alphas[it] = alpha;
+    if (betas) betas[it] = beta;
+    ++it;
+    residuals[it] = res;
+    if (!(rz >= 0.0) || !isfinite(alpha)) break;
+  }
+  free(r); free(z); free(d); free(q);
+  return it;
+}
+
+double orc_now(void) {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
