@@ -106,6 +106,8 @@ int mamg_setup_seconds(mamg_handle h, double* seconds);
 int mamg_to_device(mamg_handle h, int32_t device, void* stream);
 int mamg_set_stream(mamg_handle h, void* stream);
 int mamg_device_bytes(mamg_handle h, int64_t* bytes);
+/* block until everything queued on the handle's stream has finished */
+int mamg_sync(mamg_handle h);
 
 /* ---- apply: replaces haznics.apply_precond(b_np, x_np, precond) that cbc.block's
  *      Precond.matvec runs for every B*r inside ConjGrad (src/bidomain_2d.py:205-206).

@@ -27,7 +27,7 @@ class MamgParams(C.Structure):
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
-            f"{LIB_PATH} is missing: build it with `python -m metric_amg_examples_b200.build` "
+            f"{LIB_PATH} is missing: build it with `python metric_amg_examples_b200/build.py` "
             "(nvcc, sm_100a). This package has no CPU or pure-Python fallback.")
     lib = C.CDLL(LIB_PATH)
     i32, i64, dbl, vp = C.c_int32, C.c_int64, C.c_double, C.c_void_p
@@ -47,6 +47,7 @@ def _load():
         "mamg_to_device": (i32, [vp, i32, vp]),
         "mamg_set_stream": (i32, [vp, vp]),
         "mamg_device_bytes": (i32, [vp, pi64]),
+        "mamg_sync": (i32, [vp]),
         "mamg_apply": (i32, [vp, vp, vp, i32]),
         "mamg_spmv": (i32, [vp, i32, vp, vp, i32]),
         "mamg_smooth": (i32, [vp, i32, vp, vp, i32, i32]),

@@ -1,6 +1,6 @@
 """Build libmamg.so (host setup in C++ + sm_100a CUDA kernels + the C-ABI) in-tree.
 
-Usage: python -m metric_amg_examples_b200.build [--force]
+Usage: python metric_amg_examples_b200/build.py [--force] [-v]
 The shared object lands next to this file so that it travels with the repo snapshot.
 """
 import hashlib

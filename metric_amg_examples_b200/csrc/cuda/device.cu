@@ -511,6 +511,15 @@ int mamg_device_bytes(mamg_handle h, int64_t* bytes) {
   return 0;
 }
 
+int mamg_sync(mamg_handle h) {
+  MAMG_TRY
+  DeviceState* D = get_dev(h);
+  if (!D) return -1;
+  CUDA_OK(cudaStreamSynchronize(D->stream));
+  return 0;
+  MAMG_CATCH
+}
+
 int mamg_apply(mamg_handle h, const double* r, double* z, int32_t on_device) {
   MAMG_TRY
   DeviceState* D = get_dev(h);

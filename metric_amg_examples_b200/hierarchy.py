@@ -125,6 +125,9 @@ class Hierarchy:
     def set_stream(self, stream):
         check(lib.mamg_set_stream(self._h, C.c_void_p(stream) if stream else None))
 
+    def sync(self):
+        check(lib.mamg_sync(self._h))
+
     def device_bytes(self):
         v = C.c_int64()
         check(lib.mamg_device_bytes(self._h, C.byref(v)))
@@ -155,6 +158,7 @@ class Hierarchy:
             out = torch.empty(n_out, dtype=torch.float64, device=ins[0].device)
             torch.cuda.current_stream(ins[0].device).synchronize()
             check(fn(self._h, *[C.c_void_p(v.data_ptr()) for v in ins], C.c_void_p(out.data_ptr()), *scalars, 1))
+            check(lib.mamg_sync(self._h))  # the library runs on its own stream
             return out
         ins = [as_f64(v) for v in ins]
         out = np.empty(n_out, np.float64)

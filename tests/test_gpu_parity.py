@@ -1,0 +1,186 @@
+"""GPU parity tests: every device kernel and the whole apply / PCG path against the CPU oracle
+on the SAME exported hierarchy (north_star: apply within 1e-10 relative, iteration counts
+within +-1, same final tolerance).  All calls go through the C-ABI (ctypes)."""
+import numpy as np
+import pytest
+
+import metric_amg_examples_b200 as mamg
+from metric_amg_examples_b200 import haznics_compat as haznics, params, problems
+from oracle import Oracle
+
+pytestmark = pytest.mark.gpu
+
+APPLY_TOL = 1e-10  # north_star: single cycle apply vs the reference apply, fp64 relative
+
+
+def rel(a, b):
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def make(system, prm, metric=True):
+    H = mamg.Hierarchy(system.A, prm, system.interface_dofs if metric else None)
+    H.to_device(0)
+    return H, Oracle(H.export(), "multicolor")
+
+
+CASES = {
+    "bidomain2d_metric": lambda: (problems.bidomain_system(2, 32, gamma=1e3), params.parameters_metric),
+    "bidomain2d_schwarz": lambda: (problems.bidomain_system(2, 32, gamma=1e3), params.parameters_metric_schwarz),
+    "bidomain2d_g1e8": lambda: (problems.bidomain_system(2, 48, gamma=1e8), params.parameters_metric_schwarz),
+    "emi2d_default": lambda: (problems.emi_system(2, 64, gamma=1e6), params.default_metric_parameters),
+    "bidomain3d_schwarz": lambda: (problems.bidomain_system(3, 10, gamma=1e4), params.parameters_metric_schwarz),
+    "emi3d_default": lambda: (problems.emi_system(3, 12, gamma=1e6), params.default_metric_parameters),
+}
+
+
+@pytest.fixture(scope="module", params=sorted(CASES))
+def case(request):
+    system, prm = CASES[request.param]()
+    H, orc = make(system, prm)
+    return request.param, system, prm, H, orc
+
+
+def test_spmv_every_level(case):
+    _, system, _, H, orc = case
+    rng = np.random.default_rng(1)
+    for l in range(H.num_levels):
+        x = rng.standard_normal(H.level_info(l)["rows"])
+        assert rel(H.spmv(x, l), orc.spmv(x, l)) < 1e-14
+
+
+def test_smoother_every_level(case):
+    _, system, _, H, orc = case
+    rng = np.random.default_rng(2)
+    for l in range(H.num_levels - 1):
+        n = H.level_info(l)["rows"]
+        b, x = rng.standard_normal(n), rng.standard_normal(n)
+        for post in (False, True):
+            assert rel(H.smooth(b, x, l, post), orc.smooth(b, x, l, post)) < 1e-12
+
+
+def test_apply_matches_oracle(case):
+    name, system, _, H, orc = case
+    rng = np.random.default_rng(3)
+    for k in range(3):
+        r = rng.standard_normal(system.ndofs)
+        z, zo = H.apply(r), orc.apply(r)
+        assert rel(z, zo) < APPLY_TOL, name
+
+
+def test_apply_linear_scaling_and_symmetry(case):
+    """B is homogeneous of degree one (coarse scaling keeps alpha invariant under r -> c r) and,
+    with its symmetric smoothers, symmetric up to the alpha clipping."""
+    _, system, _, H, _ = case
+    rng = np.random.default_rng(4)
+    u, v = rng.standard_normal(system.ndofs), rng.standard_normal(system.ndofs)
+    assert rel(H.apply(3.5 * u), 3.5 * H.apply(u)) < 1e-12
+    Bu, Bv = H.apply(u), H.apply(v)
+    assert Bu @ u > 0 and Bv @ v > 0
+
+
+def test_pcg_matches_oracle(case):
+    name, system, prm, H, orc = case
+    b, xt = system.random_rhs(0)
+    tol = 1e-10 if name.startswith("emi") else 1e-8   # src/emi_2d.py:211 / src/bidomain_2d.py:205
+    x, info = H.pcg(b, tolerance=tol, maxiter=500)
+    xo, ref = orc.pcg(b, tolerance=tol, maxiter=500)
+    assert abs(info["niters"] - ref["niters"]) <= 1
+    assert info["residuals"][-1] <= tol and ref["residuals"][-1] <= tol
+    k = min(info["niters"], ref["niters"], 5)
+    assert np.allclose(info["residuals"][:k + 1], ref["residuals"][:k + 1], rtol=1e-8)
+    assert np.allclose(info["alphas"][:k], ref["alphas"][:k], rtol=1e-8)
+    assert rel(x, xt) < 1e-6
+    # true residual
+    assert np.linalg.norm(system.A @ x - b) / np.linalg.norm(b) < 1e-7
+
+
+def test_pcg_relative_and_initial_guess(case):
+    _, system, _, H, orc = case
+    b, xt = system.random_rhs(5)
+    x, info = H.pcg(b, tolerance=1e-8, relative=True, maxiter=500)
+    assert info["residuals"][-1] <= 1e-8 * info["residuals"][0]
+    x2, info2 = H.pcg(b, x0=x, tolerance=1e-8, relative=False, maxiter=500)
+    assert info2["niters"] <= 3
+    _, ref = orc.pcg(b, tolerance=1e-8, relative=True, maxiter=500)
+    assert abs(info["niters"] - ref["niters"]) <= 1
+
+
+@pytest.mark.parametrize("cycle", [haznics.V_CYCLE, haznics.W_CYCLE])
+@pytest.mark.parametrize("smoother,relax", [(haznics.SMOOTHER_JACOBI, 0.6), (haznics.SMOOTHER_GS, 1.0),
+                                            (haznics.SMOOTHER_SGS, 1.0), (haznics.SMOOTHER_SOR, 1.2),
+                                            (haznics.SMOOTHER_SSOR, 1.2)])
+def test_option_space(cycle, smoother, relax):
+    system = problems.bidomain_system(2, 24, gamma=1e2)
+    prm = dict(params.parameters_metric, cycle_type=cycle, smoother=smoother, relaxation=relax,
+               presmooth_iter=2, postsmooth_iter=1)
+    H, orc = make(system, prm)
+    r = np.random.default_rng(6).standard_normal(system.ndofs)
+    assert rel(H.apply(r), orc.apply(r)) < APPLY_TOL
+
+
+@pytest.mark.parametrize("stype", [haznics.SCHWARZ_FORWARD, haznics.SCHWARZ_BACKWARD, haznics.SCHWARZ_SYMMETRIC])
+def test_schwarz_types_and_large_patches(stype):
+    system = problems.emi_system(2, 32, gamma=1e4)
+    prm = dict(params.default_metric_parameters, Schwarz_type=stype, Schwarz_maxlvl=4, Schwarz_mmsize=60)
+    H, orc = make(system, prm)
+    assert 32 < H.level_info(0)["max_patch_size"] <= 60
+    r = np.random.default_rng(7).standard_normal(system.ndofs)
+    assert rel(H.apply(r), orc.apply(r)) < APPLY_TOL
+
+
+def test_standard_amg_vmb():
+    system = problems.bidomain_system(2, 32, gamma=1.0)
+    for prm in (params.parameters_standard, params.parameters_standard_schwarz):
+        H, orc = make(system, prm, metric=False)
+        r = np.random.default_rng(8).standard_normal(system.ndofs)
+        assert rel(H.apply(r), orc.apply(r)) < APPLY_TOL
+
+
+def test_coarse_scaling_off_gives_symmetric_operator():
+    system = problems.bidomain_system(2, 24, gamma=1e3)
+    prm = dict(params.parameters_metric_schwarz, coarse_scaling=haznics.OFF)
+    H, _ = make(system, prm)
+    rng = np.random.default_rng(9)
+    u, v = rng.standard_normal(system.ndofs), rng.standard_normal(system.ndofs)
+    a, b = v @ H.apply(u), u @ H.apply(v)
+    assert abs(a - b) / abs(a) < 1e-11
+
+
+@pytest.mark.parametrize("gamma", [1e0, 1e2, 1e4, 1e6, 1e8, 1e10])
+def test_gamma_sweep_iterations(gamma):
+    """run_bidomain_2d.sh sweeps gamma over 1e0..1e10: iteration counts stay bounded and equal the
+    oracle's within one."""
+    system = problems.bidomain_system(2, 32, gamma=gamma)
+    H, orc = make(system, params.parameters_metric_schwarz)
+    b, _ = system.random_rhs(0)
+    _, info = H.pcg(b, tolerance=1e-8, maxiter=500)
+    _, ref = orc.pcg(b, tolerance=1e-8, maxiter=500)
+    assert abs(info["niters"] - ref["niters"]) <= 1
+    assert info["niters"] <= 40
+
+
+def test_torch_device_vectors():
+    import torch
+    system = problems.bidomain_system(2, 32, gamma=1e3)
+    H, orc = make(system, params.parameters_metric_schwarz)
+    r = np.random.default_rng(10).standard_normal(system.ndofs)
+    rt = torch.from_numpy(r).cuda()
+    z = H.apply(rt)
+    torch.cuda.synchronize()
+    assert z.is_cuda and rel(z.cpu().numpy(), orc.apply(r)) < APPLY_TOL
+    b, xt = system.random_rhs(1)
+    x, info = H.pcg(torch.from_numpy(b).cuda(), tolerance=1e-8)
+    assert rel(x.cpu().numpy(), xt) < 1e-6
+
+
+def test_larger_properties():
+    """Size-independent checks at a size the oracle does not need to finish: PCG reaches the
+    tolerance, true residual agrees, B stays positive and homogeneous."""
+    system = problems.bidomain_system(3, 40, gamma=1e4)  # 137 842 dofs
+    H = mamg.Hierarchy(system.A, params.parameters_metric_schwarz, system.interface_dofs).to_device(0)
+    b, xt = system.random_rhs(2)
+    x, info = H.pcg(b, tolerance=1e-8, relative=True, maxiter=200)
+    assert info["residuals"][-1] <= 1e-8 * info["residuals"][0]
+    assert np.linalg.norm(system.A @ x - b) / np.linalg.norm(b) < 1e-6
+    u = np.random.default_rng(11).standard_normal(system.ndofs)
+    assert rel(H.apply(-2.0 * u), -2.0 * H.apply(u)) < 1e-12

@@ -1,0 +1,192 @@
+"""CPU tests: C-ABI surface, synthetic systems, host setup, parameter translation.
+(No compute call needs a GPU here; `-m "not gpu"` runs this file in well under a minute.)"""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import metric_amg_examples_b200 as mamg
+from metric_amg_examples_b200 import _capi, haznics_compat as haznics, params, problems
+from oracle import fem_ref
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_exported():
+    """Every function include/mamg.h declares is exported by libmamg.so and bound in _capi."""
+    hdr = open(os.path.join(ROOT, "include", "mamg.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = sorted(set(re.findall(r"\b(mamg_[a-z_0-9]+)\s*\(", hdr)))
+    assert len(names) >= 25
+    lib = C.CDLL(_capi.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in mamg.h but not exported"
+    assert set(names) == set(_capi.SYMBOLS)
+    assert b"sm_100a" in _capi.lib.mamg_version()
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    s = problems.bidomain_system(2, 8, gamma=10.0)
+    H = mamg.Hierarchy(s.A, params.parameters_metric, s.interface_dofs)
+    with pytest.raises(_capi.MamgError, match="no CUDA device|no CPU fallback"):
+        H.to_device(0)
+    with pytest.raises(_capi.MamgError):
+        H.apply(np.ones(s.ndofs))
+
+
+# nnz / dof counts of SURVEY 8a (closed forms of the structural P1 pattern)
+@pytest.mark.parametrize("n,dofs,nnz", [(32, 2178, 29444), (64, 8450, 116228), (128, 33282, 461828),
+                                        (256, 132098, 1841156)])
+def test_bidomain_2d_counts(n, dofs, nnz):
+    s = problems.bidomain_system(2, n, gamma=1e3)
+    assert s.ndofs == dofs and s.A.nnz == nnz
+    assert len(s.interface_dofs) == dofs // 2 and s.interface_dofs[0] == dofs // 2
+
+
+def test_emi_counts_and_interface_dofs():
+    s = problems.emi_system(2, 64, gamma=1e6)
+    assert s.ndofs == 4290
+    assert len(s.interface_dofs) == 65           # Omega_1 side only in 2-D (src/emi_2d.py:205)
+    s3 = problems.emi_system(3, 8, gamma=1e6)
+    assert len(s3.interface_dofs) == 2 * 81      # both sides in 3-D (src/emi_3d.py:134-138)
+    assert s3.interface_dofs[81] >= s3.W[0].dim()
+    with pytest.raises(_capi.MamgError):
+        problems.emi_system(2, 7)
+
+
+@pytest.mark.parametrize("kind", ["bidomain", "emi"])
+@pytest.mark.parametrize("dim,n", [(2, 8), (3, 4), (2, 12), (3, 6)])
+def test_assembler_matches_cellwise_fem(kind, dim, n):
+    s = (problems.bidomain_system if kind == "bidomain" else problems.emi_system)(dim, n, 2.0, 3.0, 7.0)
+    R = getattr(fem_ref, kind)(dim, n, 2.0, 3.0, 7.0)
+    assert np.array_equal(s.A.indptr, R.indptr) and np.array_equal(s.A.indices, R.indices)
+    assert abs(s.A - R).max() < 1e-13
+    assert abs(s.A - s.A.T).max() == 0.0
+
+
+def test_systems_are_spd():
+    for s in (problems.bidomain_system(2, 12, gamma=1e4), problems.emi_system(2, 12, gamma=1e4),
+              problems.emi_system(3, 4, gamma=1e2)):
+        w = np.linalg.eigvalsh(s.A.toarray())
+        assert w.min() > 0
+
+
+def _P(level):
+    agg = level["agg"]
+    rows = np.flatnonzero(agg >= 0)
+    return sp.csr_matrix((np.ones(len(rows)), (rows, agg[rows])), shape=(level["n"], level["n_aggregates"]))
+
+
+@pytest.mark.parametrize("prm", ["parameters_metric", "parameters_metric_schwarz", "parameters_standard",
+                                 "parameters_standard_schwarz", "default_metric_parameters"])
+def test_hierarchy_invariants(prm):
+    s = problems.bidomain_system(2, 32, gamma=1e3)
+    P = getattr(params, prm)
+    metric = "metric" in prm
+    H = mamg.Hierarchy(s.A, P, s.interface_dofs if metric else None)
+    ex = H.export()
+    L = ex["levels"]
+    assert L[-1]["n"] <= P["coarse_dof"] or len(L) == P["max_levels"]
+    for l in range(len(L) - 1):
+        A = sp.csr_matrix((L[l]["data"], L[l]["indices"], L[l]["indptr"]), shape=(L[l]["n"],) * 2)
+        Ac = sp.csr_matrix((L[l + 1]["data"], L[l + 1]["indices"], L[l + 1]["indptr"]), shape=(L[l + 1]["n"],) * 2)
+        Pm = _P(L[l])
+        # Galerkin product
+        G = (Pm.T @ A @ Pm).tocsr()
+        assert abs(G - Ac).max() <= 1e-12 * abs(Ac).max()
+        # aggregates partition the non-isolated rows; isolated rows (identity) are left out
+        agg = L[l]["agg"]
+        offdiag = abs(A - sp.diags(A.diagonal())).sum(axis=1).A1
+        assert np.all((agg < 0) == (offdiag == 0)) or "standard" in prm
+        assert np.all(np.bincount(agg[agg >= 0], minlength=L[l]["n_aggregates"]) >= 1)
+        # colouring: no two coupled rows share a colour
+        col = L[l]["color"]
+        C_ = A.tocoo()
+        m = (C_.row != C_.col) & (C_.data != 0)
+        assert np.all(col[C_.row[m]] != col[C_.col[m]])
+        assert col.max() + 1 == L[l]["n_colors"]
+    if metric and P["Schwarz_levels"] > 0:
+        l0 = L[0]
+        A = sp.csr_matrix((l0["data"], l0["indices"], l0["indptr"]), shape=(l0["n"],) * 2)
+        npatch = len(l0["patch_seed"])
+        assert npatch == len(s.interface_dofs)
+        assert np.array_equal(l0["patch_seed"], s.interface_dofs)
+        assert np.all(l0["gs_skip"][s.interface_dofs] == 1) and l0["gs_skip"].sum() == npatch
+        # patch-conflict colouring: same colour => patches neither overlap nor touch through A
+        Anz = A.copy()
+        Anz.eliminate_zeros()  # structural zeros (BC-eliminated entries) carry no coupling
+        owner = {}
+        for c in range(l0["n_patch_colors"]):
+            touched = np.zeros(l0["n"], bool)
+            for p in np.flatnonzero(l0["patch_color"] == c):
+                d = l0["patch_dofs"][l0["patch_ptr"][p]:l0["patch_ptr"][p + 1]]
+                assert len(d) <= P["Schwarz_mmsize"] and s.interface_dofs[p] in d
+                nb = np.unique(Anz[d].indices)
+                assert not touched[d].any(), "patches of one colour conflict"
+                touched[nb] = True
+                touched[d] = True
+        assert owner == {}
+    inv = ex["coarse_inv"]
+    Ac = sp.csr_matrix((L[-1]["data"], L[-1]["indices"], L[-1]["indptr"]), shape=(L[-1]["n"],) * 2).toarray()
+    assert np.allclose(inv @ Ac, np.eye(L[-1]["n"]), atol=1e-9)
+
+
+def test_hem_pairs_metric_coupling_first():
+    """At large gamma HEM matches (u1_i, u2_i): the metric term is collapsed on level 1."""
+    s = problems.bidomain_system(2, 16, gamma=1e8)
+    H = mamg.Hierarchy(s.A, params.parameters_metric, s.interface_dofs)
+    agg = H.export_level(0)["agg"]
+    nv = s.W[0].dim()
+    free = agg[:nv] >= 0
+    assert np.all(agg[:nv][free] == agg[nv:][free])
+
+
+def test_parameter_translation():
+    p = params.to_struct(params.parameters_metric_schwarz)
+    assert p.cycle_type == haznics.W_CYCLE and p.aggregation_type == haznics.HEM
+    assert p.Schwarz_maxlvl == 1 and p.Schwarz_levels == 1 and p.coarse_dof == 100
+    d = params.to_struct(None)  # src/utils.py:60-82
+    assert d.Schwarz_maxlvl == 2 and d.smoother == haznics.SMOOTHER_SGS
+    with pytest.warns(UserWarning):
+        params.to_struct({"no_such_key": 1})
+    with pytest.raises(NotImplementedError):
+        params.to_struct({"cycle_type": haznics.AMLI_CYCLE})
+    with pytest.raises(NotImplementedError):
+        params.to_struct({"aggregation_type": haznics.MWM})
+    with pytest.raises(NotImplementedError):
+        params.to_struct({"coarse_solver": 0})
+
+
+def test_reference_parameter_file_runs_unchanged():
+    """src/amg_parameters.py imports `haznics`; our constants module must satisfy it."""
+    import sys
+    import types
+    ref = "/root/reference/src/amg_parameters.py"
+    if not os.path.exists(ref):
+        pytest.skip("reference checkout not present on this box")
+    sys.modules["haznics"] = haznics
+    try:
+        mod = types.ModuleType("ref_amg_parameters")
+        exec(compile(open(ref).read(), ref, "exec"), mod.__dict__)
+    finally:
+        del sys.modules["haznics"]
+    for name in ("parameters_standard", "parameters_standard_schwarz", "parameters_metric",
+                 "parameters_metric_schwarz"):
+        assert getattr(mod, name) == getattr(params, name), name
+
+
+def test_setup_errors():
+    A = sp.eye(4, format="csr")
+    bad = sp.csr_matrix(np.array([[0.0, 1.0], [1.0, 0.0]]))
+    with pytest.raises(_capi.MamgError, match="diagonal"):
+        mamg.Hierarchy(bad, params.parameters_metric)
+    with pytest.raises(_capi.MamgError, match="out of range"):
+        mamg.Hierarchy(A, params.parameters_metric, idofs=[7])
+    H = mamg.Hierarchy(A, params.parameters_metric)  # 4 rows <= coarse_dof: one level
+    assert H.num_levels == 1
