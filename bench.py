@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py -- metric-AMG preconditioned CG solve on B200 (BASELINE.json metric:
+"V-cycle ms & solve DOF/s to rtol 1e-8 at 1/2/4/8 B200; SpMV % of HBM peak").
+
+A "step" is one complete solve of the hot path: cbc.block-style PCG to rtol 1e-8
+(relativeconv=True) with the metric-AMG cycle as preconditioner on one synthetic system.
+  value   DOF/s with b already resident in HBM (CUDA events around K solves)
+  e2e     the same solves through the public API (ConjGrad(A, precond=B) * b) with HOST
+          vectors: H2D of b and D2H of x inside the timed region
+Default workload at N=1: BASELINE.json configs[2], bidomain_3d on UnitCubeMesh(199) (16.0 M DOFs)
+with src/amg_parameters.py:parameters_metric_schwarz; the headline uses cycle_type V_CYCLE (the
+metric names the V-cycle; the W-cycle configured upstream is reported beside it with --wcycle).
+`--impl reference` times the CPU restatement (oracle/) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="mamg", choices=["mamg", "reference"])
+    ap.add_argument("--workload", default="bidomain_3d", choices=["bidomain_2d", "bidomain_3d", "emi_2d", "emi_3d"])
+    ap.add_argument("-n", type=int, default=None, help="cells per direction (default: the BASELINE config size)")
+    ap.add_argument("--gamma", type=float, default=1e4)
+    ap.add_argument("--cycle", default="V", choices=["V", "W"])
+    ap.add_argument("--wcycle", type=int, default=0, help="also time this many W-cycle applies/solve")
+    ap.add_argument("--cpu-sample-n", type=int, default=None, help="mesh size of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rtol", type=float, default=1e-8)
+    return ap.parse_args()
+
+
+DEFAULT_N = {"bidomain_2d": 256, "bidomain_3d": 199, "emi_2d": 2048, "emi_3d": 232}
+CPU_SAMPLE_N = {"bidomain_2d": 128, "bidomain_3d": 40, "emi_2d": 256, "emi_3d": 48}
+
+
+def make_system(workload, n, gamma):
+    from metric_amg_examples_b200 import params, problems
+    kind, dim = workload.split("_")
+    dim = int(dim[0])
+    if kind == "bidomain":
+        s = problems.bidomain_system(dim, n, gamma=gamma)
+        prm = dict(params.parameters_metric_schwarz)   # src/bidomain_2d.py:201, src/bidomain_3d.py:145
+    else:
+        s = problems.emi_system(dim, n, gamma=gamma)
+        prm = dict(params.default_metric_parameters)   # src/emi_2d.py:207 passes no parameters
+    return s, prm
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 7 for k in range(4) if r[3 + k].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def class_bytes(H, niters, cycle_applies):
+    """Algorithmic bytes per kernel class (fp64 values, int32 columns, every vector
+    counted once per kernel) for `cycle_applies` V-cycle applies plus `niters` CG iterations,
+    counted from the rows each launch really processes."""
+    import numpy as np
+    import ctypes as C
+    from metric_amg_examples_b200._capi import lib, ptr
+    L = H.num_levels
+    infos = [H.level_info(l) for l in range(L)]
+    prm = H.params
+    out = {k: 0.0 for k in H.KERNEL_CLASSES}
+    sgs = prm.smoother in (3, 6)
+    for l in range(L - 1):
+        n, nnz, nc = infos[l]["rows"], infos[l]["nnz"], infos[l + 1]["rows"]
+        nnzc = infos[l + 1]["nnz"]
+        # rows the point smoother really touches (Schwarz seeds are skipped) and the share of the
+        # colour that the backward SGS sweep skips
+        indptr = np.empty(n + 1, np.int32)
+        color = np.empty(n, np.int32)
+        skip = np.empty(n, np.uint8)
+        lib.mamg_level_export(H._h, l, ptr(indptr), None, None, None, ptr(color), ptr(skip))
+        rl = np.diff(indptr).astype(np.int64)
+        act = skip == 0
+        nnz_act, n_act = int(rl[act].sum()), int(act.sum())
+        last = act & (color == infos[l]["n_colors"] - 1)
+        nnz_last, n_last = int(rl[last].sum()), int(last.sum())
+        sweep = 12 * nnz_act + 4 * (n_act + 1) + 24 * n_act
+        sweep_bw = sweep - (12 * nnz_last + 28 * n_last) if prm.smoother == 3 else sweep
+        per_smooth = (sweep + sweep_bw) if sgs else sweep
+        out["gs"] += per_smooth * (prm.presmooth_iter + prm.postsmooth_iter)
+        if infos[l]["n_patches"]:
+            sw = 12 * infos[l]["patch_row_entries"] + 8 * infos[l]["patch_inv_entries"] \
+                + 28 * infos[l]["n_patch_entries"] + 8 * infos[l]["n_patches"]
+            nsw = 2 if prm.Schwarz_type == 3 else 1
+            out["schwarz"] += 2 * nsw * sw
+        agg = np.empty(n, np.int32)
+        lib.mamg_level_export(H._h, l, None, None, None, ptr(agg), None, None)
+        inagg = agg >= 0
+        out["restrict"] += 12 * int(rl[inagg].sum()) + (4 + 4 + 8 + 8) * int(inagg.sum()) + 16 * nc
+        if prm.coarse_scaling:
+            out["scale"] += 12 * nnzc + 4 * (nc + 1) + 16 * nc
+        out["prolong"] += 4 * n + 16 * int(inagg.sum()) + 8 * nc
+    ncst = infos[-1]["rows"]
+    out["coarse"] += 8 * ncst * ncst + 16 * ncst
+    for k in out:
+        out[k] *= cycle_applies
+    n0, nnz0 = infos[0]["rows"], infos[0]["nnz"]
+    out["spmv"] += niters * (12 * nnz0 + 4 * (n0 + 1) + 24 * n0)
+    out["dot"] += (niters + 1) * 16 * n0
+    # pcg update (48 n) + direction (24 n) per iteration, zero-fill of z per apply, gathers/copies at both ends
+    out["vector"] += niters * 72 * n0 + cycle_applies * 8 * n0 + 5 * 20 * n0
+    return out
+
+
+def run_mamg(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import metric_amg_examples_b200 as mamg
+    from metric_amg_examples_b200 import haznics_compat as hz
+    from metric_amg_examples_b200.iterative import ConjGrad
+    from metric_amg_examples_b200.precond import metricAMG
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = a.n or DEFAULT_N[a.workload]
+    t0 = time.time()
+    system, prm = make_system(a.workload, n, a.gamma)
+    t_asm = time.time() - t0
+    prm["cycle_type"] = hz.V_CYCLE if a.cycle == "V" else hz.W_CYCLE
+    t0 = time.time()
+    B = metricAMG(system.A, system.W, idofs=system.interface_dofs, parameters=prm, device=local)
+    H = B.hierarchy
+    t_setup = time.time() - t0
+    stream = torch.cuda.Stream()
+    t0 = time.time()
+    H.to_device(local, stream.cuda_stream)
+    t_upload = time.time() - t0
+    ndofs = system.ndofs
+    b_host, x_true = system.random_rhs(rank)
+    b_pin = torch.from_numpy(b_host).pin_memory()
+    b_dev = b_pin.cuda(non_blocking=False)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    iters = []
+
+    def solve_dev():
+        x, info = H.pcg(b_dev, tolerance=a.rtol, relative=True, maxiter=500)
+        iters.append(info["niters"])
+        return x, info
+
+    with torch.cuda.stream(stream):
+        for _ in range(a.warmup):
+            x, info = solve_dev()
+        rel_err = float(torch.linalg.norm(x - torch.from_numpy(x_true).cuda()) / np.linalg.norm(x_true))
+        # ---- device-resident timing: K solves between CUDA events on the launching stream ----
+        H.launch_count(reset=True)
+        barrier()
+        sampler = ClockSampler(local) if rank == 0 else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(a.steps):
+            x, info = solve_dev()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = H.launch_count(reset=True)
+        clocks = sampler.stop() if sampler else None
+        # ---- end-to-end through the public API with host vectors (H2D b, D2H x inside) ----
+        solver = ConjGrad(system.A, precond=B, tolerance=a.rtol, relativeconv=True, maxiter=500, show=0)
+        bh = b_pin.numpy()
+        xs = solver * bh  # warm
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            xs = solver * bh
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        assert solver.mode == "fused"
+        # ---- one V-cycle apply, and per-kernel-class times of one solve ----
+        import ctypes as C
+        from metric_amg_examples_b200._capi import lib
+        r = torch.randn(ndofs, dtype=torch.float64, device="cuda")
+        z = torch.empty_like(r)
+        for _ in range(3):
+            lib.mamg_apply(H._h, C.c_void_p(r.data_ptr()), C.c_void_p(z.data_ptr()), 1)
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(stream)
+        for _ in range(5):
+            lib.mamg_apply(H._h, C.c_void_p(r.data_ptr()), C.c_void_p(z.data_ptr()), 1)
+        c1.record(stream)
+        torch.cuda.synchronize()
+        cycle_ms = c0.elapsed_time(c1) / 5
+        H.profile_start()
+        _, pinfo = solve_dev()
+        prof = H.profile_stop()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    ms, e2e_s = float(t.item()), float(te.item())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    nit = pinfo["niters"]
+    cb = class_bytes(H, nit, nit + 1)
+    tot_ms = sum(v[0] for v in prof.values())
+    dom = max(prof, key=lambda k: prof[k][0])
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    dom_ms, dom_launches = prof[dom]
+    achieved = cb[dom] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    kernels = {k: {"ms": round(prof[k][0], 3), "launches": prof[k][1], "share": round(prof[k][0] / tot_ms, 4),
+                   "alg_GBs": round(cb[k] / (prof[k][0] * 1e-3) / 1e9, 1) if prof[k][0] > 0 else None}
+               for k in prof}
+    out = {
+        "metric": "solve DOF/s to rtol 1e-8 (metric-AMG V-cycle PCG)", "value": ndofs * world * a.steps / (ms * 1e-3),
+        "unit": "DOF/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{a.workload} UnitCubeMesh({n}) P1 gamma={a.gamma:g} ndofs={ndofs} nnz={system.A.nnz}"
+                               if a.workload.endswith("3d") else
+                               f"{a.workload} UnitSquareMesh({n}) P1 gamma={a.gamma:g} ndofs={ndofs} nnz={system.A.nnz}",
+                   "precond": "metricAMG parameters_metric_schwarz" if a.workload.startswith("bidomain") else "metricAMG default_metric_parameters",
+                   "cycle_type": a.cycle, "krylov": f"ConjGrad relativeconv tolerance={a.rtol:g}",
+                   "levels": H.num_levels, "multi_gpu": "replicas only" if world > 1 else "single",
+                   "l2_note": "inputs (matrix 5.8 GB, vectors 128 MB) exceed the 126 MB L2"},
+        "iterations": nit, "vcycle_ms": cycle_ms, "rel_error_vs_x_true": rel_err,
+        "e2e": {"value": ndofs * world * a.steps / e2e_s, "unit": "DOF/s", "h2d_bytes_per_step": 8 * ndofs,
+                "d2h_bytes_per_step": 8 * ndofs},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s",
+                     "avg_launch_ms": dom_ms / max(dom_launches, 1)},
+        "kernels": kernels,
+        "host": {"assemble_s": round(t_asm, 2), "setup_s": round(t_setup, 2), "upload_s": round(t_upload, 2),
+                 "device_GB": round(H.device_bytes() / 1e9, 2)},
+    }
+    if not a.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_sample(a, threads=1, ordering="natural")
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_sample(a, threads, ordering, steps=1):
+    """The oracle (CPU port of the path) on a bounded sample of the same workload."""
+    import metric_amg_examples_b200 as mamg
+    from metric_amg_examples_b200 import haznics_compat as hz
+    from oracle import Oracle
+    n = a.cpu_sample_n or CPU_SAMPLE_N[a.workload]
+    system, prm = make_system(a.workload, n, a.gamma)
+    prm["cycle_type"] = hz.V_CYCLE if a.cycle == "V" else hz.W_CYCLE
+    H = mamg.Hierarchy(system.A, prm, system.interface_dofs)
+    orc = Oracle(H.export(), ordering)
+    used = orc.set_threads(threads) if ordering == "multicolor" else 1
+    b, _ = system.random_rhs(0)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        _, info = orc.pcg(b, tolerance=a.rtol, relative=True, maxiter=500)
+    dt = time.perf_counter() - t0
+    return {"value": system.ndofs * steps / dt, "unit": "DOF/s", "cores": used, "kind": "port",
+            "sample": f"{a.workload} n={n} ({system.ndofs} dofs), same parameters, full PCG solve to rtol {a.rtol:g}, "
+                      f"{ordering} smoother order, {info['niters']} iterations, {dt / steps:.2f} s per solve",
+            "host_cores_available": os.cpu_count()}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = a.n or DEFAULT_N[a.workload]
+    steps = max(1, a.steps)
+    for _ in range(min(a.warmup, 1)):
+        cpu_sample(a, threads=0, ordering="multicolor")
+    t0 = time.perf_counter()
+    cb = cpu_sample(a, threads=0, ordering="multicolor", steps=steps)
+    dt = time.perf_counter() - t0
+    out = {
+        "impl": "reference", "metric": "solve DOF/s to rtol 1e-8 (metric-AMG V-cycle PCG)", "value": cb["value"],
+        "unit": "DOF/s", "n_gpus": a.gpus, "steps": steps, "warmup": min(a.warmup, 1), "ms_per_step": dt * 1e3 / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{a.workload} n={n} gamma={a.gamma:g} (timed on the bounded sample below)",
+                   "cycle_type": a.cycle, "krylov": f"ConjGrad relativeconv tolerance={a.rtol:g}"},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "DOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "HAZmath/cbc.block are not installable here (SURVEY 8c); this arm is the repo's CPU oracle of "
+                "the same path (multicolour order, OpenMP over colour classes) on all host threads",
+    }
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_mamg(args)

@@ -90,8 +90,10 @@ int mamg_destroy(mamg_handle h);
  *      applies the cycle on the identical hierarchy (north_star) */
 int mamg_num_levels(mamg_handle h, int32_t* nlevels);
 /* info[0]=rows info[1]=nnz info[2]=n_aggregates info[3]=n_colors info[4]=n_patches
- * info[5]=n_patch_entries info[6]=n_patch_colors info[7]=max_patch_size */
-int mamg_level_info(mamg_handle h, int32_t level, int64_t info[8]);
+ * info[5]=n_patch_entries info[6]=n_patch_colors info[7]=max_patch_size
+ * info[8]=matrix entries in all patch rows (sum over patches of the nnz of their rows)
+ * info[9]=packed patch-inverse entries (sum of s(s+1)/2) info[10..11] reserved */
+int mamg_level_info(mamg_handle h, int32_t level, int64_t info[12]);
 int mamg_level_export(mamg_handle h, int32_t level, int32_t* indptr, int32_t* indices, double* data,
                       int32_t* agg, int32_t* color, uint8_t* gs_skip);
 int mamg_schwarz_export(mamg_handle h, int32_t level, int32_t* patch_ptr, int32_t* patch_dofs,
@@ -147,6 +149,12 @@ int mamg_gmres(mamg_handle h, const double* b, double* x, double tolerance, int3
 /* ---- measurement helpers (bench.py): kernel launches issued on the handle's stream
  *      since the last reset, and algorithmic bytes (SURVEY 8d model) of one cycle. */
 int mamg_launch_count(mamg_handle h, int64_t* launches, int32_t reset);
+/* per-kernel-class timing with CUDA events on the handle's stream.  on=1 starts collecting;
+ * on=0 stops and returns, for the classes {0 spmv, 1 gs, 2 schwarz, 3 restrict, 4 scale,
+ * 5 prolong, 6 coarse, 7 vector, 8 dot}, the summed kernel time in ms and the launch counts
+ * (arrays of 16 entries).  Collecting adds two event records per launch; never leave it on
+ * inside a timed region. */
+int mamg_profile(mamg_handle h, int32_t on, double* ms_per_class, int64_t* launches_per_class);
 int mamg_cycle_bytes(mamg_handle h, int64_t* bytes);
 
 /* ---- synthetic systems of BASELINE.json's configs: P1 on UnitSquare/UnitCube

@@ -42,7 +42,15 @@ struct DLevel {
   DSchwarz sw;
 };
 
+enum KClass { K_SPMV = 0, K_GS, K_SCHWARZ, K_RESTRICT, K_SCALE, K_PROLONG, K_COARSE, K_VEC, K_DOT, K_NCLS };
+
+struct ProfEvent { cudaEvent_t start, stop; int cls; };
+
 struct DeviceState {
+  bool prof_on = false;
+  std::vector<ProfEvent> prof_events;
+  size_t prof_used = 0;
+  int64_t cls_launches[K_NCLS] = {0};
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
@@ -59,6 +67,29 @@ struct DeviceState {
   double *io_a = nullptr, *io_b = nullptr;  // staging for host-array calls
   std::vector<void*> allocs;
   mamg_params prm;
+};
+
+// Brackets one kernel launch: counts it and, in profiling mode, times it with a CUDA event pair
+// on the launching stream (bench.py's per-kernel durations and shares come from here).
+struct KScope {
+  DeviceState& D;
+  cudaEvent_t stop = nullptr;
+  KScope(DeviceState& d, int cls) : D(d) {
+    ++D.launches;
+    ++D.cls_launches[cls];
+    if (!D.prof_on) return;
+    if (D.prof_used == D.prof_events.size()) {
+      ProfEvent e;
+      cudaEventCreate(&e.start);
+      cudaEventCreate(&e.stop);
+      D.prof_events.push_back(e);
+    }
+    ProfEvent& e = D.prof_events[D.prof_used++];
+    e.cls = cls;
+    cudaEventRecord(e.start, D.stream);
+    stop = e.stop;
+  }
+  ~KScope() { if (stop) cudaEventRecord(stop, D.stream); }
 };
 
 template <class T>
@@ -82,6 +113,7 @@ void device_state_free(DeviceState* D) {
   cudaSetDevice(D->device);
   if (D->stream) cudaStreamSynchronize(D->stream);
   for (void* p : D->allocs) cudaFree(p);
+  for (ProfEvent& e : D->prof_events) { cudaEventDestroy(e.start); cudaEventDestroy(e.stop); }
   if (D->h_scal) cudaFreeHost(D->h_scal);
   if (D->own_stream && D->stream) cudaStreamDestroy(D->stream);
   delete D;
@@ -185,7 +217,7 @@ static void upload_hierarchy(const Hierarchy& H, DeviceState& D) {
       dl.cptr = upload(D, cptr);
       dl.cidx = upload(D, cidx);
     }
-    if (hl.sw.npatch() > 0) schwarz_upload(hl, perm[l], iperm[l], ia, ja, dl.sw, [&](size_t bytes) {
+    if (hl.sw.npatch() > 0) schwarz_upload(hl, iperm[l], dl.ia, dl.ja, dl.a, ia, dl.sw, [&](size_t bytes) {
       void* p = nullptr;
       CUDA_OK(cudaMalloc(&p, bytes ? bytes : 1));
       D.allocs.push_back(p);
@@ -223,19 +255,19 @@ static void upload_hierarchy(const Hierarchy& H, DeviceState& D) {
 static void k_spmv(DeviceState& D, const DLevel& l, const double* x, const double* b, double* y, bool resid) {
   if (l.n == 0) return;
   const int grid = cdiv((long long)l.n * l.lanes, kBlock);
+  KScope ks(D, K_SPMV);
   LANES_SWITCH(l.lanes,
     if (resid) spmv_kernel<LN, true><<<grid, kBlock, 0, D.stream>>>(l.n, l.ia, l.ja, l.a, x, b, y);
     else spmv_kernel<LN, false><<<grid, kBlock, 0, D.stream>>>(l.n, l.ia, l.ja, l.a, x, b, y));
-  ++D.launches;
 }
 
 static void k_gs_color(DeviceState& D, const DLevel& l, int c, const double* b, double* x, double omega) {
   const int r0 = l.color_ptr[c], r1 = l.color_ptr[c + 1];
   if (r1 <= r0) return;
   const int grid = cdiv((long long)(r1 - r0) * l.lanes, kBlock);
+  KScope ks(D, K_GS);
   LANES_SWITCH(l.lanes,
     gs_color_kernel<LN><<<grid, kBlock, 0, D.stream>>>(r0, r1, l.ia, l.ja, l.a, l.invd, l.skip, b, x, omega));
-  ++D.launches;
 }
 
 static void gs_forward(DeviceState& D, const DLevel& l, const double* b, double* x, double w, int first = 0) {
@@ -247,10 +279,13 @@ static void gs_backward(DeviceState& D, const DLevel& l, const double* b, double
 
 static void k_jacobi(DeviceState& D, DLevel& l, const double* b, double* x, double w) {
   const int grid = cdiv((long long)l.n * l.lanes, kBlock);
-  LANES_SWITCH(l.lanes,
-    jacobi_kernel<LN><<<grid, kBlock, 0, D.stream>>>(l.n, l.ia, l.ja, l.a, l.invd, l.skip, b, x, l.t, w));
+  {
+    KScope ks(D, K_GS);
+    LANES_SWITCH(l.lanes,
+      jacobi_kernel<LN><<<grid, kBlock, 0, D.stream>>>(l.n, l.ia, l.ja, l.a, l.invd, l.skip, b, x, l.t, w));
+  }
+  KScope ks(D, K_VEC);
   copy_kernel<<<cdiv(l.n, kBlock), kBlock, 0, D.stream>>>(l.n, l.t, x);
-  D.launches += 2;
 }
 
 // One smoothing application S(x, b) on a level.  Pre-smoothing = Schwarz on the interface
@@ -291,8 +326,16 @@ static void smooth(DeviceState& D, int lev, const double* b, double* x, bool pos
     if (type == MAMG_SCHWARZ_SYMMETRIC) { fwd = bwd = true; }
     else if (type == MAMG_SCHWARZ_FORWARD) { fwd = !post; bwd = post; }
     else { fwd = post; bwd = !post; }
-    if (fwd) D.launches += schwarz_sweep(l.sw, l.ia, l.ja, l.a, b, x, false, D.stream);
-    if (bwd) D.launches += schwarz_sweep(l.sw, l.ia, l.ja, l.a, b, x, true, D.stream);
+    auto sweep = [&](bool backward) {
+      for (int cc = 0; cc < l.sw.ncolors; ++cc) {
+        const int c = backward ? l.sw.ncolors - 1 - cc : cc;
+        if (l.sw.color_ptr[c + 1] == l.sw.color_ptr[c]) continue;
+        KScope ks(D, K_SCHWARZ);
+        schwarz_color_launch(l.sw, c, l.ia, l.ja, l.a, b, x, D.stream);
+      }
+    };
+    if (fwd) sweep(false);
+    if (bwd) sweep(true);
   };
   if (!post) { schwarz(); point(); } else { point(); schwarz(); }
 }
@@ -301,9 +344,9 @@ static void k_resid_restrict(DeviceState& D, int lev) {
   DLevel& f = D.lv[lev];
   DLevel& c = D.lv[lev + 1];
   const int grid = cdiv((long long)f.nc * f.lanes, kBlock);
+  KScope ks(D, K_RESTRICT);
   LANES_SWITCH(f.lanes,
     resid_restrict_kernel<LN><<<grid, kBlock, 0, D.stream>>>(f.nc, f.cptr, f.cidx, f.ia, f.ja, f.a, f.x, f.b, c.b, c.x));
-  ++D.launches;
 }
 
 static int red_grid(const DeviceState& D, long long threads) {
@@ -313,22 +356,22 @@ static int red_grid(const DeviceState& D, long long threads) {
 static void k_scale_dots(DeviceState& D, int lev) {
   DLevel& c = D.lv[lev];
   const int grid = red_grid(D, (long long)c.n * c.lanes);
+  KScope ks(D, K_SCALE);
   LANES_SWITCH(c.lanes,
     scale_dots_kernel<LN><<<grid, kBlock, 0, D.stream>>>(c.n, c.ia, c.ja, c.a, c.x, c.b, D.partial, D.ticket, D.scal + 8));
-  ++D.launches;
 }
 
 static void k_prolong(DeviceState& D, int lev, bool scaled) {
   DLevel& f = D.lv[lev];
   DLevel& c = D.lv[lev + 1];
+  KScope ks(D, K_PROLONG);
   prolong_kernel<<<cdiv(f.n, kBlock), kBlock, 0, D.stream>>>(f.n, f.agg, c.x, scaled ? D.scal + 10 : nullptr, f.x);
-  ++D.launches;
 }
 
 static void k_coarse_solve(DeviceState& D) {
   DLevel& c = D.lv.back();
+  KScope ks(D, K_COARSE);
   dense_gemv_kernel<<<cdiv((long long)c.n * 32, kBlock), kBlock, 0, D.stream>>>(c.n, D.coarse_inv, c.b, c.x);
-  ++D.launches;
 }
 
 static void cycle_level(DeviceState& D, int lev) {
@@ -349,13 +392,18 @@ static void cycle_level(DeviceState& D, int lev) {
 
 static void k_fill(DeviceState& D, int n, double* x, double v) {
   if (n == 0) return;
+  KScope ks(D, K_VEC);
   fill_kernel<<<cdiv(n, kBlock), kBlock, 0, D.stream>>>(n, x, v);
-  ++D.launches;
 }
 static void k_gather(DeviceState& D, int n, const int* map, const double* in, double* out) {
   if (n == 0) return;
+  KScope ks(D, K_VEC);
   gather_kernel<<<cdiv(n, kBlock), kBlock, 0, D.stream>>>(n, map, in, out);
-  ++D.launches;
+}
+static void k_copy(DeviceState& D, int n, const double* in, double* out) {
+  if (n == 0) return;
+  KScope ks(D, K_VEC);
+  copy_kernel<<<cdiv(n, kBlock), kBlock, 0, D.stream>>>(n, in, out);
 }
 
 // z' = B r' in the permuted ordering of level 0 (both device arrays of size n0)
@@ -417,13 +465,14 @@ static int pcg_device(DeviceState& D, const double* b_nat, double* x_nat, double
     k_spmv(D, l0, x, b, r, true);
   } else {
     k_fill(D, n, x, 0.0);
-    copy_kernel<<<vgrid, kBlock, 0, D.stream>>>(n, b, r);
-    ++D.launches;
+    k_copy(D, n, b, r);
   }
   apply_permuted(D, r, z);
-  copy_kernel<<<vgrid, kBlock, 0, D.stream>>>(n, z, d);
-  pcg_rz_kernel<<<rgrid, kBlock, 0, D.stream>>>(n, r, z, D.partial, D.ticket, D.scal, 1);
-  D.launches += 2;
+  k_copy(D, n, z, d);
+  {
+    KScope ks(D, K_DOT);
+    pcg_rz_kernel<<<rgrid, kBlock, 0, D.stream>>>(n, r, z, D.partial, D.ticket, D.scal, 1);
+  }
   read_scalars(D, 8);
   double rz = D.h_scal[0];
   int it = 0, status = 0;
@@ -432,14 +481,24 @@ static int pcg_device(DeviceState& D, const double* b_nat, double* x_nat, double
   double target = relative ? tol * res : tol;
   while (res > target && it < maxiter) {
     const int sgrid = red_grid(D, (long long)n * l0.lanes);
-    LANES_SWITCH(l0.lanes,
-      spmv_dot_kernel<LN><<<sgrid, kBlock, 0, D.stream>>>(n, l0.ia, l0.ja, l0.a, d, q, D.partial, D.ticket, D.scal));
-    pcg_update_kernel<<<vgrid, kBlock, 0, D.stream>>>(n, D.scal, d, q, x, r);
-    D.launches += 2;
+    {
+      KScope ks(D, K_SPMV);
+      LANES_SWITCH(l0.lanes,
+        spmv_dot_kernel<LN><<<sgrid, kBlock, 0, D.stream>>>(n, l0.ia, l0.ja, l0.a, d, q, D.partial, D.ticket, D.scal));
+    }
+    {
+      KScope ks(D, K_VEC);
+      pcg_update_kernel<<<vgrid, kBlock, 0, D.stream>>>(n, D.scal, d, q, x, r);
+    }
     apply_permuted(D, r, z);
-    pcg_rz_kernel<<<rgrid, kBlock, 0, D.stream>>>(n, r, z, D.partial, D.ticket, D.scal, 0);
-    pcg_dir_kernel<<<vgrid, kBlock, 0, D.stream>>>(n, D.scal, z, d);
-    D.launches += 2;
+    {
+      KScope ks(D, K_DOT);
+      pcg_rz_kernel<<<rgrid, kBlock, 0, D.stream>>>(n, r, z, D.partial, D.ticket, D.scal, 0);
+    }
+    {
+      KScope ks(D, K_VEC);
+      pcg_dir_kernel<<<vgrid, kBlock, 0, D.stream>>>(n, D.scal, z, d);
+    }
     read_scalars(D, 8);
     ++it;
     if (alphas) alphas[it - 1] = D.h_scal[2];
@@ -608,6 +667,30 @@ int mamg_minres(mamg_handle, const double*, double*, double, int32_t, int32_t, i
 int mamg_gmres(mamg_handle, const double*, double*, double, int32_t, int32_t, int32_t, int32_t, int32_t*, double*) {
   set_error("mamg_gmres: not built yet");
   return -5;
+}
+
+int mamg_profile(mamg_handle h, int32_t on, double* ms_per_class, int64_t* launches_per_class) {
+  MAMG_TRY
+  DeviceState* D = get_dev(h);
+  if (!D) return -1;
+  CUDA_OK(cudaStreamSynchronize(D->stream));
+  if (on) {
+    D->prof_on = true;
+    D->prof_used = 0;
+    for (int k = 0; k < K_NCLS; ++k) D->cls_launches[k] = 0;
+    return 0;
+  }
+  D->prof_on = false;
+  if (ms_per_class) for (int k = 0; k < K_NCLS; ++k) ms_per_class[k] = 0.0;
+  for (size_t i = 0; i < D->prof_used; ++i) {
+    float ms = 0.f;
+    CUDA_OK(cudaEventElapsedTime(&ms, D->prof_events[i].start, D->prof_events[i].stop));
+    if (ms_per_class) ms_per_class[D->prof_events[i].cls] += ms;
+  }
+  if (launches_per_class) for (int k = 0; k < K_NCLS; ++k) launches_per_class[k] = D->cls_launches[k];
+  D->prof_used = 0;
+  return 0;
+  MAMG_CATCH
 }
 
 int mamg_launch_count(mamg_handle h, int64_t* launches, int32_t reset) {

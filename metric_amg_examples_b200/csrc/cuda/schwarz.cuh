@@ -1,18 +1,20 @@
-// K7  interface Schwarz smoother: batched small dense patch solves in shared memory.
+// K7  interface Schwarz smoother: batched small dense patch solves.
 //
 // Replaces HAZmath smoother_dcsr_Schwarz_forward/backward (one UMFPACK solve per block,
-// sequential over blocks) configured by src/amg_parameters.py:82-87.  For every patch B:
+// sequential over blocks; blocks factorised once at setup) configured by
+// src/amg_parameters.py:82-87.  For every patch B:
 //     x_B <- x_B + A_BB^{-1} (b - A x)_B
 // Patches are coloured by conflict (schwarz_color in csrc/host/setup.cpp), so all patches of
 // one colour are solved concurrently with a result identical to visiting them one by one;
 // forward = colours ascending, backward = descending.
 //
-// One CTA (1, 2 or 4 warps) owns one patch.  The patch rows are streamed from the level's CSR
-// exactly once: the same pass accumulates the residual (b - A x)_B and scatters the A_BB
-// entries into a packed lower-triangular matrix in shared memory (a per-entry byte map gives
-// the local column or 255).  A_BB is then Cholesky-factorised and solved in shared memory;
-// storing the factors instead would cost more HBM traffic than re-reading the rows that the
-// residual needs anyway (Schwarz).
+// Setup (once, on the device): every A_BB is gathered from the level's CSR, Cholesky-factorised
+// and inverted in shared memory; the symmetric inverse is kept packed (s(s+1)/2 doubles per
+// patch) -- the analogue of HAZmath keeping one UMFPACK factorisation per block.
+// Apply: a warp (or CTA for patches > 32 dofs) streams the patch's CSR rows once to form the
+// residual (b - A x)_B, stages the packed inverse through shared memory and applies it as a
+// small symmetric mat-vec.  The kernel is HBM-bound: per patch it reads 12 B per row entry plus
+// 4 s(s+1) bytes of inverse.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -24,102 +26,172 @@
 namespace mamg {
 
 struct DSchwarz {
-  int npatch = 0, ncolors = 0, max_size = 0, warps = 1;
-  size_t smem = 0;
-  int* pptr = nullptr;        // npatch+1, patches sorted by colour
-  int* pdofs = nullptr;       // patch dofs (permuted row ids) in natural-ascending order
-  int* poff = nullptr;        // per patch dof: offset of its row inside the patch's lmap segment
-  long long* lbase = nullptr; // per patch: start of its lmap segment
-  uint8_t* lmap = nullptr;    // per (patch row, row entry): local column inside the patch or 255
-  std::vector<int> color_ptr; // host: patch range of every colour
+  int npatch = 0, ncolors = 0, max_size = 0, warps = 1, ppc = 1;
+  size_t smem_apply = 0, smem_setup = 0;
+  int* pptr = nullptr;         // npatch+1, patches sorted by colour
+  int* pdofs = nullptr;        // patch dofs (permuted row ids) in natural-ascending order
+  long long* ioff = nullptr;   // npatch+1: start of every packed inverse
+  double* pinv = nullptr;      // packed lower triangles of A_BB^{-1}
+  std::vector<int> color_ptr;  // host: patch range of every colour
+  long long alg_bytes = 0;     // algorithmic bytes of one sweep over all patches
 };
-
-constexpr int kSwSub = 8;  // lanes that share one matrix row while gathering
 
 __device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }  // i >= j
 
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
-schwarz_patch_kernel(int p0, const int* __restrict__ pptr, const int* __restrict__ pdofs,
-                     const int* __restrict__ poff, const long long* __restrict__ lbase,
-                     const uint8_t* __restrict__ lmap, const int* __restrict__ ia,
-                     const int* __restrict__ ja, const double* __restrict__ a,
-                     const double* __restrict__ b, double* x, int max_size) {
-  constexpr int T = WARPS * 32;
+// ---- setup: packed inverse of every A_BB -------------------------------------------------------
+template <int T>
+__global__ void __launch_bounds__(T)
+schwarz_invert_kernel(int npatch, const int* __restrict__ pptr, const int* __restrict__ pdofs,
+                      const long long* __restrict__ ioff, const int* __restrict__ ia,
+                      const int* __restrict__ ja, const double* __restrict__ a,
+                      double* __restrict__ pinv, int max_size) {
   extern __shared__ double smem[];
-  const int patch = p0 + blockIdx.x;
+  const int patch = blockIdx.x;
+  if (patch >= npatch) return;
   const int q0 = pptr[patch], s = pptr[patch + 1] - q0;
-  double* Lm = smem;                                   // packed lower triangle, s(s+1)/2
-  double* rhs = Lm + (size_t)max_size * (max_size + 1) / 2;  // s
-  int* idx = reinterpret_cast<int*>(rhs + max_size);   // s
+  double* Lm = smem;                                                  // packed lower triangle
+  double* col = Lm + (size_t)max_size * (max_size + 1) / 2;           // s scratch
+  int* idx = reinterpret_cast<int*>(col + max_size);                  // s
   const int tid = threadIdx.x;
   for (int k = tid; k < s * (s + 1) / 2; k += T) Lm[k] = 0.0;
   for (int k = tid; k < s; k += T) idx[k] = pdofs[q0 + k];
   __syncthreads();
-  // ---- stream the patch rows once: residual and A_BB ----
-  {
-    const int sl = tid % kSwSub, grp = tid / kSwSub;
-    const unsigned int mask = ((1u << kSwSub) - 1u) << ((tid & 31) / kSwSub * kSwSub);
-    const uint8_t* lm = lmap + lbase[patch];
-    for (int k = grp; k < s; k += T / kSwSub) {
-      const int i = idx[k];
-      const int r0 = ia[i], r1 = ia[i + 1];
-      const uint8_t* lmk = lm + poff[q0 + k];
-      double acc = 0.0;
-      for (int p = r0 + sl; p < r1; p += kSwSub) {
-        const double v = a[p];
-        acc += v * x[ja[p]];
-        const int c = lmk[p - r0];
-        if (c <= k) Lm[tri(k, c)] = v;  // 255 (outside the patch) never passes: k < 255
-      }
-#pragma unroll
-      for (int o = kSwSub / 2; o > 0; o >>= 1) acc += __shfl_down_sync(mask, acc, o, kSwSub);
-      if (sl == 0) rhs[k] = b[i] - acc;
+  // gather the lower triangle of A_BB: thread per (row k, entry) with a linear search of the column
+  for (int k = 0; k < s; ++k) {
+    const int i = idx[k];
+    for (int p = ia[i] + tid; p < ia[i + 1]; p += T) {
+      const int j = ja[p];
+      for (int c = 0; c <= k; ++c)
+        if (idx[c] == j) { Lm[tri(k, c)] = a[p]; break; }
     }
   }
   __syncthreads();
-  // ---- Cholesky A_BB = L L' (right-looking, in place) with the forward solve L y = rhs ----
+  // Cholesky A_BB = L L'
   for (int j = 0; j < s; ++j) {
     const double d = sqrt(Lm[tri(j, j)]);
     const double invd = 1.0 / d;
     __syncthreads();
-    if (tid == 0) { Lm[tri(j, j)] = d; rhs[j] *= invd; }
+    if (tid == 0) Lm[tri(j, j)] = d;
     for (int i = j + 1 + tid; i < s; i += T) Lm[tri(i, j)] *= invd;
     __syncthreads();
-    // trailing update: rows i > j, columns j < k <= i, plus the rhs as an extra column
-    // (warps stride over columns k, lanes over rows i >= k)
-    for (int k = j + 1 + tid / 32; k < s; k += WARPS) {
+    for (int k = j + 1 + tid / 32; k < s; k += T / 32) {
       const double lkj = Lm[tri(k, j)];
       for (int i = k + (tid & 31); i < s; i += 32) Lm[tri(i, k)] -= Lm[tri(i, j)] * lkj;
     }
-    for (int i = j + 1 + tid; i < s; i += T) rhs[i] -= Lm[tri(i, j)] * rhs[j];
     __syncthreads();
   }
-  // ---- backward solve L' delta = y ----
+  // W = L^{-1} in place (column by column from the right; LAPACK dtrti2 'L')
   for (int j = s - 1; j >= 0; --j) {
-    if (tid == 0) rhs[j] /= Lm[tri(j, j)];
+    const double wjj = 1.0 / Lm[tri(j, j)];
+    for (int i = j + 1 + tid; i < s; i += T) col[i] = Lm[tri(i, j)];
     __syncthreads();
-    const double dj = rhs[j];
-    for (int i = tid; i < j; i += T) rhs[i] -= Lm[tri(j, i)] * dj;
+    for (int i = j + 1 + tid; i < s; i += T) {
+      double acc = 0.0;
+      for (int k = j + 1; k <= i; ++k) acc += Lm[tri(i, k)] * col[k];   // W[i][k] (already inverted) * L[k][j]
+      Lm[tri(i, j)] = -wjj * acc;
+    }
+    if (tid == 0) Lm[tri(j, j)] = wjj;
     __syncthreads();
   }
-  for (int k = tid; k < s; k += T) x[idx[k]] += rhs[k];
+  // A_BB^{-1} = W' W in place, rows ascending (LAPACK dlauu2 'L')
+  for (int i = 0; i < s; ++i) {
+    for (int c = tid; c <= i; c += T) {
+      double acc = 0.0;
+      for (int k = i; k < s; ++k) acc += Lm[tri(k, i)] * Lm[tri(k, c)];
+      col[c] = acc;
+    }
+    __syncthreads();
+    for (int c = tid; c <= i; c += T) Lm[tri(i, c)] = col[c];
+    __syncthreads();
+  }
+  double* out = pinv + ioff[patch];
+  for (int k = tid; k < s * (s + 1) / 2; k += T) out[k] = Lm[k];
 }
 
-// Host side: reorder the patches by colour, translate dofs to the permuted numbering and
-// build the per-entry local-column map.  `alloc(bytes)` returns tracked device memory.
-inline void schwarz_upload(const Level& hl, const std::vector<int>& perm, const std::vector<int>& iperm,
-                           const std::vector<int>& pia, const std::vector<int>& pja, DSchwarz& d,
-                           const std::function<void*(size_t)>& alloc) {
-  (void)perm;
+// ---- apply ---------------------------------------------------------------------------------------
+// WPP warps per patch, PPC patches per CTA (PPC > 1 only with WPP == 1: warps are independent)
+template <int WPP, int PPC>
+__global__ void __launch_bounds__(WPP * PPC * 32)
+schwarz_apply_kernel(int p0, int p1, const int* __restrict__ pptr, const int* __restrict__ pdofs,
+                     const long long* __restrict__ ioff, const double* __restrict__ pinv,
+                     const int* __restrict__ ia, const int* __restrict__ ja,
+                     const double* __restrict__ a, const double* __restrict__ b, double* x,
+                     int max_size) {
+  constexpr int T = WPP * 32;  // threads per patch
+  extern __shared__ double smem[];
+  const int slot = threadIdx.x / T;
+  const int tid = threadIdx.x % T;
+  const int patch = p0 + blockIdx.x * PPC + slot;
+  const size_t per_patch = (size_t)max_size * (max_size + 1) / 2 + 2 * (size_t)max_size;
+  double* Inv = smem + slot * per_patch;
+  double* rhs = Inv + (size_t)max_size * (max_size + 1) / 2;
+  int* idx = reinterpret_cast<int*>(rhs + max_size);
+  const bool active = patch < p1;   // uniform per warp when PPC > 1 (WPP == 1)
+  int s = 0, q0 = 0;
+  if (active) {
+    q0 = pptr[patch];
+    s = pptr[patch + 1] - q0;
+    for (int k = tid; k < s; k += T) idx[k] = pdofs[q0 + k];
+    const double* src = pinv + ioff[patch];
+    const int np = s * (s + 1) / 2;
+    for (int k = tid; k < np; k += T) Inv[k] = src[k];
+  }
+  if (WPP == 1) __syncwarp(); else __syncthreads();
+  if (active) {
+    // residual of the patch rows: one warp per row, 4 rows in flight per warp
+    const int lane = tid & 31, wrp = tid / 32;
+    for (int k0 = wrp * 4; k0 < s; k0 += WPP * 4) {
+      double acc[4] = {0.0, 0.0, 0.0, 0.0};
+      int row[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = k0 + u;
+        row[u] = k < s ? idx[k] : -1;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (row[u] < 0) continue;
+        const int r0 = ia[row[u]], r1 = ia[row[u] + 1];
+        for (int p = r0 + lane; p < r1; p += 32) acc[u] += a[p] * x[ja[p]];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[u] += __shfl_down_sync(0xffffffffu, acc[u], o);
+        if (lane == 0 && row[u] >= 0) rhs[k0 + u] = b[row[u]] - acc[u];
+      }
+    }
+  }
+  if (WPP == 1) __syncwarp(); else __syncthreads();
+  if (active) {
+    // delta = A_BB^{-1} rhs with the packed symmetric inverse
+    for (int k = tid; k < s; k += T) {
+      double d = 0.0;
+      const int base = k * (k + 1) / 2;
+      for (int c = 0; c <= k; ++c) d += Inv[base + c] * rhs[c];
+      for (int c = k + 1; c < s; ++c) d += Inv[c * (c + 1) / 2 + k] * rhs[c];
+      x[idx[k]] += d;
+    }
+  }
+}
+
+// Host side: reorder the patches by colour, translate dofs to the permuted numbering, upload
+// and invert on the device.  `alloc(bytes)` returns tracked device memory.
+inline void schwarz_upload(const Level& hl, const std::vector<int>& iperm, const int* d_ia,
+                           const int* d_ja, const double* d_a, const std::vector<int>& pia,
+                           DSchwarz& d, const std::function<void*(size_t)>& alloc) {
   const SchwarzPatches& sw = hl.sw;
   const int np = sw.npatch();
   d.npatch = np;
   d.ncolors = sw.ncolors;
   d.max_size = sw.max_size;
-  if (d.max_size > 254) throw std::runtime_error("Schwarz_mmsize > 254 is not supported by the device patch kernel");
-  d.warps = d.max_size <= 32 ? 1 : (d.max_size <= 64 ? 2 : 4);
-  d.smem = ((size_t)d.max_size * (d.max_size + 1) / 2 + d.max_size) * sizeof(double) + (size_t)d.max_size * sizeof(int);
+  const size_t tri_max = (size_t)d.max_size * (d.max_size + 1) / 2;
+  d.smem_setup = (tri_max + d.max_size) * sizeof(double) + (size_t)d.max_size * sizeof(int);
+  if (d.smem_setup > 227 * 1024)
+    throw std::runtime_error("Schwarz patch of " + std::to_string(d.max_size) + " dofs does not fit in shared memory");
+  d.warps = d.max_size <= 32 ? 1 : (d.max_size <= 96 ? 2 : 4);
+  d.ppc = d.warps == 1 ? 4 : 1;
+  d.smem_apply = (size_t)d.ppc * (tri_max + 2 * (size_t)d.max_size) * sizeof(double);
   d.color_ptr.assign(sw.ncolors + 1, 0);
   for (int p = 0; p < np; ++p) ++d.color_ptr[sw.color[p] + 1];
   for (int c = 0; c < sw.ncolors; ++c) d.color_ptr[c + 1] += d.color_ptr[c];
@@ -128,38 +200,22 @@ inline void schwarz_upload(const Level& hl, const std::vector<int>& perm, const 
     std::vector<int> fill(d.color_ptr.begin(), d.color_ptr.end() - 1);
     for (int p = 0; p < np; ++p) order[fill[sw.color[p]]++] = p;
   }
-  std::vector<int> pptr(np + 1, 0), pdofs(sw.dofs.size()), poff(sw.dofs.size());
-  std::vector<long long> lbase(np + 1, 0);
+  std::vector<int> pptr(np + 1, 0), pdofs(sw.dofs.size());
+  std::vector<long long> ioff(np + 1, 0);
+  long long row_entries = 0;
   for (int k = 0; k < np; ++k) {
     const int p = order[k];
     const int s = sw.ptr[p + 1] - sw.ptr[p];
     pptr[k + 1] = pptr[k] + s;
-    long long len = 0;
+    ioff[k + 1] = ioff[k] + (long long)s * (s + 1) / 2;
     for (int q = 0; q < s; ++q) {
       const int i = iperm[sw.dofs[sw.ptr[p] + q]];
       pdofs[pptr[k] + q] = i;
-      poff[pptr[k] + q] = (int)len;
-      len += pia[i + 1] - pia[i];
-    }
-    lbase[k + 1] = lbase[k] + len;
-  }
-  std::vector<uint8_t> lmap((size_t)lbase[np]);
-  const int n = hl.A.n;
-#pragma omp parallel
-  {
-    std::vector<uint8_t> loc(n, 255);
-#pragma omp for schedule(dynamic, 1024)
-    for (int k = 0; k < np; ++k) {
-      const int s = pptr[k + 1] - pptr[k];
-      for (int q = 0; q < s; ++q) loc[pdofs[pptr[k] + q]] = (uint8_t)q;
-      for (int q = 0; q < s; ++q) {
-        const int i = pdofs[pptr[k] + q];
-        uint8_t* out = &lmap[(size_t)lbase[k] + poff[pptr[k] + q]];
-        for (int e = pia[i]; e < pia[i + 1]; ++e) out[e - pia[i]] = loc[pja[e]];
-      }
-      for (int q = 0; q < s; ++q) loc[pdofs[pptr[k] + q]] = 255;
+      row_entries += pia[i + 1] - pia[i];
     }
   }
+  // per sweep: row entries (val + col), packed inverse, patch index, b and x of the patch dofs
+  d.alg_bytes = 12 * row_entries + 8 * ioff[np] + (4 + 8 + 16) * (long long)pdofs.size() + 8 * (long long)np;
   auto up = [&](const void* src, size_t bytes) {
     void* p = alloc(bytes);
     if (bytes) cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice);
@@ -167,31 +223,30 @@ inline void schwarz_upload(const Level& hl, const std::vector<int>& perm, const 
   };
   d.pptr = (int*)up(pptr.data(), pptr.size() * sizeof(int));
   d.pdofs = (int*)up(pdofs.data(), pdofs.size() * sizeof(int));
-  d.poff = (int*)up(poff.data(), poff.size() * sizeof(int));
-  d.lbase = (long long*)up(lbase.data(), lbase.size() * sizeof(long long));
-  d.lmap = (uint8_t*)up(lmap.data(), lmap.size());
-  if (d.smem > 48 * 1024) {
-    cudaFuncSetAttribute(schwarz_patch_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem);
-    cudaFuncSetAttribute(schwarz_patch_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem);
+  d.ioff = (long long*)up(ioff.data(), ioff.size() * sizeof(long long));
+  d.pinv = (double*)alloc((size_t)ioff[np] * sizeof(double));
+  constexpr int TS = 128;
+  if (d.smem_setup > 48 * 1024)
+    cudaFuncSetAttribute(schwarz_invert_kernel<TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_setup);
+  schwarz_invert_kernel<TS><<<np, TS, d.smem_setup>>>(np, d.pptr, d.pdofs, d.ioff, d_ia, d_ja, d_a, d.pinv, d.max_size);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) throw std::runtime_error(std::string("Schwarz setup kernel failed: ") + cudaGetErrorString(e));
+  if (d.smem_apply > 48 * 1024) {
+    cudaFuncSetAttribute(schwarz_apply_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_apply);
+    cudaFuncSetAttribute(schwarz_apply_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_apply);
   }
 }
 
-// one multiplicative sweep over all patches; returns the number of kernel launches
-inline int schwarz_sweep(const DSchwarz& d, const int* ia, const int* ja, const double* a,
-                         const double* b, double* x, bool backward, cudaStream_t stream) {
-  int launches = 0;
-  for (int cc = 0; cc < d.ncolors; ++cc) {
-    const int c = backward ? d.ncolors - 1 - cc : cc;
-    const int p0 = d.color_ptr[c], cnt = d.color_ptr[c + 1] - p0;
-    if (cnt <= 0) continue;
-    switch (d.warps) {
-      case 1: schwarz_patch_kernel<1><<<cnt, 32, d.smem, stream>>>(p0, d.pptr, d.pdofs, d.poff, d.lbase, d.lmap, ia, ja, a, b, x, d.max_size); break;
-      case 2: schwarz_patch_kernel<2><<<cnt, 64, d.smem, stream>>>(p0, d.pptr, d.pdofs, d.poff, d.lbase, d.lmap, ia, ja, a, b, x, d.max_size); break;
-      default: schwarz_patch_kernel<4><<<cnt, 128, d.smem, stream>>>(p0, d.pptr, d.pdofs, d.poff, d.lbase, d.lmap, ia, ja, a, b, x, d.max_size); break;
-    }
-    ++launches;
+// one colour of a multiplicative sweep
+inline void schwarz_color_launch(const DSchwarz& d, int c, const int* ia, const int* ja, const double* a,
+                                 const double* b, double* x, cudaStream_t stream) {
+  const int p0 = d.color_ptr[c], p1 = d.color_ptr[c + 1];
+  const int grid = (p1 - p0 + d.ppc - 1) / d.ppc;
+  switch (d.warps) {
+    case 1: schwarz_apply_kernel<1, 4><<<grid, 128, d.smem_apply, stream>>>(p0, p1, d.pptr, d.pdofs, d.ioff, d.pinv, ia, ja, a, b, x, d.max_size); break;
+    case 2: schwarz_apply_kernel<2, 1><<<grid, 64, d.smem_apply, stream>>>(p0, p1, d.pptr, d.pdofs, d.ioff, d.pinv, ia, ja, a, b, x, d.max_size); break;
+    default: schwarz_apply_kernel<4, 1><<<grid, 128, d.smem_apply, stream>>>(p0, p1, d.pptr, d.pdofs, d.ioff, d.pinv, ia, ja, a, b, x, d.max_size); break;
   }
-  return launches;
 }
 
 }  // namespace mamg

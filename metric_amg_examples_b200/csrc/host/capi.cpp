@@ -107,9 +107,19 @@ static const Level* get_level(mamg_handle h, int level) {
   return &h->H.lv[level];
 }
 
-int mamg_level_info(mamg_handle h, int32_t level, int64_t info[8]) {
+int mamg_level_info(mamg_handle h, int32_t level, int64_t info[12]) {
   const Level* L = get_level(h, level);
   if (!L) return -1;
+  int64_t row_entries = 0, inv_entries = 0;
+  for (int p = 0; p < L->sw.npatch(); ++p) {
+    const int64_t s = L->sw.ptr[p + 1] - L->sw.ptr[p];
+    inv_entries += s * (s + 1) / 2;
+    for (int q = L->sw.ptr[p]; q < L->sw.ptr[p + 1]; ++q)
+      row_entries += L->A.ia[L->sw.dofs[q] + 1] - L->A.ia[L->sw.dofs[q]];
+  }
+  info[8] = row_entries;
+  info[9] = inv_entries;
+  info[10] = info[11] = 0;
   info[0] = L->A.n;
   info[1] = L->A.nnz();
   info[2] = L->nc;

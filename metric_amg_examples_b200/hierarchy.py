@@ -72,10 +72,10 @@ class Hierarchy:
         return v.value
 
     def level_info(self, level):
-        info = (C.c_int64 * 8)()
+        info = (C.c_int64 * 12)()
         check(lib.mamg_level_info(self._h, level, info))
         keys = ["rows", "nnz", "n_aggregates", "n_colors", "n_patches", "n_patch_entries",
-                "n_patch_colors", "max_patch_size"]
+                "n_patch_colors", "max_patch_size", "patch_row_entries", "patch_inv_entries"]
         return dict(zip(keys, [int(x) for x in info]))
 
     def export_level(self, level):
@@ -137,6 +137,18 @@ class Hierarchy:
         v = C.c_int64()
         check(lib.mamg_launch_count(self._h, C.byref(v), int(reset)))
         return v.value
+
+    KERNEL_CLASSES = ["spmv", "gs", "schwarz", "restrict", "scale", "prolong", "coarse", "vector", "dot"]
+
+    def profile_start(self):
+        check(lib.mamg_profile(self._h, 1, None, None))
+
+    def profile_stop(self):
+        """{class: (ms, launches)} of everything launched since profile_start()."""
+        ms = np.zeros(16, np.float64)
+        cnt = np.zeros(16, np.int64)
+        check(lib.mamg_profile(self._h, 0, ptr(ms), ptr(cnt)))
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.KERNEL_CLASSES)}
 
     def _require_device(self):
         if not self.on_device:

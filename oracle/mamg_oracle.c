@@ -27,6 +27,12 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#ifdef _OPENMP
+#include <omp.h>
+#else
+static int omp_get_thread_num(void) { return 0; }
+static int omp_get_max_threads(void) { return 1; }
+#endif
 
 enum { UA_AMG = 1, V_CYCLE = 1, W_CYCLE = 2, SM_JACOBI = 1, SM_GS = 2, SM_SGS = 3, SM_SOR = 5, SM_SSOR = 6,
        SW_FORWARD = 1, SW_BACKWARD = 2, SW_SYMMETRIC = 3 };
@@ -38,6 +44,10 @@ typedef struct {
   int *crow_ptr, *crow, *cpat_ptr, *cpat;
   unsigned char* skip;
   double *a, *invd, *x, *b, *w;
+  /* Schwarz blocks are factorised once at setup, as HAZmath does with UMFPACK
+   * (Schwarz_blksolver 32): packed lower Cholesky factors, pfoff[p] = start of patch p */
+  double* pfac;
+  long* pfoff;
 } orc_level;
 
 typedef struct {
@@ -46,7 +56,9 @@ typedef struct {
   int nlevels, cap;
   orc_level* lv;
   double* coarse_inv;
-  double *Lm, *rhs; /* patch scratch */
+  double* rhs;      /* patch scratch, one slice per thread */
+  int maxpatch;
+  int threads;      /* > 1 only for the multicolour ordering (bench reference arm) */
   int ordering;
   long visits;      /* level visits of the last apply (for reporting) */
 } orc_hier;
@@ -54,12 +66,42 @@ typedef struct {
 static void* xmalloc(size_t n) { void* p = malloc(n ? n : 1); if (!p) abort(); return p; }
 static void* xdup(const void* src, size_t n) { void* p = xmalloc(n); if (n) memcpy(p, src, n); return p; }
 
+#define TRI(i, j) ((size_t)(i) * ((i) + 1) / 2 + (j))
+
+/* dense Cholesky A_BB = L L' of one patch (dofs in ascending order), packed lower storage */
+static void patch_factor(orc_level* L, int p) {
+  const int q0 = L->pptr[p], s = L->pptr[p + 1] - q0;
+  const int* idx = L->pdofs + q0;
+  double* F = L->pfac + L->pfoff[p];
+  for (long k = 0; k < (long)s * (s + 1) / 2; ++k) F[k] = 0.0;
+  for (int k = 0; k < s; ++k) {
+    int i = idx[k];
+    for (int e = L->ia[i]; e < L->ia[i + 1]; ++e) {
+      int j = L->ja[e], lo = 0, hi = k;  /* idx is sorted ascending: binary search in [0, k] */
+      while (lo <= hi) {
+        int mid = (lo + hi) / 2;
+        if (idx[mid] == j) { F[TRI(k, mid)] = L->a[e]; break; }
+        if (idx[mid] < j) lo = mid + 1; else hi = mid - 1;
+      }
+    }
+  }
+  for (int j = 0; j < s; ++j) {
+    double d = sqrt(F[TRI(j, j)]);
+    F[TRI(j, j)] = d;
+    for (int i = j + 1; i < s; ++i) F[TRI(i, j)] /= d;
+    for (int k = j + 1; k < s; ++k) {
+      double lkj = F[TRI(k, j)];
+      for (int i = k; i < s; ++i) F[TRI(i, k)] -= F[TRI(i, j)] * lkj;
+    }
+  }
+}
+
 orc_hier* orc_create(int cycle_type, int maxit, int smoother, double relaxation, int presmooth,
                      int postsmooth, int coarse_scaling, int schwarz_type) {
   orc_hier* h = (orc_hier*)calloc(1, sizeof(orc_hier));
   h->cycle_type = cycle_type; h->maxit = maxit; h->smoother = smoother; h->relaxation = relaxation;
   h->presmooth = presmooth; h->postsmooth = postsmooth; h->coarse_scaling = coarse_scaling;
-  h->schwarz_type = schwarz_type; h->ordering = 1;
+  h->schwarz_type = schwarz_type; h->ordering = 1; h->threads = 1;
   return h;
 }
 
@@ -113,9 +155,18 @@ int orc_add_level(orc_hier* h, int n, const int* ia, const int* ja, const double
     int* fill = (int*)xdup(L->cpat_ptr, sizeof(int) * (npcolors + 1));
     for (int p = 0; p < npatch; ++p) L->cpat[fill[pcolor[p]]++] = p;
     free(fill);
-    size_t m = (size_t)L->maxpatch;
-    h->Lm = (double*)realloc(h->Lm, sizeof(double) * m * m);
-    h->rhs = (double*)realloc(h->rhs, sizeof(double) * m);
+    L->pfoff = (long*)xmalloc(sizeof(long) * (npatch + 1));
+    L->pfoff[0] = 0;
+    for (int p = 0; p < npatch; ++p) {
+      long s = pptr[p + 1] - pptr[p];
+      L->pfoff[p + 1] = L->pfoff[p] + s * (s + 1) / 2;
+    }
+    L->pfac = (double*)xmalloc(sizeof(double) * L->pfoff[npatch]);
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int p = 0; p < npatch; ++p) patch_factor(L, p);
+    if (L->maxpatch > h->maxpatch) h->maxpatch = L->maxpatch;
+    size_t m = (size_t)h->maxpatch, nt = (size_t)omp_get_max_threads();
+    h->rhs = (double*)realloc(h->rhs, sizeof(double) * m * nt);
   }
   return h->nlevels - 1;
 }
@@ -124,7 +175,14 @@ void orc_set_coarse(orc_hier* h, const double* inv) {
   int n = h->lv[h->nlevels - 1].n;
   h->coarse_inv = (double*)xdup(inv, sizeof(double) * (size_t)n * n);
 }
-void orc_set_ordering(orc_hier* h, int ordering) { h->ordering = ordering; }
+void orc_set_ordering(orc_hier* h, int ordering) { h->ordering = ordering; if (ordering == 0) h->threads = 1; }
+/* threads > 1 (multicolour ordering only): colour classes and vector loops run on several cores */
+int orc_set_threads(orc_hier* h, int threads) {
+  int mx = omp_get_max_threads();
+  if (threads < 1 || threads > mx) threads = mx;
+  h->threads = h->ordering == 1 ? threads : 1;
+  return h->threads;
+}
 void orc_set_cycle(orc_hier* h, int cycle_type) { h->cycle_type = cycle_type; }
 long orc_visits(orc_hier* h) { return h->visits; }
 
@@ -135,8 +193,9 @@ void orc_destroy(orc_hier* h) {
     free(L->ia); free(L->ja); free(L->a); free(L->agg); free(L->color); free(L->skip); free(L->invd);
     free(L->x); free(L->b); free(L->w); free(L->crow_ptr); free(L->crow);
     free(L->pptr); free(L->pdofs); free(L->pcolor); free(L->cpat_ptr); free(L->cpat);
+    free(L->pfac); free(L->pfoff);
   }
-  free(h->lv); free(h->coarse_inv); free(h->Lm); free(h->rhs); free(h);
+  free(h->lv); free(h->coarse_inv); free(h->rhs); free(h);
 }
 
 /* ---- kernels ------------------------------------------------------------------------------ */
@@ -168,6 +227,8 @@ static void gs_sweep(const orc_hier* h, const orc_level* L, const double* b, dou
   }
   for (int cc = skip_first_color; cc < L->ncolors; ++cc) {
     int c = backward ? L->ncolors - 1 - cc : cc;
+    /* rows of one colour do not couple: the threaded loop gives the same numbers as the serial one */
+#pragma omp parallel for schedule(static) num_threads(h->threads) if (h->threads > 1)
     for (int q = L->crow_ptr[c]; q < L->crow_ptr[c + 1]; ++q) gs_row(L, L->crow[q], b, x, w);
   }
 }
@@ -178,41 +239,22 @@ static void jacobi(const orc_level* L, const double* b, double* x, double w) {
   memcpy(x, L->w, sizeof(double) * L->n);
 }
 
-/* exact solve on one patch: x_B += A_BB^{-1} (b - A x)_B, dense Cholesky in patch order */
+/* exact solve on one patch: x_B += A_BB^{-1} (b - A x)_B with the stored Cholesky factor */
 static void patch_solve(orc_hier* h, const orc_level* L, int p, const double* b, double* x) {
   const int q0 = L->pptr[p], s = L->pptr[p + 1] - q0;
   const int* idx = L->pdofs + q0;
-  double* M = h->Lm;
-  double* r = h->rhs;
-  for (int k = 0; k < s; ++k) {
-    int i = idx[k];
-    r[k] = b[i] - row_dot(L, i, x);
-    for (int c = 0; c < s; ++c) M[k * s + c] = 0.0;
-    for (int e = L->ia[i]; e < L->ia[i + 1]; ++e) {
-      int j = L->ja[e];
-      /* idx is sorted ascending: binary search */
-      int lo = 0, hi = s - 1;
-      while (lo <= hi) {
-        int mid = (lo + hi) / 2;
-        if (idx[mid] == j) { M[k * s + mid] = L->a[e]; break; }
-        if (idx[mid] < j) lo = mid + 1; else hi = mid - 1;
-      }
-    }
+  const double* F = L->pfac + L->pfoff[p];
+  double* r = h->rhs + (size_t)omp_get_thread_num() * (size_t)h->maxpatch;
+  for (int k = 0; k < s; ++k) r[k] = b[idx[k]] - row_dot(L, idx[k], x);
+  for (int i = 0; i < s; ++i) {           /* L y = r */
+    double acc = r[i];
+    for (int k = 0; k < i; ++k) acc -= F[TRI(i, k)] * r[k];
+    r[i] = acc / F[TRI(i, i)];
   }
-  for (int j = 0; j < s; ++j) {
-    double d = sqrt(M[j * s + j]);
-    M[j * s + j] = d;
-    r[j] /= d;
-    for (int i = j + 1; i < s; ++i) M[i * s + j] /= d;
-    for (int k = j + 1; k < s; ++k) {
-      double lkj = M[k * s + j];
-      for (int i = k; i < s; ++i) M[i * s + k] -= M[i * s + j] * lkj;
-    }
-    for (int i = j + 1; i < s; ++i) r[i] -= M[i * s + j] * r[j];
-  }
-  for (int j = s - 1; j >= 0; --j) {
-    r[j] /= M[j * s + j];
-    for (int i = 0; i < j; ++i) r[i] -= M[j * s + i] * r[j];
+  for (int i = s - 1; i >= 0; --i) {      /* L' d = y */
+    double acc = r[i];
+    for (int k = i + 1; k < s; ++k) acc -= F[TRI(k, i)] * r[k];
+    r[i] = acc / F[TRI(i, i)];
   }
   for (int k = 0; k < s; ++k) x[idx[k]] += r[k];
 }
@@ -225,6 +267,7 @@ static void schwarz_sweep(orc_hier* h, const orc_level* L, const double* b, doub
   }
   for (int cc = 0; cc < L->npcolors; ++cc) {
     int c = backward ? L->npcolors - 1 - cc : cc;
+#pragma omp parallel for schedule(dynamic, 16) num_threads(h->threads) if (h->threads > 1)
     for (int q = L->cpat_ptr[c]; q < L->cpat_ptr[c + 1]; ++q) patch_solve(h, L, L->cpat[q], b, x);
   }
 }
@@ -280,15 +323,22 @@ static void cycle_level(orc_hier* h, int lev) {
     h->visits++;
     smooth(h, lev, L->b, L->x, 0);
     memset(C->b, 0, sizeof(double) * C->n);
-    for (int i = 0; i < L->n; ++i) {
-      int I = L->agg[i];
-      if (I >= 0) C->b[I] += L->b[i] - row_dot(L, i, L->x);
+    if (h->threads > 1) {
+#pragma omp parallel for schedule(static) num_threads(h->threads)
+      for (int i = 0; i < L->n; ++i) L->w[i] = L->b[i] - row_dot(L, i, L->x);
+      for (int i = 0; i < L->n; ++i) { int I = L->agg[i]; if (I >= 0) C->b[I] += L->w[i]; }
+    } else {
+      for (int i = 0; i < L->n; ++i) {
+        int I = L->agg[i];
+        if (I >= 0) C->b[I] += L->b[i] - row_dot(L, i, L->x);
+      }
     }
     memset(C->x, 0, sizeof(double) * C->n);
     cycle_level(h, lev + 1);
     double alpha = 1.0;
     if (h->coarse_scaling) {
       double num = 0.0, den = 0.0;
+#pragma omp parallel for schedule(static) reduction(+ : num, den) num_threads(h->threads) if (h->threads > 1)
       for (int i = 0; i < C->n; ++i) { num += C->x[i] * C->b[i]; den += C->x[i] * row_dot(C, i, C->x); }
       alpha = num / den;
       alpha = (alpha < 1.0) ? alpha : 1.0;  /* MIN(alpha, 1.0); NaN -> 1 */
@@ -338,6 +388,7 @@ int orc_pcg(orc_hier* h, const double* b, double* x, double tol, int relative, i
   int it = 0;
   while (res > target && it < maxiter) {
     double dq = 0.0;
+#pragma omp parallel for schedule(static) reduction(+ : dq) num_threads(h->threads) if (h->threads > 1)
     for (int i = 0; i < n; ++i) { q[i] = row_dot(L0, i, d); dq += d[i] * q[i]; }
     double alpha = rz / dq;
     for (int i = 0; i < n; ++i) { x[i] += alpha * d[i]; r[i] -= alpha * q[i]; }

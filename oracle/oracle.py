@@ -27,6 +27,8 @@ def _load():
     lib.orc_set_coarse.argtypes = [vp, vp]
     lib.orc_set_ordering.argtypes = [vp, i32]
     lib.orc_set_cycle.argtypes = [vp, i32]
+    lib.orc_set_threads.restype = i32
+    lib.orc_set_threads.argtypes = [vp, i32]
     lib.orc_visits.restype = C.c_long
     lib.orc_visits.argtypes = [vp]
     lib.orc_destroy.argtypes = [vp]
@@ -78,6 +80,10 @@ class Oracle:
 
     def set_ordering(self, ordering):
         self.lib.orc_set_ordering(self.h, {"natural": 0, "multicolor": 1}[ordering])
+
+    def set_threads(self, threads):
+        """>1 only takes effect for the multicolour ordering; returns the thread count in use."""
+        return int(self.lib.orc_set_threads(self.h, int(threads)))
 
     def set_cycle(self, cycle_type):
         self.lib.orc_set_cycle(self.h, int(cycle_type))
