@@ -128,8 +128,7 @@ def class_bytes(H, niters, cycle_applies):
         per_smooth = (sweep + sweep_bw) if sgs else sweep
         out["gs"] += per_smooth * (prm.presmooth_iter + prm.postsmooth_iter)
         if infos[l]["n_patches"]:
-            sw = 12 * infos[l]["patch_row_entries"] + 8 * infos[l]["patch_inv_entries"] \
-                + 28 * infos[l]["n_patch_entries"] + 8 * infos[l]["n_patches"]
+            sw = H.schwarz_sweep_bytes(l)
             nsw = 2 if prm.Schwarz_type == 3 else 1
             out["schwarz"] += 2 * nsw * sw
         agg = np.empty(n, np.int32)

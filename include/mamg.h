@@ -149,6 +149,9 @@ int mamg_gmres(mamg_handle h, const double* b, double* x, double tolerance, int3
 /* ---- measurement helpers (bench.py): kernel launches issued on the handle's stream
  *      since the last reset, and algorithmic bytes (SURVEY 8d model) of one cycle. */
 int mamg_launch_count(mamg_handle h, int64_t* launches, int32_t reset);
+/* algorithmic bytes of one Schwarz sweep over all patches of a level (device layout: row values,
+ * 16-bit local columns, neighbourhood lists, packed inverses; see csrc/cuda/schwarz.cuh) */
+int mamg_schwarz_sweep_bytes(mamg_handle h, int32_t level, int64_t* bytes);
 /* per-kernel-class timing with CUDA events on the handle's stream.  on=1 starts collecting;
  * on=0 stops and returns, for the classes {0 spmv, 1 gs, 2 schwarz, 3 restrict, 4 scale,
  * 5 prolong, 6 coarse, 7 vector, 8 dot}, the summed kernel time in ms and the launch counts

@@ -30,7 +30,7 @@ namespace mamg {
   } while (0)
 
 struct DLevel {
-  int n = 0, nnz = 0, nc = 0, ncolors = 0, lanes = 8;
+  int n = 0, nnz = 0, nc = 0, ncolors = 0, lanes = 8, unroll = 4;
   int *ia = nullptr, *ja = nullptr;
   double *a = nullptr, *invd = nullptr;
   uint8_t* skip = nullptr;
@@ -123,8 +123,14 @@ static int pick_lanes(double avg) {
   const char* env = getenv("MAMG_LANES");
   if (env && atoi(env) > 0) return atoi(env);
   int l = 2;
-  while (l < 32 && l * 2 <= avg + 1) l *= 2;  // largest power of two <= nnz/row (+1), 2..32
+  while (l < 32 && l * 4 <= avg + 2) l *= 2;  // about 2-4 entries per lane: 30/row -> 8, 15 -> 4, 7 -> 2
   return l;
+}
+
+static int pick_unroll(int n) {
+  const char* env = getenv("MAMG_UNROLL");
+  if (env && atoi(env) > 0) return atoi(env) >= 4 ? 4 : atoi(env);
+  return n >= (1 << 18) ? 4 : (n >= (1 << 15) ? 2 : 1);  // small levels need the parallelism more than the MLP
 }
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
@@ -166,6 +172,7 @@ static void upload_hierarchy(const Hierarchy& H, DeviceState& D) {
     dl.nnz = hl.A.nnz();
     dl.nc = hl.nc;
     dl.lanes = pick_lanes(n ? (double)dl.nnz / n : 1.0);
+    dl.unroll = pick_unroll(n);
     std::vector<int> ia(n + 1, 0), ja(dl.nnz);
     std::vector<double> a(dl.nnz), invd(n, 1.0);
     for (int i = 0; i < n; ++i) ia[i + 1] = ia[i] + (hl.A.ia[perm[l][i] + 1] - hl.A.ia[perm[l][i]]);
@@ -217,7 +224,7 @@ static void upload_hierarchy(const Hierarchy& H, DeviceState& D) {
       dl.cptr = upload(D, cptr);
       dl.cidx = upload(D, cidx);
     }
-    if (hl.sw.npatch() > 0) schwarz_upload(hl, iperm[l], dl.ia, dl.ja, dl.a, ia, dl.sw, [&](size_t bytes) {
+    if (hl.sw.npatch() > 0) schwarz_upload(hl, iperm[l], dl.ia, dl.ja, dl.a, ia, ja, dl.sw, [&](size_t bytes) {
       void* p = nullptr;
       CUDA_OK(cudaMalloc(&p, bytes ? bytes : 1));
       D.allocs.push_back(p);
@@ -251,23 +258,30 @@ static void upload_hierarchy(const Hierarchy& H, DeviceState& D) {
     case 16: { constexpr int LN = 16; __VA_ARGS__; break; } \
     default: { constexpr int LN = 32; __VA_ARGS__; break; } \
   }
+// rows per sub-warp (independent row streams in flight per lane)
+#define UNROLL_SWITCH(u, ...)                            \
+  switch (u) {                                           \
+    case 1: { constexpr int UN = 1; __VA_ARGS__; break; }   \
+    case 2: { constexpr int UN = 2; __VA_ARGS__; break; }   \
+    default: { constexpr int UN = 4; __VA_ARGS__; break; }  \
+  }
 
 static void k_spmv(DeviceState& D, const DLevel& l, const double* x, const double* b, double* y, bool resid) {
   if (l.n == 0) return;
-  const int grid = cdiv((long long)l.n * l.lanes, kBlock);
+  const int grid = cdiv((long long)cdiv(l.n, l.unroll) * l.lanes, kBlock);
   KScope ks(D, K_SPMV);
-  LANES_SWITCH(l.lanes,
-    if (resid) spmv_kernel<LN, true><<<grid, kBlock, 0, D.stream>>>(l.n, l.ia, l.ja, l.a, x, b, y);
-    else spmv_kernel<LN, false><<<grid, kBlock, 0, D.stream>>>(l.n, l.ia, l.ja, l.a, x, b, y));
+  LANES_SWITCH(l.lanes, UNROLL_SWITCH(l.unroll,
+    if (resid) spmv_kernel<LN, UN, true><<<grid, kBlock, 0, D.stream>>>(l.n, l.ia, l.ja, l.a, x, b, y);
+    else spmv_kernel<LN, UN, false><<<grid, kBlock, 0, D.stream>>>(l.n, l.ia, l.ja, l.a, x, b, y)));
 }
 
 static void k_gs_color(DeviceState& D, const DLevel& l, int c, const double* b, double* x, double omega) {
   const int r0 = l.color_ptr[c], r1 = l.color_ptr[c + 1];
   if (r1 <= r0) return;
-  const int grid = cdiv((long long)(r1 - r0) * l.lanes, kBlock);
+  const int grid = cdiv((long long)cdiv(r1 - r0, l.unroll) * l.lanes, kBlock);
   KScope ks(D, K_GS);
-  LANES_SWITCH(l.lanes,
-    gs_color_kernel<LN><<<grid, kBlock, 0, D.stream>>>(r0, r1, l.ia, l.ja, l.a, l.invd, l.skip, b, x, omega));
+  LANES_SWITCH(l.lanes, UNROLL_SWITCH(l.unroll,
+    gs_color_kernel<LN, UN><<<grid, kBlock, 0, D.stream>>>(r0, r1, l.ia, l.ja, l.a, l.invd, l.skip, b, x, omega)));
 }
 
 static void gs_forward(DeviceState& D, const DLevel& l, const double* b, double* x, double w, int first = 0) {
@@ -331,7 +345,7 @@ static void smooth(DeviceState& D, int lev, const double* b, double* x, bool pos
         const int c = backward ? l.sw.ncolors - 1 - cc : cc;
         if (l.sw.color_ptr[c + 1] == l.sw.color_ptr[c]) continue;
         KScope ks(D, K_SCHWARZ);
-        schwarz_color_launch(l.sw, c, l.ia, l.ja, l.a, b, x, D.stream);
+        schwarz_color_launch(l.sw, c, l.a, b, x, D.stream);
       }
     };
     if (fwd) sweep(false);
@@ -480,11 +494,11 @@ static int pcg_device(DeviceState& D, const double* b_nat, double* x_nat, double
   if (residuals) residuals[0] = res;
   double target = relative ? tol * res : tol;
   while (res > target && it < maxiter) {
-    const int sgrid = red_grid(D, (long long)n * l0.lanes);
+    const int sgrid = red_grid(D, (long long)cdiv(n, l0.unroll) * l0.lanes);
     {
       KScope ks(D, K_SPMV);
-      LANES_SWITCH(l0.lanes,
-        spmv_dot_kernel<LN><<<sgrid, kBlock, 0, D.stream>>>(n, l0.ia, l0.ja, l0.a, d, q, D.partial, D.ticket, D.scal));
+      LANES_SWITCH(l0.lanes, UNROLL_SWITCH(l0.unroll,
+        spmv_dot_kernel<LN, UN><<<sgrid, kBlock, 0, D.stream>>>(n, l0.ia, l0.ja, l0.a, d, q, D.partial, D.ticket, D.scal)));
     }
     {
       KScope ks(D, K_VEC);
@@ -691,6 +705,14 @@ int mamg_profile(mamg_handle h, int32_t on, double* ms_per_class, int64_t* launc
   D->prof_used = 0;
   return 0;
   MAMG_CATCH
+}
+
+int mamg_schwarz_sweep_bytes(mamg_handle h, int32_t level, int64_t* bytes) {
+  DeviceState* D = get_dev(h);
+  if (!D || !bytes) return -1;
+  if (level < 0 || level >= (int)D->lv.size()) { set_error("level out of range"); return -1; }
+  *bytes = D->lv[level].sw.alg_bytes;
+  return 0;
 }
 
 int mamg_launch_count(mamg_handle h, int64_t* launches, int32_t reset) {

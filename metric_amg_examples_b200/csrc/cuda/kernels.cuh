@@ -43,19 +43,60 @@ __device__ __forceinline__ double row_dot(const int* __restrict__ ja, const doub
   return subwarp_sum<LANES>(s);
 }
 
+// U adjacent rows [row0, row0+U) (clipped at rend) by one sub-warp, all U row streams in flight
+// at once: every lane has U independent (value, column, x) load chains outstanding, which is
+// what hides the DRAM latency of these 12-byte-per-flop kernels.  Sums valid in lane 0.
+template <int LANES, int U>
+__device__ __forceinline__ void rows_dot(const int* __restrict__ ia, const int* __restrict__ ja,
+                                         const double* __restrict__ a, const double* x, int row0,
+                                         int rend, int lane, double (&s)[U]) {
+  int p[U], e[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int r = row0 + u;
+    p[u] = r < rend ? ia[r] + lane : 0;
+    e[u] = r < rend ? ia[r + 1] : 0;
+    s[u] = 0.0;
+  }
+  bool more = true;
+  while (more) {
+    more = false;
+    double av[U], xv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool on = p[u] < e[u];
+      av[u] = on ? a[p[u]] : 0.0;
+      xv[u] = on ? x[ja[p[u]]] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      s[u] += av[u] * xv[u];
+      p[u] += LANES;
+      more |= p[u] < e[u];
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) s[u] = subwarp_sum<LANES>(s[u]);
+}
+
 // ---------------------------------------------------------------------------------------
 // K1  y = A x   |   y = b - A x          (HAZmath dcsr_mxv / dcsr_aAxpy; PETSc MatMult)
 // ---------------------------------------------------------------------------------------
-template <int LANES, bool RESID>
+template <int LANES, int U, bool RESID>
 __global__ void __launch_bounds__(kBlock)
 spmv_kernel(int n, const int* __restrict__ ia, const int* __restrict__ ja,
             const double* __restrict__ a, const double* __restrict__ x,
             const double* __restrict__ b, double* __restrict__ y) {
   const int lane = threadIdx.x % LANES;
-  const int row = (blockIdx.x * kBlock + threadIdx.x) / LANES;
-  if (row >= n) return;
-  double s = row_dot<LANES>(ja, a, x, ia[row], ia[row + 1], lane);
-  if (lane == 0) y[row] = RESID ? b[row] - s : s;
+  const int row0 = ((blockIdx.x * kBlock + threadIdx.x) / LANES) * U;
+  if (row0 >= n) return;
+  double s[U];
+  rows_dot<LANES, U>(ia, ja, a, x, row0, n, lane, s);
+  if (lane == 0) {
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (row0 + u < n) y[row0 + u] = RESID ? b[row0 + u] - s[u] : s[u];
+  }
 }
 
 // Deterministic two-stage reduction: every block writes its partial sums, the block that
@@ -109,17 +150,22 @@ __device__ __forceinline__ bool block_reduce_finish(double (&v)[NV], double* par
 // PCG scalars live on the device: sc[0]=rz, sc[1]=d.q, sc[2]=alpha, sc[3]=rz_new, sc[4]=beta
 // q = A d  with the dot product d.q in the epilogue; the finishing block sets
 // sc[1] = d.q and alpha = sc[2] = rz / d.q                       (K1 + K10 fused)
-template <int LANES>
+template <int LANES, int U>
 __global__ void __launch_bounds__(kBlock)
 spmv_dot_kernel(int n, const int* __restrict__ ia, const int* __restrict__ ja,
                 const double* __restrict__ a, const double* __restrict__ d, double* __restrict__ q,
                 double* partial, unsigned int* ticket, double* sc) {
   const int lane = threadIdx.x % LANES;
-  const int nsub = gridDim.x * (kBlock / LANES);  // fixed grid, rows strided: few tickets, fixed partial count
+  const int nsub = gridDim.x * (kBlock / LANES);  // fixed grid, row groups strided: few tickets, fixed partial count
   double v[1] = {0.0};
-  for (int row = (blockIdx.x * kBlock + threadIdx.x) / LANES; row < n; row += nsub) {
-    double s = row_dot<LANES>(ja, a, d, ia[row], ia[row + 1], lane);
-    if (lane == 0) { q[row] = s; v[0] += s * d[row]; }
+  for (int row0 = ((blockIdx.x * kBlock + threadIdx.x) / LANES) * U; row0 < n; row0 += nsub * U) {
+    double s[U];
+    rows_dot<LANES, U>(ia, ja, a, d, row0, n, lane, s);
+    if (lane == 0) {
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (row0 + u < n) { q[row0 + u] = s[u]; v[0] += s[u] * d[row0 + u]; }
+    }
   }
   if (block_reduce_finish<1>(v, partial, ticket, sc + 1) && threadIdx.x == 0) sc[2] = sc[0] / sc[1];
 }
@@ -130,18 +176,32 @@ spmv_dot_kernel(int n, const int* __restrict__ ia, const int* __restrict__ ja,
 //       x_i <- x_i + w (b_i - sum_j a_ij x_j) / a_ii
 //     Rows of one colour do not couple, so the in-place update equals the sequential sweep.
 // ---------------------------------------------------------------------------------------
-template <int LANES>
+template <int LANES, int U>
 __global__ void __launch_bounds__(kBlock)
 gs_color_kernel(int r0, int r1, const int* __restrict__ ia, const int* __restrict__ ja,
                 const double* __restrict__ a, const double* __restrict__ invd,
                 const uint8_t* __restrict__ skip, const double* __restrict__ b, double* x,
                 double omega) {
   const int lane = threadIdx.x % LANES;
-  const int row = r0 + (blockIdx.x * kBlock + threadIdx.x) / LANES;
-  if (row >= r1) return;
-  if (skip != nullptr && skip[row]) return;
-  double s = row_dot<LANES>(ja, a, x, ia[row], ia[row + 1], lane);
-  if (lane == 0) x[row] += omega * (b[row] - s) * invd[row];
+  const int row0 = r0 + ((blockIdx.x * kBlock + threadIdx.x) / LANES) * U;
+  if (row0 >= r1) return;
+  // rows smoothed by Schwarz instead (skip mask) come in long runs inside a colour: test the group
+  int rend = r1;
+  if (skip != nullptr) {
+    bool all = true;
+#pragma unroll
+    for (int u = 0; u < U; ++u) all &= (row0 + u >= r1) || skip[row0 + u];
+    if (all) return;
+  }
+  double s[U];
+  rows_dot<LANES, U>(ia, ja, a, x, row0, rend, lane, s);
+  if (lane == 0) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int row = row0 + u;
+      if (row < r1 && !(skip != nullptr && skip[row])) x[row] += omega * (b[row] - s[u]) * invd[row];
+    }
+  }
 }
 
 // damped Jacobi, out of place: xn = x + w D^-1 (b - A x)
@@ -178,10 +238,27 @@ resid_restrict_kernel(int nc, const int* __restrict__ cptr, const int* __restric
   const int I = (blockIdx.x * kBlock + threadIdx.x) / LANES;
   if (I >= nc) return;
   double acc = 0.0;
-  for (int q = cptr[I]; q < cptr[I + 1]; ++q) {
-    const int i = cidx[q];
-    double s = row_dot<LANES>(ja, a, x, ia[i], ia[i + 1], lane);
-    acc += b[i] - s;
+  const int q1 = cptr[I + 1];
+  for (int q = cptr[I]; q < q1; q += 2) {   // two member rows in flight (pairwise aggregates: one pass)
+    const int i0 = cidx[q];
+    const bool two = q + 1 < q1;
+    const int i1 = two ? cidx[q + 1] : i0;
+    int p0 = ia[i0] + lane, e0 = ia[i0 + 1];
+    int p1 = two ? ia[i1] + lane : 0, e1 = two ? ia[i1 + 1] : 0;
+    double s0 = 0.0, s1 = 0.0;
+    while (p0 < e0 || p1 < e1) {
+      const bool on0 = p0 < e0, on1 = p1 < e1;
+      const double a0 = on0 ? a[p0] : 0.0, a1 = on1 ? a[p1] : 0.0;
+      const double x0 = on0 ? x[ja[p0]] : 0.0, x1 = on1 ? x[ja[p1]] : 0.0;
+      s0 += a0 * x0;
+      s1 += a1 * x1;
+      p0 += LANES;
+      p1 += LANES;
+    }
+    s0 = subwarp_sum<LANES>(s0);
+    s1 = subwarp_sum<LANES>(s1);
+    acc += b[i0] - s0;
+    if (two) acc += b[i1] - s1;
   }
   if (lane == 0) { bc[I] = acc; xc[I] = 0.0; }
 }

@@ -11,11 +11,19 @@
 // Setup (once, on the device): every A_BB is gathered from the level's CSR, Cholesky-factorised
 // and inverted in shared memory; the symmetric inverse is kept packed (s(s+1)/2 doubles per
 // patch) -- the analogue of HAZmath keeping one UMFPACK factorisation per block.
-// Apply: a warp (or CTA for patches > 32 dofs) streams the patch's CSR rows once to form the
-// residual (b - A x)_B, stages the packed inverse through shared memory and applies it as a
-// small symmetric mat-vec.  The kernel is HBM-bound: per patch it reads 12 B per row entry plus
-// 4 s(s+1) bytes of inverse.
+//
+// Apply, per patch (one warp for <= 32 dofs, else one CTA):
+//   1. x on the patch neighbourhood N[B] (the union of the columns of the patch rows, ~130
+//      dofs for a 30-dof 3-D patch) is gathered ONCE into shared memory through a stored list;
+//      the row products then index shared memory through a stored 16-bit local column, so the
+//      900 row entries of a patch cost 900 coalesced value loads instead of 900 scattered
+//      32-byte sector gathers;
+//   2. the packed inverse is staged through shared memory with coalesced loads;
+//   3. residual rows (8 rows in flight per warp), symmetric packed mat-vec, update of x_B.
+// Algorithmic bytes per patch: 8 B per row entry (values) + 2 B (local column) + 4 B per
+// neighbour + 8 B per gathered x + 4 s(s+1) B of inverse + 28 B per patch dof.
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <cuda_runtime.h>
 #include <functional>
@@ -25,12 +33,24 @@
 
 namespace mamg {
 
+struct SwPatch {      // 32 bytes per patch
+  int q0;             // first entry in pdof arrays
+  int s;              // dofs
+  int n0;             // first entry in nbr
+  int nn;             // neighbours
+  long long e0;       // first entry in lcol
+  long long i0;       // first entry in pinv
+};
+
 struct DSchwarz {
-  int npatch = 0, ncolors = 0, max_size = 0, warps = 1, ppc = 1;
+  int npatch = 0, ncolors = 0, max_size = 0, max_nbr = 0, srow = 1, warps = 1, ppc = 1;
   size_t smem_apply = 0, smem_setup = 0;
-  int* pptr = nullptr;         // npatch+1, patches sorted by colour
-  int* pdofs = nullptr;        // patch dofs (permuted row ids) in natural-ascending order
-  long long* ioff = nullptr;   // npatch+1: start of every packed inverse
+  SwPatch* pat = nullptr;      // patches sorted by colour
+  int* pidx = nullptr;         // per patch dof: permuted row id (natural-ascending order inside a patch)
+  int* prow = nullptr;         // per patch dof: start of the row in the level CSR (= ia[pidx])
+  int* plen = nullptr;         // per patch dof: length of the row
+  int* nbr = nullptr;          // neighbourhood lists (permuted ids, ascending)
+  uint16_t* lcol = nullptr;    // per patch: s x srow (row-major, padded): position of the entry's column in nbr
   double* pinv = nullptr;      // packed lower triangles of A_BB^{-1}
   std::vector<int> color_ptr;  // host: patch range of every colour
   long long alg_bytes = 0;     // algorithmic bytes of one sweep over all patches
@@ -41,22 +61,21 @@ __device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }
 // ---- setup: packed inverse of every A_BB -------------------------------------------------------
 template <int T>
 __global__ void __launch_bounds__(T)
-schwarz_invert_kernel(int npatch, const int* __restrict__ pptr, const int* __restrict__ pdofs,
-                      const long long* __restrict__ ioff, const int* __restrict__ ia,
-                      const int* __restrict__ ja, const double* __restrict__ a,
-                      double* __restrict__ pinv, int max_size) {
+schwarz_invert_kernel(int npatch, const SwPatch* __restrict__ pat, const int* __restrict__ pidx,
+                      const int* __restrict__ ia, const int* __restrict__ ja,
+                      const double* __restrict__ a, double* __restrict__ pinv, int max_size) {
   extern __shared__ double smem[];
   const int patch = blockIdx.x;
   if (patch >= npatch) return;
-  const int q0 = pptr[patch], s = pptr[patch + 1] - q0;
+  const int q0 = pat[patch].q0, s = pat[patch].s;
   double* Lm = smem;                                                  // packed lower triangle
   double* col = Lm + (size_t)max_size * (max_size + 1) / 2;           // s scratch
   int* idx = reinterpret_cast<int*>(col + max_size);                  // s
   const int tid = threadIdx.x;
   for (int k = tid; k < s * (s + 1) / 2; k += T) Lm[k] = 0.0;
-  for (int k = tid; k < s; k += T) idx[k] = pdofs[q0 + k];
+  for (int k = tid; k < s; k += T) idx[k] = pidx[q0 + k];
   __syncthreads();
-  // gather the lower triangle of A_BB: thread per (row k, entry) with a linear search of the column
+  // gather the lower triangle of A_BB: linear search of the column among the patch dofs
   for (int k = 0; k < s; ++k) {
     const int i = idx[k];
     for (int p = ia[i] + tid; p < ia[i + 1]; p += T) {
@@ -104,94 +123,139 @@ schwarz_invert_kernel(int npatch, const int* __restrict__ pptr, const int* __res
     for (int c = tid; c <= i; c += T) Lm[tri(i, c)] = col[c];
     __syncthreads();
   }
-  double* out = pinv + ioff[patch];
+  double* out = pinv + pat[patch].i0;
   for (int k = tid; k < s * (s + 1) / 2; k += T) out[k] = Lm[k];
 }
 
 // ---- apply ---------------------------------------------------------------------------------------
-// WPP warps per patch, PPC patches per CTA (PPC > 1 only with WPP == 1: warps are independent)
+// Shared-memory layout of one patch slot (sizes from the level maxima; 16-byte aligned blocks).
+// Row values and local columns sit row-major with an ODD row stride `srow`, so that "thread k
+// walks row k" is bank-conflict free.
+struct SwLayout {
+  int max_size, max_nbr, srow;
+  __host__ __device__ size_t ent() const { return (size_t)max_size * srow; }
+  __host__ __device__ size_t inv_d() const { return ((size_t)max_size * (max_size + 1) / 2 + 2) & ~(size_t)1; }
+  __host__ __device__ size_t ls_d() const { return ((ent() + 8) * 2 + 15) / 16 * 2; }  // doubles holding the uint16 columns
+  __host__ __device__ size_t as_d() const { return (ent() + 1) & ~(size_t)1; }
+  __host__ __device__ size_t xs_d() const { return ((size_t)max_nbr + 1) & ~(size_t)1; }
+  __host__ __device__ size_t rhs_d() const { return ((size_t)max_size + 1) & ~(size_t)1; }
+  __host__ __device__ size_t int_d() const { return (3 * (size_t)max_size + 4) / 2 + 1; }
+  __host__ __device__ size_t total_d() const { return (inv_d() + ls_d() + as_d() + xs_d() + rhs_d() + int_d() + 1) & ~(size_t)1; }
+};
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// WPP warps per patch, PPC patches per CTA (PPC > 1 only with WPP == 1: warps are independent).
+// Every byte a patch needs is requested up front with cp.async (two dependent waves: the
+// descriptor-addressed arrays, then the row values / x gathers they point to), so one warp has a
+// whole patch (~15 KB) in flight; the arithmetic then runs out of shared memory with one thread
+// per patch row (no shuffles) and a packed symmetric mat-vec.
 template <int WPP, int PPC>
 __global__ void __launch_bounds__(WPP * PPC * 32)
-schwarz_apply_kernel(int p0, int p1, const int* __restrict__ pptr, const int* __restrict__ pdofs,
-                     const long long* __restrict__ ioff, const double* __restrict__ pinv,
-                     const int* __restrict__ ia, const int* __restrict__ ja,
-                     const double* __restrict__ a, const double* __restrict__ b, double* x,
-                     int max_size) {
+schwarz_apply_kernel(int p0, int p1, const SwPatch* __restrict__ pat, const int* __restrict__ pidx,
+                     const int* __restrict__ prow, const int* __restrict__ plen,
+                     const int* __restrict__ nbr, const uint16_t* __restrict__ lcol,
+                     const double* __restrict__ pinv, const double* __restrict__ a,
+                     const double* __restrict__ b, double* x, SwLayout lay) {
   constexpr int T = WPP * 32;  // threads per patch
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   const int slot = threadIdx.x / T;
   const int tid = threadIdx.x % T;
   const int patch = p0 + blockIdx.x * PPC + slot;
-  const size_t per_patch = (size_t)max_size * (max_size + 1) / 2 + 2 * (size_t)max_size;
-  double* Inv = smem + slot * per_patch;
-  double* rhs = Inv + (size_t)max_size * (max_size + 1) / 2;
-  int* idx = reinterpret_cast<int*>(rhs + max_size);
+  const int S = lay.srow;
+  double* Inv = smem + slot * lay.total_d();
+  uint16_t* Ls = reinterpret_cast<uint16_t*>(Inv + lay.inv_d());
+  double* As = Inv + lay.inv_d() + lay.ls_d();
+  double* xs = As + lay.as_d();
+  double* rhs = xs + lay.xs_d();
+  int* idx = reinterpret_cast<int*>(rhs + lay.rhs_d());   // s
+  int* rst = idx + lay.max_size;                           // s
+  int* rln = rst + lay.max_size;                           // s
   const bool active = patch < p1;   // uniform per warp when PPC > 1 (WPP == 1)
-  int s = 0, q0 = 0;
+  SwPatch P;
+  P.s = 0;
   if (active) {
-    q0 = pptr[patch];
-    s = pptr[patch + 1] - q0;
-    for (int k = tid; k < s; k += T) idx[k] = pdofs[q0 + k];
-    const double* src = pinv + ioff[patch];
-    const int np = s * (s + 1) / 2;
-    for (int k = tid; k < np; k += T) Inv[k] = src[k];
+    P = pat[patch];
+    // wave 1: packed inverse and local columns (16-byte chunks; both segments are 16-byte aligned)
+    const double* src = pinv + P.i0;
+    const int nch = (P.s * (P.s + 1) / 2 + 1) / 2;
+    for (int k = tid; k < nch; k += T) cp_async16(Inv + 2 * k, src + 2 * k);
+    const uint16_t* lsrc = lcol + P.e0;
+    const int lch = (P.s * S + 7) / 8;
+    for (int k = tid; k < lch; k += T) cp_async16(Ls + 8 * k, lsrc + 8 * k);
+    for (int k = tid; k < P.s; k += T) {
+      const int i = pidx[P.q0 + k];
+      idx[k] = i;
+      rst[k] = prow[P.q0 + k];
+      rln[k] = plen[P.q0 + k];
+      cp_async8(rhs + k, b + i);
+    }
+    for (int j = tid; j < P.nn; j += T) cp_async8(xs + j, x + nbr[P.n0 + j]);
   }
   if (WPP == 1) __syncwarp(); else __syncthreads();
   if (active) {
-    // residual of the patch rows: one warp per row, 4 rows in flight per warp
+    // wave 2: the values of the patch rows (row k -> As[k*S ...]), one warp per row, coalesced
     const int lane = tid & 31, wrp = tid / 32;
-    for (int k0 = wrp * 4; k0 < s; k0 += WPP * 4) {
-      double acc[4] = {0.0, 0.0, 0.0, 0.0};
-      int row[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int k = k0 + u;
-        row[u] = k < s ? idx[k] : -1;
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (row[u] < 0) continue;
-        const int r0 = ia[row[u]], r1 = ia[row[u] + 1];
-        for (int p = r0 + lane; p < r1; p += 32) acc[u] += a[p] * x[ja[p]];
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc[u] += __shfl_down_sync(0xffffffffu, acc[u], o);
-        if (lane == 0 && row[u] >= 0) rhs[k0 + u] = b[row[u]] - acc[u];
-      }
+    for (int k = wrp; k < P.s; k += WPP) {
+      const int r0 = rst[k], len = rln[k];
+      for (int e = lane; e < len; e += 32) cp_async8(As + k * S + e, a + r0 + e);
+    }
+  }
+  cp_async_wait_all();
+  if (WPP == 1) __syncwarp(); else __syncthreads();
+  if (active) {
+    // residual: thread k owns row k
+    for (int k = tid; k < P.s; k += T) {
+      const double* ar = As + k * S;
+      const uint16_t* lr = Ls + k * S;
+      const int len = rln[k];
+      double acc = 0.0;
+      for (int e = 0; e < len; ++e) acc += ar[e] * xs[lr[e]];
+      rhs[k] -= acc;
     }
   }
   if (WPP == 1) __syncwarp(); else __syncthreads();
   if (active) {
-    // delta = A_BB^{-1} rhs with the packed symmetric inverse
-    for (int k = tid; k < s; k += T) {
+    // delta = A_BB^{-1} rhs with the packed symmetric inverse: entry (k,c) lives at tri(max,min);
+    // walk c with two running addresses (row part c <= k, column part c > k)
+    for (int k = tid; k < P.s; k += T) {
       double d = 0.0;
-      const int base = k * (k + 1) / 2;
-      for (int c = 0; c <= k; ++c) d += Inv[base + c] * rhs[c];
-      for (int c = k + 1; c < s; ++c) d += Inv[c * (c + 1) / 2 + k] * rhs[c];
+      int a1 = k * (k + 1) / 2;   // (k, c) for c <= k
+      int a2 = a1 + k;            // (c, k) for c >= k, advanced by c + 1
+      for (int c = 0; c < P.s; ++c) {
+        const int ad = c <= k ? a1 + c : a2;
+        d += Inv[ad] * rhs[c];
+        if (c >= k) a2 += c + 1;
+      }
       x[idx[k]] += d;
     }
   }
 }
 
-// Host side: reorder the patches by colour, translate dofs to the permuted numbering, upload
-// and invert on the device.  `alloc(bytes)` returns tracked device memory.
+// Host side: reorder the patches by colour, translate to the permuted numbering, build the
+// neighbourhood lists and local columns, upload, invert on the device.
+// `alloc(bytes)` returns tracked device memory; pia/pja are the permuted CSR of the level.
 inline void schwarz_upload(const Level& hl, const std::vector<int>& iperm, const int* d_ia,
                            const int* d_ja, const double* d_a, const std::vector<int>& pia,
-                           DSchwarz& d, const std::function<void*(size_t)>& alloc) {
+                           const std::vector<int>& pja, DSchwarz& d,
+                           const std::function<void*(size_t)>& alloc) {
+  const SwPatch zero = {0, 0, 0, 0, 0, 0};
   const SchwarzPatches& sw = hl.sw;
   const int np = sw.npatch();
+  const int n = hl.A.n;
   d.npatch = np;
   d.ncolors = sw.ncolors;
   d.max_size = sw.max_size;
-  const size_t tri_max = (size_t)d.max_size * (d.max_size + 1) / 2;
-  d.smem_setup = (tri_max + d.max_size) * sizeof(double) + (size_t)d.max_size * sizeof(int);
-  if (d.smem_setup > 227 * 1024)
-    throw std::runtime_error("Schwarz patch of " + std::to_string(d.max_size) + " dofs does not fit in shared memory");
-  d.warps = d.max_size <= 32 ? 1 : (d.max_size <= 96 ? 2 : 4);
-  d.ppc = d.warps == 1 ? 4 : 1;
-  d.smem_apply = (size_t)d.ppc * (tri_max + 2 * (size_t)d.max_size) * sizeof(double);
   d.color_ptr.assign(sw.ncolors + 1, 0);
   for (int p = 0; p < np; ++p) ++d.color_ptr[sw.color[p] + 1];
   for (int c = 0; c < sw.ncolors; ++c) d.color_ptr[c + 1] += d.color_ptr[c];
@@ -200,53 +264,133 @@ inline void schwarz_upload(const Level& hl, const std::vector<int>& iperm, const
     std::vector<int> fill(d.color_ptr.begin(), d.color_ptr.end() - 1);
     for (int p = 0; p < np; ++p) order[fill[sw.color[p]]++] = p;
   }
-  std::vector<int> pptr(np + 1, 0), pdofs(sw.dofs.size());
-  std::vector<long long> ioff(np + 1, 0);
-  long long row_entries = 0;
+  std::vector<SwPatch> pat(np, zero);
+  std::vector<int> pidx(sw.dofs.size()), prow(sw.dofs.size()), plen(sw.dofs.size());
+  // pass 1: sizes (rows, entries, neighbourhoods) per patch, in parallel
+  std::vector<int> nn(np, 0);
+  std::vector<long long> ne(np, 0);
+  int max_rowlen = 1;
+#pragma omp parallel reduction(max : max_rowlen)
+  {
+    std::vector<int> mark(n, -1);
+#pragma omp for schedule(dynamic, 2048)
+    for (int k = 0; k < np; ++k) {
+      const int p = order[k];
+      int cnt = 0;
+      long long ent = 0;
+      for (int q = sw.ptr[p]; q < sw.ptr[p + 1]; ++q) {
+        const int i = iperm[sw.dofs[q]];
+        ent += pia[i + 1] - pia[i];
+        max_rowlen = std::max(max_rowlen, pia[i + 1] - pia[i]);
+        for (int e = pia[i]; e < pia[i + 1]; ++e)
+          if (mark[pja[e]] != k) { mark[pja[e]] = k; ++cnt; }
+      }
+      nn[k] = cnt;
+      ne[k] = ent;
+    }
+  }
+  const int srow = max_rowlen | 1;   // odd row stride: conflict-free "thread k walks row k"
+  d.srow = srow;
+  long long tot_e = 0, tot_i = 0, tot_val = 0;
+  long long tot_n = 0, tot_q = 0;
+  int max_nbr = 0;
   for (int k = 0; k < np; ++k) {
     const int p = order[k];
     const int s = sw.ptr[p + 1] - sw.ptr[p];
-    pptr[k + 1] = pptr[k] + s;
-    ioff[k + 1] = ioff[k] + (long long)s * (s + 1) / 2;
-    for (int q = 0; q < s; ++q) {
-      const int i = iperm[sw.dofs[sw.ptr[p] + q]];
-      pdofs[pptr[k] + q] = i;
-      row_entries += pia[i + 1] - pia[i];
+    pat[k].q0 = (int)tot_q;
+    pat[k].s = s;
+    pat[k].n0 = (int)tot_n;
+    pat[k].nn = nn[k];
+    pat[k].e0 = tot_e;
+    pat[k].i0 = tot_i;
+    tot_q += s;
+    tot_n += nn[k];
+    tot_e += ((long long)s * srow + 7) / 8 * 8;                 // 16-byte aligned uint16 segments
+    tot_val += ne[k];
+    tot_i += ((long long)s * (s + 1) / 2 + 1) / 2 * 2;          // 16-byte aligned inverses
+    max_nbr = std::max(max_nbr, nn[k]);
+
+  }
+  if (tot_n > 2000000000LL) throw std::runtime_error("Schwarz neighbourhood lists exceed int32 indexing");
+  if (max_nbr > 65535) throw std::runtime_error("Schwarz patch neighbourhood larger than 65535 dofs");
+  d.max_nbr = max_nbr;
+  std::vector<int> nbr((size_t)tot_n);
+  std::vector<uint16_t> lcol((size_t)tot_e + 8, 0);
+#pragma omp parallel
+  {
+    std::vector<int> mark(n, -1), pos(n, 0), list;
+#pragma omp for schedule(dynamic, 2048)
+    for (int k = 0; k < np; ++k) {
+      const int p = order[k];
+      const int s = pat[k].s;
+      list.clear();
+      for (int q = 0; q < s; ++q) {
+        const int i = iperm[sw.dofs[sw.ptr[p] + q]];
+        pidx[pat[k].q0 + q] = i;
+        prow[pat[k].q0 + q] = pia[i];
+        plen[pat[k].q0 + q] = pia[i + 1] - pia[i];
+        for (int e = pia[i]; e < pia[i + 1]; ++e)
+          if (mark[pja[e]] != k) { mark[pja[e]] = k; list.push_back(pja[e]); }
+      }
+      std::sort(list.begin(), list.end());
+      for (int j = 0; j < (int)list.size(); ++j) { pos[list[j]] = j; nbr[pat[k].n0 + j] = list[j]; }
+      uint16_t* out = &lcol[(size_t)pat[k].e0];
+      for (int q = 0; q < s; ++q) {
+        const int i = pidx[pat[k].q0 + q];
+        for (int e = pia[i]; e < pia[i + 1]; ++e) out[(size_t)q * srow + (e - pia[i])] = (uint16_t)pos[pja[e]];
+      }
     }
   }
-  // per sweep: row entries (val + col), packed inverse, patch index, b and x of the patch dofs
-  d.alg_bytes = 12 * row_entries + 8 * ioff[np] + (4 + 8 + 16) * (long long)pdofs.size() + 8 * (long long)np;
+  // per sweep: values + local columns of the row entries, neighbour list + gathered x, packed
+  // inverse, (idx, row start, row offset, b, x update) per patch dof, patch descriptor
+  d.alg_bytes = 10 * tot_val + 12 * tot_n + 8 * tot_i + (12 + 8 + 16) * tot_q + 32LL * np;
+  const size_t tri_max = (size_t)d.max_size * (d.max_size + 1) / 2;
+  d.smem_setup = (tri_max + d.max_size) * sizeof(double) + (size_t)d.max_size * sizeof(int);
+  d.warps = d.max_size <= 32 ? 1 : (d.max_size <= 96 ? 2 : 4);
+  d.ppc = d.warps == 1 ? 4 : 1;
+  const SwLayout lay = {d.max_size, d.max_nbr, d.srow};
+  d.ppc = d.warps == 1 ? (lay.total_d() * 8 * 4 <= 100 * 1024 ? 4 : 2) : 1;
+  d.smem_apply = (size_t)d.ppc * lay.total_d() * sizeof(double);
+  if (d.smem_setup > 227 * 1024 || d.smem_apply > 227 * 1024)
+    throw std::runtime_error("Schwarz patch of " + std::to_string(d.max_size) + " dofs does not fit in shared memory");
   auto up = [&](const void* src, size_t bytes) {
     void* p = alloc(bytes);
     if (bytes) cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice);
     return p;
   };
-  d.pptr = (int*)up(pptr.data(), pptr.size() * sizeof(int));
-  d.pdofs = (int*)up(pdofs.data(), pdofs.size() * sizeof(int));
-  d.ioff = (long long*)up(ioff.data(), ioff.size() * sizeof(long long));
-  d.pinv = (double*)alloc((size_t)ioff[np] * sizeof(double));
+  d.pat = (SwPatch*)up(pat.data(), pat.size() * sizeof(SwPatch));
+  d.pidx = (int*)up(pidx.data(), pidx.size() * sizeof(int));
+  d.prow = (int*)up(prow.data(), prow.size() * sizeof(int));
+  d.plen = (int*)up(plen.data(), plen.size() * sizeof(int));
+  d.nbr = (int*)up(nbr.data(), nbr.size() * sizeof(int));
+  d.lcol = (uint16_t*)up(lcol.data(), lcol.size() * sizeof(uint16_t));
+  d.pinv = (double*)alloc(((size_t)tot_i + 2) * sizeof(double));
   constexpr int TS = 128;
   if (d.smem_setup > 48 * 1024)
     cudaFuncSetAttribute(schwarz_invert_kernel<TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_setup);
-  schwarz_invert_kernel<TS><<<np, TS, d.smem_setup>>>(np, d.pptr, d.pdofs, d.ioff, d_ia, d_ja, d_a, d.pinv, d.max_size);
+  schwarz_invert_kernel<TS><<<np, TS, d.smem_setup>>>(np, d.pat, d.pidx, d_ia, d_ja, d_a, d.pinv, d.max_size);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) throw std::runtime_error(std::string("Schwarz setup kernel failed: ") + cudaGetErrorString(e));
   if (d.smem_apply > 48 * 1024) {
+    cudaFuncSetAttribute(schwarz_apply_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_apply);
+    cudaFuncSetAttribute(schwarz_apply_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_apply);
     cudaFuncSetAttribute(schwarz_apply_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_apply);
     cudaFuncSetAttribute(schwarz_apply_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_apply);
   }
 }
 
 // one colour of a multiplicative sweep
-inline void schwarz_color_launch(const DSchwarz& d, int c, const int* ia, const int* ja, const double* a,
-                                 const double* b, double* x, cudaStream_t stream) {
+inline void schwarz_color_launch(const DSchwarz& d, int c, const double* a, const double* b, double* x,
+                                 cudaStream_t stream) {
   const int p0 = d.color_ptr[c], p1 = d.color_ptr[c + 1];
   const int grid = (p1 - p0 + d.ppc - 1) / d.ppc;
-  switch (d.warps) {
-    case 1: schwarz_apply_kernel<1, 4><<<grid, 128, d.smem_apply, stream>>>(p0, p1, d.pptr, d.pdofs, d.ioff, d.pinv, ia, ja, a, b, x, d.max_size); break;
-    case 2: schwarz_apply_kernel<2, 1><<<grid, 64, d.smem_apply, stream>>>(p0, p1, d.pptr, d.pdofs, d.ioff, d.pinv, ia, ja, a, b, x, d.max_size); break;
-    default: schwarz_apply_kernel<4, 1><<<grid, 128, d.smem_apply, stream>>>(p0, p1, d.pptr, d.pdofs, d.ioff, d.pinv, ia, ja, a, b, x, d.max_size); break;
-  }
+  const SwLayout lay = {d.max_size, d.max_nbr, d.srow};
+#define MAMG_SW_ARGS p0, p1, d.pat, d.pidx, d.prow, d.plen, d.nbr, d.lcol, d.pinv, a, b, x, lay
+  if (d.warps == 1 && d.ppc == 4) schwarz_apply_kernel<1, 4><<<grid, 128, d.smem_apply, stream>>>(MAMG_SW_ARGS);
+  else if (d.warps == 1) schwarz_apply_kernel<1, 2><<<grid, 64, d.smem_apply, stream>>>(MAMG_SW_ARGS);
+  else if (d.warps == 2) schwarz_apply_kernel<2, 1><<<grid, 64, d.smem_apply, stream>>>(MAMG_SW_ARGS);
+  else schwarz_apply_kernel<4, 1><<<grid, 128, d.smem_apply, stream>>>(MAMG_SW_ARGS);
+#undef MAMG_SW_ARGS
 }
 
 }  // namespace mamg

@@ -140,6 +140,11 @@ class Hierarchy:
 
     KERNEL_CLASSES = ["spmv", "gs", "schwarz", "restrict", "scale", "prolong", "coarse", "vector", "dot"]
 
+    def schwarz_sweep_bytes(self, level=0):
+        v = C.c_int64()
+        check(lib.mamg_schwarz_sweep_bytes(self._h, level, C.byref(v)))
+        return v.value
+
     def profile_start(self):
         check(lib.mamg_profile(self._h, 1, None, None))
 
