@@ -63,7 +63,8 @@ struct DeviceState {
   int red_blocks = 0;
   int64_t launches = 0;
   int64_t dev_bytes = 0;
-  double *w[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // Krylov work vectors (level-0 size)
+  double* w[10] = {nullptr};  // Krylov work vectors (level-0 size)
+  std::vector<double*> basis; // GMRES Krylov basis, allocated on first use
   double *io_a = nullptr, *io_b = nullptr;  // staging for host-array calls
   std::vector<void*> allocs;
   mamg_params prm;
@@ -242,7 +243,7 @@ static void upload_hierarchy(const Hierarchy& H, DeviceState& D) {
   D.scal = dalloc<double>(D, 32);
   CUDA_OK(cudaMemset(D.scal, 0, 32 * sizeof(double)));
   CUDA_OK(cudaMallocHost(&D.h_scal, 32 * sizeof(double)));
-  for (int k = 0; k < 6; ++k) D.w[k] = dalloc<double>(D, D.lv[0].n);
+  for (int k = 0; k < 10; ++k) D.w[k] = dalloc<double>(D, D.lv[0].n);
   D.io_a = dalloc<double>(D, max_n);
   D.io_b = dalloc<double>(D, max_n);
 }
@@ -527,6 +528,150 @@ static int pcg_device(DeviceState& D, const double* b_nat, double* x_nat, double
   return status;
 }
 
+// ---- host-scalar vector helpers for MINRES / GMRES ----------------------------------------------
+static void k_axpby(DeviceState& D, int n, double a, const double* x, double b, double* y) {
+  if (n == 0) return;
+  KScope ks(D, K_VEC);
+  axpby_kernel<<<cdiv(n, kBlock), kBlock, 0, D.stream>>>(n, a, x, b, y);
+}
+static double k_dot(DeviceState& D, int n, const double* u, const double* v) {
+  {
+    KScope ks(D, K_DOT);
+    dot_kernel<<<red_grid(D, n), kBlock, 0, D.stream>>>(n, u, v, D.partial, D.ticket, D.scal + 16);
+  }
+  CUDA_OK(cudaMemcpyAsync(D.h_scal + 16, D.scal + 16, sizeof(double), cudaMemcpyDeviceToHost, D.stream));
+  CUDA_OK(cudaStreamSynchronize(D.stream));
+  return D.h_scal[16];
+}
+
+// Preconditioned MINRES (Paige-Saunders with an SPD preconditioner; the residual estimate phibar
+// is the B-norm of the residual, as in block.iterative.MinRes).  Permuted ordering.
+static int minres_device(DeviceState& D, const double* b_nat, double* x_nat, double tol, bool relative,
+                         int maxiter, int* niters, double* residuals) {
+  DLevel& l0 = D.lv[0];
+  const int n = l0.n;
+  double *x = D.w[0], *r1 = D.w[1], *r2 = D.w[2], *y = D.w[3], *v = D.w[4], *w = D.w[5], *w1 = D.w[6],
+         *w2 = D.w[7], *t = D.w[8];
+  k_gather(D, n, l0.perm, b_nat, r1);
+  k_copy(D, n, r1, r2);
+  k_fill(D, n, x, 0.0);
+  k_fill(D, n, w, 0.0);
+  k_fill(D, n, w2, 0.0);
+  apply_permuted(D, r1, y);
+  double beta1 = k_dot(D, n, r1, y);
+  if (!(beta1 >= 0.0)) return 1;
+  beta1 = std::sqrt(beta1);
+  residuals[0] = beta1;
+  const double target = relative ? tol * beta1 : tol;
+  double oldb = 0.0, beta = beta1, dbar = 0.0, epsln = 0.0, phibar = beta1, cs = -1.0, sn = 0.0;
+  int it = 0;
+  while (phibar > target && it < maxiter) {
+    ++it;
+    k_axpby(D, n, 1.0 / beta, y, 0.0, v);               // v = y / beta
+    k_spmv(D, l0, v, nullptr, y, false);                 // y = A v
+    if (it >= 2) k_axpby(D, n, -beta / oldb, r1, 1.0, y);
+    const double alfa = k_dot(D, n, v, y);
+    k_axpby(D, n, -alfa / beta, r2, 1.0, y);
+    std::swap(r1, r2);                                   // r1 = r2
+    k_copy(D, n, y, r2);                                 // r2 = y
+    apply_permuted(D, r2, y);                            // y = B r2
+    oldb = beta;
+    const double b2 = k_dot(D, n, r2, y);
+    if (!(b2 >= 0.0)) { *niters = it; return 1; }
+    beta = std::sqrt(b2);
+    const double oldeps = epsln;
+    const double delta = cs * dbar + sn * alfa;
+    const double gbar = sn * dbar - cs * alfa;
+    epsln = sn * beta;
+    dbar = -cs * beta;
+    const double gamma = std::max(std::sqrt(gbar * gbar + beta * beta), 1e-300);
+    cs = gbar / gamma;
+    sn = beta / gamma;
+    const double phi = cs * phibar;
+    phibar = sn * phibar;
+    // w1 = w2; w2 = w; w = (v - oldeps*w1 - delta*w2) / gamma
+    std::swap(w1, w2);
+    std::swap(w2, w);
+    k_axpby(D, n, 1.0 / gamma, v, 0.0, t);
+    k_axpby(D, n, -oldeps / gamma, w1, 1.0, t);
+    k_axpby(D, n, -delta / gamma, w2, 1.0, t);
+    std::swap(w, t);
+    k_axpby(D, n, phi, w, 1.0, x);
+    residuals[it] = phibar;
+  }
+  k_gather(D, n, l0.iperm, x, x_nat);
+  *niters = it;
+  return 0;
+}
+
+// Restarted GMRES(m), right-preconditioned: A B u = b, x = B u.  Modified Gram-Schmidt Arnoldi,
+// Givens rotations on the host; the residual history is the 2-norm of b - A x.  Permuted ordering.
+static int gmres_device(DeviceState& D, const double* b_nat, double* x_nat, double tol, bool relative,
+                        int maxiter, int m, int* niters, double* residuals) {
+  DLevel& l0 = D.lv[0];
+  const int n = l0.n;
+  if (m < 1) m = 30;
+  while ((int)D.basis.size() < m + 1) D.basis.push_back(dalloc<double>(D, n));
+  double *b = D.w[0], *x = D.w[1], *r = D.w[2], *z = D.w[3], *wv = D.w[4], *u = D.w[5];
+  k_gather(D, n, l0.perm, b_nat, b);
+  k_fill(D, n, x, 0.0);
+  k_copy(D, n, b, r);
+  double rn = std::sqrt(k_dot(D, n, r, r));
+  residuals[0] = rn;
+  const double target = relative ? tol * rn : tol;
+  int it = 0;
+  std::vector<double> Hm((size_t)(m + 1) * m), cs(m), sn(m), g(m + 1);
+  while (rn > target && it < maxiter) {
+    k_axpby(D, n, 1.0 / rn, r, 0.0, D.basis[0]);
+    std::fill(g.begin(), g.end(), 0.0);
+    g[0] = rn;
+    int j = 0;
+    for (; j < m && it < maxiter && rn > target; ++j) {
+      apply_permuted(D, D.basis[j], z);                   // z = B v_j
+      k_spmv(D, l0, z, nullptr, wv, false);               // w = A z
+      for (int i = 0; i <= j; ++i) {
+        const double h = k_dot(D, n, wv, D.basis[i]);
+        Hm[(size_t)i * m + j] = h;
+        k_axpby(D, n, -h, D.basis[i], 1.0, wv);
+      }
+      const double hn = std::sqrt(k_dot(D, n, wv, wv));
+      Hm[(size_t)(j + 1) * m + j] = hn;
+      if (hn > 0.0) k_axpby(D, n, 1.0 / hn, wv, 0.0, D.basis[j + 1]);
+      for (int i = 0; i < j; ++i) {
+        const double t0 = cs[i] * Hm[(size_t)i * m + j] + sn[i] * Hm[(size_t)(i + 1) * m + j];
+        Hm[(size_t)(i + 1) * m + j] = -sn[i] * Hm[(size_t)i * m + j] + cs[i] * Hm[(size_t)(i + 1) * m + j];
+        Hm[(size_t)i * m + j] = t0;
+      }
+      const double den = std::hypot(Hm[(size_t)j * m + j], hn);
+      cs[j] = den > 0 ? Hm[(size_t)j * m + j] / den : 1.0;
+      sn[j] = den > 0 ? hn / den : 0.0;
+      Hm[(size_t)j * m + j] = den;
+      g[j + 1] = -sn[j] * g[j];
+      g[j] = cs[j] * g[j];
+      rn = std::fabs(g[j + 1]);
+      ++it;
+      residuals[it] = rn;
+    }
+    // back substitution, u = sum y_i v_i, x += B u
+    std::vector<double> yv(j);
+    for (int i = j - 1; i >= 0; --i) {
+      double sacc = g[i];
+      for (int k = i + 1; k < j; ++k) sacc -= Hm[(size_t)i * m + k] * yv[k];
+      yv[i] = sacc / Hm[(size_t)i * m + i];
+    }
+    k_fill(D, n, u, 0.0);
+    for (int i = 0; i < j; ++i) k_axpby(D, n, yv[i], D.basis[i], 1.0, u);
+    apply_permuted(D, u, z);
+    k_axpby(D, n, 1.0, z, 1.0, x);
+    k_spmv(D, l0, x, b, r, true);                         // true residual for the restart
+    rn = std::sqrt(k_dot(D, n, r, r));
+    residuals[it] = rn;
+  }
+  k_gather(D, n, l0.iperm, x, x_nat);
+  *niters = it;
+  return 0;
+}
+
 }  // namespace mamg
 
 using namespace mamg;
@@ -674,13 +819,45 @@ int mamg_pcg(mamg_handle h, const double* b, double* x, double tolerance, int32_
   MAMG_CATCH
 }
 
-int mamg_minres(mamg_handle, const double*, double*, double, int32_t, int32_t, int32_t, int32_t*, double*) {
-  set_error("mamg_minres: not built yet");
-  return -5;
+int mamg_minres(mamg_handle h, const double* b, double* x, double tolerance, int32_t relative,
+                int32_t maxiter, int32_t on_device, int32_t* niters, double* residuals) {
+  MAMG_TRY
+  DeviceState* D = get_dev(h);
+  if (!D) return -1;
+  if (!b || !x || !niters || !residuals) { set_error("minres: NULL argument"); return -1; }
+  DLevel& l0 = D->lv[0];
+  IoVec io(*D, on_device != 0);
+  const double* bin = io.in(b, l0.n, D->io_a);
+  double* xio = io.out_ptr(x, D->io_b);
+  int it = 0;
+  int st = minres_device(*D, bin, xio, tolerance, relative != 0, maxiter, &it, residuals);
+  io.out(x, l0.n, D->io_b);
+  if (on_device) CUDA_OK(cudaStreamSynchronize(D->stream));
+  CUDA_OK(cudaGetLastError());
+  *niters = it;
+  if (st) { set_error("MinRes breakdown (r.Br < 0: preconditioner not positive definite)"); return 1; }
+  return 0;
+  MAMG_CATCH
 }
-int mamg_gmres(mamg_handle, const double*, double*, double, int32_t, int32_t, int32_t, int32_t, int32_t*, double*) {
-  set_error("mamg_gmres: not built yet");
-  return -5;
+
+int mamg_gmres(mamg_handle h, const double* b, double* x, double tolerance, int32_t relative,
+               int32_t maxiter, int32_t restart, int32_t on_device, int32_t* niters, double* residuals) {
+  MAMG_TRY
+  DeviceState* D = get_dev(h);
+  if (!D) return -1;
+  if (!b || !x || !niters || !residuals) { set_error("gmres: NULL argument"); return -1; }
+  DLevel& l0 = D->lv[0];
+  IoVec io(*D, on_device != 0);
+  const double* bin = io.in(b, l0.n, D->io_a);
+  double* xio = io.out_ptr(x, D->io_b);
+  int it = 0;
+  gmres_device(*D, bin, xio, tolerance, relative != 0, maxiter, restart, &it, residuals);
+  io.out(x, l0.n, D->io_b);
+  if (on_device) CUDA_OK(cudaStreamSynchronize(D->stream));
+  CUDA_OK(cudaGetLastError());
+  *niters = it;
+  return 0;
+  MAMG_CATCH
 }
 
 int mamg_profile(mamg_handle h, int32_t on, double* ms_per_class, int64_t* launches_per_class) {

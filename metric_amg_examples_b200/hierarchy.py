@@ -228,3 +228,29 @@ class Hierarchy:
         info = {"niters": k, "residuals": res[:k + 1].tolist(), "alphas": al[:k].tolist(),
                 "betas": be[:k].tolist(), "breakdown": rc == 1}
         return x, info
+
+    def _krylov(self, fn, b, tolerance, relative, maxiter, *extra):
+        self._require_device()
+        res = np.zeros(maxiter + 2, np.float64)
+        nit = C.c_int32()
+        if self._is_torch_cuda(b):
+            import torch
+            b = b.contiguous()
+            x = torch.zeros_like(b)
+            torch.cuda.current_stream(b.device).synchronize()
+            rc = fn(self._h, C.c_void_p(b.data_ptr()), C.c_void_p(x.data_ptr()), tolerance, int(relative),
+                    maxiter, *extra, 1, C.byref(nit), ptr(res))
+        else:
+            b = as_f64(b)
+            x = np.zeros(self.n, np.float64)
+            rc = fn(self._h, ptr(b), ptr(x), tolerance, int(relative), maxiter, *extra, 0, C.byref(nit), ptr(res))
+        check(rc, allow=(1,))
+        return x, {"niters": nit.value, "residuals": res[:nit.value + 1].tolist(), "breakdown": rc == 1}
+
+    def minres(self, b, tolerance=1e-8, relative=False, maxiter=500):
+        """Preconditioned MINRES on the device (mamg_minres); residuals are B-norm estimates."""
+        return self._krylov(lib.mamg_minres, b, tolerance, relative, maxiter)
+
+    def gmres(self, b, tolerance=1e-8, relative=False, maxiter=500, restart=30):
+        """Right-preconditioned restarted GMRES on the device (mamg_gmres); residuals are ||b - A x||_2."""
+        return self._krylov(lib.mamg_gmres, b, tolerance, relative, maxiter, int(restart))

@@ -409,6 +409,124 @@ int orc_pcg(orc_hier* h, const double* b, double* x, double tol, int relative, i
   return it;
 }
 
+/* ---- MINRES / GMRES: north_star names CG/MinRes/GMRES; block.iterative.MinRes and LGMRES share
+ * ConjGrad's constructor upstream.  Standard algorithms (Paige-Saunders MINRES with an SPD
+ * preconditioner, residual estimate in the B-norm; restarted right-preconditioned GMRES with
+ * modified Gram-Schmidt), restated here so the device versions have an iteration-count oracle. */
+static double vdot(int n, const double* u, const double* v) { double s = 0.0; for (int i = 0; i < n; ++i) s += u[i] * v[i]; return s; }
+
+int orc_minres(orc_hier* h, const double* b, double* x, double tol, int relative, int maxiter, double* residuals) {
+  orc_level* L0 = &h->lv[0];
+  const int n = L0->n;
+  double* buf = (double*)calloc((size_t)8 * n, sizeof(double));
+  double *r1 = buf, *r2 = buf + n, *y = buf + 2 * n, *v = buf + 3 * n, *w = buf + 4 * n, *w1 = buf + 5 * n,
+         *w2 = buf + 6 * n, *t = buf + 7 * n;
+  memset(x, 0, sizeof(double) * n);
+  memcpy(r1, b, sizeof(double) * n);
+  memcpy(r2, b, sizeof(double) * n);
+  orc_apply(h, r1, y);
+  double beta1 = sqrt(vdot(n, r1, y));
+  residuals[0] = beta1;
+  const double target = relative ? tol * beta1 : tol;
+  double oldb = 0.0, beta = beta1, dbar = 0.0, epsln = 0.0, phibar = beta1, cs = -1.0, sn = 0.0;
+  int it = 0;
+  while (phibar > target && it < maxiter) {
+    ++it;
+    for (int i = 0; i < n; ++i) v[i] = y[i] / beta;
+    orc_spmv_level(L0, v, y);
+    if (it >= 2) for (int i = 0; i < n; ++i) y[i] -= (beta / oldb) * r1[i];
+    const double alfa = vdot(n, v, y);
+    for (int i = 0; i < n; ++i) y[i] -= (alfa / beta) * r2[i];
+    double* sw = r1; r1 = r2; r2 = sw;
+    memcpy(r2, y, sizeof(double) * n);
+    orc_apply(h, r2, y);
+    oldb = beta;
+    beta = sqrt(vdot(n, r2, y));
+    const double oldeps = epsln, delta = cs * dbar + sn * alfa, gbar = sn * dbar - cs * alfa;
+    epsln = sn * beta;
+    dbar = -cs * beta;
+    double gamma = sqrt(gbar * gbar + beta * beta);
+    if (gamma < 1e-300) gamma = 1e-300;
+    cs = gbar / gamma;
+    sn = beta / gamma;
+    const double phi = cs * phibar;
+    phibar = sn * phibar;
+    sw = w1; w1 = w2; w2 = w; w = sw;   /* w1 <- w2, w2 <- w, w <- scratch */
+    for (int i = 0; i < n; ++i) t[i] = (v[i] - oldeps * w1[i] - delta * w2[i]) / gamma;
+    sw = w; w = t; t = sw;
+    for (int i = 0; i < n; ++i) x[i] += phi * w[i];
+    residuals[it] = phibar;
+  }
+  free(buf);
+  return it;
+}
+
+int orc_gmres(orc_hier* h, const double* b, double* x, double tol, int relative, int maxiter, int m, double* residuals) {
+  orc_level* L0 = &h->lv[0];
+  const int n = L0->n;
+  if (m < 1) m = 30;
+  double* V = (double*)calloc((size_t)(m + 1) * n, sizeof(double));
+  double* buf = (double*)calloc((size_t)4 * n, sizeof(double));
+  double *r = buf, *z = buf + n, *w = buf + 2 * n, *u = buf + 3 * n;
+  double* Hm = (double*)calloc((size_t)(m + 1) * m, sizeof(double));
+  double* cs = (double*)calloc(m, sizeof(double));
+  double* sn = (double*)calloc(m, sizeof(double));
+  double* g = (double*)calloc(m + 1, sizeof(double));
+  double* yv = (double*)calloc(m, sizeof(double));
+  memset(x, 0, sizeof(double) * n);
+  memcpy(r, b, sizeof(double) * n);
+  double rn = sqrt(vdot(n, r, r));
+  residuals[0] = rn;
+  const double target = relative ? tol * rn : tol;
+  int it = 0;
+  while (rn > target && it < maxiter) {
+    for (int i = 0; i < n; ++i) V[i] = r[i] / rn;
+    memset(g, 0, sizeof(double) * (m + 1));
+    g[0] = rn;
+    int j = 0;
+    for (; j < m && it < maxiter && rn > target; ++j) {
+      orc_apply(h, V + (size_t)j * n, z);
+      orc_spmv_level(L0, z, w);
+      for (int i = 0; i <= j; ++i) {
+        const double hh = vdot(n, w, V + (size_t)i * n);
+        Hm[(size_t)i * m + j] = hh;
+        for (int k = 0; k < n; ++k) w[k] -= hh * V[(size_t)i * n + k];
+      }
+      const double hn = sqrt(vdot(n, w, w));
+      Hm[(size_t)(j + 1) * m + j] = hn;
+      if (hn > 0.0) for (int k = 0; k < n; ++k) V[(size_t)(j + 1) * n + k] = w[k] / hn;
+      for (int i = 0; i < j; ++i) {
+        const double t0 = cs[i] * Hm[(size_t)i * m + j] + sn[i] * Hm[(size_t)(i + 1) * m + j];
+        Hm[(size_t)(i + 1) * m + j] = -sn[i] * Hm[(size_t)i * m + j] + cs[i] * Hm[(size_t)(i + 1) * m + j];
+        Hm[(size_t)i * m + j] = t0;
+      }
+      const double den = hypot(Hm[(size_t)j * m + j], hn);
+      cs[j] = den > 0 ? Hm[(size_t)j * m + j] / den : 1.0;
+      sn[j] = den > 0 ? hn / den : 0.0;
+      Hm[(size_t)j * m + j] = den;
+      g[j + 1] = -sn[j] * g[j];
+      g[j] = cs[j] * g[j];
+      rn = fabs(g[j + 1]);
+      ++it;
+      residuals[it] = rn;
+    }
+    for (int i = j - 1; i >= 0; --i) {
+      double sacc = g[i];
+      for (int k = i + 1; k < j; ++k) sacc -= Hm[(size_t)i * m + k] * yv[k];
+      yv[i] = sacc / Hm[(size_t)i * m + i];
+    }
+    memset(u, 0, sizeof(double) * n);
+    for (int i = 0; i < j; ++i) for (int k = 0; k < n; ++k) u[k] += yv[i] * V[(size_t)i * n + k];
+    orc_apply(h, u, z);
+    for (int k = 0; k < n; ++k) x[k] += z[k];
+    for (int k = 0; k < n; ++k) r[k] = b[k] - row_dot(L0, k, x);
+    rn = sqrt(vdot(n, r, r));
+    residuals[it] = rn;
+  }
+  free(V); free(buf); free(Hm); free(cs); free(sn); free(g); free(yv);
+  return it;
+}
+
 double orc_now(void) {
   struct timespec ts;
   clock_gettime(CLOCK_MONOTONIC, &ts);

@@ -37,6 +37,10 @@ def _load():
     lib.orc_smooth.argtypes = [vp, i32, vp, vp, i32]
     lib.orc_pcg.restype = i32
     lib.orc_pcg.argtypes = [vp, vp, vp, dbl, i32, i32, i32, vp, vp, vp]
+    lib.orc_minres.restype = i32
+    lib.orc_minres.argtypes = [vp, vp, vp, dbl, i32, i32, vp]
+    lib.orc_gmres.restype = i32
+    lib.orc_gmres.argtypes = [vp, vp, vp, dbl, i32, i32, i32, vp]
     return lib
 
 
@@ -119,3 +123,17 @@ class Oracle:
                              _p(res), _p(al), _p(be))
         return x, {"niters": k, "residuals": res[:k + 1].tolist(), "alphas": al[:k].tolist(),
                    "betas": be[:k].tolist()}
+
+    def minres(self, b, tolerance=1e-8, relative=False, maxiter=500):
+        b = np.ascontiguousarray(b, np.float64)
+        x = np.zeros(self.n)
+        res = np.zeros(maxiter + 2)
+        k = self.lib.orc_minres(self.h, _p(b), _p(x), tolerance, int(relative), maxiter, _p(res))
+        return x, {"niters": k, "residuals": res[:k + 1].tolist()}
+
+    def gmres(self, b, tolerance=1e-8, relative=False, maxiter=500, restart=30):
+        b = np.ascontiguousarray(b, np.float64)
+        x = np.zeros(self.n)
+        res = np.zeros(maxiter + 2)
+        k = self.lib.orc_gmres(self.h, _p(b), _p(x), tolerance, int(relative), maxiter, int(restart), _p(res))
+        return x, {"niters": k, "residuals": res[:k + 1].tolist()}

@@ -188,3 +188,83 @@ def test_larger_properties():
     assert np.linalg.norm(system.A @ x - b) / np.linalg.norm(b) < 1e-6
     u = np.random.default_rng(11).standard_normal(system.ndofs)
     assert rel(H.apply(-2.0 * u), -2.0 * H.apply(u)) < 1e-12
+
+
+import glob  # noqa: E402
+import importlib.util  # noqa: E402
+import os  # noqa: E402
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(_HERE, "golden", "*.npz"))))
+def test_device_reproduces_golden(path):
+    """The committed fixtures (tests/golden/make_golden.py): device apply and PCG history."""
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(_HERE, "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    name = os.path.basename(path)[:-4]
+    z = np.load(path)
+    system, prm, tol = mg.CASES[name]()
+    H = mamg.Hierarchy(system.A, prm, system.interface_dofs).to_device(0)
+    assert rel(H.apply(z["r"]), z["z_multicolor"]) < APPLY_TOL
+    _, info = H.pcg(z["b"], tolerance=tol, maxiter=500)
+    want = z["residuals_multicolor"]
+    assert abs(len(info["residuals"]) - len(want)) <= 1
+    k = min(len(want), len(info["residuals"]), 6)
+    assert np.allclose(info["residuals"][:k], want[:k], rtol=1e-7)
+
+
+def test_minres_and_gmres_match_oracle():
+    system = problems.bidomain_system(2, 32, gamma=1e3)
+    H, orc = make(system, params.parameters_metric_schwarz)
+    b, xt = system.random_rhs(3)
+    x, info = H.minres(b, tolerance=1e-8, relative=True, maxiter=200)
+    xo, ref = orc.minres(b, tolerance=1e-8, relative=True, maxiter=200)
+    assert abs(info["niters"] - ref["niters"]) <= 1
+    assert info["residuals"][-1] <= 1e-8 * info["residuals"][0]
+    assert rel(x, xt) < 1e-6
+    k = min(info["niters"], ref["niters"], 5)
+    assert np.allclose(info["residuals"][:k + 1], ref["residuals"][:k + 1], rtol=1e-7)
+    x, info = H.gmres(b, tolerance=1e-8, relative=True, maxiter=200, restart=10)
+    xo, ref = orc.gmres(b, tolerance=1e-8, relative=True, maxiter=200, restart=10)
+    assert abs(info["niters"] - ref["niters"]) <= 1
+    assert np.linalg.norm(system.A @ x - b) <= 1.1e-8 * np.linalg.norm(b)
+    assert rel(x, xt) < 1e-6
+
+
+def test_drop_in_classes_fused_and_callback():
+    """The reference's driver lines (src/bidomain_2d.py:192-216, src/emi_2d.py:204-212)."""
+    from metric_amg_examples_b200 import utils
+    from metric_amg_examples_b200.block import block_vec, split_blocks
+    from metric_amg_examples_b200.iterative import ConjGrad, MinRes, GMRES
+    s = problems.bidomain_system(2, 32, gamma=1e3)
+    b, xt = s.random_rhs(4)
+    BB = utils.get_hazmath_metric_precond_mono(s.A, s.W, None, params.parameters_metric_schwarz, s.interface_dofs)
+    AAinv = ConjGrad(s.A, precond=BB, tolerance=1e-8, show=0, maxiter=500)
+    xx = AAinv * b
+    assert AAinv.mode == "fused" and rel(xx, xt) < 1e-6
+    niters = len(AAinv.residuals) - 1
+    ev = AAinv.eigenvalue_estimates()
+    assert len(ev) == niters and ev.min() > 0 and ev.max() / ev.min() < 50
+    seen = []
+    cb = ConjGrad(s.A, precond=BB, tolerance=1e-8, show=0, maxiter=500,
+                  callback=lambda k, x, r: seen.append((k, np.linalg.norm(r))))
+    xc = cb * b
+    assert cb.mode == "drop-in" and len(seen) == len(cb.residuals) - 1
+    assert abs(len(cb.residuals) - len(AAinv.residuals)) <= 1 and rel(xc, xt) < 1e-6
+    assert rel((MinRes(s.A, precond=BB, tolerance=1e-9, show=0, maxiter=300) * b), xt) < 1e-6
+    assert rel((GMRES(s.A, precond=BB, tolerance=1e-9, show=0, maxiter=300, relativeconv=True) * b), xt) < 1e-6
+    # block variant R.T * Minv * R on a 2-block system (src/utils.py:45-53, src/emi_2d.py:207-212)
+    e = problems.emi_system(2, 32, gamma=1e4)
+    AA = split_blocks(e.A, [w.dim() for w in e.W])
+    be, xe = e.random_rhs(5)
+    n0 = e.W[0].dim()
+    bb = block_vec([be[:n0], be[n0:]])
+    Bblk = utils.get_hazmath_metric_precond(AA, e.W, None, interface_dofs=e.interface_dofs)
+    inv = ConjGrad(AA, precond=Bblk, tolerance=1e-10, show=0, maxiter=500)
+    xb = inv * bb
+    assert inv.mode == "fused" and isinstance(xb, block_vec) and len(xb) == 2
+    assert rel(np.concatenate(list(xb)), xe) < 1e-6
+    zb = Bblk * bb   # one preconditioner application on a block vector
+    assert isinstance(zb, block_vec) and len(zb[0]) == n0

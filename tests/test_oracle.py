@@ -1,0 +1,192 @@
+"""CPU tests of the oracle itself (the reference ships no vectors: SURVEY 8c, parity unpinned):
+dense linear-algebra cross-checks, the SURVEY section 6 sanity band, golden fixtures."""
+import glob
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+import metric_amg_examples_b200 as mamg
+from metric_amg_examples_b200 import haznics_compat as haznics, params, problems
+from oracle import Oracle
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_spec = importlib.util.spec_from_file_location("make_golden", os.path.join(HERE, "golden", "make_golden.py"))
+make_golden = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(make_golden)
+
+
+def level_matrix(L):
+    return sp.csr_matrix((L["data"], L["indices"], L["indptr"]), shape=(L["n"], L["n"]))
+
+
+def test_natural_gs_matches_triangular_solve():
+    """Forward GS in natural order == x + (D+L)^{-1}(b - A x); backward uses (D+U)."""
+    s = problems.bidomain_system(2, 12, gamma=50.0)
+    prm = dict(params.parameters_metric, smoother=haznics.SMOOTHER_GS)
+    H = mamg.Hierarchy(s.A, prm, s.interface_dofs)
+    ex = H.export()
+    orc = Oracle(ex, "natural")
+    A = level_matrix(ex["levels"][0])
+    rng = np.random.default_rng(0)
+    b, x = rng.standard_normal(A.shape[0]), rng.standard_normal(A.shape[0])
+    fwd = x + spla.spsolve_triangular(sp.tril(A).tocsr(), b - A @ x, lower=True)
+    bwd = x + spla.spsolve_triangular(sp.triu(A).tocsr(), b - A @ x, lower=False)
+    assert np.allclose(orc.smooth(b, x, 0, post=False), fwd, rtol=1e-12, atol=1e-13)
+    assert np.allclose(orc.smooth(b, x, 0, post=True), bwd, rtol=1e-12, atol=1e-13)
+
+
+def test_multicolor_gs_is_gs_in_colour_order():
+    s = problems.bidomain_system(2, 12, gamma=50.0)
+    prm = dict(params.parameters_metric, smoother=haznics.SMOOTHER_GS)
+    H = mamg.Hierarchy(s.A, prm, s.interface_dofs)
+    ex = H.export()
+    L0 = ex["levels"][0]
+    A = level_matrix(L0)
+    order = np.argsort(L0["color"], kind="stable")
+    Ap = A[order][:, order].tocsr()
+    rng = np.random.default_rng(1)
+    b, x = rng.standard_normal(A.shape[0]), rng.standard_normal(A.shape[0])
+    ref = x[order] + spla.spsolve_triangular(sp.tril(Ap).tocsr(), (b - A @ x)[order], lower=True)
+    out = Oracle(ex, "multicolor").smooth(b, x, 0, post=False)
+    assert np.allclose(out[order], ref, rtol=1e-12, atol=1e-13)
+
+
+def test_schwarz_patch_solve_is_exact_block_solve():
+    s = problems.bidomain_system(2, 10, gamma=1e3)
+    prm = dict(params.parameters_metric_schwarz, presmooth_iter=0, Schwarz_type=haznics.SCHWARZ_FORWARD)
+    H = mamg.Hierarchy(s.A, prm, s.interface_dofs)
+    ex = H.export()
+    L0 = ex["levels"][0]
+    A = level_matrix(L0).toarray()
+    rng = np.random.default_rng(2)
+    b, x = rng.standard_normal(A.shape[0]), rng.standard_normal(A.shape[0])
+    ref = x.copy()
+    for p in range(len(L0["patch_seed"])):
+        d = L0["patch_dofs"][L0["patch_ptr"][p]:L0["patch_ptr"][p + 1]]
+        ref[d] += np.linalg.solve(A[np.ix_(d, d)], (b - A @ ref)[d])
+    out = Oracle(ex, "natural").smooth(b, x, 0, post=False)
+    assert np.allclose(out, ref, rtol=1e-10, atol=1e-12)
+    # the multicolour order visits conflict-free patches: same fixed point structure, different order
+    out_mc = Oracle(ex, "multicolor").smooth(b, x, 0, post=False)
+    ref = x.copy()
+    for c in range(L0["n_patch_colors"]):
+        for p in np.flatnonzero(L0["patch_color"] == c):
+            d = L0["patch_dofs"][L0["patch_ptr"][p]:L0["patch_ptr"][p + 1]]
+            ref[d] += np.linalg.solve(A[np.ix_(d, d)], (b - A @ ref)[d])
+    assert np.allclose(out_mc, ref, rtol=1e-10, atol=1e-12)
+
+
+def test_two_level_cycle_matches_dense_formula():
+    """V-cycle with two levels, scaling off: z = S'(S(0,r) + P Ac^{-1} P'(r - A S(0,r)))."""
+    s = problems.bidomain_system(2, 8, gamma=10.0)
+    prm = dict(params.parameters_metric, cycle_type=haznics.V_CYCLE, coarse_scaling=haznics.OFF,
+               max_levels=2, smoother=haznics.SMOOTHER_GS)
+    H = mamg.Hierarchy(s.A, prm, s.interface_dofs)
+    ex = H.export()
+    assert len(ex["levels"]) == 2
+    L0 = ex["levels"][0]
+    A = level_matrix(L0)
+    agg = L0["agg"]
+    rows = np.flatnonzero(agg >= 0)
+    P = sp.csr_matrix((np.ones(len(rows)), (rows, agg[rows])), shape=(L0["n"], L0["n_aggregates"]))
+    Ac = (P.T @ A @ P).toarray()
+    r = np.random.default_rng(3).standard_normal(A.shape[0])
+    x = spla.spsolve_triangular(sp.tril(A).tocsr(), r, lower=True)
+    x = x + P @ np.linalg.solve(Ac, P.T @ (r - A @ x))
+    x = x + spla.spsolve_triangular(sp.triu(A).tocsr(), r - A @ x, lower=False)
+    assert np.allclose(Oracle(ex, "natural").apply(r), x, rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize("order", ["natural", "multicolor"])
+def test_cycle_symmetric_without_scaling(order):
+    s = problems.bidomain_system(2, 16, gamma=1e3)
+    prm = dict(params.parameters_metric_schwarz, coarse_scaling=haznics.OFF)
+    orc = Oracle(mamg.Hierarchy(s.A, prm, s.interface_dofs).export(), order)
+    rng = np.random.default_rng(4)
+    u, v = rng.standard_normal(s.ndofs), rng.standard_normal(s.ndofs)
+    a, b = v @ orc.apply(u), u @ orc.apply(v)
+    assert abs(a - b) / abs(a) < 1e-12
+    assert u @ orc.apply(u) > 0
+
+
+def test_w_cycle_visit_counts():
+    s = problems.bidomain_system(2, 32, gamma=1e3)
+    H = mamg.Hierarchy(s.A, params.parameters_metric, s.interface_dofs)
+    orc = Oracle(H.export(), "natural")
+    orc.apply(np.ones(s.ndofs))
+    L = H.num_levels
+    assert orc.visits() == sum(2 ** l for l in range(L - 1))   # level l visited 2^l times
+    orc.set_cycle(haznics.V_CYCLE)
+    orc.apply(np.ones(s.ndofs))
+    assert orc.visits() == L - 1
+
+
+# SURVEY section 6 sanity band (throw-away scipy sketch of the survey, NOT reference data):
+# bidomain 2-D, random rhs, abs tol 1e-8, natural order.  (n, gamma): (V, W, W+Schwarz)
+BAND = {(32, 1e3): (15, 12, 9), (64, 1e6): (22, 9, 8), (128, 1e3): (32, 14, 14)}
+
+
+@pytest.mark.parametrize("n,gamma", sorted(BAND))
+def test_iteration_counts_in_survey_band(n, gamma):
+    s = problems.bidomain_system(2, n, gamma=gamma)
+    b = np.random.default_rng(0).standard_normal(s.ndofs)
+    got = []
+    for prm in (dict(params.parameters_metric, cycle_type=haznics.V_CYCLE), params.parameters_metric,
+                params.parameters_metric_schwarz):
+        orc = Oracle(mamg.Hierarchy(s.A, prm, s.interface_dofs).export(), "natural")
+        _, info = orc.pcg(b, tolerance=1e-8, maxiter=500)
+        got.append(info["niters"])
+        assert info["residuals"][-1] <= 1e-8
+    for g, want in zip(got, BAND[(n, gamma)]):
+        assert abs(g - want) <= 2, (got, BAND[(n, gamma)])
+
+
+def test_multicolor_vs_natural_iteration_delta():
+    """the multicolour order costs +0..3 iterations over HAZmath's natural order."""
+    s = problems.bidomain_system(2, 64, gamma=1e3)
+    b = np.random.default_rng(0).standard_normal(s.ndofs)
+    ex = mamg.Hierarchy(s.A, params.parameters_metric_schwarz, s.interface_dofs).export()
+    it = {o: Oracle(ex, o).pcg(b, tolerance=1e-8)[1]["niters"] for o in ("natural", "multicolor")}
+    assert 0 <= it["multicolor"] - it["natural"] <= 3
+
+
+def test_threaded_oracle_equals_serial():
+    s = problems.bidomain_system(2, 24, gamma=1e3)
+    ex = mamg.Hierarchy(s.A, params.parameters_metric_schwarz, s.interface_dofs).export()
+    r = np.random.default_rng(5).standard_normal(s.ndofs)
+    orc = Oracle(ex, "multicolor")
+    z1 = orc.apply(r)
+    orc.set_threads(4)
+    z4 = orc.apply(r)
+    assert np.allclose(z1, z4, rtol=1e-13, atol=1e-15)
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(HERE, "golden", "*.npz"))))
+def test_oracle_reproduces_golden(path):
+    z = np.load(path)
+    hier = make_golden.unflatten(z)
+    for order in ("multicolor", "natural"):
+        orc = Oracle(hier, order)
+        out = orc.apply(z["r"])
+        assert np.linalg.norm(out - z[f"z_{order}"]) <= 1e-12 * np.linalg.norm(z[f"z_{order}"])
+        _, info = orc.pcg(z["b"], tolerance=float(z["tol"]), maxiter=500)
+        assert len(info["residuals"]) == len(z[f"residuals_{order}"])
+        assert np.allclose(info["residuals"], z[f"residuals_{order}"], rtol=1e-6)
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(HERE, "golden", "*.npz"))))
+def test_setup_reproduces_golden_hierarchy(path):
+    """The host setup is deterministic: re-building the case gives the frozen hierarchy."""
+    name = os.path.basename(path)[:-4]
+    z = np.load(path)
+    system, prm, _ = make_golden.CASES[name]()
+    ex = mamg.Hierarchy(system.A, prm, system.interface_dofs).export()
+    assert len(ex["levels"]) == int(z["nlevels"])
+    for l, L in enumerate(ex["levels"]):
+        for k in ("indptr", "indices", "agg", "color", "patch_ptr", "patch_dofs", "patch_color"):
+            assert np.array_equal(L[k], z[f"L{l}_{k}"]), (l, k)
+        assert np.allclose(L["data"], z[f"L{l}_data"], rtol=1e-13, atol=0)
