@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmamg.so")
+LIB_PATH = os.environ.get("MAMG_LIB") or os.path.join(_HERE, "libmamg.so")
 
 PARAM_FIELDS = [
     ("AMG_type", C.c_int32), ("cycle_type", C.c_int32), ("max_levels", C.c_int32),

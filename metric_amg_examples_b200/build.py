@@ -11,8 +11,11 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "libmamg.so")
-OBJ = os.path.join(HERE, "build")
+# experiment variants: MAMG_DEFS="-DMAMG_HINT=0 ..." MAMG_VARIANT=name -> libmamg_<name>.so (selected with MAMG_LIB)
+VARIANT = os.environ.get("MAMG_VARIANT", "")
+DEFS = os.environ.get("MAMG_DEFS", "").split()
+OUT = os.path.join(HERE, f"libmamg_{VARIANT}.so" if VARIANT else "libmamg.so")
+OBJ = os.path.join(HERE, "build_" + VARIANT if VARIANT else "build")
 
 HOST_SRC = ["host/assemble.cpp", "host/setup.cpp", "host/capi.cpp"]
 CUDA_SRC = ["cuda/device.cu"]
@@ -67,7 +70,7 @@ def build(force=False, verbose=False):
         o = os.path.join(OBJ, s.replace("/", "_") + ".o")
         objs.append(o)
         flags = [f for f in NVFLAGS if f != "--use_fast_math=false"]
-        jobs.append([NVCC] + ARCH + flags + ["-c", os.path.join(CSRC, s), "-o", o])
+        jobs.append([NVCC] + ARCH + flags + DEFS + ["-c", os.path.join(CSRC, s), "-o", o])
     with ThreadPoolExecutor(max_workers=4) as ex:
         list(ex.map(lambda c: _run(c, log), jobs))
     _run([NVCC] + ARCH + ["-shared", "-o", OUT] + objs + ["-Xcompiler", "-fopenmp", "-lgomp"], log)

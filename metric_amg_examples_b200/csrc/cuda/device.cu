@@ -39,6 +39,7 @@ struct DLevel {
   double *x_own = nullptr, *b_own = nullptr;
   int *perm = nullptr, *iperm = nullptr;  // device: new->old, old->new
   std::vector<int> color_ptr;             // host: row range of every colour
+  std::vector<int> color_active;          // host: rows of the colour that the point smoother touches
   DSchwarz sw;
 };
 
@@ -68,6 +69,12 @@ struct DeviceState {
   double *io_a = nullptr, *io_b = nullptr;  // staging for host-array calls
   std::vector<void*> allocs;
   mamg_params prm;
+  // one apply is a fixed launch sequence: it is captured once per (input, output) pair into a
+  // CUDA graph and replayed, which removes the host launch cost of the ~1000 small kernels of the
+  // coarse levels (MAMG_GRAPH=0 disables; not used while profiling or for very long W sequences)
+  struct GraphEntry { const double* r; double* z; cudaGraphExec_t exec; int64_t launches; int64_t cls[K_NCLS]; };
+  std::vector<GraphEntry> graphs;
+  bool use_graph = true;
 };
 
 // Brackets one kernel launch: counts it and, in profiling mode, times it with a CUDA event pair
@@ -115,6 +122,7 @@ void device_state_free(DeviceState* D) {
   if (D->stream) cudaStreamSynchronize(D->stream);
   for (void* p : D->allocs) cudaFree(p);
   for (ProfEvent& e : D->prof_events) { cudaEventDestroy(e.start); cudaEventDestroy(e.stop); }
+  for (auto& g : D->graphs) cudaGraphExecDestroy(g.exec);
   if (D->h_scal) cudaFreeHost(D->h_scal);
   if (D->own_stream && D->stream) cudaStreamDestroy(D->stream);
   delete D;
@@ -208,6 +216,9 @@ static void upload_hierarchy(const Hierarchy& H, DeviceState& D) {
       std::vector<uint8_t> sk(n);
       for (int i = 0; i < n; ++i) sk[i] = hl.gs_skip[perm[l][i]];
       dl.skip = upload(D, sk);
+      dl.color_active.assign(dl.ncolors, 0);
+      for (int c = 0; c < dl.ncolors; ++c)
+        for (int i = dl.color_ptr[c]; i < dl.color_ptr[c + 1]; ++i) dl.color_active[c] += sk[i] == 0;
     }
     if (l + 1 < L) {
       std::vector<int> agg(n), cptr(hl.nc + 1, 0), cidx;
@@ -279,6 +290,7 @@ static void k_spmv(DeviceState& D, const DLevel& l, const double* x, const doubl
 static void k_gs_color(DeviceState& D, const DLevel& l, int c, const double* b, double* x, double omega) {
   const int r0 = l.color_ptr[c], r1 = l.color_ptr[c + 1];
   if (r1 <= r0) return;
+  if (!l.color_active.empty() && l.color_active[c] == 0) return;   // every row of the colour belongs to Schwarz
   const int grid = cdiv((long long)cdiv(r1 - r0, l.unroll) * l.lanes, kBlock);
   KScope ks(D, K_GS);
   LANES_SWITCH(l.lanes, UNROLL_SWITCH(l.unroll,
@@ -421,8 +433,61 @@ static void k_copy(DeviceState& D, int n, const double* in, double* out) {
   copy_kernel<<<cdiv(n, kBlock), kBlock, 0, D.stream>>>(n, in, out);
 }
 
+static void drop_graphs(DeviceState& D) {
+  for (auto& g : D.graphs) cudaGraphExecDestroy(g.exec);
+  D.graphs.clear();
+}
+
+static int64_t apply_launch_estimate(const DeviceState& D) {
+  // launches of one apply: ~ (4 colours sweeps + 4) per visit, visits doubling per level for W
+  double visits = 1, total = 0;
+  for (size_t l = 0; l + 1 < D.lv.size(); ++l) {
+    total += visits * (4.0 * D.lv[l].ncolors + 4.0 * D.lv[l].sw.ncolors + 4.0);
+    if (D.prm.cycle_type == MAMG_W_CYCLE) visits *= 2;
+  }
+  return (int64_t)total;
+}
+
+static void apply_permuted_raw(DeviceState& D, const double* r, double* z);
+
 // z' = B r' in the permuted ordering of level 0 (both device arrays of size n0)
 static void apply_permuted(DeviceState& D, const double* r, double* z) {
+  if (!D.use_graph || D.prof_on || apply_launch_estimate(D) > 60000) { apply_permuted_raw(D, r, z); return; }
+  for (auto& g : D.graphs)
+    if (g.r == r && g.z == z) {
+      CUDA_OK(cudaGraphLaunch(g.exec, D.stream));
+      D.launches += g.launches;
+      for (int k = 0; k < K_NCLS; ++k) D.cls_launches[k] += g.cls[k];
+      return;
+    }
+  // capture (nothing executes), instantiate, then launch through the cache on the next lookup
+  const int64_t l0 = D.launches;
+  int64_t c0[K_NCLS];
+  for (int k = 0; k < K_NCLS; ++k) c0[k] = D.cls_launches[k];
+  cudaGraph_t graph = nullptr;
+  CUDA_OK(cudaStreamBeginCapture(D.stream, cudaStreamCaptureModeThreadLocal));
+  try {
+    apply_permuted_raw(D, r, z);
+  } catch (...) {
+    cudaStreamEndCapture(D.stream, &graph);
+    if (graph) cudaGraphDestroy(graph);
+    throw;
+  }
+  CUDA_OK(cudaStreamEndCapture(D.stream, &graph));
+  DeviceState::GraphEntry e;
+  e.r = r;
+  e.z = z;
+  e.launches = D.launches - l0;
+  for (int k = 0; k < K_NCLS; ++k) { e.cls[k] = D.cls_launches[k] - c0[k]; D.cls_launches[k] = c0[k]; }
+  D.launches = l0;
+  CUDA_OK(cudaGraphInstantiate(&e.exec, graph, 0));
+  cudaGraphDestroy(graph);
+  if (D.graphs.size() >= 4) { cudaGraphExecDestroy(D.graphs.front().exec); D.graphs.erase(D.graphs.begin()); }
+  D.graphs.push_back(e);
+  apply_permuted(D, r, z);
+}
+
+static void apply_permuted_raw(DeviceState& D, const double* r, double* z) {
   DLevel& l0 = D.lv[0];
   l0.b = const_cast<double*>(r);
   l0.x = z;
@@ -699,6 +764,7 @@ int mamg_to_device(mamg_handle h, int32_t device, void* stream) {
   DeviceState* D = new DeviceState();
   D->device = device;
   D->prm = h->H.prm;
+  { const char* g = getenv("MAMG_GRAPH"); if (g) D->use_graph = atoi(g) != 0; }
   try {
     if (stream) { D->stream = (cudaStream_t)stream; D->own_stream = false; }
     else { CUDA_OK(cudaStreamCreateWithFlags(&D->stream, cudaStreamNonBlocking)); D->own_stream = true; }
@@ -715,6 +781,7 @@ int mamg_set_stream(mamg_handle h, void* stream) {
   DeviceState* D = get_dev(h);
   if (!D) return -1;
   CUDA_OK(cudaStreamSynchronize(D->stream));
+  drop_graphs(*D);
   if (D->own_stream) { cudaStreamDestroy(D->stream); D->own_stream = false; }
   if (stream) D->stream = (cudaStream_t)stream;
   else { CUDA_OK(cudaStreamCreateWithFlags(&D->stream, cudaStreamNonBlocking)); D->own_stream = true; }

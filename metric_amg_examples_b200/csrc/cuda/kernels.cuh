@@ -34,12 +34,50 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// Streaming loads for data that is read exactly once per kernel (matrix values / columns, patch
+// blobs): no L1 allocation and evict-first in L2, so that the vectors that ARE re-read (x gathers)
+// keep the 126 MB L2 to themselves.
+#ifndef MAMG_HINT
+#define MAMG_HINT 0   // 0: plain loads, 1: L2 evict-first, 2: L2 evict-first + no L1 allocation
+#endif
+__device__ __forceinline__ unsigned long long stream_policy() {
+  unsigned long long pol;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+#if MAMG_HINT == 0
+__device__ __forceinline__ double ld_stream(const double* p) { return __ldg(p); }
+__device__ __forceinline__ int ld_stream(const int* p) { return __ldg(p); }
+__device__ __forceinline__ unsigned int ld_stream(const unsigned int* p) { return __ldg(p); }
+#else
+#if MAMG_HINT == 1
+#define MAMG_LD "ld.global.nc.L2::cache_hint"
+#else
+#define MAMG_LD "ld.global.nc.L1::no_allocate.L2::cache_hint"
+#endif
+__device__ __forceinline__ double ld_stream(const double* p) {
+  double v;
+  asm(MAMG_LD ".f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(stream_policy()));
+  return v;
+}
+__device__ __forceinline__ int ld_stream(const int* p) {
+  int v;
+  asm(MAMG_LD ".s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(stream_policy()));
+  return v;
+}
+__device__ __forceinline__ unsigned int ld_stream(const unsigned int* p) {
+  unsigned int v;
+  asm(MAMG_LD ".u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(stream_policy()));
+  return v;
+}
+#endif
+
 // Row dot product a_i . x by one sub-warp; the full sum is valid in lane 0 of the sub-warp.
 template <int LANES>
 __device__ __forceinline__ double row_dot(const int* __restrict__ ja, const double* __restrict__ a,
                                           const double* x, int p0, int p1, int lane) {
   double s = 0.0;
-  for (int p = p0 + lane; p < p1; p += LANES) s += a[p] * x[ja[p]];
+  for (int p = p0 + lane; p < p1; p += LANES) s += ld_stream(a + p) * x[ld_stream(ja + p)];
   return subwarp_sum<LANES>(s);
 }
 
@@ -51,6 +89,7 @@ __device__ __forceinline__ void rows_dot(const int* __restrict__ ia, const int* 
                                          const double* __restrict__ a, const double* x, int row0,
                                          int rend, int lane, double (&s)[U]) {
   int p[U], e[U];
+  const int psafe = ia[row0];   // a valid entry index for lanes that have run out of work
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     const int r = row0 + u;
@@ -61,16 +100,23 @@ __device__ __forceinline__ void rows_dot(const int* __restrict__ ia, const int* 
   bool more = true;
   while (more) {
     more = false;
+    // three unconditional load waves (columns, values, x): no branch sits between the U streams,
+    // so all of them are in flight together; finished lanes re-read a valid entry and add 0
+    int cj[U];
     double av[U], xv[U];
+    bool on[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const bool on = p[u] < e[u];
-      av[u] = on ? a[p[u]] : 0.0;
-      xv[u] = on ? x[ja[p[u]]] : 0.0;
+      on[u] = p[u] < e[u];
+      const int q = on[u] ? p[u] : psafe;
+      cj[u] = ld_stream(ja + q);
+      av[u] = ld_stream(a + q);
     }
 #pragma unroll
+    for (int u = 0; u < U; ++u) xv[u] = x[cj[u]];
+#pragma unroll
     for (int u = 0; u < U; ++u) {
-      s[u] += av[u] * xv[u];
+      s[u] += on[u] ? av[u] * xv[u] : 0.0;
       p[u] += LANES;
       more |= p[u] < e[u];
     }
@@ -246,12 +292,15 @@ resid_restrict_kernel(int nc, const int* __restrict__ cptr, const int* __restric
     int p0 = ia[i0] + lane, e0 = ia[i0 + 1];
     int p1 = two ? ia[i1] + lane : 0, e1 = two ? ia[i1 + 1] : 0;
     double s0 = 0.0, s1 = 0.0;
+    const int psafe = ia[i0];
     while (p0 < e0 || p1 < e1) {
       const bool on0 = p0 < e0, on1 = p1 < e1;
-      const double a0 = on0 ? a[p0] : 0.0, a1 = on1 ? a[p1] : 0.0;
-      const double x0 = on0 ? x[ja[p0]] : 0.0, x1 = on1 ? x[ja[p1]] : 0.0;
-      s0 += a0 * x0;
-      s1 += a1 * x1;
+      const int q0 = on0 ? p0 : psafe, q1 = on1 ? p1 : psafe;
+      const int c0 = ld_stream(ja + q0), c1 = ld_stream(ja + q1);
+      const double a0 = ld_stream(a + q0), a1 = ld_stream(a + q1);
+      const double x0 = x[c0], x1 = x[c1];
+      s0 += on0 ? a0 * x0 : 0.0;
+      s1 += on1 ? a1 * x1 : 0.0;
       p0 += LANES;
       p1 += LANES;
     }

@@ -30,6 +30,7 @@
 #include <vector>
 
 #include "../host/hierarchy.h"
+#include "kernels.cuh"
 
 namespace mamg {
 
@@ -52,6 +53,14 @@ struct DSchwarz {
   int* nbr = nullptr;          // neighbourhood lists (permuted ids, ascending)
   uint16_t* lcol = nullptr;    // per patch: s x srow (row-major, padded): position of the entry's column in nbr
   double* pinv = nullptr;      // packed lower triangles of A_BB^{-1}
+  // fast path (every patch <= 32 dofs, <= 255 neighbours, rows <= 32 entries): per-patch blobs in
+  // "lane = patch row" layout, uniform strides, so all addresses follow from the patch number
+  bool fast = false;
+  int nbq = 0, sq = 0, inv_stride = 0, sr_t = 32;
+  int* pidx32 = nullptr;       // [np][32] row id of patch dof k, -1 padding
+  int* nbrp = nullptr;         // [np][nbq][32] neighbourhood list, padded with a valid index
+  double* vt = nullptr;        // [np][srow][32] entry e of row k; 0 padding
+  uint32_t* ct4 = nullptr;     // [np][sq][32] four 8-bit local columns per word; 255 = zero slot
   std::vector<int> color_ptr;  // host: patch range of every colour
   long long alg_bytes = 0;     // algorithmic bytes of one sweep over all patches
 };
@@ -242,6 +251,115 @@ schwarz_apply_kernel(int p0, int p1, const SwPatch* __restrict__ pat, const int*
   }
 }
 
+// ---- fast path -----------------------------------------------------------------------------------
+// setup: build vt / ct4 of one patch from the level CSR (one warp per patch, lane = patch row)
+__global__ void __launch_bounds__(256)
+schwarz_blob_kernel(int np, const SwPatch* __restrict__ pat, const int* __restrict__ pidx,
+                    const int* __restrict__ nbr, const int* __restrict__ ia, const int* __restrict__ ja,
+                    const double* __restrict__ a, int srow, int sq, int nbq, int* __restrict__ pidx32,
+                    int* __restrict__ nbrp, double* __restrict__ vt, uint32_t* __restrict__ ct4) {
+  const int patch = blockIdx.x * 8 + threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (patch >= np) return;
+  const SwPatch P = pat[patch];
+  const size_t pp = (size_t)patch;
+  const int row = lane < P.s ? pidx[P.q0 + lane] : -1;
+  pidx32[pp * 32 + lane] = row;
+  const int* nb = nbr + P.n0;
+  for (int j = 0; j < nbq; ++j) {
+    const int q = j * 32 + lane;
+    nbrp[(pp * nbq + j) * 32 + lane] = q < P.nn ? nb[q] : nb[0];
+  }
+  const int r0 = row >= 0 ? ia[row] : 0, len = row >= 0 ? ia[row + 1] - r0 : 0;
+  for (int q = 0; q < sq; ++q) {
+    uint32_t word = 0;
+    for (int u = 0; u < 4; ++u) {
+      const int e = q * 4 + u;
+      uint32_t loc = 255;
+      double v = 0.0;
+      if (e < len) {
+        v = a[r0 + e];
+        const int col = ja[r0 + e];
+        int lo = 0, hi = P.nn - 1;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (nb[mid] < col) lo = mid + 1; else hi = mid; }
+        loc = (uint32_t)lo;
+      }
+      if (e < srow) vt[(pp * srow + e) * 32 + lane] = v;
+      word |= loc << (8 * u);
+    }
+    ct4[(pp * sq + q) * 32 + lane] = word;
+  }
+}
+
+#ifndef MAMG_SW_MINB
+#define MAMG_SW_MINB 2   // CTAs per SM the fast kernel is compiled for (2: ~100 registers, 3: 80 with spills)
+#endif
+constexpr int kSwFastWarps = 8;     // patches per CTA
+constexpr int kSwFastSlot = 256 + 528 + 32;  // doubles per patch slot: xs[256], packed inverse (32*33/2), rhs[32]
+
+// apply: one warp per patch, lane k = patch row k.  Wave 1 loads everything addressed by the patch
+// number (row values, packed local columns, neighbour list, inverse via cp.async); wave 2 gathers
+// x on the neighbourhood.  All loops have compile-time bounds; padding multiplies by the zero slot.
+template <int SR>
+__global__ void __launch_bounds__(kSwFastWarps * 32, MAMG_SW_MINB)
+schwarz_fast_kernel(int p0, int p1, const int* __restrict__ pidx32, const int* __restrict__ nbrp,
+                    const double* __restrict__ vt, const uint32_t* __restrict__ ct4,
+                    const double* __restrict__ pinv, const double* __restrict__ b, double* x, int srow,
+                    int sq, int nbq, int inv_stride, int smax) {
+  extern __shared__ __align__(16) double smem[];
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int patch = p0 + blockIdx.x * kSwFastWarps + warp;
+  if (patch >= p1) return;
+  double* xs = smem + warp * kSwFastSlot;
+  double* Inv = xs + 256;
+  double* rhs = Inv + 528;
+  const size_t pp = (size_t)patch;
+  // ---- wave 1 ----
+  const int my = pidx32[pp * 32 + lane];
+  int nb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) nb[j] = j < nbq ? ld_stream(nbrp + (pp * nbq + j) * 32 + lane) : 0;
+  {
+    const double* src = pinv + pp * inv_stride;
+    const int nch = inv_stride / 2;
+    for (int k = lane; k < nch; k += 32) cp_async16(Inv + 2 * k, src + 2 * k);
+  }
+  double v[SR];
+  {
+    const double* vp = vt + (pp * srow) * 32 + lane;
+#pragma unroll
+    for (int e = 0; e < SR; ++e) v[e] = e < srow ? ld_stream(vp + e * 32) : 0.0;
+  }
+  uint32_t c4[SR / 4];
+  {
+    const uint32_t* cp = ct4 + (pp * sq) * 32 + lane;
+#pragma unroll
+    for (int q = 0; q < SR / 4; ++q) c4[q] = q < sq ? ld_stream(cp + q * 32) : 0xffffffffu;
+  }
+  const double bk = my >= 0 ? b[my] : 0.0;
+  // ---- wave 2 ----
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (j < nbq) xs[j * 32 + lane] = x[nb[j]];
+  if (lane == 31) xs[255] = 0.0;   // the zero slot every padded local column points to
+  __syncwarp();
+  double acc = 0.0;
+#pragma unroll
+  for (int e = 0; e < SR; ++e) acc += v[e] * xs[(c4[e / 4] >> (8 * (e % 4))) & 255u];
+  rhs[lane] = my >= 0 ? bk - acc : 0.0;
+  cp_async_wait_all();
+  __syncwarp();
+  double d = 0.0;
+  const int base = lane * (lane + 1) / 2;
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    if (c < smax) {
+      const int ad = c <= lane ? base + c : c * (c + 1) / 2 + lane;
+      d += Inv[ad] * rhs[c];
+    }
+  }
+  if (my >= 0) x[my] += d;
+}
+
 // Host side: reorder the patches by colour, translate to the permuted numbering, build the
 // neighbourhood lists and local columns, upload, invert on the device.
 // `alloc(bytes)` returns tracked device memory; pia/pja are the permuted CSR of the level.
@@ -289,7 +407,11 @@ inline void schwarz_upload(const Level& hl, const std::vector<int>& iperm, const
       ne[k] = ent;
     }
   }
-  const int srow = max_rowlen | 1;   // odd row stride: conflict-free "thread k walks row k"
+  int max_nn = 0;
+  for (int k = 0; k < np; ++k) max_nn = std::max(max_nn, nn[k]);
+  const char* nofast = getenv("MAMG_SCHWARZ_GENERAL");
+  const bool fast_shape = d.max_size <= 32 && max_nn <= 255 && max_rowlen <= 32 && !(nofast && atoi(nofast));
+  const int srow = fast_shape ? max_rowlen : (max_rowlen | 1);   // general path: odd row stride (conflict-free)
   d.srow = srow;
   long long tot_e = 0, tot_i = 0, tot_val = 0;
   long long tot_n = 0, tot_q = 0;
@@ -302,12 +424,12 @@ inline void schwarz_upload(const Level& hl, const std::vector<int>& iperm, const
     pat[k].n0 = (int)tot_n;
     pat[k].nn = nn[k];
     pat[k].e0 = tot_e;
-    pat[k].i0 = tot_i;
+    pat[k].i0 = fast_shape ? (long long)k * 528 : tot_i;
     tot_q += s;
     tot_n += nn[k];
     tot_e += ((long long)s * srow + 7) / 8 * 8;                 // 16-byte aligned uint16 segments
     tot_val += ne[k];
-    tot_i += ((long long)s * (s + 1) / 2 + 1) / 2 * 2;          // 16-byte aligned inverses
+    tot_i += fast_shape ? 528 : ((long long)s * (s + 1) / 2 + 1) / 2 * 2;   // 16-byte aligned inverses
     max_nbr = std::max(max_nbr, nn[k]);
 
   }
@@ -315,7 +437,7 @@ inline void schwarz_upload(const Level& hl, const std::vector<int>& iperm, const
   if (max_nbr > 65535) throw std::runtime_error("Schwarz patch neighbourhood larger than 65535 dofs");
   d.max_nbr = max_nbr;
   std::vector<int> nbr((size_t)tot_n);
-  std::vector<uint16_t> lcol((size_t)tot_e + 8, 0);
+  std::vector<uint16_t> lcol(fast_shape ? 8 : (size_t)tot_e + 8, 0);
 #pragma omp parallel
   {
     std::vector<int> mark(n, -1), pos(n, 0), list;
@@ -334,8 +456,8 @@ inline void schwarz_upload(const Level& hl, const std::vector<int>& iperm, const
       }
       std::sort(list.begin(), list.end());
       for (int j = 0; j < (int)list.size(); ++j) { pos[list[j]] = j; nbr[pat[k].n0 + j] = list[j]; }
-      uint16_t* out = &lcol[(size_t)pat[k].e0];
-      for (int q = 0; q < s; ++q) {
+      uint16_t* out = fast_shape ? nullptr : &lcol[(size_t)pat[k].e0];
+      for (int q = 0; q < s && !fast_shape; ++q) {
         const int i = pidx[pat[k].q0 + q];
         for (int e = pia[i]; e < pia[i + 1]; ++e) out[(size_t)q * srow + (e - pia[i])] = (uint16_t)pos[pja[e]];
       }
@@ -344,6 +466,8 @@ inline void schwarz_upload(const Level& hl, const std::vector<int>& iperm, const
   // per sweep: values + local columns of the row entries, neighbour list + gathered x, packed
   // inverse, (idx, row start, row offset, b, x update) per patch dof, patch descriptor
   d.alg_bytes = 10 * tot_val + 12 * tot_n + 8 * tot_i + (12 + 8 + 16) * tot_q + 32LL * np;
+  if (fast_shape)  // values + 8-bit local columns, neighbour list + gathered x, packed inverse, (idx, b, x) per dof
+    d.alg_bytes = 9 * tot_val + 12 * tot_n + 4 * [&] { long long t = 0; for (int k = 0; k < np; ++k) t += (long long)pat[k].s * (pat[k].s + 1); return t; }() + (4 + 8 + 16) * tot_q;
   const size_t tri_max = (size_t)d.max_size * (d.max_size + 1) / 2;
   d.smem_setup = (tri_max + d.max_size) * sizeof(double) + (size_t)d.max_size * sizeof(int);
   d.warps = d.max_size <= 32 ? 1 : (d.max_size <= 96 ? 2 : 4);
@@ -365,12 +489,31 @@ inline void schwarz_upload(const Level& hl, const std::vector<int>& iperm, const
   d.nbr = (int*)up(nbr.data(), nbr.size() * sizeof(int));
   d.lcol = (uint16_t*)up(lcol.data(), lcol.size() * sizeof(uint16_t));
   d.pinv = (double*)alloc(((size_t)tot_i + 2) * sizeof(double));
+  if (fast_shape) cudaMemset(d.pinv, 0, ((size_t)tot_i + 2) * sizeof(double));   // padding must be 0, not NaN bits
   constexpr int TS = 128;
   if (d.smem_setup > 48 * 1024)
     cudaFuncSetAttribute(schwarz_invert_kernel<TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_setup);
   schwarz_invert_kernel<TS><<<np, TS, d.smem_setup>>>(np, d.pat, d.pidx, d_ia, d_ja, d_a, d.pinv, d.max_size);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) throw std::runtime_error(std::string("Schwarz setup kernel failed: ") + cudaGetErrorString(e));
+  if (fast_shape) {
+    d.fast = true;
+    d.nbq = (max_nn + 31) / 32;
+    d.sq = (srow + 3) / 4;
+    d.inv_stride = 528;
+    d.sr_t = srow <= 16 ? 16 : 32;
+    d.pidx32 = (int*)alloc((size_t)np * 32 * sizeof(int));
+    d.nbrp = (int*)alloc((size_t)np * d.nbq * 32 * sizeof(int));
+    d.vt = (double*)alloc((size_t)np * srow * 32 * sizeof(double));
+    d.ct4 = (uint32_t*)alloc((size_t)np * d.sq * 32 * sizeof(uint32_t));
+    schwarz_blob_kernel<<<(np + 7) / 8, 256>>>(np, d.pat, d.pidx, d.nbr, d_ia, d_ja, d_a, srow, d.sq, d.nbq,
+                                              d.pidx32, d.nbrp, d.vt, d.ct4);
+    e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) throw std::runtime_error(std::string("Schwarz blob kernel failed: ") + cudaGetErrorString(e));
+    const int fsm = kSwFastWarps * kSwFastSlot * (int)sizeof(double);
+    cudaFuncSetAttribute(schwarz_fast_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm);
+    cudaFuncSetAttribute(schwarz_fast_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm);
+  }
   if (d.smem_apply > 48 * 1024) {
     cudaFuncSetAttribute(schwarz_apply_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_apply);
     cudaFuncSetAttribute(schwarz_apply_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_apply);
@@ -383,6 +526,17 @@ inline void schwarz_upload(const Level& hl, const std::vector<int>& iperm, const
 inline void schwarz_color_launch(const DSchwarz& d, int c, const double* a, const double* b, double* x,
                                  cudaStream_t stream) {
   const int p0 = d.color_ptr[c], p1 = d.color_ptr[c + 1];
+  if (d.fast) {
+    const int g = (p1 - p0 + kSwFastWarps - 1) / kSwFastWarps;
+    const size_t sm = (size_t)kSwFastWarps * kSwFastSlot * sizeof(double);
+    if (d.sr_t == 16)
+      schwarz_fast_kernel<16><<<g, kSwFastWarps * 32, sm, stream>>>(p0, p1, d.pidx32, d.nbrp, d.vt, d.ct4, d.pinv, b, x,
+                                                                    d.srow, d.sq, d.nbq, d.inv_stride, d.max_size);
+    else
+      schwarz_fast_kernel<32><<<g, kSwFastWarps * 32, sm, stream>>>(p0, p1, d.pidx32, d.nbrp, d.vt, d.ct4, d.pinv, b, x,
+                                                                    d.srow, d.sq, d.nbq, d.inv_stride, d.max_size);
+    return;
+  }
   const int grid = (p1 - p0 + d.ppc - 1) / d.ppc;
   const SwLayout lay = {d.max_size, d.max_nbr, d.srow};
 #define MAMG_SW_ARGS p0, p1, d.pat, d.pidx, d.prow, d.plen, d.nbr, d.lcol, d.pinv, a, b, x, lay
