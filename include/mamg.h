@@ -92,12 +92,15 @@ int mamg_num_levels(mamg_handle h, int32_t* nlevels);
 /* info[0]=rows info[1]=nnz info[2]=n_aggregates info[3]=n_colors info[4]=n_patches
  * info[5]=n_patch_entries info[6]=n_patch_colors info[7]=max_patch_size
  * info[8]=matrix entries in all patch rows (sum over patches of the nnz of their rows)
- * info[9]=packed patch-inverse entries (sum of s(s+1)/2) info[10..11] reserved */
+ * info[9]=packed patch-inverse entries (sum of s(s+1)/2) info[10]=nnz of the smoothed
+ * prolongator P (SA_AMG levels, else 0) info[11] reserved */
 int mamg_level_info(mamg_handle h, int32_t level, int64_t info[12]);
 int mamg_level_export(mamg_handle h, int32_t level, int32_t* indptr, int32_t* indices, double* data,
                       int32_t* agg, int32_t* color, uint8_t* gs_skip);
 int mamg_schwarz_export(mamg_handle h, int32_t level, int32_t* patch_ptr, int32_t* patch_dofs,
                         int32_t* patch_seed, int32_t* patch_color);
+/* smoothed prolongator P (rows x n_aggregates CSR) of an SA_AMG level; R = P' */
+int mamg_prolongator_export(mamg_handle h, int32_t level, int32_t* indptr, int32_t* indices, double* data);
 /* dense row-major inverse of the coarsest operator, n_c*n_c doubles */
 int mamg_coarse_export(mamg_handle h, double* inv);
 int mamg_setup_seconds(mamg_handle h, double* seconds);
@@ -131,8 +134,9 @@ int mamg_smooth(mamg_handle h, int32_t level, const double* b, double* x, int32_
 /* ---- Krylov: replaces block.iterative.ConjGrad(A, precond=B, tolerance=, maxiter=,
  *      relativeconv=) followed by x = AAinv * b (src/bidomain_2d.py:205-206,
  *      src/emi_2d.py:211-212).  A is level 0 of the hierarchy.  Stopping rule of
- *      cbc.block: sqrt(r.Br) <= tolerance (absolute) or <= tolerance*sqrt(r0.Br0)
- *      (relative != 0).  residuals has room for maxiter+1 entries, alphas/betas for
+ *      cbc.block: sqrt(r.Br) <= tolerance (relative == 0) or <= tolerance*sqrt(r0.Br0)
+ *      (relative == 1); relative == 2 selects HAZmath's own rule ||r||_2 <= tolerance*||r0||_2
+ *      (linear_stop_type 1 of src/input_metric.dat:54, used by fenics_metric_solver_xd_1d).  residuals has room for maxiter+1 entries, alphas/betas for
  *      maxiter (may be NULL).  x holds the initial guess on entry when
  *      use_initial_guess != 0, else it is ignored. */
 int mamg_pcg(mamg_handle h, const double* b, double* x, double tolerance, int32_t relative,

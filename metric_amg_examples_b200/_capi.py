@@ -42,6 +42,7 @@ def _load():
         "mamg_level_info": (i32, [vp, i32, pi64]),
         "mamg_level_export": (i32, [vp, i32, vp, vp, vp, vp, vp, vp]),
         "mamg_schwarz_export": (i32, [vp, i32, vp, vp, vp, vp]),
+        "mamg_prolongator_export": (i32, [vp, i32, vp, vp, vp]),
         "mamg_coarse_export": (i32, [vp, vp]),
         "mamg_setup_seconds": (i32, [vp, pdbl]),
         "mamg_to_device": (i32, [vp, i32, vp]),

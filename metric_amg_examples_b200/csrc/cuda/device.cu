@@ -29,6 +29,12 @@ namespace mamg {
                                __FILE__ + ":" + std::to_string(__LINE__));                \
   } while (0)
 
+struct DCsr {
+  int n = 0, m = 0, nnz = 0, lanes = 4;
+  int *ia = nullptr, *ja = nullptr;
+  double* a = nullptr;
+};
+
 struct DLevel {
   int n = 0, nnz = 0, nc = 0, ncolors = 0, lanes = 8, unroll = 4;
   int *ia = nullptr, *ja = nullptr;
@@ -41,6 +47,7 @@ struct DLevel {
   std::vector<int> color_ptr;             // host: row range of every colour
   std::vector<int> color_active;          // host: rows of the colour that the point smoother touches
   DSchwarz sw;
+  DCsr P, R;   // SA_AMG only
 };
 
 enum KClass { K_SPMV = 0, K_GS, K_SCHWARZ, K_RESTRICT, K_SCALE, K_PROLONG, K_COARSE, K_VEC, K_DOT, K_NCLS };
@@ -220,6 +227,27 @@ static void upload_hierarchy(const Hierarchy& H, DeviceState& D) {
       for (int c = 0; c < dl.ncolors; ++c)
         for (int i = dl.color_ptr[c]; i < dl.color_ptr[c + 1]; ++i) dl.color_active[c] += sk[i] == 0;
     }
+    if (l + 1 < L && hl.P.n > 0) {
+      // SA_AMG: P (fine' x coarse') and R = P' (coarse' x fine') in the permuted numberings
+      auto permute = [&](const Csr& M, const std::vector<int>& rperm, const std::vector<int>& ciperm, DCsr& out) {
+        std::vector<int> ia2(M.n + 1, 0), ja2(M.nnz());
+        std::vector<double> a2(M.nnz());
+        for (int i = 0; i < M.n; ++i) ia2[i + 1] = ia2[i] + (M.ia[rperm[i] + 1] - M.ia[rperm[i]]);
+        for (int i = 0; i < M.n; ++i) {
+          const int o = rperm[i];
+          std::vector<std::pair<int, double>> buf;
+          for (int p = M.ia[o]; p < M.ia[o + 1]; ++p) buf.push_back({ciperm[M.ja[p]], M.a[p]});
+          std::sort(buf.begin(), buf.end(),
+                    [](const std::pair<int, double>& u, const std::pair<int, double>& v) { return u.first < v.first; });
+          for (size_t k = 0; k < buf.size(); ++k) { ja2[ia2[i] + k] = buf[k].first; a2[ia2[i] + k] = buf[k].second; }
+        }
+        out.n = M.n; out.m = M.m; out.nnz = M.nnz();
+        out.lanes = pick_lanes(M.n ? (double)M.nnz() / M.n : 1.0);
+        out.ia = upload(D, ia2); out.ja = upload(D, ja2); out.a = upload(D, a2);
+      };
+      permute(hl.P, perm[l], iperm[l + 1], dl.P);
+      permute(hl.R, perm[l + 1], iperm[l], dl.R);
+    }
     if (l + 1 < L) {
       std::vector<int> agg(n), cptr(hl.nc + 1, 0), cidx;
       for (int i = 0; i < n; ++i) {
@@ -367,9 +395,24 @@ static void smooth(DeviceState& D, int lev, const double* b, double* x, bool pos
   if (!post) { schwarz(); point(); } else { point(); schwarz(); }
 }
 
+static void k_csr_apply(DeviceState& D, const DCsr& M, const double* x, const double* alpha, double* y, double* zero,
+                        bool add, int cls) {
+  if (M.n == 0) return;
+  const int grid = cdiv((long long)M.n * M.lanes, kBlock);
+  KScope ks(D, cls);
+  LANES_SWITCH(M.lanes,
+    if (add) csr_apply_kernel<LN, true><<<grid, kBlock, 0, D.stream>>>(M.n, M.ia, M.ja, M.a, x, alpha, y, zero);
+    else csr_apply_kernel<LN, false><<<grid, kBlock, 0, D.stream>>>(M.n, M.ia, M.ja, M.a, x, alpha, y, zero));
+}
+
 static void k_resid_restrict(DeviceState& D, int lev) {
   DLevel& f = D.lv[lev];
   DLevel& c = D.lv[lev + 1];
+  if (f.R.n > 0) {   // SA_AMG: w = b - A x, b_c = R w, x_c = 0
+    k_spmv(D, f, f.x, f.b, f.t, true);
+    k_csr_apply(D, f.R, f.t, nullptr, c.b, c.x, false, K_RESTRICT);
+    return;
+  }
   const int grid = cdiv((long long)f.nc * f.lanes, kBlock);
   KScope ks(D, K_RESTRICT);
   LANES_SWITCH(f.lanes,
@@ -391,6 +434,10 @@ static void k_scale_dots(DeviceState& D, int lev) {
 static void k_prolong(DeviceState& D, int lev, bool scaled) {
   DLevel& f = D.lv[lev];
   DLevel& c = D.lv[lev + 1];
+  if (f.P.n > 0) {   // SA_AMG: x += alpha P e
+    k_csr_apply(D, f.P, c.x, scaled ? D.scal + 10 : nullptr, f.x, nullptr, true, K_PROLONG);
+    return;
+  }
   KScope ks(D, K_PROLONG);
   prolong_kernel<<<cdiv(f.n, kBlock), kBlock, 0, D.stream>>>(f.n, f.agg, c.x, scaled ? D.scal + 10 : nullptr, f.x);
 }
@@ -531,7 +578,9 @@ static void read_scalars(DeviceState& D, int count) {
 }
 
 // cbc.block ConjGrad on the device, permuted ordering.
-static int pcg_device(DeviceState& D, const double* b_nat, double* x_nat, double tol, bool relative,
+// stop: 0 sqrt(r.Br) <= tol, 1 sqrt(r.Br) <= tol*sqrt(r0.Br0) (cbc.block), 2 ||r||_2 <= tol*||r0||_2
+// (HAZmath linear_stop_type 1, src/input_metric.dat:54)
+static int pcg_device(DeviceState& D, const double* b_nat, double* x_nat, double tol, int stop,
                       int maxiter, bool use_guess, int* niters, double* residuals, double* alphas,
                       double* betas) {
   DLevel& l0 = D.lv[0];
@@ -556,9 +605,9 @@ static int pcg_device(DeviceState& D, const double* b_nat, double* x_nat, double
   read_scalars(D, 8);
   double rz = D.h_scal[0];
   int it = 0, status = 0;
-  double res = std::sqrt(rz);
+  double res = stop == 2 ? std::sqrt(D.h_scal[6]) : std::sqrt(rz);
   if (residuals) residuals[0] = res;
-  double target = relative ? tol * res : tol;
+  double target = stop != 0 ? tol * res : tol;
   while (res > target && it < maxiter) {
     const int sgrid = red_grid(D, (long long)cdiv(n, l0.unroll) * l0.lanes);
     {
@@ -584,7 +633,7 @@ static int pcg_device(DeviceState& D, const double* b_nat, double* x_nat, double
     if (alphas) alphas[it - 1] = D.h_scal[2];
     if (betas) betas[it - 1] = D.h_scal[4];
     rz = D.h_scal[0];
-    res = std::sqrt(rz);
+    res = stop == 2 ? std::sqrt(D.h_scal[6]) : std::sqrt(rz);
     if (residuals) residuals[it] = res;
     if (!(rz >= 0.0) || !std::isfinite(D.h_scal[2])) { status = 1; break; }  // "ConjGrad breakdown"
   }
@@ -875,7 +924,7 @@ int mamg_pcg(mamg_handle h, const double* b, double* x, double tolerance, int32_
   if (use_initial_guess && !on_device)
     CUDA_OK(cudaMemcpyAsync(D->io_b, x, sizeof(double) * l0.n, cudaMemcpyHostToDevice, D->stream));
   int it = 0;
-  int st = pcg_device(*D, bin, xio, tolerance, relative != 0, maxiter, use_initial_guess != 0, &it,
+  int st = pcg_device(*D, bin, xio, tolerance, relative, maxiter, use_initial_guess != 0, &it,
                       residuals, alphas, betas);
   io.out(x, l0.n, D->io_b);
   if (on_device) CUDA_OK(cudaStreamSynchronize(D->stream));

@@ -345,6 +345,23 @@ prolong_kernel(int n, const int* __restrict__ agg, const double* __restrict__ e,
   if (I >= 0) x[i] += (alpha ? *alpha : 1.0) * e[I];
 }
 
+// K5  general CSR transfer operators of SA_AMG (smoothed prolongator P, restriction R = P'):
+//     y = M x   or   y += alpha (M x)   (HAZmath dcsr_mxv / dcsr_aAxpy with P, R)
+template <int LANES, bool ADD>
+__global__ void __launch_bounds__(kBlock)
+csr_apply_kernel(int n, const int* __restrict__ ia, const int* __restrict__ ja,
+                 const double* __restrict__ a, const double* __restrict__ x,
+                 const double* __restrict__ alpha, double* __restrict__ y, double* __restrict__ zero) {
+  const int lane = threadIdx.x % LANES;
+  const int row = (blockIdx.x * kBlock + threadIdx.x) / LANES;
+  if (row >= n) return;
+  double s = row_dot<LANES>(ja, a, x, ia[row], ia[row + 1], lane);
+  if (lane == 0) {
+    if (ADD) y[row] += (alpha ? *alpha : 1.0) * s;
+    else { y[row] = s; if (zero) zero[row] = 0.0; }
+  }
+}
+
 // K8  coarsest solve x = Ainv b with the precomputed dense inverse, one warp per row
 __global__ void __launch_bounds__(kBlock)
 dense_gemv_kernel(int n, const double* __restrict__ M, const double* __restrict__ b,
@@ -402,9 +419,14 @@ dot2_kernel(int n, const double* __restrict__ u, const double* __restrict__ v,
 __global__ void __launch_bounds__(kBlock)
 pcg_rz_kernel(int n, const double* __restrict__ r, const double* __restrict__ z, double* partial,
               unsigned int* ticket, double* sc, int first) {
-  double acc[1] = {0.0};
-  for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) acc[0] += r[i] * z[i];
-  if (block_reduce_finish<1>(acc, partial, ticket, sc + 3) && threadIdx.x == 0) {
+  double acc[2] = {0.0, 0.0};   // r.z and r.r (the latter for HAZmath's ||r||/||r0|| stopping rule)
+  for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+    const double ri = r[i];
+    acc[0] += ri * z[i];
+    acc[1] += ri * ri;
+  }
+  if (block_reduce_finish<2>(acc, partial, ticket, sc + 5) && threadIdx.x == 0) {
+    sc[3] = sc[5];
     if (!first) sc[4] = sc[3] / sc[0];
     sc[0] = sc[3];
   }

@@ -119,7 +119,8 @@ int mamg_level_info(mamg_handle h, int32_t level, int64_t info[12]) {
   }
   info[8] = row_entries;
   info[9] = inv_entries;
-  info[10] = info[11] = 0;
+  info[10] = L->P.nnz();
+  info[11] = 0;
   info[0] = L->A.n;
   info[1] = L->A.nnz();
   info[2] = L->nc;
@@ -163,6 +164,16 @@ int mamg_schwarz_export(mamg_handle h, int32_t level, int32_t* patch_ptr, int32_
   if (patch_dofs && !s.dofs.empty()) std::memcpy(patch_dofs, s.dofs.data(), sizeof(int) * s.dofs.size());
   if (patch_seed && !s.seed.empty()) std::memcpy(patch_seed, s.seed.data(), sizeof(int) * s.seed.size());
   if (patch_color && !s.color.empty()) std::memcpy(patch_color, s.color.data(), sizeof(int) * s.color.size());
+  return 0;
+}
+
+int mamg_prolongator_export(mamg_handle h, int32_t level, int32_t* indptr, int32_t* indices, double* data) {
+  const Level* L = get_level(h, level);
+  if (!L) return -1;
+  if (L->P.n == 0) { set_error("level has no stored prolongator (UA_AMG uses the aggregate map)"); return -1; }
+  if (indptr) std::memcpy(indptr, L->P.ia.data(), sizeof(int) * (L->P.n + 1));
+  if (indices) std::memcpy(indices, L->P.ja.data(), sizeof(int) * L->P.ja.size());
+  if (data) std::memcpy(data, L->P.a.data(), sizeof(double) * L->P.a.size());
   return 0;
 }
 

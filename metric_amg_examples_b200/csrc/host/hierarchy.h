@@ -44,7 +44,7 @@ struct Level {
   int ncolors = 0;
   std::vector<uint8_t> gs_skip;  // 1: row is smoothed by Schwarz, not by GS (level < Schwarz_levels)
   SchwarzPatches sw;           // empty unless level < Schwarz_levels
-  Csr P;                       // only for SA_AMG (smoothed prolongator), else empty
+  Csr P, R;                    // only for SA_AMG: smoothed prolongator (n x nc) and R = P' (nc x n)
 };
 
 struct Hierarchy {
@@ -58,6 +58,9 @@ struct Hierarchy {
 void aggregate_hem(const Csr& A, std::vector<int>& agg, int& nc);
 void aggregate_vmb(const Csr& A, double strong, int max_agg, std::vector<int>& agg, int& nc);
 void galerkin_ua(const Csr& A, const std::vector<int>& agg, int nc, Csr& Ac);
+void csr_transpose(const Csr& A, Csr& At);
+void csr_multiply(const Csr& A, const Csr& B, Csr& C);   // C = A B, columns sorted
+void smoothed_prolongator(const Csr& A, const std::vector<int>& agg, int nc, double omega, Csr& P);
 void multicolor_greedy(const Csr& A, std::vector<int>& color, int& ncolors);
 void schwarz_patches(const Csr& A, const int* seeds, int nseeds, int maxlvl, int mmsize,
                      SchwarzPatches& out);

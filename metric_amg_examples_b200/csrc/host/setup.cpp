@@ -187,6 +187,107 @@ void galerkin_ua(const Csr& A, const std::vector<int>& agg, int nc, Csr& Ac) {
   }
 }
 
+void csr_transpose(const Csr& A, Csr& At) {
+  At.n = A.m;
+  At.m = A.n;
+  At.ia.assign(At.n + 1, 0);
+  for (int p = 0; p < A.nnz(); ++p) ++At.ia[A.ja[p] + 1];
+  for (int i = 0; i < At.n; ++i) At.ia[i + 1] += At.ia[i];
+  At.ja.resize(A.nnz());
+  At.a.resize(A.nnz());
+  std::vector<int> fill(At.ia.begin(), At.ia.end() - 1);
+  for (int i = 0; i < A.n; ++i)
+    for (int p = A.ia[i]; p < A.ia[i + 1]; ++p) {
+      const int q = fill[A.ja[p]]++;
+      At.ja[q] = i;
+      At.a[q] = A.a[p];
+    }
+}
+
+// C = A B (Gustavson, row by row; columns of every row sorted ascending)
+void csr_multiply(const Csr& A, const Csr& B, Csr& C) {
+  C.n = A.n;
+  C.m = B.m;
+  C.ia.assign(A.n + 1, 0);
+  std::vector<std::vector<std::pair<int, double>>> rows(A.n);
+#pragma omp parallel
+  {
+    std::vector<int> pos(B.m, -1);
+    std::vector<std::pair<int, double>> acc;
+#pragma omp for schedule(dynamic, 256)
+    for (int i = 0; i < A.n; ++i) {
+      acc.clear();
+      for (int p = A.ia[i]; p < A.ia[i + 1]; ++p) {
+        const int k = A.ja[p];
+        const double v = A.a[p];
+        for (int q = B.ia[k]; q < B.ia[k + 1]; ++q) {
+          const int j = B.ja[q];
+          if (pos[j] < 0) { pos[j] = (int)acc.size(); acc.push_back({j, v * B.a[q]}); }
+          else acc[pos[j]].second += v * B.a[q];
+        }
+      }
+      for (auto& e : acc) pos[e.first] = -1;
+      std::sort(acc.begin(), acc.end(),
+                [](const std::pair<int, double>& x, const std::pair<int, double>& y) { return x.first < y.first; });
+      rows[i] = acc;
+      C.ia[i + 1] = (int)acc.size();
+    }
+  }
+  for (int i = 0; i < A.n; ++i) C.ia[i + 1] += C.ia[i];
+  C.ja.resize(C.ia[A.n]);
+  C.a.resize(C.ia[A.n]);
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < A.n; ++i)
+    for (size_t k = 0; k < rows[i].size(); ++k) {
+      C.ja[C.ia[i] + k] = rows[i][k].first;
+      C.a[C.ia[i] + k] = rows[i][k].second;
+    }
+}
+
+// SA_AMG (src/input_metric.dat:68): P = (I - omega D^{-1} A) P_tent with the boolean tentative
+// prolongator of the aggregates (near-kernel = constants) and the FASP-lineage default
+// omega = tentative_smooth = 0.67; strong_coupled = 0.0 in that file means no filtering of A.
+void smoothed_prolongator(const Csr& A, const std::vector<int>& agg, int nc, double omega, Csr& P) {
+  const int n = A.n;
+  P.n = n;
+  P.m = nc;
+  P.ia.assign(n + 1, 0);
+  std::vector<std::vector<std::pair<int, double>>> rows(n);
+#pragma omp parallel
+  {
+    std::vector<int> pos(nc, -1);
+    std::vector<std::pair<int, double>> acc;
+#pragma omp for schedule(dynamic, 1024)
+    for (int i = 0; i < n; ++i) {
+      acc.clear();
+      double d = 1.0;
+      for (int p = A.ia[i]; p < A.ia[i + 1]; ++p)
+        if (A.ja[p] == i) d = A.a[p];
+      auto add = [&](int J, double v) {
+        if (J < 0) return;
+        if (pos[J] < 0) { pos[J] = (int)acc.size(); acc.push_back({J, v}); }
+        else acc[pos[J]].second += v;
+      };
+      add(agg[i], 1.0);
+      if (agg[i] >= 0)   // rows outside every aggregate (Dirichlet) keep an empty P row
+        for (int p = A.ia[i]; p < A.ia[i + 1]; ++p) add(agg[A.ja[p]], -omega * A.a[p] / d);
+      for (auto& e : acc) pos[e.first] = -1;
+      std::sort(acc.begin(), acc.end(),
+                [](const std::pair<int, double>& x, const std::pair<int, double>& y) { return x.first < y.first; });
+      rows[i] = acc;
+      P.ia[i + 1] = (int)acc.size();
+    }
+  }
+  for (int i = 0; i < n; ++i) P.ia[i + 1] += P.ia[i];
+  P.ja.resize(P.ia[n]);
+  P.a.resize(P.ia[n]);
+  for (int i = 0; i < n; ++i)
+    for (size_t k = 0; k < rows[i].size(); ++k) {
+      P.ja[P.ia[i] + k] = rows[i][k].first;
+      P.a[P.ia[i] + k] = rows[i][k].second;
+    }
+}
+
 // Greedy multicolouring in natural row order over the nonzero off-diagonal couplings:
 // the fixed ordering the Gauss-Seidel sweeps use on the device AND in the oracle
 // (north_star: "Gauss-Seidel via a fixed multicolour ordering applied identically in
@@ -339,7 +440,7 @@ bool build_hierarchy(const mamg_params& prm, Csr&& A0, const int* idofs, int n_i
   H.lv.clear();
   H.lv.emplace_back();
   H.lv[0].A = std::move(A0);
-  if (prm.AMG_type != MAMG_UA_AMG) { err = "AMG_type: only UA_AMG is implemented (SA_AMG pending)"; return false; }
+  if (prm.AMG_type != MAMG_UA_AMG && prm.AMG_type != MAMG_SA_AMG) { err = "AMG_type: only UA_AMG and SA_AMG are implemented"; return false; }
   if (prm.cycle_type != MAMG_V_CYCLE && prm.cycle_type != MAMG_W_CYCLE) {
     err = "cycle_type: only V_CYCLE and W_CYCLE are implemented";
     return false;
@@ -382,7 +483,16 @@ bool build_hierarchy(const mamg_params& prm, Csr&& A0, const int* idofs, int n_i
     }
     multicolor_greedy(L.A, L.color, L.ncolors);
     H.lv.emplace_back();
-    galerkin_ua(H.lv[l].A, H.lv[l].agg, H.lv[l].nc, H.lv[l + 1].A);
+    if (prm.AMG_type == MAMG_SA_AMG) {
+      Level& F = H.lv[l];
+      smoothed_prolongator(F.A, F.agg, F.nc, 0.67, F.P);
+      csr_transpose(F.P, F.R);
+      Csr AP;
+      csr_multiply(F.A, F.P, AP);
+      csr_multiply(F.R, AP, H.lv[l + 1].A);
+    } else {
+      galerkin_ua(H.lv[l].A, H.lv[l].agg, H.lv[l].nc, H.lv[l + 1].A);
+    }
     if (metric && l + 1 < prm.Schwarz_levels) {  // carry the interface seeds to the next level
       std::vector<int> nxt;
       std::vector<char> seen(H.lv[l].nc, 0);

@@ -75,7 +75,7 @@ class Hierarchy:
         info = (C.c_int64 * 12)()
         check(lib.mamg_level_info(self._h, level, info))
         keys = ["rows", "nnz", "n_aggregates", "n_colors", "n_patches", "n_patch_entries",
-                "n_patch_colors", "max_patch_size", "patch_row_entries", "patch_inv_entries"]
+                "n_patch_colors", "max_patch_size", "patch_row_entries", "patch_inv_entries", "nnz_P"]
         return dict(zip(keys, [int(x) for x in info]))
 
     def export_level(self, level):
@@ -91,6 +91,12 @@ class Hierarchy:
         check(lib.mamg_level_export(self._h, level, ptr(out["indptr"]), ptr(out["indices"]),
                                     ptr(out["data"]), ptr(out["agg"]), ptr(out["color"]),
                                     ptr(out["gs_skip"])))
+        if info["nnz_P"]:
+            out["P_indptr"] = np.empty(n + 1, np.int32)
+            out["P_indices"] = np.empty(info["nnz_P"], np.int32)
+            out["P_data"] = np.empty(info["nnz_P"], np.float64)
+            check(lib.mamg_prolongator_export(self._h, level, ptr(out["P_indptr"]), ptr(out["P_indices"]),
+                                              ptr(out["P_data"])))
         npatch = info["n_patches"]
         out["patch_ptr"] = np.zeros(npatch + 1, np.int32)
         out["patch_dofs"] = np.empty(info["n_patch_entries"], np.int32)

@@ -48,6 +48,9 @@ typedef struct {
    * (Schwarz_blksolver 32): packed lower Cholesky factors, pfoff[p] = start of patch p */
   double* pfac;
   long* pfoff;
+  /* SA_AMG: smoothed prolongator P (n x nc CSR); NULL for unsmoothed aggregation */
+  int *pia, *pja;
+  double* pa;
 } orc_level;
 
 typedef struct {
@@ -63,6 +66,7 @@ typedef struct {
   long visits;      /* level visits of the last apply (for reporting) */
 } orc_hier;
 
+static double vdot(int n, const double* u, const double* v);
 static void* xmalloc(size_t n) { void* p = malloc(n ? n : 1); if (!p) abort(); return p; }
 static void* xdup(const void* src, size_t n) { void* p = xmalloc(n); if (n) memcpy(p, src, n); return p; }
 
@@ -171,6 +175,14 @@ int orc_add_level(orc_hier* h, int n, const int* ia, const int* ja, const double
   return h->nlevels - 1;
 }
 
+/* smoothed prolongator of level lev (SA_AMG, src/input_metric.dat:68); restriction is its transpose */
+void orc_set_prolongator(orc_hier* h, int lev, const int* pia, const int* pja, const double* pa) {
+  orc_level* L = &h->lv[lev];
+  L->pia = (int*)xdup(pia, sizeof(int) * (L->n + 1));
+  L->pja = (int*)xdup(pja, sizeof(int) * pia[L->n]);
+  L->pa = (double*)xdup(pa, sizeof(double) * pia[L->n]);
+}
+
 void orc_set_coarse(orc_hier* h, const double* inv) {
   int n = h->lv[h->nlevels - 1].n;
   h->coarse_inv = (double*)xdup(inv, sizeof(double) * (size_t)n * n);
@@ -193,7 +205,7 @@ void orc_destroy(orc_hier* h) {
     free(L->ia); free(L->ja); free(L->a); free(L->agg); free(L->color); free(L->skip); free(L->invd);
     free(L->x); free(L->b); free(L->w); free(L->crow_ptr); free(L->crow);
     free(L->pptr); free(L->pdofs); free(L->pcolor); free(L->cpat_ptr); free(L->cpat);
-    free(L->pfac); free(L->pfoff);
+    free(L->pfac); free(L->pfoff); free(L->pia); free(L->pja); free(L->pa);
   }
   free(h->lv); free(h->coarse_inv); free(h->rhs); free(h);
 }
@@ -323,7 +335,12 @@ static void cycle_level(orc_hier* h, int lev) {
     h->visits++;
     smooth(h, lev, L->b, L->x, 0);
     memset(C->b, 0, sizeof(double) * C->n);
-    if (h->threads > 1) {
+    if (L->pia) {   /* SA_AMG: b_c = P' (b - A x) */
+      for (int i = 0; i < L->n; ++i) {
+        const double w = L->b[i] - row_dot(L, i, L->x);
+        for (int p = L->pia[i]; p < L->pia[i + 1]; ++p) C->b[L->pja[p]] += L->pa[p] * w;
+      }
+    } else if (h->threads > 1) {
 #pragma omp parallel for schedule(static) num_threads(h->threads)
       for (int i = 0; i < L->n; ++i) L->w[i] = L->b[i] - row_dot(L, i, L->x);
       for (int i = 0; i < L->n; ++i) { int I = L->agg[i]; if (I >= 0) C->b[I] += L->w[i]; }
@@ -343,9 +360,17 @@ static void cycle_level(orc_hier* h, int lev) {
       alpha = num / den;
       alpha = (alpha < 1.0) ? alpha : 1.0;  /* MIN(alpha, 1.0); NaN -> 1 */
     }
-    for (int i = 0; i < L->n; ++i) {
-      int I = L->agg[i];
-      if (I >= 0) L->x[i] += alpha * C->x[I];
+    if (L->pia) {   /* SA_AMG: x += alpha P e */
+      for (int i = 0; i < L->n; ++i) {
+        double s = 0.0;
+        for (int p = L->pia[i]; p < L->pia[i + 1]; ++p) s += L->pa[p] * C->x[L->pja[p]];
+        L->x[i] += alpha * s;
+      }
+    } else {
+      for (int i = 0; i < L->n; ++i) {
+        int I = L->agg[i];
+        if (I >= 0) L->x[i] += alpha * C->x[I];
+      }
     }
     smooth(h, lev, L->b, L->x, 1);
   }
@@ -382,7 +407,7 @@ int orc_pcg(orc_hier* h, const double* b, double* x, double tol, int relative, i
   memcpy(d, z, sizeof(double) * n);
   double rz = 0.0;
   for (int i = 0; i < n; ++i) rz += r[i] * z[i];
-  double res = sqrt(rz);
+  double res = relative == 2 ? sqrt(vdot(n, r, r)) : sqrt(rz);
   residuals[0] = res;
   const double target = relative ? tol * res : tol;
   int it = 0;
@@ -398,7 +423,7 @@ int orc_pcg(orc_hier* h, const double* b, double* x, double tol, int relative, i
     double beta = rz2 / rz;
     for (int i = 0; i < n; ++i) d[i] = z[i] + beta * d[i];
     rz = rz2;
-    res = sqrt(rz);
+    res = relative == 2 ? sqrt(vdot(n, r, r)) : sqrt(rz);
     if (alphas) alphas[it] = alpha;
     if (betas) betas[it] = beta;
     ++it;

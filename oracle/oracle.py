@@ -25,6 +25,7 @@ def _load():
     lib.orc_add_level.restype = i32
     lib.orc_add_level.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp, i32, vp, i32, vp, vp, vp, i32]
     lib.orc_set_coarse.argtypes = [vp, vp]
+    lib.orc_set_prolongator.argtypes = [vp, i32, vp, vp, vp]
     lib.orc_set_ordering.argtypes = [vp, i32]
     lib.orc_set_cycle.argtypes = [vp, i32]
     lib.orc_set_threads.restype = i32
@@ -68,9 +69,14 @@ class Oracle:
                     np.ascontiguousarray(L["patch_color"], np.int32)]
             ia, ja, a, agg, color, skip, pptr, pdofs, pcolor = arrs
             npatch = len(pptr) - 1
-            self.lib.orc_add_level(self.h, int(L["n"]), _p(ia), _p(ja), _p(a), _p(agg), int(L["n_aggregates"]),
-                                   _p(color), int(L["n_colors"]), _p(skip), npatch, _p(pptr), _p(pdofs),
-                                   _p(pcolor), int(L["n_patch_colors"]))
+            lev = self.lib.orc_add_level(self.h, int(L["n"]), _p(ia), _p(ja), _p(a), _p(agg), int(L["n_aggregates"]),
+                                         _p(color), int(L["n_colors"]), _p(skip), npatch, _p(pptr), _p(pdofs),
+                                         _p(pcolor), int(L["n_patch_colors"]))
+            if "P_indptr" in L:
+                pi = np.ascontiguousarray(L["P_indptr"], np.int32)
+                pj = np.ascontiguousarray(L["P_indices"], np.int32)
+                pv = np.ascontiguousarray(L["P_data"], np.float64)
+                self.lib.orc_set_prolongator(self.h, lev, _p(pi), _p(pj), _p(pv))
         inv = np.ascontiguousarray(hier["coarse_inv"], np.float64)
         self.lib.orc_set_coarse(self.h, _p(inv))
         self.n = int(hier["levels"][0]["n"])
