@@ -84,6 +84,14 @@ int mamg_params_default(mamg_params* p);
  *      n_idofs = 0 means "no interface dofs" (plain AMG).  Host only: needs no GPU. */
 int mamg_setup(const mamg_params* p, int32_t n, const int32_t* indptr, const int32_t* indices,
                const double* data, int32_t n_idofs, const int32_t* idofs, mamg_handle* out);
+/* Same, with a row partition for multi-GPU execution: part[i] in [0, nparts) is the owner of row i
+ * (NULL = one part).  Aggregates never cross parts, so restriction and prolongation stay local to
+ * an owner on every level; the hierarchy (and hence the iteration count) depends on the partition,
+ * not on how many GPUs later execute it. */
+int mamg_setup_partitioned(const mamg_params* p, int32_t n, const int32_t* indptr, const int32_t* indices,
+                           const double* data, int32_t n_idofs, const int32_t* idofs, const int32_t* part,
+                           int32_t nparts, mamg_handle* out);
+int mamg_part_export(mamg_handle h, int32_t level, int32_t* part);
 int mamg_destroy(mamg_handle h);
 
 /* ---- hierarchy introspection / export (natural ordering) so that the CPU oracle
@@ -110,6 +118,18 @@ int mamg_setup_seconds(mamg_handle h, double* seconds);
  *      library creates its own non-blocking stream). Fails if no CUDA device. */
 int mamg_to_device(mamg_handle h, int32_t device, void* stream);
 int mamg_set_stream(mamg_handle h, void* stream);
+
+/* ---- multi-GPU, one process per GPU (torch.distributed / torchrun launches the ranks).
+ *      Every rank calls mamg_setup_partitioned with the same matrix and partition and
+ *      mamg_to_device on its GPU; rank 0 creates an NCCL id (mamg_nccl_unique_id, 128 bytes) that
+ *      the host side broadcasts; then mamg_dist_init.  Afterwards apply / pcg run row-distributed
+ *      on the levels with at least MAMG_DIST_MIN_ROWS rows: rank r executes the rows of parts
+ *      [r*P/world, (r+1)*P/world) and the updated ranges are all-gathered over NCCL; smaller levels
+ *      are executed redundantly by every rank.  Vectors handed over the ABI are complete on every
+ *      rank.  world == 1 is valid (a partitioned hierarchy on one GPU: same numbers, no NCCL). */
+int mamg_nccl_unique_id(void* out128);
+int mamg_dist_init(mamg_handle h, int32_t rank, int32_t world, const void* unique_id128);
+int mamg_collective_count(mamg_handle h, int64_t* count, int32_t reset);
 int mamg_device_bytes(mamg_handle h, int64_t* bytes);
 /* block until everything queued on the handle's stream has finished */
 int mamg_sync(mamg_handle h);

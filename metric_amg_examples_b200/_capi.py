@@ -29,6 +29,19 @@ def _load():
         raise ImportError(
             f"{LIB_PATH} is missing: build it with `python metric_amg_examples_b200/build.py` "
             "(nvcc, sm_100a). This package has no CPU or pure-Python fallback.")
+    # libmamg.so needs libnccl.so.2.  PyTorch bundles a newer NCCL under the same soname and fails to
+    # import if an older one is already mapped, so map PyTorch's copy first when it exists (the
+    # system library is the fallback; the few entry points used here are stable across both).
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia")
+        for base in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(base, "nccl", "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                C.CDLL(cand, mode=C.RTLD_GLOBAL)
+                break
+    except OSError:
+        pass
     lib = C.CDLL(LIB_PATH)
     i32, i64, dbl, vp = C.c_int32, C.c_int64, C.c_double, C.c_void_p
     pi32, pi64, pdbl, pu8 = C.POINTER(i32), C.POINTER(i64), C.POINTER(dbl), C.POINTER(C.c_uint8)
@@ -37,6 +50,8 @@ def _load():
         "mamg_version": (C.c_char_p, []),
         "mamg_params_default": (i32, [C.POINTER(MamgParams)]),
         "mamg_setup": (i32, [C.POINTER(MamgParams), i32, vp, vp, vp, i32, vp, C.POINTER(vp)]),
+        "mamg_setup_partitioned": (i32, [C.POINTER(MamgParams), i32, vp, vp, vp, i32, vp, vp, i32, C.POINTER(vp)]),
+        "mamg_part_export": (i32, [vp, i32, vp]),
         "mamg_destroy": (i32, [vp]),
         "mamg_num_levels": (i32, [vp, pi32]),
         "mamg_level_info": (i32, [vp, i32, pi64]),
@@ -47,6 +62,9 @@ def _load():
         "mamg_setup_seconds": (i32, [vp, pdbl]),
         "mamg_to_device": (i32, [vp, i32, vp]),
         "mamg_set_stream": (i32, [vp, vp]),
+        "mamg_nccl_unique_id": (i32, [vp]),
+        "mamg_dist_init": (i32, [vp, i32, i32, vp]),
+        "mamg_collective_count": (i32, [vp, pi64, i32]),
         "mamg_device_bytes": (i32, [vp, pi64]),
         "mamg_sync": (i32, [vp]),
         "mamg_apply": (i32, [vp, vp, vp, i32]),

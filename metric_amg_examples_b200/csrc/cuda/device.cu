@@ -15,6 +15,8 @@
 #include <string>
 #include <vector>
 
+#include <nccl.h>
+
 #include "../host/handle.h"
 #include "kernels.cuh"
 #include "schwarz.cuh"
@@ -44,8 +46,13 @@ struct DLevel {
   double *x = nullptr, *b = nullptr, *t = nullptr;
   double *x_own = nullptr, *b_own = nullptr;
   int *perm = nullptr, *iperm = nullptr;  // device: new->old, old->new
-  std::vector<int> color_ptr;             // host: row range of every colour
-  std::vector<int> color_active;          // host: rows of the colour that the point smoother touches
+  // Row layout: nb blocks (1, or the parts of a partitioned hierarchy on levels big enough to be
+  // row-distributed), inside a block the colours, inside a colour the natural order.
+  int nb = 1;
+  std::vector<int> bc_ptr;                // host: row offset of (block b, colour c) at [b*ncolors + c]; size nb*ncolors+1
+  std::vector<int> color_active;          // host: rows of (b, c) that the point smoother touches (empty: all)
+  int row0(int b, int c) const { return bc_ptr[b * ncolors + c]; }
+  int row1(int b, int c) const { return bc_ptr[b * ncolors + c + 1]; }
   DSchwarz sw;
   DCsr P, R;   // SA_AMG only
 };
@@ -76,6 +83,12 @@ struct DeviceState {
   double *io_a = nullptr, *io_b = nullptr;  // staging for host-array calls
   std::vector<void*> allocs;
   mamg_params prm;
+  // multi-GPU (one process per GPU): every rank holds the hierarchy and complete vectors, executes
+  // the rows of its blocks on the distributed levels and all-gathers the updated ranges over NCCL
+  int rank = 0, world = 1;
+  ncclComm_t comm = nullptr;
+  int64_t collectives = 0;
+  double* xbuf = nullptr;     // staging for the Schwarz patch-dof exchange
   // one apply is a fixed launch sequence: it is captured once per (input, output) pair into a
   // CUDA graph and replayed, which removes the host launch cost of the ~1000 small kernels of the
   // coarse levels (MAMG_GRAPH=0 disables; not used while profiling or for very long W sequences)
@@ -130,6 +143,7 @@ void device_state_free(DeviceState* D) {
   for (void* p : D->allocs) cudaFree(p);
   for (ProfEvent& e : D->prof_events) { cudaEventDestroy(e.start); cudaEventDestroy(e.stop); }
   for (auto& g : D->graphs) cudaGraphExecDestroy(g.exec);
+  if (D->comm) ncclCommDestroy(D->comm);
   if (D->h_scal) cudaFreeHost(D->h_scal);
   if (D->own_stream && D->stream) cudaStreamDestroy(D->stream);
   delete D;
@@ -141,6 +155,11 @@ static int pick_lanes(double avg) {
   int l = 2;
   while (l < 32 && l * 4 <= avg + 2) l *= 2;  // about 2-4 entries per lane: 30/row -> 8, 15 -> 4, 7 -> 2
   return l;
+}
+
+static int dist_min_rows() {
+  const char* env = getenv("MAMG_DIST_MIN_ROWS");
+  return env ? atoi(env) : 100000;   // smaller levels are executed redundantly by every rank (no communication)
 }
 
 static int pick_unroll(int n) {
@@ -166,15 +185,19 @@ static void upload_hierarchy(const Hierarchy& H, DeviceState& D) {
     DLevel& dl = D.lv[l];
     if (hl.color.empty()) {
       std::iota(perm[l].begin(), perm[l].end(), 0);
-      dl.color_ptr = {0, n};
+      dl.bc_ptr = {0, n};
       dl.ncolors = 1;
+      dl.nb = 1;
     } else {
       dl.ncolors = hl.ncolors;
-      dl.color_ptr.assign(hl.ncolors + 1, 0);
-      for (int i = 0; i < n; ++i) ++dl.color_ptr[hl.color[i] + 1];
-      for (int c = 0; c < hl.ncolors; ++c) dl.color_ptr[c + 1] += dl.color_ptr[c];
-      std::vector<int> fill(dl.color_ptr.begin(), dl.color_ptr.end() - 1);
-      for (int i = 0; i < n; ++i) perm[l][fill[hl.color[i]]++] = i;
+      dl.nb = (H.nparts > 1 && !hl.part.empty() && n >= dist_min_rows()) ? H.nparts : 1;
+      const int nbc = dl.nb * dl.ncolors;
+      auto key = [&](int i) { return (dl.nb > 1 ? hl.part[i] : 0) * dl.ncolors + hl.color[i]; };
+      dl.bc_ptr.assign(nbc + 1, 0);
+      for (int i = 0; i < n; ++i) ++dl.bc_ptr[key(i) + 1];
+      for (int k = 0; k < nbc; ++k) dl.bc_ptr[k + 1] += dl.bc_ptr[k];
+      std::vector<int> fill(dl.bc_ptr.begin(), dl.bc_ptr.end() - 1);
+      for (int i = 0; i < n; ++i) perm[l][fill[key(i)]++] = i;
     }
     for (int i = 0; i < n; ++i) iperm[l][perm[l][i]] = i;
   }
@@ -223,9 +246,9 @@ static void upload_hierarchy(const Hierarchy& H, DeviceState& D) {
       std::vector<uint8_t> sk(n);
       for (int i = 0; i < n; ++i) sk[i] = hl.gs_skip[perm[l][i]];
       dl.skip = upload(D, sk);
-      dl.color_active.assign(dl.ncolors, 0);
-      for (int c = 0; c < dl.ncolors; ++c)
-        for (int i = dl.color_ptr[c]; i < dl.color_ptr[c + 1]; ++i) dl.color_active[c] += sk[i] == 0;
+      dl.color_active.assign(dl.nb * dl.ncolors, 0);
+      for (int k = 0; k < dl.nb * dl.ncolors; ++k)
+        for (int i = dl.bc_ptr[k]; i < dl.bc_ptr[k + 1]; ++i) dl.color_active[k] += sk[i] == 0;
     }
     if (l + 1 < L && hl.P.n > 0) {
       // SA_AMG: P (fine' x coarse') and R = P' (coarse' x fine') in the permuted numberings
@@ -264,13 +287,21 @@ static void upload_hierarchy(const Hierarchy& H, DeviceState& D) {
       dl.cptr = upload(D, cptr);
       dl.cidx = upload(D, cidx);
     }
-    if (hl.sw.npatch() > 0) schwarz_upload(hl, iperm[l], dl.ia, dl.ja, dl.a, ia, ja, dl.sw, [&](size_t bytes) {
+    if (hl.sw.npatch() > 0) schwarz_upload(hl, dl.nb, iperm[l], dl.ia, dl.ja, dl.a, ia, ja, dl.sw, [&](size_t bytes) {
       void* p = nullptr;
       CUDA_OK(cudaMalloc(&p, bytes ? bytes : 1));
       D.allocs.push_back(p);
       D.dev_bytes += (int64_t)bytes;
       return p;
     });
+  }
+  {
+    size_t mx = 0;
+    for (auto& dl : D.lv)
+      if (dl.sw.nb > 1)
+        for (int c = 0; c < dl.sw.ncolors; ++c)
+          mx = std::max(mx, (size_t)(dl.sw.qoff[dl.sw.cb_ptr[(c + 1) * dl.sw.nb]] - dl.sw.qoff[dl.sw.cb_ptr[c * dl.sw.nb]]));
+    if (mx) D.xbuf = dalloc<double>(D, mx);
   }
   D.coarse_inv = upload(D, H.coarse_inv);
   int sms = 148;
@@ -306,23 +337,68 @@ static void upload_hierarchy(const Hierarchy& H, DeviceState& D) {
     default: { constexpr int UN = 4; __VA_ARGS__; break; }  \
   }
 
+#define NCCL_OK(call)                                                                      \
+  do {                                                                                     \
+    ncclResult_t r_ = (call);                                                              \
+    if (r_ != ncclSuccess)                                                                 \
+      throw std::runtime_error(std::string("NCCL error: ") + ncclGetErrorString(r_) + " at " + \
+                               __FILE__ + ":" + std::to_string(__LINE__));                 \
+  } while (0)
+
+// ---- row distribution ----------------------------------------------------------------------------
+// A level with nb > 1 blocks is row-distributed: rank r executes blocks [b_lo, b_hi); every vector
+// is complete on every rank, so after a kernel has updated the owned rows the updated ranges are
+// all-gathered (one ncclBroadcast per block inside one group).  With world == 1 a partitioned
+// hierarchy simply runs all blocks on the one GPU: same arithmetic, same order, no communication.
+static bool is_dist(const DeviceState& D, const DLevel& l) { return l.nb > 1; }
+static int blk_lo(const DeviceState& D, const DLevel& l) { return l.nb > 1 ? D.rank * (l.nb / D.world) : 0; }
+static int blk_hi(const DeviceState& D, const DLevel& l) { return l.nb > 1 ? (D.rank + 1) * (l.nb / D.world) : 1; }
+static int own_lo(const DeviceState& D, const DLevel& l) { return l.bc_ptr[blk_lo(D, l) * l.ncolors]; }
+static int own_hi(const DeviceState& D, const DLevel& l) { return l.bc_ptr[blk_hi(D, l) * l.ncolors]; }
+static void k_fill(DeviceState& D, int n, double* x, double v);
+
+// all-gather of vector v on a distributed level: colour c of every block (c >= 0) or whole blocks (c < 0)
+static void exchange(DeviceState& D, const DLevel& l, double* v, int c) {
+  if (D.world == 1 || !is_dist(D, l)) return;
+  const int per = l.nb / D.world;
+  NCCL_OK(ncclGroupStart());
+  for (int b = 0; b < l.nb; ++b) {
+    const int r0 = c >= 0 ? l.row0(b, c) : l.bc_ptr[b * l.ncolors];
+    const int r1 = c >= 0 ? l.row1(b, c) : l.bc_ptr[(b + 1) * l.ncolors];
+    if (r1 > r0) NCCL_OK(ncclBroadcast(v + r0, v + r0, (size_t)(r1 - r0), ncclDouble, b / per, D.comm, D.stream));
+  }
+  NCCL_OK(ncclGroupEnd());
+  ++D.collectives;
+}
+
 static void k_spmv(DeviceState& D, const DLevel& l, const double* x, const double* b, double* y, bool resid) {
   if (l.n == 0) return;
-  const int grid = cdiv((long long)cdiv(l.n, l.unroll) * l.lanes, kBlock);
-  KScope ks(D, K_SPMV);
-  LANES_SWITCH(l.lanes, UNROLL_SWITCH(l.unroll,
-    if (resid) spmv_kernel<LN, UN, true><<<grid, kBlock, 0, D.stream>>>(l.n, l.ia, l.ja, l.a, x, b, y);
-    else spmv_kernel<LN, UN, false><<<grid, kBlock, 0, D.stream>>>(l.n, l.ia, l.ja, l.a, x, b, y)));
+  const int r0 = own_lo(D, l), r1 = own_hi(D, l);
+  if (r1 > r0) {
+    const int grid = cdiv((long long)cdiv(r1 - r0, l.unroll) * l.lanes, kBlock);
+    KScope ks(D, K_SPMV);
+    LANES_SWITCH(l.lanes, UNROLL_SWITCH(l.unroll,
+      if (resid) spmv_kernel<LN, UN, true><<<grid, kBlock, 0, D.stream>>>(r0, r1, l.ia, l.ja, l.a, x, b, y);
+      else spmv_kernel<LN, UN, false><<<grid, kBlock, 0, D.stream>>>(r0, r1, l.ia, l.ja, l.a, x, b, y)));
+  }
+  exchange(D, l, y, -1);
 }
 
 static void k_gs_color(DeviceState& D, const DLevel& l, int c, const double* b, double* x, double omega) {
-  const int r0 = l.color_ptr[c], r1 = l.color_ptr[c + 1];
-  if (r1 <= r0) return;
-  if (!l.color_active.empty() && l.color_active[c] == 0) return;   // every row of the colour belongs to Schwarz
-  const int grid = cdiv((long long)cdiv(r1 - r0, l.unroll) * l.lanes, kBlock);
-  KScope ks(D, K_GS);
-  LANES_SWITCH(l.lanes, UNROLL_SWITCH(l.unroll,
-    gs_color_kernel<LN, UN><<<grid, kBlock, 0, D.stream>>>(r0, r1, l.ia, l.ja, l.a, l.invd, l.skip, b, x, omega)));
+  bool any = false;
+  for (int blk = 0; blk < l.nb; ++blk)
+    any |= l.row1(blk, c) > l.row0(blk, c) && (l.color_active.empty() || l.color_active[blk * l.ncolors + c] > 0);
+  if (!any) return;   // every row of the colour belongs to Schwarz (same decision on every rank)
+  for (int blk = blk_lo(D, l); blk < blk_hi(D, l); ++blk) {
+    const int r0 = l.row0(blk, c), r1 = l.row1(blk, c);
+    if (r1 <= r0) continue;
+    if (!l.color_active.empty() && l.color_active[blk * l.ncolors + c] == 0) continue;
+    const int grid = cdiv((long long)cdiv(r1 - r0, l.unroll) * l.lanes, kBlock);
+    KScope ks(D, K_GS);
+    LANES_SWITCH(l.lanes, UNROLL_SWITCH(l.unroll,
+      gs_color_kernel<LN, UN><<<grid, kBlock, 0, D.stream>>>(r0, r1, l.ia, l.ja, l.a, l.invd, l.skip, b, x, omega)));
+  }
+  exchange(D, l, x, c);
 }
 
 static void gs_forward(DeviceState& D, const DLevel& l, const double* b, double* x, double w, int first = 0) {
@@ -333,12 +409,14 @@ static void gs_backward(DeviceState& D, const DLevel& l, const double* b, double
 }
 
 static void k_jacobi(DeviceState& D, DLevel& l, const double* b, double* x, double w) {
-  const int grid = cdiv((long long)l.n * l.lanes, kBlock);
-  {
+  const int r0 = own_lo(D, l), r1 = own_hi(D, l);
+  if (r1 > r0) {
+    const int grid = cdiv((long long)(r1 - r0) * l.lanes, kBlock);
     KScope ks(D, K_GS);
     LANES_SWITCH(l.lanes,
-      jacobi_kernel<LN><<<grid, kBlock, 0, D.stream>>>(l.n, l.ia, l.ja, l.a, l.invd, l.skip, b, x, l.t, w));
+      jacobi_kernel<LN><<<grid, kBlock, 0, D.stream>>>(r0, r1, l.ia, l.ja, l.a, l.invd, l.skip, b, x, l.t, w));
   }
+  exchange(D, l, l.t, -1);
   KScope ks(D, K_VEC);
   copy_kernel<<<cdiv(l.n, kBlock), kBlock, 0, D.stream>>>(l.n, l.t, x);
 }
@@ -382,11 +460,36 @@ static void smooth(DeviceState& D, int lev, const double* b, double* x, bool pos
     else if (type == MAMG_SCHWARZ_FORWARD) { fwd = !post; bwd = post; }
     else { fwd = post; bwd = !post; }
     auto sweep = [&](bool backward) {
+      const int snb = l.sw.nb, per = snb > 1 ? snb / D.world : 1;
       for (int cc = 0; cc < l.sw.ncolors; ++cc) {
         const int c = backward ? l.sw.ncolors - 1 - cc : cc;
-        if (l.sw.color_ptr[c + 1] == l.sw.color_ptr[c]) continue;
-        KScope ks(D, K_SCHWARZ);
-        schwarz_color_launch(l.sw, c, l.a, b, x, D.stream);
+        const int lo = snb > 1 ? D.rank * per : 0, hi = snb > 1 ? (D.rank + 1) * per : 1;
+        for (int blk = lo; blk < hi; ++blk) {
+          const int p0 = l.sw.cb_ptr[c * snb + blk], p1 = l.sw.cb_ptr[c * snb + blk + 1];
+          if (p1 == p0) continue;
+          KScope ks(D, K_SCHWARZ);
+          schwarz_range_launch(l.sw, p0, p1, l.a, b, x, D.stream);
+        }
+        if (D.world > 1 && snb > 1) {
+          // every rank receives the patch dofs the other ranks have just updated
+          const int pa = l.sw.cb_ptr[c * snb], pb = l.sw.cb_ptr[(c + 1) * snb];
+          const int qa = l.sw.qoff[pa], qb = l.sw.qoff[pb];
+          if (qb == qa) continue;
+          const int mq0 = l.sw.qoff[l.sw.cb_ptr[c * snb + lo]], mq1 = l.sw.qoff[l.sw.cb_ptr[c * snb + hi]];
+          if (mq1 > mq0) {
+            KScope ks(D, K_VEC);
+            pack_kernel<<<cdiv(mq1 - mq0, kBlock), kBlock, 0, D.stream>>>(mq1 - mq0, l.sw.pidx + mq0, x, D.xbuf + (mq0 - qa));
+          }
+          NCCL_OK(ncclGroupStart());
+          for (int blk = 0; blk < snb; ++blk) {
+            const int q0 = l.sw.qoff[l.sw.cb_ptr[c * snb + blk]], q1 = l.sw.qoff[l.sw.cb_ptr[c * snb + blk + 1]];
+            if (q1 > q0) NCCL_OK(ncclBroadcast(D.xbuf + (q0 - qa), D.xbuf + (q0 - qa), (size_t)(q1 - q0), ncclDouble, blk / per, D.comm, D.stream));
+          }
+          NCCL_OK(ncclGroupEnd());
+          ++D.collectives;
+          KScope ks(D, K_VEC);
+          unpack_kernel<<<cdiv(qb - qa, kBlock), kBlock, 0, D.stream>>>(qb - qa, l.sw.pidx + qa, D.xbuf, x);
+        }
       }
     };
     if (fwd) sweep(false);
@@ -395,28 +498,35 @@ static void smooth(DeviceState& D, int lev, const double* b, double* x, bool pos
   if (!post) { schwarz(); point(); } else { point(); schwarz(); }
 }
 
-static void k_csr_apply(DeviceState& D, const DCsr& M, const double* x, const double* alpha, double* y, double* zero,
-                        bool add, int cls) {
-  if (M.n == 0) return;
-  const int grid = cdiv((long long)M.n * M.lanes, kBlock);
+static void k_csr_apply(DeviceState& D, const DCsr& M, int r0, int r1, const double* x, const double* alpha, double* y,
+                        double* zero, bool add, int cls) {
+  if (r1 <= r0) return;
+  const int grid = cdiv((long long)(r1 - r0) * M.lanes, kBlock);
   KScope ks(D, cls);
   LANES_SWITCH(M.lanes,
-    if (add) csr_apply_kernel<LN, true><<<grid, kBlock, 0, D.stream>>>(M.n, M.ia, M.ja, M.a, x, alpha, y, zero);
-    else csr_apply_kernel<LN, false><<<grid, kBlock, 0, D.stream>>>(M.n, M.ia, M.ja, M.a, x, alpha, y, zero));
+    if (add) csr_apply_kernel<LN, true><<<grid, kBlock, 0, D.stream>>>(r0, r1, M.ia, M.ja, M.a, x, alpha, y, zero);
+    else csr_apply_kernel<LN, false><<<grid, kBlock, 0, D.stream>>>(r0, r1, M.ia, M.ja, M.a, x, alpha, y, zero));
 }
 
 static void k_resid_restrict(DeviceState& D, int lev) {
   DLevel& f = D.lv[lev];
   DLevel& c = D.lv[lev + 1];
+  // coarse rows this rank computes: its own blocks when the coarse level is distributed too, else all
+  // of them (every rank then forms the small coarse right-hand side redundantly, without communication)
+  const int c0 = own_lo(D, c), c1 = own_hi(D, c);
   if (f.R.n > 0) {   // SA_AMG: w = b - A x, b_c = R w, x_c = 0
     k_spmv(D, f, f.x, f.b, f.t, true);
-    k_csr_apply(D, f.R, f.t, nullptr, c.b, c.x, false, K_RESTRICT);
-    return;
+    k_csr_apply(D, f.R, c0, c1, f.t, nullptr, c.b, c.x, false, K_RESTRICT);
+  } else if (c1 > c0) {
+    const int grid = cdiv((long long)(c1 - c0) * f.lanes, kBlock);
+    KScope ks(D, K_RESTRICT);
+    LANES_SWITCH(f.lanes,
+      resid_restrict_kernel<LN><<<grid, kBlock, 0, D.stream>>>(c0, c1, f.cptr, f.cidx, f.ia, f.ja, f.a, f.x, f.b, c.b, c.x));
   }
-  const int grid = cdiv((long long)f.nc * f.lanes, kBlock);
-  KScope ks(D, K_RESTRICT);
-  LANES_SWITCH(f.lanes,
-    resid_restrict_kernel<LN><<<grid, kBlock, 0, D.stream>>>(f.nc, f.cptr, f.cidx, f.ia, f.ja, f.a, f.x, f.b, c.b, c.x));
+  if (is_dist(D, c) && D.world > 1) {
+    exchange(D, c, c.b, -1);
+    k_fill(D, c.n, c.x, 0.0);
+  }
 }
 
 static int red_grid(const DeviceState& D, long long threads) {
@@ -425,6 +535,12 @@ static int red_grid(const DeviceState& D, long long threads) {
 
 static void k_scale_dots(DeviceState& D, int lev) {
   DLevel& c = D.lv[lev];
+  if (is_dist(D, c) && D.world > 1) {   // t = A_c e on the owned rows, all-gather, then the two dots on complete vectors
+    k_spmv(D, c, c.x, nullptr, c.t, false);
+    KScope ks(D, K_SCALE);
+    scale_dots_vec_kernel<<<red_grid(D, c.n), kBlock, 0, D.stream>>>(c.n, c.x, c.b, c.t, D.partial, D.ticket, D.scal + 8);
+    return;
+  }
   const int grid = red_grid(D, (long long)c.n * c.lanes);
   KScope ks(D, K_SCALE);
   LANES_SWITCH(c.lanes,
@@ -434,12 +550,14 @@ static void k_scale_dots(DeviceState& D, int lev) {
 static void k_prolong(DeviceState& D, int lev, bool scaled) {
   DLevel& f = D.lv[lev];
   DLevel& c = D.lv[lev + 1];
+  const int r0 = own_lo(D, f), r1 = own_hi(D, f);
   if (f.P.n > 0) {   // SA_AMG: x += alpha P e
-    k_csr_apply(D, f.P, c.x, scaled ? D.scal + 10 : nullptr, f.x, nullptr, true, K_PROLONG);
-    return;
+    k_csr_apply(D, f.P, r0, r1, c.x, scaled ? D.scal + 10 : nullptr, f.x, nullptr, true, K_PROLONG);
+  } else if (r1 > r0) {
+    KScope ks(D, K_PROLONG);
+    prolong_kernel<<<cdiv(r1 - r0, kBlock), kBlock, 0, D.stream>>>(r0, r1, f.agg, c.x, scaled ? D.scal + 10 : nullptr, f.x);
   }
-  KScope ks(D, K_PROLONG);
-  prolong_kernel<<<cdiv(f.n, kBlock), kBlock, 0, D.stream>>>(f.n, f.agg, c.x, scaled ? D.scal + 10 : nullptr, f.x);
+  exchange(D, f, f.x, -1);
 }
 
 static void k_coarse_solve(DeviceState& D) {
@@ -499,7 +617,7 @@ static void apply_permuted_raw(DeviceState& D, const double* r, double* z);
 
 // z' = B r' in the permuted ordering of level 0 (both device arrays of size n0)
 static void apply_permuted(DeviceState& D, const double* r, double* z) {
-  if (!D.use_graph || D.prof_on || apply_launch_estimate(D) > 60000) { apply_permuted_raw(D, r, z); return; }
+  if (!D.use_graph || D.prof_on || D.world > 1 || apply_launch_estimate(D) > 60000) { apply_permuted_raw(D, r, z); return; }
   for (auto& g : D.graphs)
     if (g.r == r && g.z == z) {
       CUDA_OK(cudaGraphLaunch(g.exec, D.stream));
@@ -609,8 +727,12 @@ static int pcg_device(DeviceState& D, const double* b_nat, double* x_nat, double
   if (residuals) residuals[0] = res;
   double target = stop != 0 ? tol * res : tol;
   while (res > target && it < maxiter) {
-    const int sgrid = red_grid(D, (long long)cdiv(n, l0.unroll) * l0.lanes);
-    {
+    if (is_dist(D, l0) && D.world > 1) {   // q = A d on the owned rows, all-gather, then d.q on complete vectors
+      k_spmv(D, l0, d, nullptr, q, false);
+      KScope ks(D, K_DOT);
+      pcg_dq_kernel<<<rgrid, kBlock, 0, D.stream>>>(n, d, q, D.partial, D.ticket, D.scal);
+    } else {
+      const int sgrid = red_grid(D, (long long)cdiv(n, l0.unroll) * l0.lanes);
       KScope ks(D, K_SPMV);
       LANES_SWITCH(l0.lanes, UNROLL_SWITCH(l0.unroll,
         spmv_dot_kernel<LN, UN><<<sgrid, kBlock, 0, D.stream>>>(n, l0.ia, l0.ja, l0.a, d, q, D.partial, D.ticket, D.scal)));
@@ -823,6 +945,45 @@ int mamg_to_device(mamg_handle h, int32_t device, void* stream) {
   h->dev = D;
   return 0;
   MAMG_CATCH
+}
+
+int mamg_nccl_unique_id(void* out128) {
+  MAMG_TRY
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  if (!out128) { set_error("nccl_unique_id: NULL"); return -1; }
+  NCCL_OK(ncclGetUniqueId((ncclUniqueId*)out128));
+  return 0;
+  MAMG_CATCH
+}
+
+int mamg_dist_init(mamg_handle h, int32_t rank, int32_t world, const void* unique_id128) {
+  MAMG_TRY
+  DeviceState* D = get_dev(h);
+  if (!D) return -1;
+  if (world < 1 || rank < 0 || rank >= world) { set_error("dist_init: bad rank/world"); return -1; }
+  if (h->H.nparts % world != 0) {
+    set_error("dist_init: the hierarchy has " + std::to_string(h->H.nparts) + " parts, not a multiple of world size " + std::to_string(world));
+    return -1;
+  }
+  if (world > 1) {
+    if (!unique_id128) { set_error("dist_init: NULL unique id"); return -1; }
+    ncclUniqueId id;
+    std::memcpy(&id, unique_id128, sizeof(id));
+    NCCL_OK(ncclCommInitRank(&D->comm, world, id, rank));
+  }
+  D->rank = rank;
+  D->world = world;
+  drop_graphs(*D);
+  return 0;
+  MAMG_CATCH
+}
+
+int mamg_collective_count(mamg_handle h, int64_t* count, int32_t reset) {
+  DeviceState* D = get_dev(h);
+  if (!D || !count) return -1;
+  *count = D->collectives;
+  if (reset) D->collectives = 0;
+  return 0;
 }
 
 int mamg_set_stream(mamg_handle h, void* stream) {

@@ -130,11 +130,12 @@ __device__ __forceinline__ void rows_dot(const int* __restrict__ ia, const int* 
 // ---------------------------------------------------------------------------------------
 template <int LANES, int U, bool RESID>
 __global__ void __launch_bounds__(kBlock)
-spmv_kernel(int n, const int* __restrict__ ia, const int* __restrict__ ja,
+spmv_kernel(int rbeg, int n, const int* __restrict__ ia, const int* __restrict__ ja,
             const double* __restrict__ a, const double* __restrict__ x,
             const double* __restrict__ b, double* __restrict__ y) {
+  // rows [rbeg, n): the whole level, or the rows this rank owns on a row-distributed level
   const int lane = threadIdx.x % LANES;
-  const int row0 = ((blockIdx.x * kBlock + threadIdx.x) / LANES) * U;
+  const int row0 = rbeg + ((blockIdx.x * kBlock + threadIdx.x) / LANES) * U;
   if (row0 >= n) return;
   double s[U];
   rows_dot<LANES, U>(ia, ja, a, x, row0, n, lane, s);
@@ -253,12 +254,12 @@ gs_color_kernel(int r0, int r1, const int* __restrict__ ia, const int* __restric
 // damped Jacobi, out of place: xn = x + w D^-1 (b - A x)
 template <int LANES>
 __global__ void __launch_bounds__(kBlock)
-jacobi_kernel(int n, const int* __restrict__ ia, const int* __restrict__ ja,
+jacobi_kernel(int rbeg, int n, const int* __restrict__ ia, const int* __restrict__ ja,
               const double* __restrict__ a, const double* __restrict__ invd,
               const uint8_t* __restrict__ skip, const double* __restrict__ b,
               const double* __restrict__ x, double* __restrict__ xn, double omega) {
   const int lane = threadIdx.x % LANES;
-  const int row = (blockIdx.x * kBlock + threadIdx.x) / LANES;
+  const int row = rbeg + (blockIdx.x * kBlock + threadIdx.x) / LANES;
   if (row >= n) return;
   double s = row_dot<LANES>(ja, a, x, ia[row], ia[row + 1], lane);
   if (lane == 0) {
@@ -275,13 +276,13 @@ jacobi_kernel(int n, const int* __restrict__ ia, const int* __restrict__ ja,
 // ---------------------------------------------------------------------------------------
 template <int LANES>
 __global__ void __launch_bounds__(kBlock)
-resid_restrict_kernel(int nc, const int* __restrict__ cptr, const int* __restrict__ cidx,
+resid_restrict_kernel(int cbeg, int nc, const int* __restrict__ cptr, const int* __restrict__ cidx,
                       const int* __restrict__ ia, const int* __restrict__ ja,
                       const double* __restrict__ a, const double* __restrict__ x,
                       const double* __restrict__ b, double* __restrict__ bc,
                       double* __restrict__ xc) {
   const int lane = threadIdx.x % LANES;
-  const int I = (blockIdx.x * kBlock + threadIdx.x) / LANES;
+  const int I = cbeg + (blockIdx.x * kBlock + threadIdx.x) / LANES;
   if (I >= nc) return;
   double acc = 0.0;
   const int q1 = cptr[I + 1];
@@ -335,11 +336,46 @@ scale_dots_kernel(int n, const int* __restrict__ ia, const int* __restrict__ ja,
   }
 }
 
+// distributed variant of the coarse scaling: t = A_c e was all-gathered; out[0] = e.r, out[1] = e.t, out[2] = alpha
+__global__ void __launch_bounds__(kBlock)
+scale_dots_vec_kernel(int n, const double* __restrict__ e, const double* __restrict__ r,
+                      const double* __restrict__ t, double* partial, unsigned int* ticket, double* out) {
+  double v[2] = {0.0, 0.0};
+  for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+    const double ei = e[i];
+    v[0] += ei * r[i];
+    v[1] += ei * t[i];
+  }
+  if (block_reduce_finish<2>(v, partial, ticket, out) && threadIdx.x == 0) {
+    double al = out[0] / out[1];
+    out[2] = (al < 1.0) ? al : 1.0;
+  }
+}
+// sc[1] = d.q, sc[2] = alpha = rz / d.q      (distributed PCG: q was all-gathered)
+__global__ void __launch_bounds__(kBlock)
+pcg_dq_kernel(int n, const double* __restrict__ d, const double* __restrict__ q, double* partial,
+              unsigned int* ticket, double* sc) {
+  double v[1] = {0.0};
+  for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) v[0] += d[i] * q[i];
+  if (block_reduce_finish<1>(v, partial, ticket, sc + 1) && threadIdx.x == 0) sc[2] = sc[0] / sc[1];
+}
+// buf[q] = x[idx[q0 + q]]  /  x[idx[q0 + q]] = buf[q]   (Schwarz patch-dof exchange)
+__global__ void __launch_bounds__(kBlock)
+pack_kernel(int cnt, const int* __restrict__ idx, const double* __restrict__ x, double* __restrict__ buf) {
+  const int q = blockIdx.x * kBlock + threadIdx.x;
+  if (q < cnt) buf[q] = x[idx[q]];
+}
+__global__ void __launch_bounds__(kBlock)
+unpack_kernel(int cnt, const int* __restrict__ idx, const double* __restrict__ buf, double* __restrict__ x) {
+  const int q = blockIdx.x * kBlock + threadIdx.x;
+  if (q < cnt) x[idx[q]] = buf[q];
+}
+
 // K4  x_i += alpha * e[agg(i)]      (HAZmath dcsr_aAxpy_agg)
 __global__ void __launch_bounds__(kBlock)
-prolong_kernel(int n, const int* __restrict__ agg, const double* __restrict__ e,
+prolong_kernel(int rbeg, int n, const int* __restrict__ agg, const double* __restrict__ e,
                const double* __restrict__ alpha, double* __restrict__ x) {
-  const int i = blockIdx.x * kBlock + threadIdx.x;
+  const int i = rbeg + blockIdx.x * kBlock + threadIdx.x;
   if (i >= n) return;
   const int I = agg[i];
   if (I >= 0) x[i] += (alpha ? *alpha : 1.0) * e[I];
@@ -349,11 +385,11 @@ prolong_kernel(int n, const int* __restrict__ agg, const double* __restrict__ e,
 //     y = M x   or   y += alpha (M x)   (HAZmath dcsr_mxv / dcsr_aAxpy with P, R)
 template <int LANES, bool ADD>
 __global__ void __launch_bounds__(kBlock)
-csr_apply_kernel(int n, const int* __restrict__ ia, const int* __restrict__ ja,
+csr_apply_kernel(int rbeg, int n, const int* __restrict__ ia, const int* __restrict__ ja,
                  const double* __restrict__ a, const double* __restrict__ x,
                  const double* __restrict__ alpha, double* __restrict__ y, double* __restrict__ zero) {
   const int lane = threadIdx.x % LANES;
-  const int row = (blockIdx.x * kBlock + threadIdx.x) / LANES;
+  const int row = rbeg + (blockIdx.x * kBlock + threadIdx.x) / LANES;
   if (row >= n) return;
   double s = row_dot<LANES>(ja, a, x, ia[row], ia[row + 1], lane);
   if (lane == 0) {

@@ -61,7 +61,10 @@ struct DSchwarz {
   int* nbrp = nullptr;         // [np][nbq][32] neighbourhood list, padded with a valid index
   double* vt = nullptr;        // [np][srow][32] entry e of row k; 0 padding
   uint32_t* ct4 = nullptr;     // [np][sq][32] four 8-bit local columns per word; 255 = zero slot
-  std::vector<int> color_ptr;  // host: patch range of every colour
+  // patches sorted by (conflict colour, block of the seed): cb_ptr[c*nb + b] .. [c*nb + b + 1]
+  int nb = 1;
+  std::vector<int> cb_ptr;     // host: size ncolors*nb + 1
+  std::vector<int> qoff;       // host: first entry of every patch in pidx (size npatch + 1)
   long long alg_bytes = 0;     // algorithmic bytes of one sweep over all patches
 };
 
@@ -363,7 +366,7 @@ schwarz_fast_kernel(int p0, int p1, const int* __restrict__ pidx32, const int* _
 // Host side: reorder the patches by colour, translate to the permuted numbering, build the
 // neighbourhood lists and local columns, upload, invert on the device.
 // `alloc(bytes)` returns tracked device memory; pia/pja are the permuted CSR of the level.
-inline void schwarz_upload(const Level& hl, const std::vector<int>& iperm, const int* d_ia,
+inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iperm, const int* d_ia,
                            const int* d_ja, const double* d_a, const std::vector<int>& pia,
                            const std::vector<int>& pja, DSchwarz& d,
                            const std::function<void*(size_t)>& alloc) {
@@ -374,13 +377,15 @@ inline void schwarz_upload(const Level& hl, const std::vector<int>& iperm, const
   d.npatch = np;
   d.ncolors = sw.ncolors;
   d.max_size = sw.max_size;
-  d.color_ptr.assign(sw.ncolors + 1, 0);
-  for (int p = 0; p < np; ++p) ++d.color_ptr[sw.color[p] + 1];
-  for (int c = 0; c < sw.ncolors; ++c) d.color_ptr[c + 1] += d.color_ptr[c];
+  d.nb = nb;
+  auto pkey = [&](int p) { return sw.color[p] * nb + (nb > 1 ? hl.part[sw.seed[p]] : 0); };
+  d.cb_ptr.assign(sw.ncolors * nb + 1, 0);
+  for (int p = 0; p < np; ++p) ++d.cb_ptr[pkey(p) + 1];
+  for (int k = 0; k < sw.ncolors * nb; ++k) d.cb_ptr[k + 1] += d.cb_ptr[k];
   std::vector<int> order(np);
   {
-    std::vector<int> fill(d.color_ptr.begin(), d.color_ptr.end() - 1);
-    for (int p = 0; p < np; ++p) order[fill[sw.color[p]]++] = p;
+    std::vector<int> fill(d.cb_ptr.begin(), d.cb_ptr.end() - 1);
+    for (int p = 0; p < np; ++p) order[fill[pkey(p)]++] = p;
   }
   std::vector<SwPatch> pat(np, zero);
   std::vector<int> pidx(sw.dofs.size()), prow(sw.dofs.size()), plen(sw.dofs.size());
@@ -433,6 +438,9 @@ inline void schwarz_upload(const Level& hl, const std::vector<int>& iperm, const
     max_nbr = std::max(max_nbr, nn[k]);
 
   }
+  d.qoff.resize(np + 1);
+  for (int k = 0; k < np; ++k) d.qoff[k] = pat[k].q0;
+  d.qoff[np] = (int)tot_q;
   if (tot_n > 2000000000LL) throw std::runtime_error("Schwarz neighbourhood lists exceed int32 indexing");
   if (max_nbr > 65535) throw std::runtime_error("Schwarz patch neighbourhood larger than 65535 dofs");
   d.max_nbr = max_nbr;
@@ -522,10 +530,9 @@ inline void schwarz_upload(const Level& hl, const std::vector<int>& iperm, const
   }
 }
 
-// one colour of a multiplicative sweep
-inline void schwarz_color_launch(const DSchwarz& d, int c, const double* a, const double* b, double* x,
+// patches [p0, p1) of one conflict colour (they commute, so they run concurrently)
+inline void schwarz_range_launch(const DSchwarz& d, int p0, int p1, const double* a, const double* b, double* x,
                                  cudaStream_t stream) {
-  const int p0 = d.color_ptr[c], p1 = d.color_ptr[c + 1];
   if (d.fast) {
     const int g = (p1 - p0 + kSwFastWarps - 1) / kSwFastWarps;
     const size_t sm = (size_t)kSwFastWarps * kSwFastSlot * sizeof(double);

@@ -54,6 +54,12 @@ int mamg_params_default(mamg_params* p) {
 
 int mamg_setup(const mamg_params* p, int32_t n, const int32_t* indptr, const int32_t* indices,
                const double* data, int32_t n_idofs, const int32_t* idofs, mamg_handle* out) {
+  return mamg_setup_partitioned(p, n, indptr, indices, data, n_idofs, idofs, nullptr, 1, out);
+}
+
+int mamg_setup_partitioned(const mamg_params* p, int32_t n, const int32_t* indptr, const int32_t* indices,
+                           const double* data, int32_t n_idofs, const int32_t* idofs, const int32_t* part,
+                           int32_t nparts, mamg_handle* out) {
   MAMG_TRY
   if (!p || !indptr || !indices || !data || !out) { set_error("setup: NULL argument"); return -1; }
   if (n <= 0) { set_error("setup: matrix has no rows"); return -1; }
@@ -76,9 +82,14 @@ int mamg_setup(const mamg_params* p, int32_t n, const int32_t* indptr, const int
     }
     if (!has_diag) { set_error("setup: row " + std::to_string(i) + " has no nonzero diagonal"); return -1; }
   }
+  if (part) {
+    if (nparts < 1) { set_error("setup: nparts < 1"); return -1; }
+    for (int i = 0; i < n; ++i)
+      if (part[i] < 0 || part[i] >= nparts) { set_error("setup: part id out of range"); return -1; }
+  }
   mamg_handle h = new mamg_handle_s();
   std::string err;
-  if (!build_hierarchy(*p, std::move(A), idofs, n_idofs, h->H, err)) {
+  if (!build_hierarchy(*p, std::move(A), idofs, n_idofs, part, nparts, h->H, err)) {
     delete h;
     set_error("AMG levels failed to set up: " + err);
     return -3;
@@ -164,6 +175,13 @@ int mamg_schwarz_export(mamg_handle h, int32_t level, int32_t* patch_ptr, int32_
   if (patch_dofs && !s.dofs.empty()) std::memcpy(patch_dofs, s.dofs.data(), sizeof(int) * s.dofs.size());
   if (patch_seed && !s.seed.empty()) std::memcpy(patch_seed, s.seed.data(), sizeof(int) * s.seed.size());
   if (patch_color && !s.color.empty()) std::memcpy(patch_color, s.color.data(), sizeof(int) * s.color.size());
+  return 0;
+}
+
+int mamg_part_export(mamg_handle h, int32_t level, int32_t* part) {
+  const Level* L = get_level(h, level);
+  if (!L || !part) return -1;
+  for (int i = 0; i < L->A.n; ++i) part[i] = L->part.empty() ? 0 : L->part[i];
   return 0;
 }
 

@@ -45,18 +45,20 @@ struct Level {
   std::vector<uint8_t> gs_skip;  // 1: row is smoothed by Schwarz, not by GS (level < Schwarz_levels)
   SchwarzPatches sw;           // empty unless level < Schwarz_levels
   Csr P, R;                    // only for SA_AMG: smoothed prolongator (n x nc) and R = P' (nc x n)
+  std::vector<int> part;       // owner part of every row (empty: not partitioned); aggregates never cross parts
 };
 
 struct Hierarchy {
   mamg_params prm;
+  int nparts = 1;
   std::vector<Level> lv;
   std::vector<double> coarse_inv;  // dense row-major inverse of the coarsest A (n_c x n_c)
   double setup_seconds = 0;
 };
 
 // ---- setup pieces (each file states the reference lines it restates) -------
-void aggregate_hem(const Csr& A, std::vector<int>& agg, int& nc);
-void aggregate_vmb(const Csr& A, double strong, int max_agg, std::vector<int>& agg, int& nc);
+void aggregate_hem(const Csr& A, const int* part, std::vector<int>& agg, int& nc);
+void aggregate_vmb(const Csr& A, const int* part, double strong, int max_agg, std::vector<int>& agg, int& nc);
 void galerkin_ua(const Csr& A, const std::vector<int>& agg, int nc, Csr& Ac);
 void csr_transpose(const Csr& A, Csr& At);
 void csr_multiply(const Csr& A, const Csr& B, Csr& C);   // C = A B, columns sorted
@@ -67,7 +69,7 @@ void schwarz_patches(const Csr& A, const int* seeds, int nseeds, int maxlvl, int
 void schwarz_color(const Csr& A, SchwarzPatches& sw);
 bool dense_inverse(const Csr& A, std::vector<double>& inv);
 bool build_hierarchy(const mamg_params& prm, Csr&& A0, const int* idofs, int n_idofs,
-                     Hierarchy& H, std::string& err);
+                     const int* part, int nparts, Hierarchy& H, std::string& err);
 
 // structured P1 problems (assemble.cpp)
 void p1_scalar(int dim, const int* ncell, const double* h, double cK, double cM, Csr& out);

@@ -32,7 +32,10 @@ static inline bool row_isolated(const Csr& A, int i) {
   return true;
 }
 
-void aggregate_hem(const Csr& A, std::vector<int>& agg, int& nc) {
+// `part` (may be NULL): owner part of every row; matches are made inside a part only, so that the
+// aggregates -- and with them restriction and prolongation -- never cross a partition boundary
+// ("Aggregates never cross partitions on distributed levels (setup constraint)").
+void aggregate_hem(const Csr& A, const int* part, std::vector<int>& agg, int& nc) {
   const int n = A.n;
   agg.assign(n, -2);
   nc = 0;
@@ -45,6 +48,7 @@ void aggregate_hem(const Csr& A, std::vector<int>& agg, int& nc) {
     for (int p = A.ia[i]; p < A.ia[i + 1]; ++p) {
       int j = A.ja[p];
       if (j == i || agg[j] != -2) continue;
+      if (part && part[j] != part[i]) continue;
       double w = std::fabs(A.a[p]);
       if (w > bw) { bw = w; best = j; }
     }
@@ -60,6 +64,7 @@ void aggregate_hem(const Csr& A, std::vector<int>& agg, int& nc) {
     for (int p = A.ia[i]; p < A.ia[i + 1]; ++p) {
       int j = A.ja[p];
       if (j == i || agg[j] < 0) continue;
+      if (part && part[j] != part[i]) continue;
       double w = std::fabs(A.a[p]);
       if (w > bw) { bw = w; best = j; }
     }
@@ -67,7 +72,7 @@ void aggregate_hem(const Csr& A, std::vector<int>& agg, int& nc) {
   }
 }
 
-void aggregate_vmb(const Csr& A, double strong, int max_agg, std::vector<int>& agg, int& nc) {
+void aggregate_vmb(const Csr& A, const int* part, double strong, int max_agg, std::vector<int>& agg, int& nc) {
   const int n = A.n;
   std::vector<double> diag(n, 0.0);
   for (int i = 0; i < n; ++i)
@@ -77,6 +82,7 @@ void aggregate_vmb(const Csr& A, double strong, int max_agg, std::vector<int>& a
   auto is_strong = [&](int i, int p) {
     int j = A.ja[p];
     if (j == i || A.a[p] == 0.0) return false;
+    if (part && part[j] != part[i]) return false;
     return A.a[p] * A.a[p] >= s2 * std::fabs(diag[i] * diag[j]);
   };
   agg.assign(n, -2);
@@ -434,12 +440,14 @@ static void greedy_mis(const Csr& A, std::vector<int>& seeds) {
 }
 
 bool build_hierarchy(const mamg_params& prm, Csr&& A0, const int* idofs, int n_idofs,
-                     Hierarchy& H, std::string& err) {
+                     const int* part, int nparts, Hierarchy& H, std::string& err) {
   auto t0 = std::chrono::steady_clock::now();
   H.prm = prm;
+  H.nparts = part ? std::max(1, nparts) : 1;
   H.lv.clear();
   H.lv.emplace_back();
   H.lv[0].A = std::move(A0);
+  if (part) H.lv[0].part.assign(part, part + H.lv[0].A.n);
   if (prm.AMG_type != MAMG_UA_AMG && prm.AMG_type != MAMG_SA_AMG) { err = "AMG_type: only UA_AMG and SA_AMG are implemented"; return false; }
   if (prm.cycle_type != MAMG_V_CYCLE && prm.cycle_type != MAMG_W_CYCLE) {
     err = "cycle_type: only V_CYCLE and W_CYCLE are implemented";
@@ -475,8 +483,9 @@ bool build_hierarchy(const mamg_params& prm, Csr&& A0, const int* idofs, int n_i
       if (metric) for (int s : seeds) L.gs_skip[s] = 1;
     }
     if (last) break;
-    if (prm.aggregation_type == MAMG_HEM) aggregate_hem(L.A, L.agg, L.nc);
-    else aggregate_vmb(L.A, prm.strong_coupled, prm.max_aggregation, L.agg, L.nc);
+    const int* lpart = L.part.empty() ? nullptr : L.part.data();
+    if (prm.aggregation_type == MAMG_HEM) aggregate_hem(L.A, lpart, L.agg, L.nc);
+    else aggregate_vmb(L.A, lpart, prm.strong_coupled, prm.max_aggregation, L.agg, L.nc);
     if (L.nc == 0 || L.nc >= n) {  // no coarsening possible: this level becomes the coarsest
       L.agg.clear(); L.nc = 0; L.sw = SchwarzPatches(); L.gs_skip.clear();
       break;
@@ -492,6 +501,12 @@ bool build_hierarchy(const mamg_params& prm, Csr&& A0, const int* idofs, int n_i
       csr_multiply(F.R, AP, H.lv[l + 1].A);
     } else {
       galerkin_ua(H.lv[l].A, H.lv[l].agg, H.lv[l].nc, H.lv[l + 1].A);
+    }
+    if (!H.lv[l].part.empty()) {   // a coarse row belongs to the part of its members
+      std::vector<int>& cp = H.lv[l + 1].part;
+      cp.assign(H.lv[l].nc, 0);
+      for (int i = 0; i < H.lv[l].A.n; ++i)
+        if (H.lv[l].agg[i] >= 0) cp[H.lv[l].agg[i]] = H.lv[l].part[i];
     }
     if (metric && l + 1 < prm.Schwarz_levels) {  // carry the interface seeds to the next level
       std::vector<int> nxt;

@@ -39,15 +39,22 @@ def csr_arrays(A):
 class Hierarchy:
     """Owns one metric-AMG hierarchy (host) and, after to_device(), its copy on one B200."""
 
-    def __init__(self, A, parameters=None, idofs=None):
+    def __init__(self, A, parameters=None, idofs=None, part=None, nparts=None):
         indptr, indices, data, n = csr_arrays(A)
         self.n = int(n)
         self.params = to_struct(parameters)
         idofs = as_i32(idofs) if idofs is not None else np.zeros(0, np.int32)
         self.idofs = idofs
         h = C.c_void_p()
-        check(lib.mamg_setup(C.byref(self.params), self.n, ptr(indptr), ptr(indices), ptr(data),
-                             len(idofs), ptr(idofs), C.byref(h)))
+        if part is not None:
+            part = as_i32(part)
+            if len(part) != self.n:
+                raise ValueError("part must have one entry per row")
+            self.nparts = int(nparts if nparts is not None else part.max() + 1)
+        else:
+            self.nparts = 1
+        check(lib.mamg_setup_partitioned(C.byref(self.params), self.n, ptr(indptr), ptr(indices), ptr(data),
+                                         len(idofs), ptr(idofs), ptr(part), self.nparts, C.byref(h)))
         self._h = h
         self.on_device = False
         self.device = None
@@ -87,7 +94,9 @@ class Hierarchy:
             "data": np.empty(nnz, np.float64), "agg": np.empty(n, np.int32),
             "color": np.empty(n, np.int32), "gs_skip": np.empty(n, np.uint8),
             "n_aggregates": info["n_aggregates"], "n_colors": info["n_colors"],
+            "part": np.empty(n, np.int32),
         }
+        check(lib.mamg_part_export(self._h, level, ptr(out["part"])))
         check(lib.mamg_level_export(self._h, level, ptr(out["indptr"]), ptr(out["indices"]),
                                     ptr(out["data"]), ptr(out["agg"]), ptr(out["color"]),
                                     ptr(out["gs_skip"])))
@@ -127,6 +136,36 @@ class Hierarchy:
         self.on_device = True
         self.device = int(device)
         return self
+
+    def dist_init(self, rank=None, world=None, group=None):
+        """Join the NCCL communicator of a torchrun job (one process per GPU).  Needs an initialised
+        torch.distributed process group: rank 0 creates the NCCL id, it is broadcast as a byte tensor."""
+        self._require_device()
+        if world is None:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                rank, world = dist.get_rank(group), dist.get_world_size(group)
+            else:
+                rank, world = 0, 1
+        buf = (C.c_ubyte * 128)()
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+            if rank == 0:
+                check(lib.mamg_nccl_unique_id(buf))
+            dev = torch.device("cuda", self.device) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+            t = torch.tensor(list(buf), dtype=torch.uint8, device=dev)
+            dist.broadcast(t, src=0, group=group)
+            for i, v in enumerate(t.cpu().tolist()):
+                buf[i] = v
+        check(lib.mamg_dist_init(self._h, int(rank), int(world), buf))
+        self.rank, self.world = int(rank), int(world)
+        return self
+
+    def collective_count(self, reset=False):
+        v = C.c_int64()
+        check(lib.mamg_collective_count(self._h, C.byref(v), int(reset)))
+        return v.value
 
     def set_stream(self, stream):
         check(lib.mamg_set_stream(self._h, C.c_void_p(stream) if stream else None))

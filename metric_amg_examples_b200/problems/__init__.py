@@ -114,6 +114,31 @@ def emi_system(dim, n, kappa1=2.0, kappa2=3.0, gamma=5.0, both_sides=None):
                   dict(kappa1=kappa1, kappa2=kappa2, gamma=gamma))
 
 
+def slab_partition(system, nparts):
+    """Owner part of every dof for multi-GPU runs: slabs along the last axis (z in 3-D, y in 2-D), both
+    fields of a vertex in the same part.  For EMI the slab boundaries keep the interface
+    plane and 3 planes on either side inside one part, so that no Schwarz patch straddles parts."""
+    n, dim = system.ncell, system.gdim
+    plane = (n + 1) ** (dim - 1)
+    nv = system.W[0].dim()
+    if system.name.startswith("bidomain"):
+        z = np.tile(np.arange(nv) // plane, 2)                  # physical plane of every dof
+        cuts = [round(k * (n + 1) / nparts) for k in range(1, nparts)]
+    elif system.name.startswith("emi") and system.name != "emi_3d1d":
+        half = n // 2
+        k = np.arange(nv) // plane
+        z = np.concatenate([k + half, k])                        # Omega_1 sits on top of Omega_2
+        cuts = []
+        for q in range(1, nparts):
+            c = round(q * (n + 1) / nparts)
+            if abs(c - half) <= 3:
+                c = half + 4
+            cuts.append(c)
+    else:
+        raise NotImplementedError(f"no slab partition for {system.name}")
+    return np.searchsorted(np.array(sorted(cuts)), z, side="right").astype(np.int32)
+
+
 def scalar_p1(dim, ncell, h, cK=1.0, cM=0.0):
     """cK*K + cM*M for P1 on a box mesh (used for mass-matrix right-hand sides and tests)."""
     ncell = np.ascontiguousarray(ncell, np.int32)
