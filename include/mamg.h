@@ -131,6 +131,9 @@ int mamg_nccl_unique_id(void* out128);
 int mamg_dist_init(mamg_handle h, int32_t rank, int32_t world, const void* unique_id128);
 int mamg_collective_count(mamg_handle h, int64_t* count, int32_t reset);
 int mamg_device_bytes(mamg_handle h, int64_t* bytes);
+/* free the host copy of the level matrices once they are on the device (exports fail afterwards;
+ * sizes stay available): saves host memory when several ranks hold large hierarchies on one node */
+int mamg_release_host(mamg_handle h);
 /* block until everything queued on the handle's stream has finished */
 int mamg_sync(mamg_handle h);
 

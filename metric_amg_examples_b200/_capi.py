@@ -67,6 +67,7 @@ def _load():
         "mamg_collective_count": (i32, [vp, pi64, i32]),
         "mamg_device_bytes": (i32, [vp, pi64]),
         "mamg_sync": (i32, [vp]),
+        "mamg_release_host": (i32, [vp]),
         "mamg_apply": (i32, [vp, vp, vp, i32]),
         "mamg_spmv": (i32, [vp, i32, vp, vp, i32]),
         "mamg_smooth": (i32, [vp, i32, vp, vp, i32, i32]),

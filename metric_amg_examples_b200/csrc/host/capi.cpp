@@ -106,6 +106,20 @@ int mamg_destroy(mamg_handle h) {
   return 0;
 }
 
+int mamg_release_host(mamg_handle h) {
+  if (!h) { set_error("NULL handle"); return -1; }
+  if (!h->dev) { set_error("release_host: hierarchy is not on a device yet"); return -1; }
+  for (Level& L : h->H.lv) {
+    std::vector<int>().swap(L.A.ja);
+    std::vector<double>().swap(L.A.a);
+    std::vector<int>().swap(L.sw.dofs);
+    Csr().ia.swap(L.P.ia); std::vector<int>().swap(L.P.ja); std::vector<double>().swap(L.P.a);
+    std::vector<int>().swap(L.R.ja); std::vector<double>().swap(L.R.a);
+  }
+  h->H.released = true;
+  return 0;
+}
+
 int mamg_num_levels(mamg_handle h, int32_t* nlevels) {
   if (!h || !nlevels) { set_error("num_levels: NULL"); return -1; }
   *nlevels = (int32_t)h->H.lv.size();
@@ -114,6 +128,7 @@ int mamg_num_levels(mamg_handle h, int32_t* nlevels) {
 
 static const Level* get_level(mamg_handle h, int level) {
   if (!h) { set_error("NULL handle"); return nullptr; }
+  if (h->H.released) { set_error("host hierarchy was released (mamg_release_host)"); return nullptr; }
   if (level < 0 || level >= (int)h->H.lv.size()) { set_error("level out of range"); return nullptr; }
   return &h->H.lv[level];
 }

@@ -51,6 +51,7 @@ struct Level {
 struct Hierarchy {
   mamg_params prm;
   int nparts = 1;
+  bool released = false;       // host matrices freed after the device upload
   std::vector<Level> lv;
   std::vector<double> coarse_inv;  // dense row-major inverse of the coarsest A (n_c x n_c)
   double setup_seconds = 0;

@@ -79,6 +79,8 @@ class Hierarchy:
         return v.value
 
     def level_info(self, level):
+        if getattr(self, "_infos", None):
+            return self._infos[level]
         info = (C.c_int64 * 12)()
         check(lib.mamg_level_info(self._h, level, info))
         keys = ["rows", "nnz", "n_aggregates", "n_colors", "n_patches", "n_patch_entries",
@@ -169,6 +171,11 @@ class Hierarchy:
 
     def set_stream(self, stream):
         check(lib.mamg_set_stream(self._h, C.c_void_p(stream) if stream else None))
+
+    def release_host(self):
+        """Free the host copy of the level matrices (after to_device); export() is no longer possible."""
+        self._infos = [self.level_info(l) for l in range(self.num_levels)]
+        check(lib.mamg_release_host(self._h))
 
     def sync(self):
         check(lib.mamg_sync(self._h))

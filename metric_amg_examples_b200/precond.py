@@ -21,11 +21,11 @@ from .params import default_amg_parameters, default_metric_parameters
 
 
 class _Precond(block_base):
-    def __init__(self, A, parameters, idofs, device=0):
+    def __init__(self, A, parameters, idofs, device=0, part=None):
         self.A = A
         self.parameters = dict(parameters)
         try:
-            self.hierarchy = Hierarchy(A, self.parameters, idofs)
+            self.hierarchy = Hierarchy(A, self.parameters, idofs, part=part)
         except MamgError as e:
             raise RuntimeError(str(e)) from e
         self.n = self.hierarchy.n
@@ -81,7 +81,7 @@ class metricAMG(_Precond):
     """block.algebraic.hazmath.metricAMG(A, W, idofs=None, parameters=None) (src/utils.py:86,88).
     W is only used for the block sizes (list of objects with .dim() or ints)."""
 
-    def __init__(self, A, W=None, idofs=None, parameters=None, device=0):
+    def __init__(self, A, W=None, idofs=None, parameters=None, device=0, part=None):
         self.W = W
         if W is not None:
             dims = [w.dim() if hasattr(w, "dim") else int(w) for w in W]
@@ -93,4 +93,4 @@ class metricAMG(_Precond):
             if idofs.dtype == bool:
                 idofs = np.flatnonzero(idofs)
         super().__init__(A, parameters if parameters is not None else default_metric_parameters,
-                         idofs, device)
+                         idofs, device, part)
