@@ -22,6 +22,10 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# torchrun pins OMP_NUM_THREADS=1; the host setup (aggregation, Galerkin products, patch lists) is
+# OpenMP code: give every rank its share of the cores before libgomp starts
+if int(os.environ.get("WORLD_SIZE", "1")) > 1 and os.environ.get("OMP_NUM_THREADS", "1") == "1":
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // int(os.environ.get("LOCAL_WORLD_SIZE", os.environ["WORLD_SIZE"]))))
 
 
 def parse():
@@ -275,6 +279,7 @@ def run_mamg(a):
         cycle_ms = c0.elapsed_time(c1) / 5
         H.profile_start()
         _, pinfo = solve_dev()
+        prof_lv = H.profile_levels()
         prof = H.profile_stop()
         ncoll = H.collective_count(reset=True)
         _, _ = solve_dev()
@@ -300,9 +305,12 @@ def run_mamg(a):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     dom_ms, dom_launches = prof[dom]
-    achieved = cb[dom] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    # with several ranks the smoothing / transfer / SpMV classes run on 1/world of the rows of the
+    # distributed levels (per-rank numbers; small replicated levels make this a slight under-estimate)
+    share = {k: (1.0 / world if k in ("spmv", "gs", "schwarz", "restrict", "scale", "prolong") else 1.0) for k in cb}
+    achieved = cb[dom] * share[dom] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     kernels = {k: {"ms": round(prof[k][0], 3), "launches": prof[k][1], "share": round(prof[k][0] / tot_ms, 4),
-                   "alg_GBs": round(cb[k] / (prof[k][0] * 1e-3) / 1e9, 1) if prof[k][0] > 0 else None}
+                   "alg_GBs": round(cb[k] * share[k] / (prof[k][0] * 1e-3) / 1e9, 1) if prof[k][0] > 0 else None}
                for k in prof}
     out = {
         "metric": "solve DOF/s to rtol 1e-8 (metric-AMG V-cycle PCG)", "value": ndofs * a.steps / (ms * 1e-3),
@@ -328,6 +336,8 @@ def run_mamg(a):
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s",
                      "avg_launch_ms": dom_ms / max(dom_launches, 1)},
         "kernels": kernels,
+        "gs_ms_by_level": [round(float(v), 2) for v in prof_lv[:, 1]],
+        "level_rows": [H.level_info(l)["rows"] for l in range(H.num_levels)],
         "host": {"assemble_s": round(t_asm, 2), "setup_s": round(t_setup, 2), "upload_s": round(t_upload, 2),
                  "device_GB": round(H.device_bytes() / 1e9, 2)},
     }

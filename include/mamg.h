@@ -176,6 +176,9 @@ int mamg_gmres(mamg_handle h, const double* b, double* x, double tolerance, int3
 /* ---- measurement helpers (bench.py): kernel launches issued on the handle's stream
  *      since the last reset, and algorithmic bytes (SURVEY 8d model) of one cycle. */
 int mamg_launch_count(mamg_handle h, int64_t* launches, int32_t reset);
+/* while collecting (before mamg_profile(h, 0, ...)): the same times split by level,
+ * ms_level_class[level*16 + class], max_levels rows */
+int mamg_profile_levels(mamg_handle h, double* ms_level_class, int32_t max_levels);
 /* algorithmic bytes of one Schwarz sweep over all patches of a level (device layout: row values,
  * 16-bit local columns, neighbourhood lists, packed inverses; see csrc/cuda/schwarz.cuh) */
 int mamg_schwarz_sweep_bytes(mamg_handle h, int32_t level, int64_t* bytes);

@@ -76,6 +76,7 @@ def _load():
         "mamg_gmres": (i32, [vp, vp, vp, dbl, i32, i32, i32, i32, pi32, vp]),
         "mamg_launch_count": (i32, [vp, pi64, i32]),
         "mamg_profile": (i32, [vp, i32, vp, vp]),
+        "mamg_profile_levels": (i32, [vp, vp, i32]),
         "mamg_schwarz_sweep_bytes": (i32, [vp, i32, pi64]),
         "mamg_cycle_bytes": (i32, [vp, pi64]),
         "mamg_assemble_scalar": (i32, [i32, vp, vp, dbl, dbl, pi64, pi64, vp, vp, vp]),

@@ -59,10 +59,11 @@ struct DLevel {
 
 enum KClass { K_SPMV = 0, K_GS, K_SCHWARZ, K_RESTRICT, K_SCALE, K_PROLONG, K_COARSE, K_VEC, K_DOT, K_NCLS };
 
-struct ProfEvent { cudaEvent_t start, stop; int cls; };
+struct ProfEvent { cudaEvent_t start, stop; int cls; int lev; };
 
 struct DeviceState {
   bool prof_on = false;
+  int cur_level = 0;          // level the cycle is working on (profiling breakdown only)
   std::vector<ProfEvent> prof_events;
   size_t prof_used = 0;
   int64_t cls_launches[K_NCLS] = {0};
@@ -114,6 +115,7 @@ struct KScope {
     }
     ProfEvent& e = D.prof_events[D.prof_used++];
     e.cls = cls;
+    e.lev = D.cur_level;
     cudaEventRecord(e.start, D.stream);
     stop = e.stop;
   }
@@ -300,7 +302,7 @@ static void upload_hierarchy(const Hierarchy& H, DeviceState& D) {
     for (auto& dl : D.lv)
       if (dl.sw.nb > 1)
         for (int c = 0; c < dl.sw.ncolors; ++c)
-          mx = std::max(mx, (size_t)(dl.sw.qoff[dl.sw.cb_ptr[(c + 1) * dl.sw.nb]] - dl.sw.qoff[dl.sw.cb_ptr[c * dl.sw.nb]]));
+          mx = std::max(mx, (size_t)(dl.sw.xoff[(c + 1) * dl.sw.nb] - dl.sw.xoff[c * dl.sw.nb]));
     if (mx) D.xbuf = dalloc<double>(D, mx);
   }
   D.coarse_inv = upload(D, H.coarse_inv);
@@ -427,6 +429,7 @@ static void k_jacobi(DeviceState& D, DLevel& l, const double* b, double* x, doub
 // for one-directional variants) so that the cycle stays symmetric.
 static void smooth(DeviceState& D, int lev, const double* b, double* x, bool post) {
   DLevel& l = D.lv[lev];
+  D.cur_level = lev;
   const mamg_params& P = D.prm;
   const int iters = post ? P.postsmooth_iter : P.presmooth_iter;
   auto point = [&]() {
@@ -471,26 +474,27 @@ static void smooth(DeviceState& D, int lev, const double* b, double* x, bool pos
           schwarz_range_launch(l.sw, p0, p1, l.a, b, x, D.stream);
         }
         if (D.world > 1 && snb > 1) {
-          // every rank receives the patch dofs the other ranks have just updated
-          const int pa = l.sw.cb_ptr[c * snb], pb = l.sw.cb_ptr[(c + 1) * snb];
-          const int qa = l.sw.qoff[pa], qb = l.sw.qoff[pb];
+          // the other ranks receive the just-updated dofs that they read in later colours (or that
+          // sit in their row block); everything else travels once, at the end of the sweep
+          const int qa = l.sw.xoff[c * snb], qb = l.sw.xoff[(c + 1) * snb];
           if (qb == qa) continue;
-          const int mq0 = l.sw.qoff[l.sw.cb_ptr[c * snb + lo]], mq1 = l.sw.qoff[l.sw.cb_ptr[c * snb + hi]];
+          const int mq0 = l.sw.xoff[c * snb + lo], mq1 = l.sw.xoff[c * snb + hi];
           if (mq1 > mq0) {
             KScope ks(D, K_VEC);
-            pack_kernel<<<cdiv(mq1 - mq0, kBlock), kBlock, 0, D.stream>>>(mq1 - mq0, l.sw.pidx + mq0, x, D.xbuf + (mq0 - qa));
+            pack_kernel<<<cdiv(mq1 - mq0, kBlock), kBlock, 0, D.stream>>>(mq1 - mq0, l.sw.xidx + mq0, x, D.xbuf + (mq0 - qa));
           }
           NCCL_OK(ncclGroupStart());
           for (int blk = 0; blk < snb; ++blk) {
-            const int q0 = l.sw.qoff[l.sw.cb_ptr[c * snb + blk]], q1 = l.sw.qoff[l.sw.cb_ptr[c * snb + blk + 1]];
+            const int q0 = l.sw.xoff[c * snb + blk], q1 = l.sw.xoff[c * snb + blk + 1];
             if (q1 > q0) NCCL_OK(ncclBroadcast(D.xbuf + (q0 - qa), D.xbuf + (q0 - qa), (size_t)(q1 - q0), ncclDouble, blk / per, D.comm, D.stream));
           }
           NCCL_OK(ncclGroupEnd());
           ++D.collectives;
           KScope ks(D, K_VEC);
-          unpack_kernel<<<cdiv(qb - qa, kBlock), kBlock, 0, D.stream>>>(qb - qa, l.sw.pidx + qa, D.xbuf, x);
+          unpack_kernel<<<cdiv(qb - qa, kBlock), kBlock, 0, D.stream>>>(qb - qa, l.sw.xidx + qa, D.xbuf, x);
         }
       }
+      if (D.world > 1 && snb > 1) exchange(D, l, x, -1);   // every rank's own row block is complete: all-gather it
     };
     if (fwd) sweep(false);
     if (bwd) sweep(true);
@@ -509,6 +513,7 @@ static void k_csr_apply(DeviceState& D, const DCsr& M, int r0, int r1, const dou
 }
 
 static void k_resid_restrict(DeviceState& D, int lev) {
+  D.cur_level = lev;
   DLevel& f = D.lv[lev];
   DLevel& c = D.lv[lev + 1];
   // coarse rows this rank computes: its own blocks when the coarse level is distributed too, else all
@@ -1167,6 +1172,22 @@ int mamg_schwarz_sweep_bytes(mamg_handle h, int32_t level, int64_t* bytes) {
   if (level < 0 || level >= (int)D->lv.size()) { set_error("level out of range"); return -1; }
   *bytes = D->lv[level].sw.alg_bytes;
   return 0;
+}
+
+int mamg_profile_levels(mamg_handle h, double* ms_level_class, int32_t max_levels) {
+  MAMG_TRY
+  DeviceState* D = get_dev(h);
+  if (!D || !ms_level_class) return -1;
+  CUDA_OK(cudaStreamSynchronize(D->stream));
+  for (int k = 0; k < max_levels * 16; ++k) ms_level_class[k] = 0.0;
+  for (size_t i = 0; i < D->prof_used; ++i) {
+    float ms = 0.f;
+    CUDA_OK(cudaEventElapsedTime(&ms, D->prof_events[i].start, D->prof_events[i].stop));
+    const int lev = std::min(D->prof_events[i].lev, max_levels - 1);
+    ms_level_class[lev * 16 + D->prof_events[i].cls] += ms;
+  }
+  return 0;
+  MAMG_CATCH
 }
 
 int mamg_launch_count(mamg_handle h, int64_t* launches, int32_t reset) {

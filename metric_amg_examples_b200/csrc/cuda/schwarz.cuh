@@ -65,6 +65,10 @@ struct DSchwarz {
   int nb = 1;
   std::vector<int> cb_ptr;     // host: size ncolors*nb + 1
   std::vector<int> qoff;       // host: first entry of every patch in pidx (size npatch + 1)
+  // multi-GPU: after a conflict colour only the updated dofs that another part reads (or that sit in
+  // another part's row block) are exchanged; xoff[c*nb + b] .. delimit them inside xidx
+  std::vector<int> xoff;
+  int* xidx = nullptr;
   long long alg_bytes = 0;     // algorithmic bytes of one sweep over all patches
 };
 
@@ -445,6 +449,8 @@ inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iper
   if (max_nbr > 65535) throw std::runtime_error("Schwarz patch neighbourhood larger than 65535 dofs");
   d.max_nbr = max_nbr;
   std::vector<int> nbr((size_t)tot_n);
+  if (nb > 64) throw std::runtime_error("more than 64 parts are not supported by the Schwarz exchange lists");
+  std::vector<unsigned long long> readers(nb > 1 ? n : 0, 0ull);
   std::vector<uint16_t> lcol(fast_shape ? 8 : (size_t)tot_e + 8, 0);
 #pragma omp parallel
   {
@@ -464,6 +470,13 @@ inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iper
       }
       std::sort(list.begin(), list.end());
       for (int j = 0; j < (int)list.size(); ++j) { pos[list[j]] = j; nbr[pat[k].n0 + j] = list[j]; }
+      if (nb > 1) {   // which parts read which dof (permuted ids)
+        const unsigned long long bit = 1ull << hl.part[sw.seed[p]];
+        for (int j : list) {
+#pragma omp atomic
+          readers[j] |= bit;
+        }
+      }
       uint16_t* out = fast_shape ? nullptr : &lcol[(size_t)pat[k].e0];
       for (int q = 0; q < s && !fast_shape; ++q) {
         const int i = pidx[pat[k].q0 + q];
@@ -491,6 +504,22 @@ inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iper
     return p;
   };
   d.pat = (SwPatch*)up(pat.data(), pat.size() * sizeof(SwPatch));
+  if (nb > 1) {
+    std::vector<int> xidx;
+    d.xoff.assign(sw.ncolors * nb + 1, 0);
+    for (int kb = 0; kb < sw.ncolors * nb; ++kb) {
+      for (int k = d.cb_ptr[kb]; k < d.cb_ptr[kb + 1]; ++k) {
+        const int p = order[k];
+        const int pp = hl.part[sw.seed[p]];
+        for (int q = 0; q < pat[k].s; ++q) {
+          const int nat = sw.dofs[sw.ptr[p] + q], dof = pidx[pat[k].q0 + q];
+          if ((readers[dof] & ~(1ull << pp)) || hl.part[nat] != pp) xidx.push_back(dof);
+        }
+      }
+      d.xoff[kb + 1] = (int)xidx.size();
+    }
+    d.xidx = (int*)up(xidx.data(), xidx.size() * sizeof(int));
+  }
   d.pidx = (int*)up(pidx.data(), pidx.size() * sizeof(int));
   d.prow = (int*)up(prow.data(), prow.size() * sizeof(int));
   d.plen = (int*)up(plen.data(), plen.size() * sizeof(int));

@@ -200,6 +200,13 @@ class Hierarchy:
     def profile_start(self):
         check(lib.mamg_profile(self._h, 1, None, None))
 
+    def profile_levels(self):
+        """ms[level][class] of everything launched since profile_start() (call before profile_stop)."""
+        L = self.num_levels
+        ms = np.zeros((L, 16), np.float64)
+        check(lib.mamg_profile_levels(self._h, ptr(ms), L))
+        return ms[:, :len(self.KERNEL_CLASSES)]
+
     def profile_stop(self):
         """{class: (ms, launches)} of everything launched since profile_start()."""
         ms = np.zeros(16, np.float64)
