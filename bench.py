@@ -205,8 +205,15 @@ def run_mamg(a):
     if world > 1:
         B.A = None
         system.A = None                          # the library has its own copy; free the scipy one
-        for r in range(world):                   # uploads take turns: their host temporaries are large
-            if r == rank:
+        # the upload builds large host temporaries (permuted CSR, patch lists: ~1.2 KB per DOF): as many
+        # ranks at a time as the node's free memory allows
+        import psutil
+        need = 1200.0 * ndofs if a.workload.startswith("bidomain") else 500.0 * ndofs
+        free_t = torch.tensor([psutil.virtual_memory().available], dtype=torch.float64, device="cuda")
+        dist.all_reduce(free_t, op=dist.ReduceOp.MIN)
+        conc = int(max(1, min(world, free_t.item() * 0.7 // need)))
+        for r0 in range(0, world, conc):
+            if r0 <= rank < r0 + conc:
                 H.to_device(local, stream.cuda_stream)
             dist.barrier()
         H.dist_init()
