@@ -274,21 +274,24 @@ schwarz_blob_kernel(int np, const SwPatch* __restrict__ pat, const int* __restri
   const int* nb = nbr + P.n0;
   for (int j = 0; j < nbq; ++j) {
     const int q = j * 32 + lane;
-    nbrp[(pp * nbq + j) * 32 + lane] = q < P.nn ? nb[q] : nb[0];
+    nbrp[(pp * nbq + j) * 32 + lane] = q < P.nn ? nb[q] : 0;   // padding: any valid row id (never referenced)
   }
+  // off-patch entries of this lane's row, compacted to the front (columns not found in the list of
+  // outside neighbours belong to the patch itself and live in the stored inverse)
   const int r0 = row >= 0 ? ia[row] : 0, len = row >= 0 ? ia[row + 1] - r0 : 0;
+  int src = 0;
   for (int q = 0; q < sq; ++q) {
     uint32_t word = 0;
     for (int u = 0; u < 4; ++u) {
       const int e = q * 4 + u;
       uint32_t loc = 255;
       double v = 0.0;
-      if (e < len) {
-        v = a[r0 + e];
-        const int col = ja[r0 + e];
+      while (src < len) {
+        const int col = ja[r0 + src];
         int lo = 0, hi = P.nn - 1;
         while (lo < hi) { const int mid = (lo + hi) >> 1; if (nb[mid] < col) lo = mid + 1; else hi = mid; }
-        loc = (uint32_t)lo;
+        if (P.nn > 0 && nb[lo] == col) { loc = (uint32_t)lo; v = a[r0 + src]; ++src; break; }
+        ++src;
       }
       if (e < srow) vt[(pp * srow + e) * 32 + lane] = v;
       word |= loc << (8 * u);
@@ -327,7 +330,8 @@ schwarz_fast_kernel(int p0, int p1, const int* __restrict__ pidx32, const int* _
   for (int j = 0; j < 8; ++j) nb[j] = j < nbq ? ld_stream(nbrp + (pp * nbq + j) * 32 + lane) : 0;
   {
     const double* src = pinv + pp * inv_stride;
-    const int nch = inv_stride / 2;
+    const int s = __popc(__ballot_sync(0xffffffffu, my >= 0));   // dofs of this patch
+    const int nch = (s * (s + 1) / 2 + 1) / 2;                  // 16-byte chunks of its packed inverse
     for (int k = lane; k < nch; k += 32) cp_async16(Inv + 2 * k, src + 2 * k);
   }
   double v[SR];
@@ -364,7 +368,7 @@ schwarz_fast_kernel(int p0, int p1, const int* __restrict__ pidx32, const int* _
       d += Inv[ad] * rhs[c];
     }
   }
-  if (my >= 0) x[my] += d;
+  if (my >= 0) x[my] = d;   // x_B = A_BB^{-1} (b_B - A_{B,out} x_out)
 }
 
 // Host side: reorder the patches by colour, translate to the permuted numbering, build the
@@ -394,34 +398,47 @@ inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iper
   std::vector<SwPatch> pat(np, zero);
   std::vector<int> pidx(sw.dofs.size()), prow(sw.dofs.size()), plen(sw.dofs.size());
   // pass 1: sizes (rows, entries, neighbourhoods) per patch, in parallel
-  std::vector<int> nn(np, 0);
-  std::vector<long long> ne(np, 0);
-  int max_rowlen = 1;
-#pragma omp parallel reduction(max : max_rowlen)
+  std::vector<int> nn(np, 0), nn_out(np, 0);
+  std::vector<long long> ne(np, 0), ne_out(np, 0);
+  int max_rowlen = 1, max_rowlen_out = 1;
+#pragma omp parallel reduction(max : max_rowlen, max_rowlen_out)
   {
-    std::vector<int> mark(n, -1);
+    std::vector<int> mark(n, -1), inb(n, -1);
 #pragma omp for schedule(dynamic, 2048)
     for (int k = 0; k < np; ++k) {
       const int p = order[k];
-      int cnt = 0;
-      long long ent = 0;
+      int cnt = 0, cnt_out = 0;
+      long long ent = 0, ent_out = 0;
+      for (int q = sw.ptr[p]; q < sw.ptr[p + 1]; ++q) inb[iperm[sw.dofs[q]]] = k;
       for (int q = sw.ptr[p]; q < sw.ptr[p + 1]; ++q) {
         const int i = iperm[sw.dofs[q]];
         ent += pia[i + 1] - pia[i];
         max_rowlen = std::max(max_rowlen, pia[i + 1] - pia[i]);
-        for (int e = pia[i]; e < pia[i + 1]; ++e)
-          if (mark[pja[e]] != k) { mark[pja[e]] = k; ++cnt; }
+        int row_out = 0;
+        for (int e = pia[i]; e < pia[i + 1]; ++e) {
+          const bool outside = inb[pja[e]] != k;
+          row_out += outside;
+          if (mark[pja[e]] != k) { mark[pja[e]] = k; ++cnt; cnt_out += outside; }
+        }
+        ent_out += row_out;
+        max_rowlen_out = std::max(max_rowlen_out, row_out);
       }
       nn[k] = cnt;
       ne[k] = ent;
+      nn_out[k] = cnt_out;
+      ne_out[k] = ent_out;
     }
   }
   int max_nn = 0;
   for (int k = 0; k < np; ++k) max_nn = std::max(max_nn, nn[k]);
   const char* nofast = getenv("MAMG_SCHWARZ_GENERAL");
   const bool fast_shape = d.max_size <= 32 && max_nn <= 255 && max_rowlen <= 32 && !(nofast && atoi(nofast));
-  const int srow = fast_shape ? max_rowlen : (max_rowlen | 1);   // general path: odd row stride (conflict-free)
+  // fast path: x_B + A_BB^{-1}(b - A x)_B = A_BB^{-1}(b_B - A_{B,out} x_out): the entries of the patch rows
+  // that fall inside the patch are already in the stored inverse, so only the off-patch entries
+  // (and the neighbours outside the patch) are kept -- about a quarter less traffic per patch
+  const int srow = fast_shape ? max_rowlen_out : (max_rowlen | 1);   // general path: odd row stride (conflict-free)
   d.srow = srow;
+  if (fast_shape) { nn = nn_out; ne = ne_out; }
   long long tot_e = 0, tot_i = 0, tot_val = 0;
   long long tot_n = 0, tot_q = 0;
   int max_nbr = 0;
@@ -460,6 +477,8 @@ inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iper
       const int p = order[k];
       const int s = pat[k].s;
       list.clear();
+      if (fast_shape)   // the patch's own dofs are never gathered on the fast path
+        for (int q = 0; q < s; ++q) mark[iperm[sw.dofs[sw.ptr[p] + q]]] = k;
       for (int q = 0; q < s; ++q) {
         const int i = iperm[sw.dofs[sw.ptr[p] + q]];
         pidx[pat[k].q0 + q] = i;
@@ -488,7 +507,7 @@ inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iper
   // inverse, (idx, row start, row offset, b, x update) per patch dof, patch descriptor
   d.alg_bytes = 10 * tot_val + 12 * tot_n + 8 * tot_i + (12 + 8 + 16) * tot_q + 32LL * np;
   if (fast_shape)  // values + 8-bit local columns, neighbour list + gathered x, packed inverse, (idx, b, x) per dof
-    d.alg_bytes = 9 * tot_val + 12 * tot_n + 4 * [&] { long long t = 0; for (int k = 0; k < np; ++k) t += (long long)pat[k].s * (pat[k].s + 1); return t; }() + (4 + 8 + 16) * tot_q;
+    d.alg_bytes = 9 * tot_val + 12 * tot_n + 4 * [&] { long long t = 0; for (int k = 0; k < np; ++k) t += (long long)pat[k].s * (pat[k].s + 1); return t; }() + (4 + 8 + 8) * tot_q;
   const size_t tri_max = (size_t)d.max_size * (d.max_size + 1) / 2;
   d.smem_setup = (tri_max + d.max_size) * sizeof(double) + (size_t)d.max_size * sizeof(int);
   d.warps = d.max_size <= 32 ? 1 : (d.max_size <= 96 ? 2 : 4);
