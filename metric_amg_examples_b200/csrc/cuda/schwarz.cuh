@@ -328,9 +328,9 @@ schwarz_fast_kernel(int p0, int p1, const int* __restrict__ pidx32, const int* _
   int nb[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) nb[j] = j < nbq ? ld_stream(nbrp + (pp * nbq + j) * 32 + lane) : 0;
+  const int s = __popc(__ballot_sync(0xffffffffu, my >= 0));     // dofs of this patch
   {
     const double* src = pinv + pp * inv_stride;
-    const int s = __popc(__ballot_sync(0xffffffffu, my >= 0));   // dofs of this patch
     const int nch = (s * (s + 1) / 2 + 1) / 2;                  // 16-byte chunks of its packed inverse
     for (int k = lane; k < nch; k += 32) cp_async16(Inv + 2 * k, src + 2 * k);
   }
@@ -363,7 +363,7 @@ schwarz_fast_kernel(int p0, int p1, const int* __restrict__ pidx32, const int* _
   const int base = lane * (lane + 1) / 2;
 #pragma unroll
   for (int c = 0; c < 32; ++c) {
-    if (c < smax) {
+    if (c < s && lane < s) {   // only the s x s part of the staged inverse is defined
       const int ad = c <= lane ? base + c : c * (c + 1) / 2 + lane;
       d += Inv[ad] * rhs[c];
     }
