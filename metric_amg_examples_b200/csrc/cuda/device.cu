@@ -20,6 +20,7 @@
 #include "../host/handle.h"
 #include "kernels.cuh"
 #include "schwarz.cuh"
+#include "tail.cuh"
 
 namespace mamg {
 
@@ -55,6 +56,7 @@ struct DLevel {
   int row1(int b, int c) const { return bc_ptr[b * ncolors + c + 1]; }
   DSchwarz sw;
   DCsr P, R;   // SA_AMG only
+  int* d_color_ptr = nullptr;   // device copy of bc_ptr (tail kernel)
 };
 
 enum KClass { K_SPMV = 0, K_GS, K_SCHWARZ, K_RESTRICT, K_SCALE, K_PROLONG, K_COARSE, K_VEC, K_DOT, K_NCLS };
@@ -90,6 +92,9 @@ struct DeviceState {
   ncclComm_t comm = nullptr;
   int64_t collectives = 0;
   double* xbuf = nullptr;     // staging for the Schwarz patch-dof exchange
+  int tail_k0 = -1;           // first level executed by the single-CTA tail kernel (-1: none)
+  TailArgs tail;
+  size_t tail_smem = 0;
   // one apply is a fixed launch sequence: it is captured once per (input, output) pair into a
   // CUDA graph and replayed, which removes the host launch cost of the ~1000 small kernels of the
   // coarse levels (MAMG_GRAPH=0 disables; not used while profiling or for very long W sequences)
@@ -306,6 +311,46 @@ static void upload_hierarchy(const Hierarchy& H, DeviceState& D) {
     if (mx) D.xbuf = dalloc<double>(D, mx);
   }
   D.coarse_inv = upload(D, H.coarse_inv);
+  {
+    // persistent tail: the longest suffix of levels that are small, undistributed, plain UA levels
+    const char* env = getenv("MAMG_TAIL_ROWS");
+    const int tail_rows = env ? atoi(env) : 4096;
+    const bool smoother_ok = H.prm.smoother != MAMG_SMOOTHER_JACOBI;
+    int k0 = L;
+    while (k0 > 0) {
+      const DLevel& dl = D.lv[k0 - 1];
+      if (dl.n > tail_rows || dl.nb != 1 || dl.sw.npatch > 0 || dl.P.n > 0) break;
+      --k0;
+    }
+    if (smoother_ok && tail_rows > 0 && L - k0 >= 2 && L - k0 <= kTailMaxLevels) {
+      TailArgs& T = D.tail;
+      T.nlev = L - k0;
+      int off = 0;
+      for (int l = k0; l < L; ++l) {
+        DLevel& dl = D.lv[l];
+        dl.d_color_ptr = upload(D, dl.bc_ptr);
+        TailLevel& t = T.lv[l - k0];
+        t.n = dl.n; t.nc = dl.nc; t.ncolors = dl.ncolors;
+        t.ia = dl.ia; t.ja = dl.ja; t.a = dl.a; t.invd = dl.invd; t.color_ptr = dl.d_color_ptr;
+        t.agg = dl.agg; t.cptr = dl.cptr; t.cidx = dl.cidx;
+        t.off = off;
+        off += dl.n;
+      }
+      T.total = off;
+      T.cycle_type = H.prm.cycle_type;
+      T.smoother = H.prm.smoother;
+      T.pre = H.prm.presmooth_iter;
+      T.post = H.prm.postsmooth_iter;
+      T.scaling = H.prm.coarse_scaling == MAMG_ON;
+      T.omega = H.prm.relaxation;
+      T.coarse_inv = D.coarse_inv;
+      D.tail_smem = ((size_t)2 * off + 80) * sizeof(double);
+      if (D.tail_smem <= 220 * 1024) {
+        CUDA_OK(cudaFuncSetAttribute(tail_cycle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D.tail_smem));
+        D.tail_k0 = k0;
+      }
+    }
+  }
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, D.device);
   D.red_blocks = sms * 8;
@@ -573,6 +618,17 @@ static void k_coarse_solve(DeviceState& D) {
 
 static void cycle_level(DeviceState& D, int lev) {
   const int L = (int)D.lv.size();
+  if (lev == D.tail_k0) {   // everything from here down runs inside one kernel
+    D.cur_level = lev;
+    TailArgs T = D.tail;
+    T.top_reps = (lev > 0 && D.prm.cycle_type == MAMG_W_CYCLE) ? 2 : 1;
+    T.b_in = D.lv[lev].b;
+    T.x_io = D.lv[lev].x;
+    T.x_nonzero = lev == 0 ? 1 : 0;
+    KScope ks(D, K_COARSE);
+    tail_cycle_kernel<<<1, kTailThreads, D.tail_smem, D.stream>>>(T);
+    return;
+  }
   if (lev == L - 1) { k_coarse_solve(D); return; }
   const int reps = (lev > 0 && D.prm.cycle_type == MAMG_W_CYCLE) ? 2 : 1;
   for (int rep = 0; rep < reps; ++rep) {
@@ -612,6 +668,7 @@ static int64_t apply_launch_estimate(const DeviceState& D) {
   // launches of one apply: ~ (4 colours sweeps + 4) per visit, visits doubling per level for W
   double visits = 1, total = 0;
   for (size_t l = 0; l + 1 < D.lv.size(); ++l) {
+    if ((int)l == D.tail_k0) { total += visits; break; }   // one kernel for everything below
     total += visits * (4.0 * D.lv[l].ncolors + 4.0 * D.lv[l].sw.ncolors + 4.0);
     if (D.prm.cycle_type == MAMG_W_CYCLE) visits *= 2;
   }
