@@ -130,6 +130,13 @@ int mamg_set_stream(mamg_handle h, void* stream);
 int mamg_nccl_unique_id(void* out128);
 int mamg_dist_init(mamg_handle h, int32_t rank, int32_t world, const void* unique_id128);
 int mamg_collective_count(mamg_handle h, int64_t* count, int32_t reset);
+/* Peer-memory exchange (same node, NVLink): every rank publishes the CUDA IPC handle of its vector
+ * arena (mamg_ipc_handle, 64 bytes), the host side all-gathers them, mamg_dist_peers maps the peers'
+ * arenas.  From then on the owner of a row range stores it directly into the peers' vectors and
+ * raises a flag there; NCCL is only the fallback (MAMG_P2P=0).  A host barrier must separate
+ * mamg_dist_peers from the first apply. */
+int mamg_ipc_handle(mamg_handle h, void* out64);
+int mamg_dist_peers(mamg_handle h, const void* handles64_per_rank);
 int mamg_device_bytes(mamg_handle h, int64_t* bytes);
 /* free the host copy of the level matrices once they are on the device (exports fail afterwards;
  * sizes stay available): saves host memory when several ranks hold large hierarchies on one node */

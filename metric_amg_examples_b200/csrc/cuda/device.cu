@@ -92,6 +92,18 @@ struct DeviceState {
   ncclComm_t comm = nullptr;
   int64_t collectives = 0;
   double* xbuf = nullptr;     // staging for the Schwarz patch-dof exchange
+  // Every vector that is ever exchanged between ranks lives in ONE allocation (the arena) that is
+  // shared with the peer processes through CUDA IPC: the owner of a row range stores it straight
+  // into the peers' copies over NVLink and raises a flag there (no NCCL call, no host hop).
+  double* arena = nullptr;
+  size_t arena_doubles = 0;
+  std::vector<double*> peer_arena;   // arena base of every rank (own entry = arena)
+  double** d_peer_arena = nullptr;   // device copy
+  unsigned int* push_ticket = nullptr;
+  long long phase = 0;               // exchanges so far (same sequence on every rank)
+  bool use_p2p = false;
+  size_t xcap = 0;
+  long long xflip = 0;
   int tail_k0 = -1;           // first level executed by the single-CTA tail kernel (-1: none)
   TailArgs tail;
   size_t tail_smem = 0;
@@ -151,6 +163,8 @@ void device_state_free(DeviceState* D) {
   for (ProfEvent& e : D->prof_events) { cudaEventDestroy(e.start); cudaEventDestroy(e.stop); }
   for (auto& g : D->graphs) cudaGraphExecDestroy(g.exec);
   if (D->comm) ncclCommDestroy(D->comm);
+  for (int q = 0; q < (int)D->peer_arena.size(); ++q)
+    if (q != D->rank && D->peer_arena[q]) cudaIpcCloseMemHandle(D->peer_arena[q]);
   if (D->h_scal) cudaFreeHost(D->h_scal);
   if (D->own_stream && D->stream) cudaStreamDestroy(D->stream);
   delete D;
@@ -209,6 +223,21 @@ static void upload_hierarchy(const Hierarchy& H, DeviceState& D) {
     for (int i = 0; i < n; ++i) iperm[l][perm[l][i]] = i;
   }
   size_t max_n = 0;
+  {
+    size_t need = 64;
+    for (int l = 0; l < L; ++l) need += 3 * (size_t)H.lv[l].A.n + 6;
+    need += 10 * ((size_t)H.lv[0].A.n + 2) + 2 * (size_t)H.lv[0].A.n + 8;
+    D.arena = dalloc<double>(D, need);
+    D.arena_doubles = need;
+    CUDA_OK(cudaMemset(D.arena, 0, need * sizeof(double)));
+  }
+  size_t arena_used = 64;   // the first 64 doubles hold the per-rank arrival flags
+  auto carve = [&](size_t count) {
+    double* p = D.arena + arena_used;
+    arena_used += (count + 1) & ~(size_t)1;
+    if (arena_used > D.arena_doubles) throw std::runtime_error("vector arena overflow");
+    return p;
+  };
   for (int l = 0; l < L; ++l) {
     const Level& hl = H.lv[l];
     DLevel& dl = D.lv[l];
@@ -246,9 +275,9 @@ static void upload_hierarchy(const Hierarchy& H, DeviceState& D) {
     dl.invd = upload(D, invd);
     dl.perm = upload(D, perm[l]);
     dl.iperm = upload(D, iperm[l]);
-    dl.x_own = dl.x = dalloc<double>(D, n);
-    dl.b_own = dl.b = dalloc<double>(D, n);
-    dl.t = dalloc<double>(D, n);
+    dl.x_own = dl.x = carve(n);
+    dl.b_own = dl.b = carve(n);
+    dl.t = carve(n);
     if (!hl.gs_skip.empty()) {
       std::vector<uint8_t> sk(n);
       for (int i = 0; i < n; ++i) sk[i] = hl.gs_skip[perm[l][i]];
@@ -308,7 +337,7 @@ static void upload_hierarchy(const Hierarchy& H, DeviceState& D) {
       if (dl.sw.nb > 1)
         for (int c = 0; c < dl.sw.ncolors; ++c)
           mx = std::max(mx, (size_t)(dl.sw.xoff[(c + 1) * dl.sw.nb] - dl.sw.xoff[c * dl.sw.nb]));
-    if (mx) D.xbuf = dalloc<double>(D, mx);
+    if (mx) { D.xbuf = carve(2 * mx); D.xcap = mx; }   // two halves: a fast peer may already send the next colour
   }
   D.coarse_inv = upload(D, H.coarse_inv);
   {
@@ -360,7 +389,9 @@ static void upload_hierarchy(const Hierarchy& H, DeviceState& D) {
   D.scal = dalloc<double>(D, 32);
   CUDA_OK(cudaMemset(D.scal, 0, 32 * sizeof(double)));
   CUDA_OK(cudaMallocHost(&D.h_scal, 32 * sizeof(double)));
-  for (int k = 0; k < 10; ++k) D.w[k] = dalloc<double>(D, D.lv[0].n);
+  for (int k = 0; k < 10; ++k) D.w[k] = carve(D.lv[0].n);
+  D.push_ticket = dalloc<unsigned int>(D, 4);
+  CUDA_OK(cudaMemset(D.push_ticket, 0, 4 * sizeof(unsigned int)));
   D.io_a = dalloc<double>(D, max_n);
   D.io_b = dalloc<double>(D, max_n);
 }
@@ -405,9 +436,77 @@ static int own_hi(const DeviceState& D, const DLevel& l) { return l.bc_ptr[blk_h
 static void k_fill(DeviceState& D, int n, double* x, double v);
 
 // all-gather of vector v on a distributed level: colour c of every block (c >= 0) or whole blocks (c < 0)
+// ---- peer-memory exchange (CUDA IPC over NVLink) --------------------------------------------------
+struct PushRanges { int n; int beg[8]; int len[8]; };
+
+// Copies the listed ranges of the local vector (offset `voff` inside the arena) into every peer's
+// arena, then the block that finishes last raises this rank's flag (= phase) in every peer.
+__global__ void __launch_bounds__(kBlock)
+push_kernel(PushRanges R, long long voff, double* const* __restrict__ peers, int me, int world,
+            unsigned int* ticket, long long phase) {
+  int total = 0;
+  for (int k = 0; k < R.n; ++k) total += R.len[k];
+  const double* mine = peers[me] + voff;
+  for (int i = blockIdx.x * kBlock + threadIdx.x; i < total; i += gridDim.x * kBlock) {
+    int k = 0, j = i;
+    while (j >= R.len[k]) { j -= R.len[k]; ++k; }
+    const double val = mine[R.beg[k] + j];
+    for (int q = 0; q < world; ++q)
+      if (q != me) peers[q][voff + R.beg[k] + j] = val;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicInc(ticket, gridDim.x - 1);
+    if (t == gridDim.x - 1) {
+      __threadfence_system();
+      for (int q = 0; q < world; ++q)
+        if (q != me) reinterpret_cast<volatile long long*>(peers[q])[me] = phase;
+    }
+  }
+}
+
+// Waits until every peer has raised its flag for this phase (their ranges have landed here).
+__global__ void wait_kernel(const double* arena, int me, int world, long long phase) {
+  const int q = threadIdx.x;
+  if (q >= world || q == me) return;
+  const volatile long long* flag = reinterpret_cast<const volatile long long*>(arena) + q;
+  const long long t0 = clock64();
+  while (*flag < phase) {
+    if (clock64() - t0 > 20000000000LL) { printf("mamg: peer %d never reached exchange %lld\n", q, phase); __trap(); }
+  }
+  __threadfence_system();
+}
+
+static void push_ranges(DeviceState& D, const double* v, const PushRanges& R) {
+  ++D.phase;
+  int total = 0;
+  for (int k = 0; k < R.n; ++k) total += R.len[k];
+  const long long voff = v - D.arena;
+  const int grid = std::max(1, std::min(D.red_blocks, cdiv(std::max(total, 1), kBlock)));
+  {
+    KScope ks(D, K_VEC);
+    push_kernel<<<grid, kBlock, 0, D.stream>>>(R, voff, D.d_peer_arena, D.rank, D.world, D.push_ticket, D.phase);
+  }
+  KScope ks(D, K_VEC);
+  wait_kernel<<<1, 32, 0, D.stream>>>(D.arena, D.rank, D.world, D.phase);
+  ++D.collectives;
+}
+
 static void exchange(DeviceState& D, const DLevel& l, double* v, int c) {
   if (D.world == 1 || !is_dist(D, l)) return;
   const int per = l.nb / D.world;
+  if (D.use_p2p && per <= 8 && v >= D.arena && v < D.arena + D.arena_doubles) {
+    PushRanges R;
+    R.n = 0;
+    for (int b = D.rank * per; b < (D.rank + 1) * per; ++b) {
+      const int r0 = c >= 0 ? l.row0(b, c) : l.bc_ptr[b * l.ncolors];
+      const int r1 = c >= 0 ? l.row1(b, c) : l.bc_ptr[(b + 1) * l.ncolors];
+      if (r1 > r0) { R.beg[R.n] = r0; R.len[R.n] = r1 - r0; ++R.n; }
+    }
+    push_ranges(D, v, R);
+    return;
+  }
   NCCL_OK(ncclGroupStart());
   for (int b = 0; b < l.nb; ++b) {
     const int r0 = c >= 0 ? l.row0(b, c) : l.bc_ptr[b * l.ncolors];
@@ -524,19 +623,28 @@ static void smooth(DeviceState& D, int lev, const double* b, double* x, bool pos
           const int qa = l.sw.xoff[c * snb], qb = l.sw.xoff[(c + 1) * snb];
           if (qb == qa) continue;
           const int mq0 = l.sw.xoff[c * snb + lo], mq1 = l.sw.xoff[c * snb + hi];
+          double* xb = D.xbuf + (D.xflip++ & 1) * D.xcap;
           if (mq1 > mq0) {
             KScope ks(D, K_VEC);
-            pack_kernel<<<cdiv(mq1 - mq0, kBlock), kBlock, 0, D.stream>>>(mq1 - mq0, l.sw.xidx + mq0, x, D.xbuf + (mq0 - qa));
+            pack_kernel<<<cdiv(mq1 - mq0, kBlock), kBlock, 0, D.stream>>>(mq1 - mq0, l.sw.xidx + mq0, x, xb + (mq0 - qa));
           }
-          NCCL_OK(ncclGroupStart());
-          for (int blk = 0; blk < snb; ++blk) {
-            const int q0 = l.sw.xoff[c * snb + blk], q1 = l.sw.xoff[c * snb + blk + 1];
-            if (q1 > q0) NCCL_OK(ncclBroadcast(D.xbuf + (q0 - qa), D.xbuf + (q0 - qa), (size_t)(q1 - q0), ncclDouble, blk / per, D.comm, D.stream));
+          if (D.use_p2p) {
+            PushRanges R;
+            R.n = mq1 > mq0 ? 1 : 0;
+            R.beg[0] = mq0 - qa;
+            R.len[0] = mq1 - mq0;
+            push_ranges(D, xb, R);
+          } else {
+            NCCL_OK(ncclGroupStart());
+            for (int blk = 0; blk < snb; ++blk) {
+              const int q0 = l.sw.xoff[c * snb + blk], q1 = l.sw.xoff[c * snb + blk + 1];
+              if (q1 > q0) NCCL_OK(ncclBroadcast(xb + (q0 - qa), xb + (q0 - qa), (size_t)(q1 - q0), ncclDouble, blk / per, D.comm, D.stream));
+            }
+            NCCL_OK(ncclGroupEnd());
+            ++D.collectives;
           }
-          NCCL_OK(ncclGroupEnd());
-          ++D.collectives;
           KScope ks(D, K_VEC);
-          unpack_kernel<<<cdiv(qb - qa, kBlock), kBlock, 0, D.stream>>>(qb - qa, l.sw.xidx + qa, D.xbuf, x);
+          unpack_kernel<<<cdiv(qb - qa, kBlock), kBlock, 0, D.stream>>>(qb - qa, l.sw.xidx + qa, xb, x);
         }
       }
       if (D.world > 1 && snb > 1) exchange(D, l, x, -1);   // every rank's own row block is complete: all-gather it
@@ -1014,6 +1122,38 @@ int mamg_nccl_unique_id(void* out128) {
   static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
   if (!out128) { set_error("nccl_unique_id: NULL"); return -1; }
   NCCL_OK(ncclGetUniqueId((ncclUniqueId*)out128));
+  return 0;
+  MAMG_CATCH
+}
+
+int mamg_ipc_handle(mamg_handle h, void* out64) {
+  MAMG_TRY
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  DeviceState* D = get_dev(h);
+  if (!D || !out64) return -1;
+  CUDA_OK(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)out64, D->arena));
+  return 0;
+  MAMG_CATCH
+}
+
+int mamg_dist_peers(mamg_handle h, const void* handles64_per_rank) {
+  MAMG_TRY
+  DeviceState* D = get_dev(h);
+  if (!D || !handles64_per_rank) return -1;
+  if (D->world <= 1) return 0;
+  D->peer_arena.assign(D->world, nullptr);
+  for (int q = 0; q < D->world; ++q) {
+    if (q == D->rank) { D->peer_arena[q] = D->arena; continue; }
+    cudaIpcMemHandle_t hd;
+    std::memcpy(&hd, (const char*)handles64_per_rank + 64 * q, 64);
+    void* p = nullptr;
+    CUDA_OK(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+    D->peer_arena[q] = (double*)p;
+  }
+  D->d_peer_arena = dalloc<double*>(*D, D->world);
+  CUDA_OK(cudaMemcpy(D->d_peer_arena, D->peer_arena.data(), sizeof(double*) * D->world, cudaMemcpyHostToDevice));
+  const char* env = getenv("MAMG_P2P");
+  D->use_p2p = !(env && atoi(env) == 0);
   return 0;
   MAMG_CATCH
 }

@@ -162,6 +162,19 @@ class Hierarchy:
                 buf[i] = v
         check(lib.mamg_dist_init(self._h, int(rank), int(world), buf))
         self.rank, self.world = int(rank), int(world)
+        if world > 1:
+            # peer-memory exchange: all-gather the CUDA IPC handles of the vector arenas
+            import torch
+            import torch.distributed as dist
+            mine = (C.c_ubyte * 64)()
+            check(lib.mamg_ipc_handle(self._h, mine))
+            dev = torch.device("cuda", self.device) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+            t = torch.tensor(list(mine), dtype=torch.uint8, device=dev)
+            allh = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(allh, t, group=group)
+            flat = (C.c_ubyte * (64 * world))(*[v for h in allh for v in h.cpu().tolist()])
+            check(lib.mamg_dist_peers(self._h, flat))
+            dist.barrier(group=group)
         return self
 
     def collective_count(self, reset=False):
