@@ -493,6 +493,18 @@ static void push_ranges(DeviceState& D, const double* v, const PushRanges& R) {
   ++D.collectives;
 }
 
+// Peer stores of exchange k+1 may land while the receiver is still busy with work it queued after
+// barrier k.  That is harmless along the colour / restrict / prolong chains (the ranges written
+// are never the ranges read or written locally in between), but not after a replicated local
+// write or read of the same vector (zero-fill, gather, Krylov vector updates): those call this
+// flag-only barrier first, so that no peer starts the next push before everyone is past them.
+static void barrier_only(DeviceState& D) {
+  if (D.world == 1 || !D.use_p2p) return;
+  PushRanges R;
+  R.n = 0;
+  push_ranges(D, D.arena + 64, R);
+}
+
 static void exchange(DeviceState& D, const DLevel& l, double* v, int c) {
   if (D.world == 1 || !is_dist(D, l)) return;
   const int per = l.nb / D.world;
@@ -520,6 +532,7 @@ static void exchange(DeviceState& D, const DLevel& l, double* v, int c) {
 static void k_spmv(DeviceState& D, const DLevel& l, const double* x, const double* b, double* y, bool resid) {
   if (l.n == 0) return;
   const int r0 = own_lo(D, l), r1 = own_hi(D, l);
+  if (is_dist(D, l)) barrier_only(D);   // y may still be in local use on a peer (Krylov vector updates)
   if (r1 > r0) {
     const int grid = cdiv((long long)cdiv(r1 - r0, l.unroll) * l.lanes, kBlock);
     KScope ks(D, K_SPMV);
@@ -563,8 +576,11 @@ static void k_jacobi(DeviceState& D, DLevel& l, const double* b, double* x, doub
       jacobi_kernel<LN><<<grid, kBlock, 0, D.stream>>>(r0, r1, l.ia, l.ja, l.a, l.invd, l.skip, b, x, l.t, w));
   }
   exchange(D, l, l.t, -1);
-  KScope ks(D, K_VEC);
-  copy_kernel<<<cdiv(l.n, kBlock), kBlock, 0, D.stream>>>(l.n, l.t, x);
+  {
+    KScope ks(D, K_VEC);
+    copy_kernel<<<cdiv(l.n, kBlock), kBlock, 0, D.stream>>>(l.n, l.t, x);
+  }
+  if (is_dist(D, l)) barrier_only(D);
 }
 
 // One smoothing application S(x, b) on a level.  Pre-smoothing = Schwarz on the interface
@@ -682,8 +698,8 @@ static void k_resid_restrict(DeviceState& D, int lev) {
       resid_restrict_kernel<LN><<<grid, kBlock, 0, D.stream>>>(c0, c1, f.cptr, f.cidx, f.ia, f.ja, f.a, f.x, f.b, c.b, c.x));
   }
   if (is_dist(D, c) && D.world > 1) {
+    k_fill(D, c.n, c.x, 0.0);   // before the barrier of the exchange: afterwards peers push into c.x
     exchange(D, c, c.b, -1);
-    k_fill(D, c.n, c.x, 0.0);
   }
 }
 
@@ -709,6 +725,8 @@ static void k_prolong(DeviceState& D, int lev, bool scaled) {
   DLevel& f = D.lv[lev];
   DLevel& c = D.lv[lev + 1];
   const int r0 = own_lo(D, f), r1 = own_hi(D, f);
+  // a peer may still be reading f.x in its residual/restriction when nothing below was exchanged
+  if (is_dist(D, f) && !is_dist(D, c)) barrier_only(D);
   if (f.P.n > 0) {   // SA_AMG: x += alpha P e
     k_csr_apply(D, f.P, r0, r1, c.x, scaled ? D.scal + 10 : nullptr, f.x, nullptr, true, K_PROLONG);
   } else if (r1 > r0) {
@@ -830,6 +848,7 @@ static void apply_permuted_raw(DeviceState& D, const double* r, double* z) {
     k_coarse_solve(D);
   } else {
     k_fill(D, l0.n, z, 0.0);
+    if (is_dist(D, l0)) barrier_only(D);   // peers push into z from the first colour on
     for (int it = 0; it < std::max(1, D.prm.maxit); ++it) cycle_level(D, 0);
   }
   l0.b = l0.b_own;
@@ -1264,6 +1283,7 @@ int mamg_smooth(mamg_handle h, int32_t level, const double* b, double* x, int32_
   const double* xin = io.in(x, l.n, D->io_b);
   k_gather(*D, l.n, l.perm, bin, l.b_own);
   k_gather(*D, l.n, l.perm, xin, l.x_own);
+  if (is_dist(*D, l)) barrier_only(*D);
   smooth(*D, level, l.b_own, l.x_own, post != 0);
   double* xout = io.out_ptr(x, D->io_b);
   k_gather(*D, l.n, l.iperm, l.x_own, xout);
