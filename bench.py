@@ -391,7 +391,7 @@ def run_reference(a):
     out = {
         "impl": "reference", "metric": "solve DOF/s to rtol 1e-8 (metric-AMG V-cycle PCG)", "value": cb["value"],
         "unit": "DOF/s", "n_gpus": a.gpus, "steps": steps, "warmup": min(a.warmup, 1), "ms_per_step": dt * 1e3 / steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{a.workload} n={n} gamma={a.gamma:g} (timed on the bounded sample below)",
                    "cycle_type": a.cycle, "krylov": f"ConjGrad relativeconv tolerance={a.rtol:g}"},
         "cpu_baseline": cb,
