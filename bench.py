@@ -319,6 +319,14 @@ def run_mamg(a):
     kernels = {k: {"ms": round(prof[k][0], 3), "launches": prof[k][1], "share": round(prof[k][0] / tot_ms, 4),
                    "alg_GBs": round(cb[k] * share[k] / (prof[k][0] * 1e-3) / 1e9, 1) if prof[k][0] > 0 else None}
                for k in prof}
+    traffic = None
+    try:   # DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/traffic.json)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if dom == "schwarz" and a.workload == "bidomain_3d":
+            l0 = H.level_info(0)
+            traffic = tj["schwarz"]["dram_bytes_per_patch"] * l0["n_patches"] / max(l0["n_patch_colors"], 1) / world
+    except Exception:
+        pass
     out = {
         "metric": "solve DOF/s to rtol 1e-8 (metric-AMG V-cycle PCG)", "value": ndofs * a.steps / (ms * 1e-3),
         "unit": "DOF/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
@@ -339,7 +347,8 @@ def run_mamg(a):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None,
+                     "frac": achieved / peak, "traffic": traffic,
+                     "algorithmic_bytes_per_launch": cb[dom] * share[dom] / max(dom_launches, 1),
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s",
                      "avg_launch_ms": dom_ms / max(dom_launches, 1)},
         "kernels": kernels,

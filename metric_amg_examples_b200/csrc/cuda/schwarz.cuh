@@ -309,8 +309,8 @@ constexpr int kSwFastSlot = 256 + 528 + 32;  // doubles per patch slot: xs[256],
 // apply: one warp per patch, lane k = patch row k.  Wave 1 loads everything addressed by the patch
 // number (row values, packed local columns, neighbour list, inverse via cp.async); wave 2 gathers
 // x on the neighbourhood.  All loops have compile-time bounds; padding multiplies by the zero slot.
-template <int SR>
-__global__ void __launch_bounds__(kSwFastWarps * 32, MAMG_SW_MINB)
+template <int SR, int NBQ>
+__global__ void __launch_bounds__(kSwFastWarps * 32, (SR <= 24 && NBQ <= 4) ? 3 : MAMG_SW_MINB)
 schwarz_fast_kernel(int p0, int p1, const int* __restrict__ pidx32, const int* __restrict__ nbrp,
                     const double* __restrict__ vt, const uint32_t* __restrict__ ct4,
                     const double* __restrict__ pinv, const double* __restrict__ b, double* x, int srow,
@@ -325,9 +325,9 @@ schwarz_fast_kernel(int p0, int p1, const int* __restrict__ pidx32, const int* _
   const size_t pp = (size_t)patch;
   // ---- wave 1 ----
   const int my = pidx32[pp * 32 + lane];
-  int nb[8];
+  int nb[NBQ];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) nb[j] = j < nbq ? ld_stream(nbrp + (pp * nbq + j) * 32 + lane) : 0;
+  for (int j = 0; j < NBQ; ++j) nb[j] = j < nbq ? ld_stream(nbrp + (pp * nbq + j) * 32 + lane) : 0;
   const int s = __popc(__ballot_sync(0xffffffffu, my >= 0));     // dofs of this patch
   {
     const double* src = pinv + pp * inv_stride;
@@ -349,7 +349,7 @@ schwarz_fast_kernel(int p0, int p1, const int* __restrict__ pidx32, const int* _
   const double bk = my >= 0 ? b[my] : 0.0;
   // ---- wave 2 ----
 #pragma unroll
-  for (int j = 0; j < 8; ++j)
+  for (int j = 0; j < NBQ; ++j)
     if (j < nbq) xs[j * 32 + lane] = x[nb[j]];
   if (lane == 31) xs[255] = 0.0;   // the zero slot every padded local column points to
   __syncwarp();
@@ -557,7 +557,7 @@ inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iper
     d.nbq = (max_nn + 31) / 32;
     d.sq = (srow + 3) / 4;
     d.inv_stride = 528;
-    d.sr_t = srow <= 16 ? 16 : 32;
+    d.sr_t = (srow <= 12 && d.nbq <= 1) ? 12 : ((srow <= 24 && d.nbq <= 4) ? 24 : 32);
     d.pidx32 = (int*)alloc((size_t)np * 32 * sizeof(int));
     d.nbrp = (int*)alloc((size_t)np * d.nbq * 32 * sizeof(int));
     d.vt = (double*)alloc((size_t)np * srow * 32 * sizeof(double));
@@ -567,8 +567,9 @@ inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iper
     e = cudaDeviceSynchronize();
     if (e != cudaSuccess) throw std::runtime_error(std::string("Schwarz blob kernel failed: ") + cudaGetErrorString(e));
     const int fsm = kSwFastWarps * kSwFastSlot * (int)sizeof(double);
-    cudaFuncSetAttribute(schwarz_fast_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm);
-    cudaFuncSetAttribute(schwarz_fast_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm);
+    cudaFuncSetAttribute(schwarz_fast_kernel<12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm);
+    cudaFuncSetAttribute(schwarz_fast_kernel<24, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm);
+    cudaFuncSetAttribute(schwarz_fast_kernel<32, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm);
   }
   if (d.smem_apply > 48 * 1024) {
     cudaFuncSetAttribute(schwarz_apply_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_apply);
@@ -584,12 +585,11 @@ inline void schwarz_range_launch(const DSchwarz& d, int p0, int p1, const double
   if (d.fast) {
     const int g = (p1 - p0 + kSwFastWarps - 1) / kSwFastWarps;
     const size_t sm = (size_t)kSwFastWarps * kSwFastSlot * sizeof(double);
-    if (d.sr_t == 16)
-      schwarz_fast_kernel<16><<<g, kSwFastWarps * 32, sm, stream>>>(p0, p1, d.pidx32, d.nbrp, d.vt, d.ct4, d.pinv, b, x,
-                                                                    d.srow, d.sq, d.nbq, d.inv_stride, d.max_size);
-    else
-      schwarz_fast_kernel<32><<<g, kSwFastWarps * 32, sm, stream>>>(p0, p1, d.pidx32, d.nbrp, d.vt, d.ct4, d.pinv, b, x,
-                                                                    d.srow, d.sq, d.nbq, d.inv_stride, d.max_size);
+#define MAMG_SWF_ARGS p0, p1, d.pidx32, d.nbrp, d.vt, d.ct4, d.pinv, b, x, d.srow, d.sq, d.nbq, d.inv_stride, d.max_size
+    if (d.sr_t == 12) schwarz_fast_kernel<12, 1><<<g, kSwFastWarps * 32, sm, stream>>>(MAMG_SWF_ARGS);
+    else if (d.sr_t == 24) schwarz_fast_kernel<24, 4><<<g, kSwFastWarps * 32, sm, stream>>>(MAMG_SWF_ARGS);
+    else schwarz_fast_kernel<32, 8><<<g, kSwFastWarps * 32, sm, stream>>>(MAMG_SWF_ARGS);
+#undef MAMG_SWF_ARGS
     return;
   }
   const int grid = (p1 - p0 + d.ppc - 1) / d.ppc;
