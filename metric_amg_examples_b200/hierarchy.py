@@ -36,6 +36,39 @@ def csr_arrays(A):
     raise TypeError(f"cannot interpret {type(A)} as a CSR matrix")
 
 
+def _comm_device(group, device):
+    import torch
+    import torch.distributed as dist
+    return torch.device("cuda", device) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+
+
+def broadcast_bytes(payload, src=0, group=None, device=0):
+    """Broadcast a fixed-size byte string (NCCL unique id) through torch.distributed (nccl or gloo)."""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(list(payload), dtype=torch.uint8, device=_comm_device(group, device))
+    dist.broadcast(t, src=src, group=group)
+    return bytes(t.cpu().tolist())
+
+
+def allgather_bytes(payload, group=None, device=0):
+    """All-gather equal-size byte strings (CUDA IPC handles): list indexed by rank."""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(list(payload), dtype=torch.uint8, device=_comm_device(group, device))
+    out = [torch.empty_like(t) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(out, t, group=group)
+    return [bytes(o.cpu().tolist()) for o in out]
+
+
+def owned_blocks(nparts, rank, world):
+    """Parts executed by `rank` (contiguous): the host-side mirror of blk_lo/blk_hi in device.cu."""
+    if nparts % world:
+        raise ValueError(f"{nparts} parts cannot be spread evenly over {world} ranks")
+    per = nparts // world
+    return range(rank * per, (rank + 1) * per)
+
+
 class Hierarchy:
     """Owns one metric-AMG hierarchy (host) and, after to_device(), its copy on one B200."""
 
@@ -151,28 +184,18 @@ class Hierarchy:
                 rank, world = 0, 1
         buf = (C.c_ubyte * 128)()
         if world > 1:
-            import torch
-            import torch.distributed as dist
             if rank == 0:
                 check(lib.mamg_nccl_unique_id(buf))
-            dev = torch.device("cuda", self.device) if dist.get_backend(group) == "nccl" else torch.device("cpu")
-            t = torch.tensor(list(buf), dtype=torch.uint8, device=dev)
-            dist.broadcast(t, src=0, group=group)
-            for i, v in enumerate(t.cpu().tolist()):
-                buf[i] = v
+            buf = (C.c_ubyte * 128)(*broadcast_bytes(bytes(buf), 0, group, self.device))
         check(lib.mamg_dist_init(self._h, int(rank), int(world), buf))
         self.rank, self.world = int(rank), int(world)
         if world > 1:
             # peer-memory exchange: all-gather the CUDA IPC handles of the vector arenas
-            import torch
             import torch.distributed as dist
             mine = (C.c_ubyte * 64)()
             check(lib.mamg_ipc_handle(self._h, mine))
-            dev = torch.device("cuda", self.device) if dist.get_backend(group) == "nccl" else torch.device("cpu")
-            t = torch.tensor(list(mine), dtype=torch.uint8, device=dev)
-            allh = [torch.empty_like(t) for _ in range(world)]
-            dist.all_gather(allh, t, group=group)
-            flat = (C.c_ubyte * (64 * world))(*[v for h in allh for v in h.cpu().tolist()])
+            handles = allgather_bytes(bytes(mine), group, self.device)
+            flat = (C.c_ubyte * (64 * world))(*b"".join(handles))
             check(lib.mamg_dist_peers(self._h, flat))
             dist.barrier(group=group)
         return self
