@@ -192,7 +192,10 @@ static int dist_min_rows() {
 static int pick_unroll(int n) {
   const char* env = getenv("MAMG_UNROLL");
   if (env && atoi(env) > 0) return atoi(env) >= 4 ? 4 : atoi(env);
-  return n >= (1 << 18) ? 4 : (n >= (1 << 15) ? 2 : 1);  // small levels need the parallelism more than the MLP
+  // measured on B200 (bidomain_3d, 16 M DOFs): 2 rows in flight per sub-warp beat 4 (SpMV 4.16 vs 3.13 TB/s,
+  // GS 2.09 vs 2.01) -- twice the CTAs per colour launch matter more than the extra loads in flight;
+  // small levels need the parallelism more than the MLP
+  return n >= (1 << 15) ? 2 : 1;
 }
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
