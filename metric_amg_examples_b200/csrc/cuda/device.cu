@@ -481,13 +481,26 @@ push_kernel(PushRanges R, long long voff, double* const* __restrict__ peers, int
   }
   __threadfence_system();
   __syncthreads();
+  __shared__ bool last;
   if (threadIdx.x == 0) {
     const unsigned int t = atomicInc(ticket, gridDim.x - 1);
-    if (t == gridDim.x - 1) {
+    last = t == gridDim.x - 1;
+    if (last) {
       __threadfence_system();
       for (int q = 0; q < world; ++q)
         if (q != me) reinterpret_cast<volatile long long*>(peers[q])[me] = phase;
     }
+  }
+  __syncthreads();
+  // the block that finished last also waits for the peers' flags: when this kernel retires, every
+  // peer's ranges of this exchange have landed here (one launch per exchange instead of two)
+  if (last && threadIdx.x < world && (int)threadIdx.x != me) {
+    const volatile long long* flag = reinterpret_cast<const volatile long long*>(peers[me]) + threadIdx.x;
+    const long long t0 = clock64();
+    while (*flag < phase) {
+      if (clock64() - t0 > 20000000000LL) { printf("mamg: peer %d never reached exchange %lld\n", (int)threadIdx.x, phase); __trap(); }
+    }
+    __threadfence_system();
   }
 }
 
@@ -509,12 +522,8 @@ static void push_ranges(DeviceState& D, const double* v, const PushRanges& R) {
   for (int k = 0; k < R.n; ++k) total += R.len[k];
   const long long voff = v - D.arena;
   const int grid = std::max(1, std::min(D.red_blocks, cdiv(std::max(total, 1), kBlock)));
-  {
-    KScope ks(D, K_VEC);
-    push_kernel<<<grid, kBlock, 0, D.stream>>>(R, voff, D.d_peer_arena, D.rank, D.world, D.push_ticket, D.phase);
-  }
   KScope ks(D, K_VEC);
-  wait_kernel<<<1, 32, 0, D.stream>>>(D.arena, D.rank, D.world, D.phase);
+  push_kernel<<<grid, kBlock, 0, D.stream>>>(R, voff, D.d_peer_arena, D.rank, D.world, D.push_ticket, D.phase);
   ++D.collectives;
 }
 
