@@ -338,7 +338,7 @@ def run_mamg(a):
                    "cycle_type": a.cycle, "krylov": f"ConjGrad relativeconv tolerance={a.rtol:g}",
                    "levels": H.num_levels,
                    "multi_gpu": (f"one system row-partitioned over {world} GPUs ({world} z-slabs), NCCL all-gather of the "
-                                 f"updated row ranges, {ncoll} collectives per solve; levels < 100k rows replicated")
+                                 f"updated row ranges, {ncoll} collectives per solve; levels < 1M rows replicated")
                    if world > 1 else "single",
                    "l2_note": "inputs (matrix 5.8 GB, vectors 128 MB) exceed the 126 MB L2"},
         "iterations": nit, "vcycle_ms": cycle_ms, "rel_error_vs_x_true": rel_err,

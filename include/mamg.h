@@ -123,7 +123,7 @@ int mamg_set_stream(mamg_handle h, void* stream);
  *      Every rank calls mamg_setup_partitioned with the same matrix and partition and
  *      mamg_to_device on its GPU; rank 0 creates an NCCL id (mamg_nccl_unique_id, 128 bytes) that
  *      the host side broadcasts; then mamg_dist_init.  Afterwards apply / pcg run row-distributed
- *      on the levels with at least MAMG_DIST_MIN_ROWS rows: rank r executes the rows of parts
+ *      on the levels with at least MAMG_DIST_MIN_ROWS (default 1 M) rows: rank r executes the rows of parts
  *      [r*P/world, (r+1)*P/world) and the updated ranges are all-gathered over NCCL; smaller levels
  *      are executed redundantly by every rank.  Vectors handed over the ABI are complete on every
  *      rank.  world == 1 is valid (a partitioned hierarchy on one GPU: same numbers, no NCCL). */

@@ -186,7 +186,9 @@ static int pick_lanes(double avg) {
 
 static int dist_min_rows() {
   const char* env = getenv("MAMG_DIST_MIN_ROWS");
-  return env ? atoi(env) : 100000;   // smaller levels are executed redundantly by every rank (no communication)
+  // smaller levels are executed redundantly by every rank (no communication); measured on 4 x B200 at
+  // 16 M DOFs: 1 M rows -> 994 ms per solve, 100 k rows -> 1076 ms (each exchange costs ~35 us of latency + skew)
+  return env ? atoi(env) : 1000000;
 }
 
 static int pick_unroll(int n) {
