@@ -506,18 +506,6 @@ push_kernel(PushRanges R, long long voff, double* const* __restrict__ peers, int
   }
 }
 
-// Waits until every peer has raised its flag for this phase (their ranges have landed here).
-__global__ void wait_kernel(const double* arena, int me, int world, long long phase) {
-  const int q = threadIdx.x;
-  if (q >= world || q == me) return;
-  const volatile long long* flag = reinterpret_cast<const volatile long long*>(arena) + q;
-  const long long t0 = clock64();
-  while (*flag < phase) {
-    if (clock64() - t0 > 20000000000LL) { printf("mamg: peer %d never reached exchange %lld\n", q, phase); __trap(); }
-  }
-  __threadfence_system();
-}
-
 static void push_ranges(DeviceState& D, const double* v, const PushRanges& R) {
   ++D.phase;
   int total = 0;

@@ -437,19 +437,6 @@ dot_kernel(int n, const double* __restrict__ u, const double* __restrict__ v, do
   for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) acc[0] += u[i] * v[i];
   block_reduce_finish<1>(acc, partial, ticket, out);
 }
-// out[0] = u.v, out[1] = u.w
-__global__ void __launch_bounds__(kBlock)
-dot2_kernel(int n, const double* __restrict__ u, const double* __restrict__ v,
-            const double* __restrict__ w, double* partial, unsigned int* ticket, double* out) {
-  double acc[2] = {0.0, 0.0};
-  for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
-    double ui = u[i];
-    acc[0] += ui * v[i];
-    acc[1] += ui * w[i];
-  }
-  block_reduce_finish<2>(acc, partial, ticket, out);
-}
-
 // rz_new = r.z; the finishing block sets sc[3] = rz_new, beta = sc[4] = rz_new / rz, sc[0] = rz_new
 // (first == 1: only sc[0] = r.z, the initial residual)
 __global__ void __launch_bounds__(kBlock)
