@@ -26,7 +26,9 @@
 #include <algorithm>
 #include <cstdint>
 #include <cuda_runtime.h>
+#include <cstring>
 #include <functional>
+#include <numeric>
 #include <vector>
 
 #include "../host/hierarchy.h"
@@ -43,6 +45,14 @@ struct SwPatch {      // 32 bytes per patch
   long long i0;       // first entry in pinv
 };
 
+// Jagged layout of the patch row values on the fast path: the rows of a patch are ordered by
+// decreasing number of off-patch entries, and entry e is stored only for the first cnt[e] lanes
+// (cnt = the level-wide maximum over all patches), at offset off[e] inside the patch's slab.
+struct SwProfile {
+  int off[33];
+  int cnt[32];
+};
+
 struct DSchwarz {
   int npatch = 0, ncolors = 0, max_size = 0, max_nbr = 0, srow = 1, warps = 1, ppc = 1;
   size_t smem_apply = 0, smem_setup = 0;
@@ -56,7 +66,8 @@ struct DSchwarz {
   // fast path (every patch <= 32 dofs, <= 255 neighbours, rows <= 32 entries): per-patch blobs in
   // "lane = patch row" layout, uniform strides, so all addresses follow from the patch number
   bool fast = false;
-  int nbq = 0, sq = 0, inv_stride = 0, sr_t = 32;
+  int nbq = 0, sq = 0, inv_stride = 0, sr_t = 32, vstride = 0;
+  SwProfile prof;
   int* pidx32 = nullptr;       // [np][32] row id of patch dof k, -1 padding
   int* nbrp = nullptr;         // [np][nbq][32] neighbourhood list, padded with a valid index
   double* vt = nullptr;        // [np][srow][32] entry e of row k; 0 padding
@@ -264,7 +275,8 @@ __global__ void __launch_bounds__(256)
 schwarz_blob_kernel(int np, const SwPatch* __restrict__ pat, const int* __restrict__ pidx,
                     const int* __restrict__ nbr, const int* __restrict__ ia, const int* __restrict__ ja,
                     const double* __restrict__ a, int srow, int sq, int nbq, int* __restrict__ pidx32,
-                    int* __restrict__ nbrp, double* __restrict__ vt, uint32_t* __restrict__ ct4) {
+                    int* __restrict__ nbrp, double* __restrict__ vt, uint32_t* __restrict__ ct4,
+                    const SwProfile prof, int vstride) {
   const int patch = blockIdx.x * 8 + threadIdx.x / 32, lane = threadIdx.x % 32;
   if (patch >= np) return;
   const SwPatch P = pat[patch];
@@ -293,13 +305,16 @@ schwarz_blob_kernel(int np, const SwPatch* __restrict__ pat, const int* __restri
         if (P.nn > 0 && nb[lo] == col) { loc = (uint32_t)lo; v = a[r0 + src]; ++src; break; }
         ++src;
       }
-      if (e < srow) vt[(pp * srow + e) * 32 + lane] = v;
+      if (e < srow && lane < prof.cnt[e]) vt[pp * vstride + prof.off[e] + lane] = v;
       word |= loc << (8 * u);
     }
     ct4[(pp * sq + q) * 32 + lane] = word;
   }
 }
 
+#ifndef MAMG_SW_MINB24
+#define MAMG_SW_MINB24 3   // CTAs per SM for the <24,4> specialisation (78 registers, no spills)
+#endif
 #ifndef MAMG_SW_MINB
 #define MAMG_SW_MINB 2   // CTAs per SM the fast kernel is compiled for (2: ~100 registers, 3: 80 with spills)
 #endif
@@ -310,11 +325,11 @@ constexpr int kSwFastSlot = 256 + 528 + 32;  // doubles per patch slot: xs[256],
 // number (row values, packed local columns, neighbour list, inverse via cp.async); wave 2 gathers
 // x on the neighbourhood.  All loops have compile-time bounds; padding multiplies by the zero slot.
 template <int SR, int NBQ>
-__global__ void __launch_bounds__(kSwFastWarps * 32, (SR <= 24 && NBQ <= 4) ? 3 : MAMG_SW_MINB)
+__global__ void __launch_bounds__(kSwFastWarps * 32, (SR <= 24 && NBQ <= 4) ? MAMG_SW_MINB24 : MAMG_SW_MINB)
 schwarz_fast_kernel(int p0, int p1, const int* __restrict__ pidx32, const int* __restrict__ nbrp,
                     const double* __restrict__ vt, const uint32_t* __restrict__ ct4,
                     const double* __restrict__ pinv, const double* __restrict__ b, double* x, int srow,
-                    int sq, int nbq, int inv_stride, int smax) {
+                    int sq, int nbq, int inv_stride, int smax, const SwProfile prof, int vstride) {
   extern __shared__ __align__(16) double smem[];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int patch = p0 + blockIdx.x * kSwFastWarps + warp;
@@ -336,9 +351,9 @@ schwarz_fast_kernel(int p0, int p1, const int* __restrict__ pidx32, const int* _
   }
   double v[SR];
   {
-    const double* vp = vt + (pp * srow) * 32 + lane;
+    const double* vp = vt + pp * vstride + lane;
 #pragma unroll
-    for (int e = 0; e < SR; ++e) v[e] = e < srow ? ld_stream(vp + e * 32) : 0.0;
+    for (int e = 0; e < SR; ++e) v[e] = (e < srow && lane < prof.cnt[e]) ? ld_stream(vp + prof.off[e]) : 0.0;
   }
   uint32_t c4[SR / 4];
   {
@@ -398,7 +413,7 @@ inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iper
   std::vector<SwPatch> pat(np, zero);
   std::vector<int> pidx(sw.dofs.size()), prow(sw.dofs.size()), plen(sw.dofs.size());
   // pass 1: sizes (rows, entries, neighbourhoods) per patch, in parallel
-  std::vector<int> nn(np, 0), nn_out(np, 0);
+  std::vector<int> nn(np, 0), nn_out(np, 0), rlen_out(sw.dofs.size(), 0);
   std::vector<long long> ne(np, 0), ne_out(np, 0);
   int max_rowlen = 1, max_rowlen_out = 1;
 #pragma omp parallel reduction(max : max_rowlen, max_rowlen_out)
@@ -421,6 +436,7 @@ inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iper
           if (mark[pja[e]] != k) { mark[pja[e]] = k; ++cnt; cnt_out += outside; }
         }
         ent_out += row_out;
+        rlen_out[q] = row_out;
         max_rowlen_out = std::max(max_rowlen_out, row_out);
       }
       nn[k] = cnt;
@@ -429,16 +445,37 @@ inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iper
       ne_out[k] = ent_out;
     }
   }
-  int max_nn = 0;
-  for (int k = 0; k < np; ++k) max_nn = std::max(max_nn, nn[k]);
+  int max_nn = 0;   // on the fast path only the neighbours outside the patch are gathered
+  for (int k = 0; k < np; ++k) max_nn = std::max(max_nn, nn_out[k]);
   const char* nofast = getenv("MAMG_SCHWARZ_GENERAL");
-  const bool fast_shape = d.max_size <= 32 && max_nn <= 255 && max_rowlen <= 32 && !(nofast && atoi(nofast));
+  const bool fast_shape = d.max_size <= 32 && max_nn <= 255 && max_rowlen_out <= 32 && !(nofast && atoi(nofast));
   // fast path: x_B + A_BB^{-1}(b - A x)_B = A_BB^{-1}(b_B - A_{B,out} x_out): the entries of the patch rows
   // that fall inside the patch are already in the stored inverse, so only the off-patch entries
   // (and the neighbours outside the patch) are kept -- about a quarter less traffic per patch
   const int srow = fast_shape ? max_rowlen_out : (max_rowlen | 1);   // general path: odd row stride (conflict-free)
   d.srow = srow;
   if (fast_shape) { nn = nn_out; ne = ne_out; }
+  std::vector<int> dord(sw.dofs.size());   // sorted position -> position inside sw.dofs (identity on the general path)
+  std::iota(dord.begin(), dord.end(), 0);
+  SwProfile prof;
+  std::memset(&prof, 0, sizeof(prof));
+  if (fast_shape) {
+#pragma omp parallel for schedule(static)
+    for (int p = 0; p < np; ++p)
+      std::stable_sort(dord.begin() + sw.ptr[p], dord.begin() + sw.ptr[p + 1],
+                       [&](int u, int v) { return rlen_out[u] > rlen_out[v]; });
+    for (int p = 0; p < np; ++p) {
+      int covered = 0;   // rows are sorted by decreasing length: walk them from the shortest
+      for (int q = sw.ptr[p + 1] - 1; q >= sw.ptr[p]; --q) {
+        const int lane = q - sw.ptr[p], len = std::min(rlen_out[dord[q]], 32);
+        for (int e = covered; e < len; ++e) prof.cnt[e] = std::max(prof.cnt[e], lane + 1);
+        covered = std::max(covered, len);
+      }
+    }
+    for (int e = 0; e < 32; ++e) prof.off[e + 1] = prof.off[e] + ((prof.cnt[e] + 3) & ~3);   // 32-byte aligned rows
+  }
+  d.prof = prof;
+  d.vstride = prof.off[32];
   long long tot_e = 0, tot_i = 0, tot_val = 0;
   long long tot_n = 0, tot_q = 0;
   int max_nbr = 0;
@@ -478,9 +515,9 @@ inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iper
       const int s = pat[k].s;
       list.clear();
       if (fast_shape)   // the patch's own dofs are never gathered on the fast path
-        for (int q = 0; q < s; ++q) mark[iperm[sw.dofs[sw.ptr[p] + q]]] = k;
+        for (int q = 0; q < s; ++q) mark[iperm[sw.dofs[dord[sw.ptr[p] + q]]]] = k;
       for (int q = 0; q < s; ++q) {
-        const int i = iperm[sw.dofs[sw.ptr[p] + q]];
+        const int i = iperm[sw.dofs[dord[sw.ptr[p] + q]]];
         pidx[pat[k].q0 + q] = i;
         prow[pat[k].q0 + q] = pia[i];
         plen[pat[k].q0 + q] = pia[i + 1] - pia[i];
@@ -531,7 +568,7 @@ inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iper
         const int p = order[k];
         const int pp = hl.part[sw.seed[p]];
         for (int q = 0; q < pat[k].s; ++q) {
-          const int nat = sw.dofs[sw.ptr[p] + q], dof = pidx[pat[k].q0 + q];
+          const int nat = sw.dofs[dord[sw.ptr[p] + q]], dof = pidx[pat[k].q0 + q];
           if ((readers[dof] & ~(1ull << pp)) || hl.part[nat] != pp) xidx.push_back(dof);
         }
       }
@@ -560,10 +597,10 @@ inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iper
     d.sr_t = (srow <= 12 && d.nbq <= 1) ? 12 : ((srow <= 24 && d.nbq <= 4) ? 24 : 32);
     d.pidx32 = (int*)alloc((size_t)np * 32 * sizeof(int));
     d.nbrp = (int*)alloc((size_t)np * d.nbq * 32 * sizeof(int));
-    d.vt = (double*)alloc((size_t)np * srow * 32 * sizeof(double));
+    d.vt = (double*)alloc(((size_t)np * d.vstride + 32) * sizeof(double));
     d.ct4 = (uint32_t*)alloc((size_t)np * d.sq * 32 * sizeof(uint32_t));
     schwarz_blob_kernel<<<(np + 7) / 8, 256>>>(np, d.pat, d.pidx, d.nbr, d_ia, d_ja, d_a, srow, d.sq, d.nbq,
-                                              d.pidx32, d.nbrp, d.vt, d.ct4);
+                                              d.pidx32, d.nbrp, d.vt, d.ct4, d.prof, d.vstride);
     e = cudaDeviceSynchronize();
     if (e != cudaSuccess) throw std::runtime_error(std::string("Schwarz blob kernel failed: ") + cudaGetErrorString(e));
     const int fsm = kSwFastWarps * kSwFastSlot * (int)sizeof(double);
@@ -585,7 +622,7 @@ inline void schwarz_range_launch(const DSchwarz& d, int p0, int p1, const double
   if (d.fast) {
     const int g = (p1 - p0 + kSwFastWarps - 1) / kSwFastWarps;
     const size_t sm = (size_t)kSwFastWarps * kSwFastSlot * sizeof(double);
-#define MAMG_SWF_ARGS p0, p1, d.pidx32, d.nbrp, d.vt, d.ct4, d.pinv, b, x, d.srow, d.sq, d.nbq, d.inv_stride, d.max_size
+#define MAMG_SWF_ARGS p0, p1, d.pidx32, d.nbrp, d.vt, d.ct4, d.pinv, b, x, d.srow, d.sq, d.nbq, d.inv_stride, d.max_size, d.prof, d.vstride
     if (d.sr_t == 12) schwarz_fast_kernel<12, 1><<<g, kSwFastWarps * 32, sm, stream>>>(MAMG_SWF_ARGS);
     else if (d.sr_t == 24) schwarz_fast_kernel<24, 4><<<g, kSwFastWarps * 32, sm, stream>>>(MAMG_SWF_ARGS);
     else schwarz_fast_kernel<32, 8><<<g, kSwFastWarps * 32, sm, stream>>>(MAMG_SWF_ARGS);
