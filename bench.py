@@ -189,6 +189,16 @@ def run_mamg(a):
             n -= 8
         if n != DEFAULT_N[a.workload]:
             note = f" (mesh reduced from {DEFAULT_N[a.workload]} to fit {world} host copies of the hierarchy)"
+    if world == 1 and a.n is not None:
+        # refuse rather than drive the host out of memory: setup + upload temporaries per DOF
+        import psutil
+        dim = int(a.workload[-2])
+        ndof_est = 2 * (n + 1) ** dim if a.workload.startswith("bidomain") else (n + 1) ** (dim - 1) * (n + 2)
+        need = (3600.0 if a.workload.startswith("bidomain") else 1400.0) * ndof_est
+        avail = psutil.virtual_memory().available
+        if need > 0.9 * avail:
+            raise SystemExit(f"bench.py: {a.workload} n={n} needs ~{need / 1e9:.0f} GB of host memory for the "
+                             f"setup, {avail / 1e9:.0f} GB available")
     t0 = time.time()
     system, prm = make_system(a.workload, n, a.gamma)
     t_asm = time.time() - t0

@@ -244,7 +244,7 @@ static int check_problem(int dim, int n, bool emi) {
   if (emi && (n < 4 || n % 2)) { set_error("assemble_emi: ncell must be even and >= 4 (src/utils.py:192)"); return -1; }
   double nv = 1;
   for (int a = 0; a < dim; ++a) nv *= (a == dim - 1 && emi) ? n / 2 + 1 : n + 1;
-  double nnz_est = 2 * nv * (dim == 2 ? 14 : 30);
+  double nnz_est = 2 * nv * (dim == 2 ? 7 : 15) * (emi ? 1.05 : 2);
   if (2 * nv > 2.0e9 || nnz_est > 2.1e9) { set_error("assemble: system exceeds int32 indexing"); return -1; }
   return 0;
 }
