@@ -24,6 +24,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 # torchrun pins OMP_NUM_THREADS=1; the host setup (aggregation, Galerkin products, patch lists) is
 # OpenMP code: give every rank its share of the cores before libgomp starts
+# stdout carries exactly one JSON line: NCCL's own banner (NCCL_DEBUG=VERSION/INFO on some boxes) goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 if int(os.environ.get("WORLD_SIZE", "1")) > 1 and os.environ.get("OMP_NUM_THREADS", "1") == "1":
     os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // int(os.environ.get("LOCAL_WORLD_SIZE", os.environ["WORLD_SIZE"]))))
 
@@ -312,6 +314,8 @@ def run_mamg(a):
             dist.destroy_process_group()
         return
     nit = pinfo["niters"]
+    exch_mode = ("NCCL grouped broadcasts" if os.environ.get("MAMG_P2P", "1") == "0"
+                 else "peer-memory stores over NVLink fused with the flag barrier (CUDA IPC)")
     cb = class_bytes(H, nit, nit + 1)
     tot_ms = sum(v[0] for v in prof.values())
     dom = max(prof, key=lambda k: prof[k][0])
@@ -347,10 +351,12 @@ def run_mamg(a):
                    "precond": "metricAMG parameters_metric_schwarz" if a.workload.startswith("bidomain") else "metricAMG default_metric_parameters",
                    "cycle_type": a.cycle, "krylov": f"ConjGrad relativeconv tolerance={a.rtol:g}",
                    "levels": H.num_levels,
-                   "multi_gpu": (f"one system row-partitioned over {world} GPUs ({world} z-slabs), NCCL all-gather of the "
-                                 f"updated row ranges, {ncoll} collectives per solve; levels < 1M rows replicated")
+                   "multi_gpu": (f"one system row-partitioned over {world} GPUs ({world} z-slabs); updated row ranges "
+                                 f"exchanged by {exch_mode}, {ncoll} exchanges per solve; levels < "
+                                 f"{os.environ.get('MAMG_DIST_MIN_ROWS', '1000000')} rows replicated")
                    if world > 1 else "single",
-                   "l2_note": "inputs (matrix 5.8 GB, vectors 128 MB) exceed the 126 MB L2"},
+                   "l2_note": (f"level-0 matrix {12 * nnz0 / 1e9:.2f} GB and vectors {8 * ndofs / 1e6:.0f} MB each: "
+                               + ("larger than" if 12 * nnz0 > 126e6 else "NOT larger than") + " the 126 MB L2")},
         "iterations": nit, "vcycle_ms": cycle_ms, "rel_error_vs_x_true": rel_err,
         "e2e": {"value": ndofs * a.steps / e2e_s, "unit": "DOF/s", "h2d_bytes_per_step": 8 * ndofs,
                 "d2h_bytes_per_step": 8 * ndofs},

@@ -59,7 +59,7 @@ struct DLevel {
   int* d_color_ptr = nullptr;   // device copy of bc_ptr (tail kernel)
 };
 
-enum KClass { K_SPMV = 0, K_GS, K_SCHWARZ, K_RESTRICT, K_SCALE, K_PROLONG, K_COARSE, K_VEC, K_DOT, K_NCLS };
+enum KClass { K_SPMV = 0, K_GS, K_SCHWARZ, K_RESTRICT, K_SCALE, K_PROLONG, K_COARSE, K_VEC, K_DOT, K_EXCH, K_NCLS };
 
 struct ProfEvent { cudaEvent_t start, stop; int cls; int lev; };
 
@@ -512,7 +512,7 @@ static void push_ranges(DeviceState& D, const double* v, const PushRanges& R) {
   for (int k = 0; k < R.n; ++k) total += R.len[k];
   const long long voff = v - D.arena;
   const int grid = std::max(1, std::min(D.red_blocks, cdiv(std::max(total, 1), kBlock)));
-  KScope ks(D, K_VEC);
+  KScope ks(D, K_EXCH);
   push_kernel<<<grid, kBlock, 0, D.stream>>>(R, voff, D.d_peer_arena, D.rank, D.world, D.push_ticket, D.phase);
   ++D.collectives;
 }

@@ -226,7 +226,7 @@ class Hierarchy:
         check(lib.mamg_launch_count(self._h, C.byref(v), int(reset)))
         return v.value
 
-    KERNEL_CLASSES = ["spmv", "gs", "schwarz", "restrict", "scale", "prolong", "coarse", "vector", "dot"]
+    KERNEL_CLASSES = ["spmv", "gs", "schwarz", "restrict", "scale", "prolong", "coarse", "vector", "dot", "exchange"]
 
     def schwarz_sweep_bytes(self, level=0):
         v = C.c_int64()
