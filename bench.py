@@ -375,7 +375,7 @@ def run_mamg(a):
     }
     if not a.no_cpu_baseline:
         out["cpu_baseline"] = cpu_sample(a, threads=1, ordering="natural")
-    print(json.dumps(out))
+    print(json.dumps(out), file=RESULT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -424,11 +424,16 @@ def run_reference(a):
         "note": "HAZmath/cbc.block are not installable here (SURVEY 8c); this arm is the repo's CPU oracle of "
                 "the same path (multicolour order, OpenMP over colour classes) on all host threads",
     }
-    print(json.dumps(out))
+    print(json.dumps(out), file=RESULT, flush=True)
 
 
 if __name__ == "__main__":
     args = parse()
+    # the real stdout carries exactly one JSON line; whatever libraries print to fd 1 (NCCL's version
+    # banner under NCCL_DEBUG=VERSION ignores NCCL_DEBUG_FILE) is sent to stderr instead
+    sys.stdout.flush()
+    RESULT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -100,7 +100,7 @@ struct DeviceState {
   std::vector<double*> peer_arena;   // arena base of every rank (own entry = arena)
   double** d_peer_arena = nullptr;   // device copy
   unsigned int* push_ticket = nullptr;
-  long long phase = 0;               // exchanges so far (same sequence on every rank)
+  long long* d_phase = nullptr;      // exchanges so far (device counter; the same sequence on every rank)
   bool use_p2p = false;
   size_t xcap = 0;
   long long xflip = 0;
@@ -119,6 +119,8 @@ struct DeviceState {
   struct GraphEntry { const double* r; double* z; cudaGraphExec_t exec; int64_t launches; int64_t cls[K_NCLS]; };
   std::vector<GraphEntry> graphs;
   bool use_graph = true;
+  bool graph_dist = true;            // capture the cycle with several ranks too (MAMG_GRAPH_DIST=0 disables)
+  bool capturing = false;
 };
 
 // Brackets one kernel launch: counts it and, in profiling mode, times it with a CUDA event pair
@@ -403,6 +405,8 @@ static void upload_hierarchy(const Hierarchy& H, DeviceState& D) {
   for (int k = 0; k < 10; ++k) D.w[k] = carve(D.lv[0].n);
   D.push_ticket = dalloc<unsigned int>(D, 4);
   CUDA_OK(cudaMemset(D.push_ticket, 0, 4 * sizeof(unsigned int)));
+  D.d_phase = dalloc<long long>(D, 2);
+  CUDA_OK(cudaMemset(D.d_phase, 0, 2 * sizeof(long long)));
   D.io_a = dalloc<double>(D, max_n);
   D.io_b = dalloc<double>(D, max_n);
 }
@@ -470,7 +474,7 @@ struct PushRanges { int n; int beg[8]; int len[8]; };
 // arena, then the block that finishes last raises this rank's flag (= phase) in every peer.
 __global__ void __launch_bounds__(kBlock)
 push_kernel(PushRanges R, long long voff, double* const* __restrict__ peers, int me, int world,
-            unsigned int* ticket, long long phase) {
+            unsigned int* ticket, long long* phase_ctr) {
   int total = 0;
   for (int k = 0; k < R.n; ++k) total += R.len[k];
   const double* mine = peers[me] + voff;
@@ -483,17 +487,22 @@ push_kernel(PushRanges R, long long voff, double* const* __restrict__ peers, int
   }
   __threadfence_system();
   __syncthreads();
+  // the exchange number lives in device memory (every rank runs the same sequence of exchanges), so
+  // that a captured graph of the cycle can be replayed
   __shared__ bool last;
+  __shared__ long long phase_s;
   if (threadIdx.x == 0) {
     const unsigned int t = atomicInc(ticket, gridDim.x - 1);
     last = t == gridDim.x - 1;
     if (last) {
+      phase_s = *reinterpret_cast<volatile long long*>(phase_ctr) + 1;
       __threadfence_system();
       for (int q = 0; q < world; ++q)
-        if (q != me) reinterpret_cast<volatile long long*>(peers[q])[me] = phase;
+        if (q != me) reinterpret_cast<volatile long long*>(peers[q])[me] = phase_s;
     }
   }
   __syncthreads();
+  const long long phase = last ? phase_s : 0;
   // the block that finished last also waits for the peers' flags: when this kernel retires, every
   // peer's ranges of this exchange have landed here (one launch per exchange instead of two)
   if (last && threadIdx.x < world && (int)threadIdx.x != me) {
@@ -504,16 +513,19 @@ push_kernel(PushRanges R, long long voff, double* const* __restrict__ peers, int
     }
     __threadfence_system();
   }
+  if (last) {   // block-uniform
+    __syncthreads();
+    if (threadIdx.x == 0) *phase_ctr = phase;
+  }
 }
 
 static void push_ranges(DeviceState& D, const double* v, const PushRanges& R) {
-  ++D.phase;
   int total = 0;
   for (int k = 0; k < R.n; ++k) total += R.len[k];
   const long long voff = v - D.arena;
   const int grid = std::max(1, std::min(D.red_blocks, cdiv(std::max(total, 1), kBlock)));
   KScope ks(D, K_EXCH);
-  push_kernel<<<grid, kBlock, 0, D.stream>>>(R, voff, D.d_peer_arena, D.rank, D.world, D.push_ticket, D.phase);
+  push_kernel<<<grid, kBlock, 0, D.stream>>>(R, voff, D.d_peer_arena, D.rank, D.world, D.push_ticket, D.d_phase);
   ++D.collectives;
 }
 
@@ -543,6 +555,7 @@ static void exchange(DeviceState& D, const DLevel& l, double* v, int c) {
     push_ranges(D, v, R);
     return;
   }
+  if (D.capturing) throw std::runtime_error("exchange of a vector outside the peer arena while capturing the cycle (set MAMG_GRAPH_DIST=0)");
   NCCL_OK(ncclGroupStart());
   for (int b = 0; b < l.nb; ++b) {
     const int r0 = c >= 0 ? l.row0(b, c) : l.bc_ptr[b * l.ncolors];
@@ -830,7 +843,11 @@ static void apply_permuted_raw(DeviceState& D, const double* r, double* z);
 
 // z' = B r' in the permuted ordering of level 0 (both device arrays of size n0)
 static void apply_permuted(DeviceState& D, const double* r, double* z) {
-  if (!D.use_graph || D.prof_on || D.world > 1 || apply_launch_estimate(D) > 60000) { apply_permuted_raw(D, r, z); return; }
+  // several ranks: only the peer-memory exchange is captured (its exchange counter lives on the device)
+  if (!D.use_graph || D.prof_on || (D.world > 1 && !(D.use_p2p && D.graph_dist)) || apply_launch_estimate(D) > 60000) {
+    apply_permuted_raw(D, r, z);
+    return;
+  }
   for (auto& g : D.graphs)
     if (g.r == r && g.z == z) {
       CUDA_OK(cudaGraphLaunch(g.exec, D.stream));
@@ -844,13 +861,16 @@ static void apply_permuted(DeviceState& D, const double* r, double* z) {
   for (int k = 0; k < K_NCLS; ++k) c0[k] = D.cls_launches[k];
   cudaGraph_t graph = nullptr;
   CUDA_OK(cudaStreamBeginCapture(D.stream, cudaStreamCaptureModeThreadLocal));
+  D.capturing = true;
   try {
     apply_permuted_raw(D, r, z);
   } catch (...) {
+    D.capturing = false;
     cudaStreamEndCapture(D.stream, &graph);
     if (graph) cudaGraphDestroy(graph);
     throw;
   }
+  D.capturing = false;
   CUDA_OK(cudaStreamEndCapture(D.stream, &graph));
   DeviceState::GraphEntry e;
   e.r = r;
@@ -1151,6 +1171,7 @@ int mamg_to_device(mamg_handle h, int32_t device, void* stream) {
   D->device = device;
   D->prm = h->H.prm;
   { const char* g = getenv("MAMG_GRAPH"); if (g) D->use_graph = atoi(g) != 0; }
+  { const char* g = getenv("MAMG_GRAPH_DIST"); if (g) D->graph_dist = atoi(g) != 0; }
   {
     const char* e2 = getenv("MAMG_L2_PERSIST_MB");   // 0 disables; default: what the device allows
     int maxp = 0;
