@@ -268,3 +268,59 @@ def test_drop_in_classes_fused_and_callback():
     assert rel(np.concatenate(list(xb)), xe) < 1e-6
     zb = Bblk * bb   # one preconditioner application on a block vector
     assert isinstance(zb, block_vec) and len(zb[0]) == n0
+
+
+# ---- edge cases: degenerate hierarchies and inputs ------------------------------------------------
+def test_single_level_hierarchy_is_a_direct_solve():
+    """n <= coarse_dof: no coarsening at all, the apply is the dense coarse solve (UMFPACK upstream)."""
+    s = problems.bidomain_system(2, 6, gamma=1e3)   # 98 dofs <= coarse_dof 100
+    H, orc = make(s, params.parameters_metric_schwarz)
+    assert H.num_levels == 1
+    b, _ = s.random_rhs(0)
+    z = H.apply(b)
+    assert rel(z, orc.apply(b)) < APPLY_TOL
+    assert rel(z, np.linalg.solve(s.A.toarray(), b)) < 1e-10
+    x, info = H.pcg(b, tolerance=1e-10, relative=True, maxiter=20)
+    assert info["niters"] == orc.pcg(b, tolerance=1e-10, relative=True, maxiter=20)[1]["niters"] <= 2
+
+
+def test_zero_right_hand_side():
+    """b = 0: zero iterations, x = 0, no NaN from the 0/0 of the relative stopping rule."""
+    s = problems.bidomain_system(2, 24, gamma=1e3)
+    H, orc = make(s, params.parameters_metric_schwarz)
+    b = np.zeros(s.ndofs)
+    for relative in (False, True):
+        x, info = H.pcg(b, tolerance=1e-8, relative=relative, maxiter=50)
+        xo, io = orc.pcg(b, tolerance=1e-8, relative=relative, maxiter=50)
+        assert info["niters"] == io["niters"] == 0
+        assert np.all(x == 0.0) and np.all(np.isfinite(x))
+    assert np.all(H.apply(b) == 0.0)
+
+
+def test_truncated_hierarchy_and_two_cycles_per_apply():
+    """max_levels 2 leaves a 575-row coarsest level (dense inverse far above coarse_dof); maxit 2 runs two
+    cycles per apply."""
+    s = problems.bidomain_system(2, 24, gamma=1e3)
+    prm = dict(params.parameters_metric_schwarz, max_levels=2, maxit=2)
+    H, orc = make(s, prm)
+    assert H.num_levels == 2 and H.level_info(1)["rows"] > 500
+    rng = np.random.default_rng(11)
+    r = rng.standard_normal(s.ndofs)
+    assert rel(H.apply(r), orc.apply(r)) < APPLY_TOL
+    b, _ = s.random_rhs(2)
+    x, info = H.pcg(b, tolerance=1e-8, relative=True, maxiter=100)
+    xo, io = orc.pcg(b, tolerance=1e-8, relative=True, maxiter=100)
+    assert abs(info["niters"] - io["niters"]) <= 1 and rel(x, xo) < 1e-6
+
+
+def test_metric_amg_without_interface_dofs():
+    """metricAMG(A, W, parameters=...) (src/utils.py:88): no idofs, an empty list means the same; the
+    Schwarz seeds then come from an independent set over all dofs."""
+    s = problems.bidomain_system(2, 24, gamma=1e3)
+    Hn = mamg.Hierarchy(s.A, params.parameters_metric_schwarz, None)
+    He = mamg.Hierarchy(s.A, params.parameters_metric_schwarz, np.zeros(0, np.int32))
+    assert Hn.level_info(0)["n_patches"] == He.level_info(0)["n_patches"] > 0
+    He.to_device(0)
+    orc = Oracle(He.export(), "multicolor")
+    r = np.random.default_rng(12).standard_normal(s.ndofs)
+    assert rel(He.apply(r), orc.apply(r)) < APPLY_TOL
