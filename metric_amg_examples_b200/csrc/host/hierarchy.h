@@ -64,7 +64,7 @@ void galerkin_ua(const Csr& A, const std::vector<int>& agg, int nc, Csr& Ac);
 void csr_transpose(const Csr& A, Csr& At);
 void csr_multiply(const Csr& A, const Csr& B, Csr& C);   // C = A B, columns sorted
 void smoothed_prolongator(const Csr& A, const std::vector<int>& agg, int nc, double omega, Csr& P);
-void multicolor_greedy(const Csr& A, std::vector<int>& color, int& ncolors);
+void multicolor_greedy(const Csr& A, const std::vector<uint8_t>& skip, std::vector<int>& color, int& ncolors);
 void schwarz_patches(const Csr& A, const int* seeds, int nseeds, int maxlvl, int mmsize,
                      SchwarzPatches& out);
 void schwarz_color(const Csr& A, SchwarzPatches& sw);

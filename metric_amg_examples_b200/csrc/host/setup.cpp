@@ -297,25 +297,36 @@ void smoothed_prolongator(const Csr& A, const std::vector<int>& agg, int nc, dou
 // Greedy multicolouring in natural row order over the nonzero off-diagonal couplings:
 // the fixed ordering the Gauss-Seidel sweeps use on the device AND in the oracle
 // (north_star: "Gauss-Seidel via a fixed multicolour ordering applied identically in
-// the reference comparison").
-void multicolor_greedy(const Csr& A, std::vector<int>& color, int& ncolors) {
+// the reference comparison").  Rows that the point smoother never touches (`skip`: the Schwarz
+// seeds) are left out of the graph: they all get colour 0, which no sweep launches, and the rows
+// that are smoothed share colours 1..k computed on their own subgraph.  On the device this keeps the
+// Schwarz-only rows in one block in natural order (contiguous x-runs for the patch gathers) and
+// gives the smoothed rows fewer, fully populated colour blocks.
+void multicolor_greedy(const Csr& A, const std::vector<uint8_t>& skip, std::vector<int>& color, int& ncolors) {
   const int n = A.n;
   color.assign(n, -1);
-  ncolors = 0;
+  bool any_skip = false;
+  for (int i = 0; i < n && !skip.empty(); ++i) any_skip = any_skip || skip[i];
+  const int base = any_skip ? 1 : 0;
+  ncolors = base;
   std::vector<int> forbid;  // forbid[c] == i  <=> colour c taken by a neighbour of row i
   for (int i = 0; i < n; ++i) {
+    if (any_skip && skip[i]) continue;
     for (int p = A.ia[i]; p < A.ia[i + 1]; ++p) {
       int j = A.ja[p];
       if (j == i || A.a[p] == 0.0 || color[j] < 0) continue;
       if ((int)forbid.size() <= color[j]) forbid.resize(color[j] + 1, -1);
       forbid[color[j]] = i;
     }
-    int c = 0;
+    int c = base;
     while (c < (int)forbid.size() && forbid[c] == i) ++c;
     color[i] = c;
     if (c + 1 > ncolors) ncolors = c + 1;
     if ((int)forbid.size() < ncolors) forbid.resize(ncolors, -1);
   }
+  if (any_skip)
+    for (int i = 0; i < n; ++i)
+      if (skip[i]) color[i] = 0;
 }
 
 // Schwarz blocks: seed + Schwarz_maxlvl graph rings (breadth first over nonzero couplings),
@@ -490,7 +501,7 @@ bool build_hierarchy(const mamg_params& prm, Csr&& A0, const int* idofs, int n_i
       L.agg.clear(); L.nc = 0; L.sw = SchwarzPatches(); L.gs_skip.clear();
       break;
     }
-    multicolor_greedy(L.A, L.color, L.ncolors);
+    multicolor_greedy(L.A, L.gs_skip, L.color, L.ncolors);
     H.lv.emplace_back();
     if (prm.AMG_type == MAMG_SA_AMG) {
       Level& F = H.lv[l];

@@ -105,12 +105,16 @@ def test_hierarchy_invariants(prm):
         offdiag = abs(A - sp.diags(A.diagonal())).sum(axis=1).A1
         assert np.all((agg < 0) == (offdiag == 0)) or "standard" in prm
         assert np.all(np.bincount(agg[agg >= 0], minlength=L[l]["n_aggregates"]) >= 1)
-        # colouring: no two coupled rows share a colour
+        # colouring: no two coupled rows that the point smoother touches share a colour; the rows
+        # it never touches (Schwarz seeds) all sit in colour 0, which then holds nothing else
         col = L[l]["color"]
+        skip = L[l]["gs_skip"].astype(bool) if len(L[l].get("gs_skip", ())) else np.zeros(len(col), bool)
         C_ = A.tocoo()
-        m = (C_.row != C_.col) & (C_.data != 0)
+        m = (C_.row != C_.col) & (C_.data != 0) & ~skip[C_.row] & ~skip[C_.col]
         assert np.all(col[C_.row[m]] != col[C_.col[m]])
         assert col.max() + 1 == L[l]["n_colors"]
+        if skip.any():
+            assert np.all(col[skip] == 0) and np.all(col[~skip] > 0)
     if metric and P["Schwarz_levels"] > 0:
         l0 = L[0]
         A = sp.csr_matrix((l0["data"], l0["indices"], l0["indptr"]), shape=(l0["n"],) * 2)
