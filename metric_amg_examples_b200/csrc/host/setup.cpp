@@ -17,6 +17,8 @@
 //   * the coarsest operator is inverted densely (coarse_solver 32 = direct).
 #include <algorithm>
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 #include <numeric>
@@ -374,19 +376,16 @@ void schwarz_color(const Csr& A, SchwarzPatches& sw) {
   sw.color.assign(np, 0);
   sw.ncolors = 0;
   if (np == 0) return;
-  int W = 4;  // 64-bit words per dof mask, grown on demand
-  std::vector<uint64_t> mask((size_t)A.n * W, 0), forb;
+  // reach[j] = colours of the patches that contain j or a dof coupled to j (the pattern of A is
+  // symmetric), so the colours forbidden to a patch are the union of reach over its own dofs:
+  // s word-vector ORs per patch to query, one single-word OR per row entry to record
+  int W = 2;  // 64-bit words per dof mask, grown on demand
+  std::vector<uint64_t> reach((size_t)A.n * W, 0), forb;
   for (int p = 0; p < np; ++p) {
     forb.assign(W, 0);
     for (int q = sw.ptr[p]; q < sw.ptr[p + 1]; ++q) {
-      int i = sw.dofs[q];
-      const uint64_t* mi = &mask[(size_t)i * W];
+      const uint64_t* mi = &reach[(size_t)sw.dofs[q] * W];
       for (int w = 0; w < W; ++w) forb[w] |= mi[w];
-      for (int e = A.ia[i]; e < A.ia[i + 1]; ++e) {
-        if (A.a[e] == 0.0) continue;
-        const uint64_t* mj = &mask[(size_t)A.ja[e] * W];
-        for (int w = 0; w < W; ++w) forb[w] |= mj[w];
-      }
     }
     int c = -1;
     for (int w = 0; w < W && c < 0; ++w)
@@ -395,15 +394,21 @@ void schwarz_color(const Csr& A, SchwarzPatches& sw) {
       const int W2 = W * 2;
       std::vector<uint64_t> m2((size_t)A.n * W2, 0);
       for (size_t i = 0; i < (size_t)A.n; ++i)
-        for (int w = 0; w < W; ++w) m2[i * W2 + w] = mask[i * W + w];
-      mask.swap(m2);
+        for (int w = 0; w < W; ++w) m2[i * W2 + w] = reach[i * W + w];
+      reach.swap(m2);
       c = W * 64;
       W = W2;
     }
     sw.color[p] = c;
     sw.ncolors = std::max(sw.ncolors, c + 1);
-    for (int q = sw.ptr[p]; q < sw.ptr[p + 1]; ++q)
-      mask[(size_t)sw.dofs[q] * W + c / 64] |= 1ull << (c % 64);
+    const size_t cw = c / 64;
+    const uint64_t bit = 1ull << (c % 64);
+    for (int q = sw.ptr[p]; q < sw.ptr[p + 1]; ++q) {
+      const int i = sw.dofs[q];
+      reach[(size_t)i * W + cw] |= bit;
+      for (int e = A.ia[i]; e < A.ia[i + 1]; ++e)
+        if (A.a[e] != 0.0) reach[(size_t)A.ja[e] * W + cw] |= bit;
+    }
   }
 }
 
@@ -479,6 +484,14 @@ bool build_hierarchy(const mamg_params& prm, Csr&& A0, const int* idofs, int n_i
     return false;
   }
   const int max_levels = std::max(1, prm.max_levels);
+  const bool timing = getenv("MAMG_SETUP_TIMING") != nullptr;   // per-phase seconds on stderr
+  auto tp = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what, int lev) {
+    if (!timing) return;
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[mamg setup] level %d %-16s %.3f s\n", lev, what, std::chrono::duration<double>(now - tp).count());
+    tp = now;
+  };
   std::vector<int> seeds(idofs, idofs + n_idofs);
   const bool metric = n_idofs > 0;
   int l = 0;
@@ -489,7 +502,9 @@ bool build_hierarchy(const mamg_params& prm, Csr&& A0, const int* idofs, int n_i
     if (!last && l < prm.Schwarz_levels) {
       if (!metric) greedy_mis(L.A, seeds);
       schwarz_patches(L.A, seeds.data(), (int)seeds.size(), prm.Schwarz_maxlvl, prm.Schwarz_mmsize, L.sw);
+      lap("schwarz_patches", l);
       schwarz_color(L.A, L.sw);
+      lap("schwarz_color", l);
       L.gs_skip.assign(n, metric ? 0 : 1);
       if (metric) for (int s : seeds) L.gs_skip[s] = 1;
     }
@@ -497,11 +512,13 @@ bool build_hierarchy(const mamg_params& prm, Csr&& A0, const int* idofs, int n_i
     const int* lpart = L.part.empty() ? nullptr : L.part.data();
     if (prm.aggregation_type == MAMG_HEM) aggregate_hem(L.A, lpart, L.agg, L.nc);
     else aggregate_vmb(L.A, lpart, prm.strong_coupled, prm.max_aggregation, L.agg, L.nc);
+    lap("aggregate", l);
     if (L.nc == 0 || L.nc >= n) {  // no coarsening possible: this level becomes the coarsest
       L.agg.clear(); L.nc = 0; L.sw = SchwarzPatches(); L.gs_skip.clear();
       break;
     }
     multicolor_greedy(L.A, L.gs_skip, L.color, L.ncolors);
+    lap("multicolor", l);
     H.lv.emplace_back();
     if (prm.AMG_type == MAMG_SA_AMG) {
       Level& F = H.lv[l];
@@ -513,6 +530,7 @@ bool build_hierarchy(const mamg_params& prm, Csr&& A0, const int* idofs, int n_i
     } else {
       galerkin_ua(H.lv[l].A, H.lv[l].agg, H.lv[l].nc, H.lv[l + 1].A);
     }
+    lap("galerkin", l);
     if (!H.lv[l].part.empty()) {   // a coarse row belongs to the part of its members
       std::vector<int>& cp = H.lv[l + 1].part;
       cp.assign(H.lv[l].nc, 0);
