@@ -114,26 +114,40 @@ def emi_system(dim, n, kappa1=2.0, kappa2=3.0, gamma=5.0, both_sides=None):
                   dict(kappa1=kappa1, kappa2=kappa2, gamma=gamma))
 
 
-def slab_partition(system, nparts):
-    """Owner part of every dof for multi-GPU runs: slabs along the last axis (z in 3-D, y in 2-D), both
-    fields of a vertex in the same part.  For EMI the slab boundaries keep the interface
-    plane and 3 planes on either side inside one part, so that no Schwarz patch straddles parts."""
+def slab_partition(system, nparts, axis=None):
+    """Owner part of every dof for multi-GPU runs: slabs along one mesh axis, both fields (bidomain) or
+    both sides of the interface (EMI) of a vertex column in the same part.
+
+    axis=None: the last axis (z in 3-D, y in 2-D).  For EMI that axis is the interface normal, so the
+    slab boundaries keep the interface plane and 3 planes on either side inside one part and no Schwarz
+    patch straddles parts -- but then one rank owns every patch.  axis=0 (x-strips) cuts across the
+    interface instead: every part owns a strip of it, patches near a cut straddle parts (their updates
+    travel through the export lists, as for bidomain)."""
     n, dim = system.ncell, system.gdim
     plane = (n + 1) ** (dim - 1)
     nv = system.W[0].dim()
+    last = axis is None or axis == dim - 1
+    if not last and not 0 <= axis < dim - 1:
+        raise ValueError(f"axis={axis} for a {dim}-d mesh")
+    stride = 1 if last else (n + 1) ** axis
     if system.name.startswith("bidomain"):
-        z = np.tile(np.arange(nv) // plane, 2)                  # physical plane of every dof
-        cuts = [round(k * (n + 1) / nparts) for k in range(1, nparts)]
+        k = np.arange(nv) // plane if last else (np.arange(nv) // stride) % (n + 1)
+        z = np.tile(k, 2)                                        # index of every dof along the cut axis
+        cuts = [round(q * (n + 1) / nparts) for q in range(1, nparts)]
     elif system.name.startswith("emi") and system.name != "emi_3d1d":
         half = n // 2
-        k = np.arange(nv) // plane
-        z = np.concatenate([k + half, k])                        # Omega_1 sits on top of Omega_2
-        cuts = []
-        for q in range(1, nparts):
-            c = round(q * (n + 1) / nparts)
-            if abs(c - half) <= 3:
-                c = half + 4
-            cuts.append(c)
+        if last:
+            k = np.arange(nv) // plane
+            z = np.concatenate([k + half, k])                    # Omega_1 sits on top of Omega_2
+            cuts = []
+            for q in range(1, nparts):
+                c = round(q * (n + 1) / nparts)
+                if abs(c - half) <= 3:
+                    c = half + 4
+                cuts.append(c)
+        else:
+            z = np.tile((np.arange(nv) // stride) % (n + 1), 2)   # both halves are (n+1)^(dim-1) x (half+1) boxes
+            cuts = [round(q * (n + 1) / nparts) for q in range(1, nparts)]
     else:
         raise NotImplementedError(f"no slab partition for {system.name}")
     return np.searchsorted(np.array(sorted(cuts)), z, side="right").astype(np.int32)

@@ -30,11 +30,13 @@ def main():
         ("bidomain3d", problems.bidomain_system(3, 16, gamma=1e4), params.parameters_metric_schwarz, 1e-8),
         ("emi3d", problems.emi_system(3, 24, gamma=1e6), params.default_metric_parameters, 1e-10),
         ("bidomain2d", problems.bidomain_system(2, 96, gamma=1e3), params.parameters_metric, 1e-8),
+        # x-strips: every rank owns a strip of the interface, 2-ring patches straddle the cuts (general kernel)
+        ("emi3d_strips", problems.emi_system(3, 24, gamma=1e6), params.default_metric_parameters, 1e-10),
     ]
     ok = True
     for name, s, prm, tol in cases:
         nparts = 4 if world in (1, 2, 4) else world
-        part = problems.slab_partition(s, nparts)
+        part = problems.slab_partition(s, nparts, axis=0 if name.endswith("strips") else None)
         H = mamg.Hierarchy(s.A, prm, s.interface_dofs, part=part)
         H.to_device(local)
         H.dist_init()
