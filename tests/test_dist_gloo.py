@@ -55,6 +55,22 @@ def _worker(rank, world, port, out):
             assert len(set(L0["part"][d])) == 1
         with pytest.raises(ValueError):
             owned_blocks(3, rank, world)
+        # x-strips cut across the interface: every rank owns patches (by the part of the seed), some
+        # patches straddle parts, aggregates still do not; the hierarchy is the same on both ranks
+        px = problems.slab_partition(s, nparts, axis=0)
+        Hx = mamg.Hierarchy(s.A, params.default_metric_parameters, s.interface_dofs, part=px)
+        X0 = Hx.export()["levels"][0]
+        seeds_mine = int(np.isin(X0["part"][X0["patch_seed"]], mine).sum())
+        assert seeds_mine > 0
+        got = allgather_bytes(seeds_mine.to_bytes(8, "little"), None)
+        assert sum(int.from_bytes(c, "little") for c in got) == len(X0["patch_seed"])
+        straddle = sum(len(set(X0["part"][X0["patch_dofs"][X0["patch_ptr"][p]:X0["patch_ptr"][p + 1]]])) > 1
+                       for p in range(len(X0["patch_seed"])))
+        assert straddle > 0
+        ok = X0["agg"] >= 0
+        assert np.array_equal(Hx.export()["levels"][1]["part"][X0["agg"][ok]], X0["part"][ok])
+        hx = hashlib.sha256(np.ascontiguousarray(X0["color"]).tobytes() + np.ascontiguousarray(X0["patch_color"]).tobytes())
+        assert len(set(allgather_bytes(hx.digest(), None))) == 1
         out[rank] = 1
     finally:
         dist.destroy_process_group()
