@@ -190,3 +190,35 @@ def test_setup_reproduces_golden_hierarchy(path):
         for k in ("indptr", "indices", "agg", "color", "patch_ptr", "patch_dofs", "patch_color"):
             assert np.array_equal(L[k], z[f"L{l}_{k}"]), (l, k)
         assert np.allclose(L["data"], z[f"L{l}_data"], rtol=1e-13, atol=0)
+
+
+def test_krylov_solvers_against_scipy():
+    """Independent pin of the Krylov restatements: scipy's CG / MINRES / GMRES with the oracle's cycle as
+    the preconditioner M reach the same solution, and CG with HAZmath's stop rule (||r|| <= tol ||b||,
+    relative=2, which is scipy's rule for x0 = 0) takes the same number of iterations (+-1)."""
+    import scipy.sparse.linalg as spla
+    s = problems.bidomain_system(2, 24, gamma=1e3)
+    prm = dict(params.parameters_metric_schwarz, coarse_scaling=haznics.OFF)   # a linear, symmetric B
+    H = mamg.Hierarchy(s.A, prm, s.interface_dofs)
+    orc = Oracle(H.export(), "natural")
+    b, xt = s.random_rhs(5)
+    M = spla.LinearOperator(s.A.shape, matvec=orc.apply, dtype=np.float64)
+    its = [0]
+
+    def count(_):
+        its[0] += 1
+
+    x_sp, info = spla.cg(s.A, b, rtol=1e-9, atol=0.0, M=M, maxiter=200, callback=count)
+    assert info == 0
+    x, mine = orc.pcg(b, tolerance=1e-9, relative=2, maxiter=200)
+    assert abs(mine["niters"] - its[0]) <= 1
+    assert np.linalg.norm(x - x_sp) <= 1e-7 * np.linalg.norm(x_sp)
+    assert np.linalg.norm(x - xt) <= 1e-6 * np.linalg.norm(xt)
+    x_mr, info = spla.minres(s.A, b, M=M, rtol=1e-10, maxiter=300)
+    assert info == 0
+    xm, _ = orc.minres(b, tolerance=1e-10, relative=True, maxiter=300)
+    assert np.linalg.norm(xm - x_mr) <= 1e-6 * np.linalg.norm(x_mr)
+    x_gm, info = spla.gmres(s.A, b, M=M, rtol=1e-10, atol=0.0, restart=30, maxiter=20)
+    assert info == 0
+    xg, _ = orc.gmres(b, tolerance=1e-10, relative=True, maxiter=300, restart=30)
+    assert np.linalg.norm(xg - x_gm) <= 1e-6 * np.linalg.norm(x_gm)
