@@ -157,8 +157,10 @@ def class_bytes(H, niters, cycle_applies):
 
 
 def problems_slab(system, nparts):
+    """z-slabs for bidomain; x-strips for EMI, so that every rank owns a strip of the interface and its
+    Schwarz patches (z-slabs would hand the whole interface to one rank)."""
     from metric_amg_examples_b200 import problems
-    return problems.slab_partition(system, nparts)
+    return problems.slab_partition(system, nparts, axis=0 if system.name.startswith("emi") else None)
 
 
 def run_mamg(a):
@@ -351,7 +353,7 @@ def run_mamg(a):
                    "precond": "metricAMG parameters_metric_schwarz" if a.workload.startswith("bidomain") else "metricAMG default_metric_parameters",
                    "cycle_type": a.cycle, "krylov": f"ConjGrad relativeconv tolerance={a.rtol:g}",
                    "levels": H.num_levels,
-                   "multi_gpu": (f"one system row-partitioned over {world} GPUs ({world} z-slabs); updated row ranges "
+                   "multi_gpu": (f"one system row-partitioned over {world} GPUs ({world} {'x-strips' if a.workload.startswith('emi') else 'z-slabs'}); updated row ranges "
                                  f"exchanged by {exch_mode}, {ncoll} exchanges per solve; levels < "
                                  f"{os.environ.get('MAMG_DIST_MIN_ROWS', '1000000')} rows replicated")
                    if world > 1 else "single",
