@@ -191,7 +191,8 @@ int mamg_profile_levels(mamg_handle h, double* ms_level_class, int32_t max_level
 int mamg_schwarz_sweep_bytes(mamg_handle h, int32_t level, int64_t* bytes);
 /* per-kernel-class timing with CUDA events on the handle's stream.  on=1 starts collecting;
  * on=0 stops and returns, for the classes {0 spmv, 1 gs, 2 schwarz, 3 restrict, 4 scale,
- * 5 prolong, 6 coarse, 7 vector, 8 dot}, the summed kernel time in ms and the launch counts
+ * 5 prolong, 6 coarse, 7 vector, 8 dot, 9 exchange (multi-GPU peer-memory push + flag barrier)}, the
+ * summed kernel time in ms and the launch counts
  * (arrays of 16 entries).  Collecting adds two event records per launch; never leave it on
  * inside a timed region. */
 int mamg_profile(mamg_handle h, int32_t on, double* ms_per_class, int64_t* launches_per_class);
