@@ -8,7 +8,7 @@ import scipy.sparse as sp
 
 import metric_amg_examples_b200 as mamg
 from metric_amg_examples_b200 import datfile, haznics_compat as haznics, params, problems, solver_files
-from metric_amg_examples_b200.problems.emi3d1d import emi3d1d_system, segment_graph
+from metric_amg_examples_b200.problems.emi3d1d import circle_average, emi3d1d_system, segment_graph
 from oracle import Oracle
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -52,6 +52,37 @@ def test_3d1d_system_properties():
     length = s.params["nsegments"] and sum(
         np.linalg.norm(s.W[1].coords[a] - s.W[1].coords[b]) for a, b in segment_graph(8, s.params["nsegments"], 0)[1])
     assert abs(one @ (s.A @ one) - (3.0 * 1.0 + 7.0 * np.pi * length)) < 1e-9
+
+
+def test_circle_averaged_coupling():
+    """radius > 0 (src/emi_3d1d.py:63-66): Pi averages over a circle around the curve."""
+    n = 12
+    ids, edges, xyz = segment_graph(n, 48, 3)
+    Pi = circle_average(n, xyz, edges, 0.07)
+    assert abs(np.asarray(Pi.sum(axis=1)).ravel() - 1.0).max() < 1e-14 and Pi.data.min() > 0
+    assert Pi.nnz / Pi.shape[0] > 8                       # a row touches every tetrahedron its circle crosses
+    idx = np.indices((n + 1,) * 3)[::-1]
+    x3 = np.stack([idx[a].ravel() / n for a in range(3)], axis=1)
+    coef = np.array([0.3, -1.7, 0.9])
+    inside = np.all((xyz > 0.08) & (xyz < 0.92), axis=1)
+    assert inside.sum() > 5
+    # the average of a linear function over a circle is its value at the centre; P1 interpolation is exact for it
+    assert abs(Pi @ (x3 @ coef + 0.2) - (xyz @ coef + 0.2))[inside].max() < 1e-13
+    # radius -> 0 is the trace coupling
+    s0, se = emi3d1d_system(8, gamma=1e2, seed=2), emi3d1d_system(8, gamma=1e2, seed=2, radius=1e-13)
+    assert abs(s0.A - se.A).max() < 1e-9
+    with pytest.raises(ValueError):
+        emi3d1d_system(8, radius=-1.0)
+    # the averaged system: symmetric positive definite, denser rows near the curve, and the path converges on it
+    s = emi3d1d_system(10, gamma=1e3, radius=0.1)
+    assert abs(s.A - s.A.T).max() < 1e-12 and np.linalg.eigvalsh(s.A.toarray()).min() > 0
+    assert np.diff(s.A.indptr).max() > 2 * np.diff(s0.A.indptr).max()
+    _, amg = datfile.read_input(DAT)
+    H = mamg.Hierarchy(s.A, amg, s.interface_dofs)
+    for order in ("natural", "multicolor"):
+        x, info = Oracle(H.export(), order).pcg(s.b, tolerance=1e-6, relative=2, maxiter=1000)
+        assert info["niters"] < 60
+        assert np.linalg.norm(s.A @ x - s.b) <= 1.05e-6 * np.linalg.norm(s.b)
 
 
 def test_sa_amg_hierarchy():
