@@ -16,6 +16,9 @@
 //   * coarsening stops at coarse_dof rows or max_levels (src/amg_parameters.py:50,56);
 //   * the coarsest operator is inverted densely (coarse_solver 32 = direct).
 #include <algorithm>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -335,36 +338,57 @@ void multicolor_greedy(const Csr& A, const std::vector<uint8_t>& skip, std::vect
 // at most Schwarz_mmsize dofs (src/amg_parameters.py:83-85); dofs sorted ascending.
 void schwarz_patches(const Csr& A, const int* seeds, int nseeds, int maxlvl, int mmsize,
                      SchwarzPatches& out) {
-  out.ptr.assign(1, 0);
+  out.ptr.assign(nseeds + 1, 0);
   out.dofs.clear();
   out.seed.assign(seeds, seeds + nseeds);
   out.max_size = 0;
   if (mmsize < 1) mmsize = 1;
-  std::vector<int> mark(A.n, -1), cur, nxt, blk;
-  for (int s = 0; s < nseeds; ++s) {
-    const int seed = seeds[s];
-    blk.assign(1, seed);
-    mark[seed] = s;
-    cur.assign(1, seed);
-    for (int ring = 0; ring < maxlvl && (int)blk.size() < mmsize; ++ring) {
-      nxt.clear();
-      for (int i : cur) {
-        for (int p = A.ia[i]; p < A.ia[i + 1]; ++p) {
-          int j = A.ja[p];
-          if (A.a[p] == 0.0 || mark[j] == s) continue;
-          if ((int)blk.size() >= mmsize) break;
-          mark[j] = s;
-          blk.push_back(j);
-          nxt.push_back(j);
+  // the breadth-first searches are independent: every thread takes one contiguous range of seeds
+  // (static schedule) and the per-thread lists are concatenated in thread order
+  int nthreads = 1;
+#ifdef _OPENMP
+  nthreads = std::max(1, omp_get_max_threads());
+#endif
+  std::vector<std::vector<int>> part(nthreads);
+  int max_size = 0;
+#pragma omp parallel num_threads(nthreads) reduction(max : max_size)
+  {
+    int tid = 0;
+#ifdef _OPENMP
+    tid = omp_get_thread_num();
+#endif
+    std::vector<int> mark(A.n, -1), cur, nxt, blk;
+    std::vector<int>& mine = part[tid];
+#pragma omp for schedule(static)
+    for (int s = 0; s < nseeds; ++s) {
+      const int seed = seeds[s];
+      blk.assign(1, seed);
+      mark[seed] = s;
+      cur.assign(1, seed);
+      for (int ring = 0; ring < maxlvl && (int)blk.size() < mmsize; ++ring) {
+        nxt.clear();
+        for (int i : cur) {
+          for (int p = A.ia[i]; p < A.ia[i + 1]; ++p) {
+            int j = A.ja[p];
+            if (A.a[p] == 0.0 || mark[j] == s) continue;
+            if ((int)blk.size() >= mmsize) break;
+            mark[j] = s;
+            blk.push_back(j);
+            nxt.push_back(j);
+          }
         }
+        cur.swap(nxt);
       }
-      cur.swap(nxt);
+      std::sort(blk.begin(), blk.end());
+      mine.insert(mine.end(), blk.begin(), blk.end());
+      out.ptr[s + 1] = (int)blk.size();
+      max_size = std::max(max_size, (int)blk.size());
     }
-    std::sort(blk.begin(), blk.end());
-    out.dofs.insert(out.dofs.end(), blk.begin(), blk.end());
-    out.ptr.push_back((int)out.dofs.size());
-    out.max_size = std::max(out.max_size, (int)blk.size());
   }
+  out.max_size = max_size;
+  for (int s = 0; s < nseeds; ++s) out.ptr[s + 1] += out.ptr[s];
+  out.dofs.reserve(out.ptr[nseeds]);
+  for (int t = 0; t < nthreads; ++t) out.dofs.insert(out.dofs.end(), part[t].begin(), part[t].end());
 }
 
 // Conflict colouring of the patches, greedy in patch order.  Two patches conflict when one
