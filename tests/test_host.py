@@ -194,3 +194,60 @@ def test_setup_errors():
         mamg.Hierarchy(A, params.parameters_metric, idofs=[7])
     H = mamg.Hierarchy(A, params.parameters_metric)  # 4 rows <= coarse_dof: one level
     assert H.num_levels == 1
+
+
+def test_header_is_plain_c_and_usable_from_c(tmp_path):
+    """include/mamg.h must compile as C (the boundary is a C-ABI: no C++ or torch types), and a C
+    program can drive the host part of the library through it (setup, queries, errors, destroy)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "mamg.h"
+int main(void) {
+  /* 1-D Laplacian, 300 rows: coarsened by HEM down to <= 100 rows */
+  enum { N = 300 };
+  static int32_t ia[N + 1], ja[3 * N];
+  static double a[3 * N];
+  int k = 0;
+  for (int i = 0; i < N; ++i) {
+    ia[i] = k;
+    if (i > 0) { ja[k] = i - 1; a[k++] = -1.0; }
+    ja[k] = i; a[k++] = 2.0;
+    if (i < N - 1) { ja[k] = i + 1; a[k++] = -1.0; }
+  }
+  ia[N] = k;
+  mamg_params p;
+  if (mamg_params_default(&p) != 0) return 1;
+  mamg_handle h = NULL;
+  int32_t idofs[3] = {10, 11, 12};
+  if (mamg_setup(&p, N, ia, ja, a, 3, idofs, &h) != 0) { printf("setup: %s\n", mamg_last_error()); return 2; }
+  int32_t nl = 0;
+  if (mamg_num_levels(h, &nl) != 0 || nl < 2) return 3;
+  int64_t info[12];
+  if (mamg_level_info(h, 0, info) != 0 || info[0] != N || info[1] != k) return 4;
+  if (mamg_level_info(h, nl, info) == 0) return 5;             /* out of range must fail ... */
+  if (strlen(mamg_last_error()) == 0) return 6;                /* ... with a message */
+  double r[N], z[N];
+  for (int i = 0; i < N; ++i) r[i] = 1.0;
+  if (mamg_apply(h, r, z, 0) == 0) return 7;                   /* not on a device: no CPU fallback */
+  printf("levels %d version %s\n", (int)nl, mamg_version());
+  return mamg_destroy(h);
+}
+''')
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(_capi.LIB_PATH)
+    cmd = [gcc, "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+           "-L", libdir, "-l:libmamg.so", f"-Wl,-rpath,{libdir}"]
+    nccl = os.path.dirname(getattr(_capi, "NCCL_PATH", "") or "")
+    if nccl:
+        cmd += [f"-Wl,-rpath,{nccl}", f"-Wl,-rpath-link,{nccl}"]
+    subprocess.run(cmd, check=True, capture_output=True, text=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert "sm_100a" in out.stdout
