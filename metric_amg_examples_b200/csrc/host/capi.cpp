@@ -1,5 +1,6 @@
 // Host half of the C-ABI declared in include/mamg.h (setup, export, synthetic systems).
 // The device half (mamg_to_device, mamg_apply, mamg_pcg, ...) is in csrc/cuda/device.cu.
+#include <algorithm>
 #include <cstring>
 #include <exception>
 #include <string>
@@ -74,12 +75,38 @@ int mamg_setup_partitioned(const mamg_params* p, int32_t n, const int32_t* indpt
   A.ia.assign(indptr, indptr + n + 1);
   A.ja.assign(indices, indices + nnz);
   A.a.assign(data, data + nnz);
-  for (int i = 0; i < n; ++i) {
-    bool has_diag = false;
+  bool canonical = true;   // columns strictly ascending inside every row (what PETSc / scipy hand over)
+  for (int i = 0; i < n; ++i)
     for (int q = A.ia[i]; q < A.ia[i + 1]; ++q) {
       if (A.ja[q] < 0 || A.ja[q] >= n) { set_error("setup: column index out of range"); return -1; }
-      if (A.ja[q] == i && A.a[q] != 0.0) has_diag = true;
+      if (q > A.ia[i] && A.ja[q] <= A.ja[q - 1]) canonical = false;
     }
+  if (!canonical) {
+    // the aggregation and colouring break ties by position inside the row: sort the rows and add up
+    // duplicate entries so that the hierarchy does not depend on the caller's storage order
+    Csr B;
+    B.n = B.m = n;
+    B.ia.assign(n + 1, 0);
+    B.ja.reserve(nnz);
+    B.a.reserve(nnz);
+    std::vector<std::pair<int, double>> row;
+    for (int i = 0; i < n; ++i) {
+      row.clear();
+      for (int q = A.ia[i]; q < A.ia[i + 1]; ++q) row.emplace_back(A.ja[q], A.a[q]);
+      std::stable_sort(row.begin(), row.end(),
+                       [](const std::pair<int, double>& u, const std::pair<int, double>& v) { return u.first < v.first; });
+      for (size_t k = 0; k < row.size(); ++k) {
+        if (k > 0 && row[k].first == row[k - 1].first) B.a.back() += row[k].second;
+        else { B.ja.push_back(row[k].first); B.a.push_back(row[k].second); }
+      }
+      B.ia[i + 1] = (int)B.ja.size();
+    }
+    A = std::move(B);
+  }
+  for (int i = 0; i < n; ++i) {
+    bool has_diag = false;
+    for (int q = A.ia[i]; q < A.ia[i + 1]; ++q)
+      if (A.ja[q] == i && A.a[q] != 0.0) has_diag = true;
     if (!has_diag) { set_error("setup: row " + std::to_string(i) + " has no nonzero diagonal"); return -1; }
   }
   if (part) {

@@ -251,3 +251,29 @@ int main(void) {
     out = subprocess.run([str(exe)], capture_output=True, text=True, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
     assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
     assert "sm_100a" in out.stdout
+
+
+def test_setup_does_not_depend_on_storage_order():
+    """Unsorted rows and duplicate entries (a COO-style hand-over) give the hierarchy of the canonical CSR."""
+    s = problems.bidomain_system(2, 16, gamma=1e3)
+    A = s.A
+    ref = mamg.Hierarchy(A, params.parameters_metric_schwarz, s.interface_dofs).export()
+    rng = np.random.default_rng(0)
+    indptr, indices, data = A.indptr.copy(), A.indices.copy(), A.data.copy()
+    for i in range(A.shape[0]):
+        sl = slice(indptr[i], indptr[i + 1])
+        p = rng.permutation(indptr[i + 1] - indptr[i])
+        indices[sl], data[sl] = indices[sl][p], data[sl][p]
+    # split every entry into two halves stored apart: duplicates that must be summed (0.5 a + 0.5 a is exact)
+    ip2 = 2 * indptr
+    idx2, dat2 = np.empty(2 * len(indices), np.int32), np.empty(2 * len(indices))
+    for i in range(A.shape[0]):
+        k = indptr[i + 1] - indptr[i]
+        idx2[ip2[i]:ip2[i] + k] = idx2[ip2[i] + k:ip2[i + 1]] = indices[indptr[i]:indptr[i + 1]]
+        dat2[ip2[i]:ip2[i] + k] = dat2[ip2[i] + k:ip2[i + 1]] = 0.5 * data[indptr[i]:indptr[i + 1]]
+    for trip in ((indptr, indices, data), (ip2.astype(np.int32), idx2, dat2)):
+        ex = mamg.Hierarchy(trip, params.parameters_metric_schwarz, s.interface_dofs).export()
+        assert len(ex["levels"]) == len(ref["levels"])
+        for L, R in zip(ex["levels"], ref["levels"]):
+            for k in ("indptr", "indices", "data", "agg", "color"):
+                assert np.array_equal(L[k], R[k]), k
