@@ -277,21 +277,31 @@ class Hierarchy:
         check(fn(self._h, *[ptr(v) for v in ins], ptr(out), *scalars, 0))
         return out
 
+    @staticmethod
+    def _check_len(v, n, what="vector"):
+        """The C-ABI takes bare pointers: a wrong length must be caught on this side."""
+        shape = tuple(v.shape) if hasattr(v, "shape") else (len(v),)
+        if len(shape) != 1 or shape[0] != n:
+            raise ValueError(f"{what} has shape {shape}, expected ({n},)")
+
     def apply(self, r):
         """z = B r: one multigrid cycle (mamg_apply)."""
-        if r.shape[0] != self.n:
-            raise ValueError(f"vector has {r.shape[0]} entries, operator has {self.n}")
+        self._check_len(r, self.n)
         return self._vec_call(lib.mamg_apply, [r], self.n)
 
     def spmv(self, x, level=0):
-        self._require_device()
         n = self.level_info(level)["rows"]
+        self._check_len(x, n)
+        self._require_device()
         x = as_f64(x)
         y = np.empty(n, np.float64)
         check(lib.mamg_spmv(self._h, level, ptr(x), ptr(y), 0))
         return y
 
     def smooth(self, b, x, level=0, post=False):
+        n = self.level_info(level)["rows"]
+        self._check_len(b, n, "b")
+        self._check_len(x, n, "x")
         self._require_device()
         b = as_f64(b)
         x = as_f64(x).copy()
@@ -300,6 +310,11 @@ class Hierarchy:
 
     def pcg(self, b, x0=None, tolerance=1e-8, relative=False, maxiter=500):
         """cbc.block ConjGrad on the device; returns (x, info)."""
+        self._check_len(b, self.n, "b")
+        if x0 is not None:
+            self._check_len(x0, self.n, "x0")
+        if maxiter < 0:
+            raise ValueError("maxiter must be >= 0")
         self._require_device()
         res = np.zeros(maxiter + 1, np.float64)
         al = np.zeros(max(maxiter, 1), np.float64)
@@ -325,6 +340,9 @@ class Hierarchy:
         return x, info
 
     def _krylov(self, fn, b, tolerance, relative, maxiter, *extra):
+        self._check_len(b, self.n, "b")
+        if maxiter < 0:
+            raise ValueError("maxiter must be >= 0")
         self._require_device()
         res = np.zeros(maxiter + 2, np.float64)
         nit = C.c_int32()

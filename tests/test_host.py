@@ -277,3 +277,16 @@ def test_setup_does_not_depend_on_storage_order():
         for L, R in zip(ex["levels"], ref["levels"]):
             for k in ("indptr", "indices", "data", "agg", "color"):
                 assert np.array_equal(L[k], R[k]), k
+
+
+def test_vector_lengths_are_checked_before_the_abi():
+    """The C-ABI takes bare pointers; the Python face rejects wrong shapes before any device call."""
+    s = problems.bidomain_system(2, 8, gamma=10.0)
+    H = mamg.Hierarchy(s.A, params.parameters_metric, s.interface_dofs)
+    bad = np.ones(s.ndofs + 1)
+    for call in (lambda: H.apply(bad), lambda: H.pcg(bad), lambda: H.pcg(np.ones(s.ndofs), x0=bad),
+                 lambda: H.minres(bad), lambda: H.gmres(bad), lambda: H.spmv(bad, 0),
+                 lambda: H.smooth(bad, bad, 0), lambda: H.apply(np.ones((s.ndofs, 1))),
+                 lambda: H.pcg(np.ones(s.ndofs), maxiter=-1)):
+        with pytest.raises(ValueError):
+            call()
