@@ -62,6 +62,7 @@ void aggregate_hem(const Csr& A, const int* part, std::vector<int>& agg, int& nc
 void aggregate_vmb(const Csr& A, const int* part, double strong, int max_agg, std::vector<int>& agg, int& nc);
 void galerkin_ua(const Csr& A, const std::vector<int>& agg, int nc, Csr& Ac);
 void csr_transpose(const Csr& A, Csr& At);
+void csr_drop_zeros(Csr& A);                              // removes exact zeros off the diagonal
 void csr_multiply(const Csr& A, const Csr& B, Csr& C);   // C = A B, columns sorted
 void smoothed_prolongator(const Csr& A, const std::vector<int>& agg, int nc, double omega, Csr& P);
 void multicolor_greedy(const Csr& A, const std::vector<uint8_t>& skip, std::vector<int>& color, int& ncolors);

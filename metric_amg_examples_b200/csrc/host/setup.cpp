@@ -198,6 +198,24 @@ void galerkin_ua(const Csr& A, const std::vector<int>& agg, int nc, Csr& Ac) {
   }
 }
 
+// FEniCS/PETSc hand over the full P1 pattern; entries that are exactly zero (stiffness couplings along
+// the diagonals of the Kuhn mesh, eliminated Dirichlet couplings) contribute nothing to any sum and
+// the setup already ignores them.  Removing them is bit-neutral for every kernel.  The diagonal stays.
+void csr_drop_zeros(Csr& A) {
+  int k = 0;
+  for (int i = 0; i < A.n; ++i) {
+    const int p0 = A.ia[i], p1 = A.ia[i + 1];
+    A.ia[i] = k;
+    for (int p = p0; p < p1; ++p)
+      if (A.a[p] != 0.0 || A.ja[p] == i) { A.ja[k] = A.ja[p]; A.a[k] = A.a[p]; ++k; }
+  }
+  A.ia[A.n] = k;
+  A.ja.resize(k);
+  A.a.resize(k);
+  A.ja.shrink_to_fit();
+  A.a.shrink_to_fit();
+}
+
 void csr_transpose(const Csr& A, Csr& At) {
   At.n = A.m;
   At.m = A.n;
@@ -510,6 +528,9 @@ bool build_hierarchy(const mamg_params& prm, Csr&& A0, const int* idofs, int n_i
     return false;
   }
   const int max_levels = std::max(1, prm.max_levels);
+  // MAMG_DROP_ZEROS=1 (default off until verified on the device): store no explicit zeros on any level
+  const bool drop_zeros = getenv("MAMG_DROP_ZEROS") && atoi(getenv("MAMG_DROP_ZEROS")) != 0;
+  if (drop_zeros) csr_drop_zeros(H.lv[0].A);
   const bool timing = getenv("MAMG_SETUP_TIMING") != nullptr;   // per-phase seconds on stderr
   auto tp = std::chrono::steady_clock::now();
   auto lap = [&](const char* what, int lev) {
@@ -556,6 +577,7 @@ bool build_hierarchy(const mamg_params& prm, Csr&& A0, const int* idofs, int n_i
     } else {
       galerkin_ua(H.lv[l].A, H.lv[l].agg, H.lv[l].nc, H.lv[l + 1].A);
     }
+    if (drop_zeros) csr_drop_zeros(H.lv[l + 1].A);
     lap("galerkin", l);
     if (!H.lv[l].part.empty()) {   // a coarse row belongs to the part of its members
       std::vector<int>& cp = H.lv[l + 1].part;
