@@ -290,3 +290,32 @@ def test_vector_lengths_are_checked_before_the_abi():
                  lambda: H.pcg(np.ones(s.ndofs), maxiter=-1)):
         with pytest.raises(ValueError):
             call()
+
+
+def test_params_struct_layout_matches_ctypes(tmp_path):
+    """struct mamg_params: the header, the ctypes mirror in _capi.py and the stub in INTEGRATION.md list
+    the same fields in the same order, and gcc lays them out as ctypes does."""
+    import shutil
+    import subprocess
+    hdr = open(os.path.join(ROOT, "include", "mamg.h")).read()
+    body = re.search(r"typedef struct mamg_params \{(.*?)\} mamg_params;", hdr, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = re.findall(r"(int32_t|double)\s+(\w+)(\[\d+\])?;", body)
+    names = [f[1] for f in fields]
+    assert names == [n for n, _ in _capi.PARAM_FIELDS]
+    for (ctype, name, arr), (_, pyt) in zip(fields, _capi.PARAM_FIELDS):
+        assert (ctype == "double") == (pyt is C.c_double), name
+    stub = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    stub_names = re.findall(r'"(\w+)"', stub[stub.index("class Params(C.Structure)"):stub.index("lib.mamg_last_error.restype")])
+    assert stub_names == names
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "mamg.h"\nint main(void){printf("%zu", sizeof(mamg_params));'
+                   + "".join(f'printf(" %zu", offsetof(mamg_params, {n}));' for n in names) + "return 0;}\n")
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert got[0] == C.sizeof(_capi.MamgParams)
+    assert got[1:] == [getattr(_capi.MamgParams, n).offset for n in names]
