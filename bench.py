@@ -48,7 +48,7 @@ def parse():
 
 
 DEFAULT_N = {"bidomain_2d": 256, "bidomain_3d": 199, "emi_2d": 2048, "emi_3d": 232}
-CPU_SAMPLE_N = {"bidomain_2d": 128, "bidomain_3d": 40, "emi_2d": 256, "emi_3d": 48}
+CPU_SAMPLE_N = {"bidomain_2d": 128, "bidomain_3d": 56, "emi_2d": 256, "emi_3d": 64}
 
 
 def make_system(workload, n, gamma):
