@@ -9,7 +9,8 @@ A "step" is one complete solve of the hot path: cbc.block-style PCG to rtol 1e-8
           vectors: H2D of b and D2H of x inside the timed region
 Default workload at N=1: BASELINE.json configs[2], bidomain_3d on UnitCubeMesh(199) (16.0 M DOFs)
 with src/amg_parameters.py:parameters_metric_schwarz; the headline uses cycle_type V_CYCLE (the
-metric names the V-cycle; the W-cycle configured upstream is reported beside it with --wcycle).
+metric names the V-cycle); the W-cycle that src/amg_parameters.py configures is timed beside it on the
+same hierarchy (`wcycle_ms`, --wcycle K applies; 0 disables).
 `--impl reference` times the CPU restatement (oracle/) on a bounded sample of the same workload.
 """
 import argparse
@@ -27,7 +28,11 @@ sys.path.insert(0, ROOT)
 # stdout carries exactly one JSON line: NCCL's own banner (NCCL_DEBUG=VERSION/INFO on some boxes) goes to stderr
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 if int(os.environ.get("WORLD_SIZE", "1")) > 1 and os.environ.get("OMP_NUM_THREADS", "1") == "1":
-    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // int(os.environ.get("LOCAL_WORLD_SIZE", os.environ["WORLD_SIZE"]))))
+    _ref_arm = any(sys.argv[k] == "--impl" and sys.argv[k + 1] == "reference" for k in range(len(sys.argv) - 1)) \
+        or "--impl=reference" in sys.argv
+    # the reference arm runs on rank 0 alone and gets every host core at every N; the GPU arm's ranks share them
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1) if _ref_arm else \
+        str(max(1, (os.cpu_count() or 1) // int(os.environ.get("LOCAL_WORLD_SIZE", os.environ["WORLD_SIZE"]))))
 
 
 def parse():
@@ -40,14 +45,14 @@ def parse():
     ap.add_argument("-n", type=int, default=None, help="cells per direction (default: the BASELINE config size)")
     ap.add_argument("--gamma", type=float, default=1e4)
     ap.add_argument("--cycle", default="V", choices=["V", "W"])
-    ap.add_argument("--wcycle", type=int, default=0, help="also time this many W-cycle applies/solve")
+    ap.add_argument("--wcycle", type=int, default=1, help="also time this many W-cycle applies on the same hierarchy (0: skip)")
     ap.add_argument("--cpu-sample-n", type=int, default=None, help="mesh size of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--rtol", type=float, default=1e-8)
     return ap.parse_args()
 
 
-DEFAULT_N = {"bidomain_2d": 256, "bidomain_3d": 199, "emi_2d": 2048, "emi_3d": 232}
+DEFAULT_N = {"bidomain_2d": 256, "bidomain_3d": 199, "emi_2d": 2048, "emi_3d": 464}
 CPU_SAMPLE_N = {"bidomain_2d": 128, "bidomain_3d": 56, "emi_2d": 256, "emi_3d": 64}
 
 
@@ -156,6 +161,11 @@ def class_bytes(H, niters, cycle_applies):
     return out
 
 
+def host_copies(world):
+    """Ranks that hold a host copy of the whole hierarchy while it is built."""
+    return world
+
+
 def problems_slab(system, nparts):
     """z-slabs for bidomain; x-strips for EMI, so that every rank owns a strip of the interface and its
     Schwarz patches (z-slabs would hand the whole interface to one rank)."""
@@ -182,27 +192,17 @@ def run_mamg(a):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n = a.n or DEFAULT_N[a.workload]
     note = ""
-    if world > 1 and a.n is None:
-        # every rank holds the whole hierarchy on the host while it is built (~2.4 KB per DOF for
-        # bidomain_3d with Schwarz): shrink the mesh if the node's memory cannot take `world` copies
-        import psutil
-        avail = psutil.virtual_memory().available * 0.8
-        per_dof = 2400.0 if a.workload.startswith("bidomain") else 900.0
-        dim = int(a.workload[-2])
-        while n > 16 and world * per_dof * 2 * (n + 1) ** dim > avail:
-            n -= 8
-        if n != DEFAULT_N[a.workload]:
-            note = f" (mesh reduced from {DEFAULT_N[a.workload]} to fit {world} host copies of the hierarchy)"
-    if world == 1 and a.n is not None:
-        # refuse rather than drive the host out of memory: setup + upload temporaries per DOF
+    if True:
+        # refuse rather than drive the host out of memory or silently run another workload: setup + upload
+        # temporaries per DOF, one copy per rank that builds the hierarchy
         import psutil
         dim = int(a.workload[-2])
         ndof_est = 2 * (n + 1) ** dim if a.workload.startswith("bidomain") else (n + 1) ** (dim - 1) * (n + 2)
-        need = (3600.0 if a.workload.startswith("bidomain") else 1400.0) * ndof_est
+        need = (3600.0 if a.workload.startswith("bidomain") else 1400.0) * ndof_est * host_copies(world)
         avail = psutil.virtual_memory().available
         if need > 0.9 * avail:
-            raise SystemExit(f"bench.py: {a.workload} n={n} needs ~{need / 1e9:.0f} GB of host memory for the "
-                             f"setup, {avail / 1e9:.0f} GB available")
+            raise SystemExit(f"bench.py: {a.workload} n={n} on {world} rank(s) needs ~{need / 1e9:.0f} GB of host memory "
+                             f"for the setup, {avail / 1e9:.0f} GB available; the mesh is never reduced silently")
     t0 = time.time()
     system, prm = make_system(a.workload, n, a.gamma)
     t_asm = time.time() - t0
@@ -251,6 +251,12 @@ def run_mamg(a):
         return x, info
 
     with torch.cuda.stream(stream):
+        # the first solve through the public API with host vectors: what the reference's timer sees after
+        # its setup (src/bidomain_2d.py:184-207 times metricAMG(...) + ConjGrad solve); graph capture included
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        H.pcg(b_pin.numpy(), tolerance=a.rtol, relative=True, maxiter=500)
+        t_first = time.perf_counter() - t0
         for _ in range(a.warmup):
             x, info = solve_dev()
         rel_err = float(torch.linalg.norm(x - torch.from_numpy(x_true).cuda()) / np.linalg.norm(x_true))
@@ -298,6 +304,19 @@ def run_mamg(a):
         c1.record(stream)
         torch.cuda.synchronize()
         cycle_ms = c0.elapsed_time(c1) / 5
+        # the W-cycle that src/amg_parameters.py:5,25,49,69 configures, on the same hierarchy
+        wcycle_ms = None
+        if a.wcycle > 0 and a.cycle == "V":
+            H.set_cycle(hz.W_CYCLE)
+            lib.mamg_apply(H._h, C.c_void_p(r.data_ptr()), C.c_void_p(z.data_ptr()), 1)   # warm
+            torch.cuda.synchronize()
+            c0.record(stream)
+            for _ in range(a.wcycle):
+                lib.mamg_apply(H._h, C.c_void_p(r.data_ptr()), C.c_void_p(z.data_ptr()), 1)
+            c1.record(stream)
+            torch.cuda.synchronize()
+            wcycle_ms = c0.elapsed_time(c1) / a.wcycle
+            H.set_cycle(hz.V_CYCLE)
         H.profile_start()
         _, pinfo = solve_dev()
         prof_lv = H.profile_levels()
@@ -335,12 +354,16 @@ def run_mamg(a):
     kernels = {k: {"ms": round(prof[k][0], 3), "launches": prof[k][1], "share": round(prof[k][0] / tot_ms, 4),
                    "alg_GBs": round(cb[k] * share[k] / (prof[k][0] * 1e-3) / 1e9, 1) if prof[k][0] > 0 else None}
                for k in prof}
-    traffic = None
-    try:   # DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/traffic.json)
+    # DRAM traffic per launch of the dominant class: (dram bytes / algorithmic bytes) of that kernel class in
+    # the committed `ncu --set full` capture of this workload (profiles/traffic.json, smaller mesh, same
+    # kernels) x this run's algorithmic bytes per launch; null when no capture of that class is committed
+    traffic, traffic_src = None, "no committed ncu --set full capture of this kernel class for this workload"
+    try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        if dom == "schwarz" and a.workload == "bidomain_3d":
-            l0 = H.level_info(0)
-            traffic = tj["schwarz"]["dram_bytes_per_patch"] * l0["n_patches"] / max(l0["n_patch_colors"], 1) / world
+        ent = tj.get(a.workload, {}).get(dom)
+        if ent:
+            traffic = ent["dram_over_algorithmic"] * cb[dom] * share[dom] / max(prof[dom][1], 1)
+            traffic_src = ent["source"]
     except Exception:
         pass
     out = {
@@ -359,13 +382,20 @@ def run_mamg(a):
                    if world > 1 else "single",
                    "l2_note": (f"level-0 matrix {12 * nnz0 / 1e9:.2f} GB and vectors {8 * ndofs / 1e6:.0f} MB each: "
                                + ("larger than" if 12 * nnz0 > 126e6 else "NOT larger than") + " the 126 MB L2")},
-        "iterations": nit, "vcycle_ms": cycle_ms, "rel_error_vs_x_true": rel_err,
+        "iterations": nit, "vcycle_ms": cycle_ms, "wcycle_ms": wcycle_ms, "rel_error_vs_x_true": rel_err,
+        "first_solve_e2e_s": round(t_setup + t_upload + t_first, 2),
+        "first_solve_note": "host setup + upload + first solve with host vectors (assembly excluded): what the "
+                            "reference's timer brackets (src/bidomain_2d.py:184-207)",
+        "spmv_hbm_frac": {"alg_GBs": kernels["spmv"]["alg_GBs"],
+                          "of_nominal_8000": round((kernels["spmv"]["alg_GBs"] or 0) / 8000.0, 3),
+                          "of_measured": round((kernels["spmv"]["alg_GBs"] or 0) / peak, 3)},
+        "nnz_stored_vs_structural": [[H.level_info(l)["nnz"], H.level_info(l)["nnz_structural"]] for l in range(min(H.num_levels, 4))],
         "e2e": {"value": ndofs * a.steps / e2e_s, "unit": "DOF/s", "h2d_bytes_per_step": 8 * ndofs,
                 "d2h_bytes_per_step": 8 * ndofs},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic,
+                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                      "algorithmic_bytes_per_launch": cb[dom] * share[dom] / max(dom_launches, 1),
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s",
                      "avg_launch_ms": dom_ms / max(dom_launches, 1)},
@@ -375,15 +405,18 @@ def run_mamg(a):
         "host": {"assemble_s": round(t_asm, 2), "setup_s": round(t_setup, 2), "upload_s": round(t_upload, 2),
                  "device_GB": round(H.device_bytes() / 1e9, 2)},
     }
-    if not a.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_sample(a, threads=1, ordering="natural")
+    if not a.no_cpu_baseline and world == 1:
+        out["cpu_baseline"] = cpu_sample(a, threads=1, ordering="natural", gpu_check=True)
+        out["sample_iters"] = {"gpu": out["cpu_baseline"].pop("iters_gpu"), "oracle_multicolor": out["cpu_baseline"].pop("iters_oracle_multicolor"),
+                               "oracle_natural": out["cpu_baseline"]["iters"]}
     print(json.dumps(out), file=RESULT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def cpu_sample(a, threads, ordering, steps=1):
-    """The oracle (CPU port of the path) on a bounded sample of the same workload."""
+def cpu_sample(a, threads, ordering, steps=1, gpu_check=False):
+    """The oracle (CPU port of the path) on a bounded sample of the same workload.  gpu_check: also run
+    the device path on the sample's mesh, so that the line carries a GPU-vs-oracle iteration check."""
     import metric_amg_examples_b200 as mamg
     from metric_amg_examples_b200 import haznics_compat as hz
     from oracle import Oracle
@@ -398,7 +431,16 @@ def cpu_sample(a, threads, ordering, steps=1):
     for _ in range(steps):
         _, info = orc.pcg(b, tolerance=a.rtol, relative=True, maxiter=500)
     dt = time.perf_counter() - t0
-    return {"value": system.ndofs * steps / dt, "unit": "DOF/s", "cores": used, "kind": "port",
+    extra = {}
+    if gpu_check:
+        orc.set_ordering("multicolor")
+        orc.set_threads(0)
+        _, im = orc.pcg(b, tolerance=a.rtol, relative=True, maxiter=500)
+        H.to_device(int(os.environ.get("LOCAL_RANK", "0")))
+        _, ig = H.pcg(b, tolerance=a.rtol, relative=True, maxiter=500)
+        extra = {"iters_gpu": ig["niters"], "iters_oracle_multicolor": im["niters"]}
+    return {**extra, "iters": info["niters"],
+            "value": system.ndofs * steps / dt, "unit": "DOF/s", "cores": used, "kind": "port",
             "sample": f"{a.workload} n={n} ({system.ndofs} dofs), same parameters, full PCG solve to rtol {a.rtol:g}, "
                       f"{ordering} smoother order, {info['niters']} iterations, {dt / steps:.2f} s per solve",
             "host_cores_available": os.cpu_count(), "seconds_per_solve": dt / steps}

@@ -101,7 +101,8 @@ int mamg_num_levels(mamg_handle h, int32_t* nlevels);
  * info[5]=n_patch_entries info[6]=n_patch_colors info[7]=max_patch_size
  * info[8]=matrix entries in all patch rows (sum over patches of the nnz of their rows)
  * info[9]=packed patch-inverse entries (sum of s(s+1)/2) info[10]=nnz of the smoothed
- * prolongator P (SA_AMG levels, else 0) info[11] reserved */
+ * prolongator P (SA_AMG levels, else 0) info[11]=nnz of the pattern before explicit zeros were
+ * dropped (info[1] counts the stored entries, which is what every kernel streams) */
 int mamg_level_info(mamg_handle h, int32_t level, int64_t info[12]);
 int mamg_level_export(mamg_handle h, int32_t level, int32_t* indptr, int32_t* indices, double* data,
                       int32_t* agg, int32_t* color, uint8_t* gs_skip);
@@ -138,6 +139,9 @@ int mamg_collective_count(mamg_handle h, int64_t* count, int32_t reset);
 int mamg_ipc_handle(mamg_handle h, void* out64);
 int mamg_dist_peers(mamg_handle h, const void* handles64_per_rank);
 int mamg_device_bytes(mamg_handle h, int64_t* bytes);
+/* switch between V_CYCLE and W_CYCLE on an existing hierarchy (the hierarchy does not depend on the
+ * cycle type; src/amg_parameters.py configures W, BASELINE.json's metric names the V-cycle) */
+int mamg_set_cycle(mamg_handle h, int32_t cycle_type);
 /* free the host copy of the level matrices once they are on the device (exports fail afterwards;
  * sizes stay available): saves host memory when several ranks hold large hierarchies on one node */
 int mamg_release_host(mamg_handle h);

@@ -68,6 +68,7 @@ def _load():
         "mamg_ipc_handle": (i32, [vp, vp]),
         "mamg_dist_peers": (i32, [vp, vp]),
         "mamg_device_bytes": (i32, [vp, pi64]),
+        "mamg_set_cycle": (i32, [vp, i32]),
         "mamg_sync": (i32, [vp]),
         "mamg_release_host": (i32, [vp]),
         "mamg_apply": (i32, [vp, vp, vp, i32]),

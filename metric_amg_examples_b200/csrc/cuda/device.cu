@@ -20,6 +20,7 @@
 #include "../host/handle.h"
 #include "kernels.cuh"
 #include "schwarz.cuh"
+#include "sell.cuh"
 #include "tail.cuh"
 
 namespace mamg {
@@ -57,6 +58,11 @@ struct DLevel {
   DSchwarz sw;
   DCsr P, R;   // SA_AMG only
   int* d_color_ptr = nullptr;   // device copy of bc_ptr (tail kernel)
+  // sliced-ELL copy of the level matrix (sell.cuh): the layout the row kernels stream; the CSR arrays
+  // ja / a are released after the conversion unless something else reads them (tail kernel, Schwarz)
+  SellView S;
+  bool use_sell = false, has_csr = true;
+  int64_t sell_slots = 0;       // stored entry slots (padding included)
 };
 
 enum KClass { K_SPMV = 0, K_GS, K_SCHWARZ, K_RESTRICT, K_SCALE, K_PROLONG, K_COARSE, K_VEC, K_DOT, K_EXCH, K_NCLS };
@@ -157,6 +163,14 @@ static T* dalloc(DeviceState& D, size_t count) {
   return p;
 }
 template <class T>
+static void dfree(DeviceState& D, T* p, size_t count) {
+  if (!p) return;
+  auto it = std::find(D.allocs.begin(), D.allocs.end(), (void*)p);
+  if (it != D.allocs.end()) D.allocs.erase(it);
+  cudaFree(p);
+  D.dev_bytes -= (int64_t)(count * sizeof(T));
+}
+template <class T>
 static T* upload(DeviceState& D, const std::vector<T>& v) {
   T* p = dalloc<T>(D, v.size());
   if (!v.empty()) CUDA_OK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
@@ -203,6 +217,41 @@ static int pick_unroll(int n) {
 }
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+static bool rows_sell() {
+  const char* env = getenv("MAMG_ROWS");   // "csr": the sub-warp-per-row CSR kernels of round 1 (kept for comparison)
+  return !(env && std::string(env) == "csr");
+}
+
+// sliced-ELL copy of a level, filled on the device from the permuted CSR that was just uploaded
+static void build_sell(DeviceState& D, DLevel& dl, const std::vector<int>& ia) {
+  const int n = dl.n, ns = (n + 31) / 32;
+  std::vector<int> sp(ns + 1, 0);
+  for (int s = 0; s < ns; ++s) {
+    int w = 0;
+    for (int i = s * 32; i < std::min(n, s * 32 + 32); ++i) w = std::max(w, ia[i + 1] - ia[i]);
+    sp[s + 1] = w;
+  }
+  int64_t tot = 0;
+  for (int s = 0; s < ns; ++s) {
+    tot += sp[s + 1];
+    if (tot > 0x7fffffffLL) throw std::runtime_error("sliced-ELL slot count exceeds int32");
+    sp[s + 1] = (int)tot;
+  }
+  dl.sell_slots = tot * 32;
+  int* d_sp = upload(D, sp);
+  double* val = dalloc<double>(D, (size_t)tot * 32 + 2);
+  int* col = dalloc<int>(D, (size_t)tot * 32 + 4);
+  if (ns > 0) {
+    sell_fill_kernel<<<(ns + kSellWarps - 1) / kSellWarps, kBlock>>>(n, dl.ia, dl.ja, dl.a, d_sp, val, col);
+    CUDA_OK(cudaGetLastError());
+  }
+  dl.S.sp = d_sp;
+  dl.S.val = val;
+  dl.S.col = col;
+  dl.S.n = n;
+  dl.use_sell = true;
+}
 
 // ------------------------------------------------------------------------------------------
 // upload: colour-permute every level (rows of one colour contiguous, stable inside a colour)
@@ -343,6 +392,7 @@ static void upload_hierarchy(const Hierarchy& H, DeviceState& D) {
       D.dev_bytes += (int64_t)bytes;
       return p;
     });
+    if (rows_sell()) build_sell(D, dl, ia);
   }
   {
     size_t mx = 0;
@@ -392,6 +442,19 @@ static void upload_hierarchy(const Hierarchy& H, DeviceState& D) {
         D.tail_k0 = k0;
       }
     }
+  }
+  // the row kernels stream the sliced-ELL copy: drop the CSR entries wherever nothing else reads them
+  // (the tail kernel walks CSR rows; the Schwarz kernels read the row values of their level)
+  CUDA_OK(cudaDeviceSynchronize());
+  for (int l = 0; l < L; ++l) {
+    DLevel& dl = D.lv[l];
+    const bool in_tail = D.tail_k0 >= 0 && l >= D.tail_k0;
+    if (!dl.use_sell || in_tail || dl.sw.npatch > 0) continue;
+    dfree(D, dl.ja, (size_t)dl.nnz);
+    dfree(D, dl.a, (size_t)dl.nnz);
+    dl.ja = nullptr;
+    dl.a = nullptr;
+    dl.has_csr = false;
   }
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, D.device);
@@ -566,11 +629,19 @@ static void exchange(DeviceState& D, const DLevel& l, double* v, int c) {
   ++D.collectives;
 }
 
+// CTAs that cover the slices overlapping rows [r0, r1)
+static int sell_grid(int r0, int r1) { return cdiv((r1 + 31) / 32 - r0 / 32, kSellWarps); }
+
 static void k_spmv(DeviceState& D, const DLevel& l, const double* x, const double* b, double* y, bool resid) {
   if (l.n == 0) return;
   const int r0 = own_lo(D, l), r1 = own_hi(D, l);
   if (is_dist(D, l)) barrier_only(D);   // y may still be in local use on a peer (Krylov vector updates)
-  if (r1 > r0) {
+  if (r1 > r0 && l.use_sell) {
+    const int grid = sell_grid(r0, r1);
+    KScope ks(D, K_SPMV);
+    if (resid) sell_spmv_kernel<true><<<grid, kBlock, 0, D.stream>>>(r0, r1, l.S, x, b, y);
+    else sell_spmv_kernel<false><<<grid, kBlock, 0, D.stream>>>(r0, r1, l.S, x, b, y);
+  } else if (r1 > r0) {
     const int grid = cdiv((long long)cdiv(r1 - r0, l.unroll) * l.lanes, kBlock);
     KScope ks(D, K_SPMV);
     LANES_SWITCH(l.lanes, UNROLL_SWITCH(l.unroll,
@@ -589,8 +660,12 @@ static void k_gs_color(DeviceState& D, const DLevel& l, int c, const double* b, 
     const int r0 = l.row0(blk, c), r1 = l.row1(blk, c);
     if (r1 <= r0) continue;
     if (!l.color_active.empty() && l.color_active[blk * l.ncolors + c] == 0) continue;
-    const int grid = cdiv((long long)cdiv(r1 - r0, l.unroll) * l.lanes, kBlock);
     KScope ks(D, K_GS);
+    if (l.use_sell) {
+      sell_gs_kernel<<<sell_grid(r0, r1), kBlock, 0, D.stream>>>(r0, r1, l.S, l.invd, l.skip, b, x, omega);
+      continue;
+    }
+    const int grid = cdiv((long long)cdiv(r1 - r0, l.unroll) * l.lanes, kBlock);
     LANES_SWITCH(l.lanes, UNROLL_SWITCH(l.unroll,
       gs_color_kernel<LN, UN><<<grid, kBlock, 0, D.stream>>>(r0, r1, l.ia, l.ja, l.a, l.invd, l.skip, b, x, omega)));
   }
@@ -609,7 +684,8 @@ static void k_jacobi(DeviceState& D, DLevel& l, const double* b, double* x, doub
   if (r1 > r0) {
     const int grid = cdiv((long long)(r1 - r0) * l.lanes, kBlock);
     KScope ks(D, K_GS);
-    LANES_SWITCH(l.lanes,
+    if (l.use_sell) sell_jacobi_kernel<<<sell_grid(r0, r1), kBlock, 0, D.stream>>>(r0, r1, l.S, l.invd, l.skip, b, x, l.t, w);
+    else LANES_SWITCH(l.lanes,
       jacobi_kernel<LN><<<grid, kBlock, 0, D.stream>>>(r0, r1, l.ia, l.ja, l.a, l.invd, l.skip, b, x, l.t, w));
   }
   exchange(D, l, l.t, -1);
@@ -729,6 +805,20 @@ static void k_resid_restrict(DeviceState& D, int lev) {
   if (f.R.n > 0) {   // SA_AMG: w = b - A x, b_c = R w, x_c = 0
     k_spmv(D, f, f.x, f.b, f.t, true);
     k_csr_apply(D, f.R, c0, c1, f.t, nullptr, c.b, c.x, false, K_RESTRICT);
+  } else if (f.use_sell) {
+    // t = b - A x on the fine rows this rank owns (aggregates never cross parts, so the members of the
+    // coarse rows [c0, c1) are among them), streamed once in layout order; then the aggregate sums
+    const int r0 = own_lo(D, f), r1 = own_hi(D, f);
+    const bool all = !(is_dist(D, f) && D.world > 1) || !(is_dist(D, c));
+    const int a0 = all ? 0 : r0, a1 = all ? f.n : r1;
+    if (a1 > a0) {
+      KScope ks(D, K_RESTRICT);
+      sell_spmv_kernel<true><<<sell_grid(a0, a1), kBlock, 0, D.stream>>>(a0, a1, f.S, f.x, f.b, f.t);
+    }
+    if (c1 > c0) {
+      KScope ks(D, K_RESTRICT);
+      agg_sum_kernel<<<cdiv(c1 - c0, kBlock), kBlock, 0, D.stream>>>(c0, c1, f.cptr, f.cidx, f.t, c.b, c.x);
+    }
   } else if (c1 > c0) {
     const int grid = cdiv((long long)(c1 - c0) * f.lanes, kBlock);
     KScope ks(D, K_RESTRICT);
@@ -753,8 +843,12 @@ static void k_scale_dots(DeviceState& D, int lev) {
     scale_dots_vec_kernel<<<red_grid(D, c.n), kBlock, 0, D.stream>>>(c.n, c.x, c.b, c.t, D.partial, D.ticket, D.scal + 8);
     return;
   }
-  const int grid = red_grid(D, (long long)c.n * c.lanes);
   KScope ks(D, K_SCALE);
+  if (c.use_sell) {
+    sell_scale_dots_kernel<<<red_grid(D, c.n), kBlock, 0, D.stream>>>(c.S, c.x, c.b, D.partial, D.ticket, D.scal + 8);
+    return;
+  }
+  const int grid = red_grid(D, (long long)c.n * c.lanes);
   LANES_SWITCH(c.lanes,
     scale_dots_kernel<LN><<<grid, kBlock, 0, D.stream>>>(c.n, c.ia, c.ja, c.a, c.x, c.b, D.partial, D.ticket, D.scal + 8));
 }
@@ -967,10 +1061,14 @@ static int pcg_device(DeviceState& D, const double* b_nat, double* x_nat, double
       KScope ks(D, K_DOT);
       pcg_dq_kernel<<<rgrid, kBlock, 0, D.stream>>>(n, d, q, D.partial, D.ticket, D.scal);
     } else {
-      const int sgrid = red_grid(D, (long long)cdiv(n, l0.unroll) * l0.lanes);
       KScope ks(D, K_SPMV);
-      LANES_SWITCH(l0.lanes, UNROLL_SWITCH(l0.unroll,
-        spmv_dot_kernel<LN, UN><<<sgrid, kBlock, 0, D.stream>>>(n, l0.ia, l0.ja, l0.a, d, q, D.partial, D.ticket, D.scal)));
+      if (l0.use_sell) {
+        sell_spmv_dot_kernel<<<red_grid(D, n), kBlock, 0, D.stream>>>(l0.S, d, q, D.partial, D.ticket, D.scal);
+      } else {
+        const int sgrid = red_grid(D, (long long)cdiv(n, l0.unroll) * l0.lanes);
+        LANES_SWITCH(l0.lanes, UNROLL_SWITCH(l0.unroll,
+          spmv_dot_kernel<LN, UN><<<sgrid, kBlock, 0, D.stream>>>(n, l0.ia, l0.ja, l0.a, d, q, D.partial, D.ticket, D.scal)));
+      }
     }
     {
       KScope ks(D, K_VEC);
@@ -1165,6 +1263,7 @@ int mamg_to_device(mamg_handle h, int32_t device, void* stream) {
     return -4;
   }
   if (device < 0 || device >= ndev) { set_error("device index out of range"); return -1; }
+  if (h->H.released) { set_error("to_device: the host matrices were released (mamg_release_host); build a new handle to upload again"); return -1; }
   if (h->dev) { device_state_free(h->dev); h->dev = nullptr; }
   CUDA_OK(cudaSetDevice(device));
   DeviceState* D = new DeviceState();
@@ -1241,6 +1340,7 @@ int mamg_dist_init(mamg_handle h, int32_t rank, int32_t world, const void* uniqu
   DeviceState* D = get_dev(h);
   if (!D) return -1;
   if (world < 1 || rank < 0 || rank >= world) { set_error("dist_init: bad rank/world"); return -1; }
+  if (world > 64) { set_error("dist_init: at most 64 ranks (the arrival flags occupy the first 64 slots of the vector arena; CUDA IPC peers are single-node anyway)"); return -1; }
   if (h->H.nparts % world != 0) {
     set_error("dist_init: the hierarchy has " + std::to_string(h->H.nparts) + " parts, not a multiple of world size " + std::to_string(world));
     return -1;
@@ -1275,6 +1375,22 @@ int mamg_set_stream(mamg_handle h, void* stream) {
   if (D->own_stream) { cudaStreamDestroy(D->stream); D->own_stream = false; }
   if (stream) D->stream = (cudaStream_t)stream;
   else { CUDA_OK(cudaStreamCreateWithFlags(&D->stream, cudaStreamNonBlocking)); D->own_stream = true; }
+  return 0;
+  MAMG_CATCH
+}
+
+int mamg_set_cycle(mamg_handle h, int32_t cycle_type) {
+  MAMG_TRY
+  if (!h) { set_error("NULL handle"); return -1; }
+  if (cycle_type != MAMG_V_CYCLE && cycle_type != MAMG_W_CYCLE) { set_error("set_cycle: only V_CYCLE and W_CYCLE"); return -1; }
+  h->H.prm.cycle_type = cycle_type;
+  if (h->dev) {
+    cudaSetDevice(h->dev->device);
+    CUDA_OK(cudaStreamSynchronize(h->dev->stream));
+    drop_graphs(*h->dev);
+    h->dev->prm.cycle_type = cycle_type;
+    h->dev->tail.cycle_type = cycle_type;
+  }
   return 0;
   MAMG_CATCH
 }

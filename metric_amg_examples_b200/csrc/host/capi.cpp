@@ -68,8 +68,17 @@ int mamg_setup_partitioned(const mamg_params* p, int32_t n, const int32_t* indpt
   for (int i = 0; i < n; ++i)
     if (indptr[i + 1] < indptr[i]) { set_error("setup: indptr not monotone"); return -1; }
   const int nnz = indptr[n];
+  if (n_idofs < 0 || (n_idofs > 0 && !idofs)) { set_error("setup: n_idofs > 0 but idofs is NULL"); return -1; }
   for (int q = 0; q < n_idofs; ++q)
     if (idofs[q] < 0 || idofs[q] >= n) { set_error("setup: interface dof out of range"); return -1; }
+  // a dof listed twice would seed the same patch twice (applied twice per sweep): keep the first occurrence
+  std::vector<int> seeds;
+  {
+    std::vector<char> seen(n, 0);
+    seeds.reserve(n_idofs);
+    for (int q = 0; q < n_idofs; ++q)
+      if (!seen[idofs[q]]) { seen[idofs[q]] = 1; seeds.push_back(idofs[q]); }
+  }
   Csr A;
   A.n = A.m = n;
   A.ia.assign(indptr, indptr + n + 1);
@@ -109,6 +118,26 @@ int mamg_setup_partitioned(const mamg_params* p, int32_t n, const int32_t* indpt
       if (A.ja[q] == i && A.a[q] != 0.0) has_diag = true;
     if (!has_diag) { set_error("setup: row " + std::to_string(i) + " has no nonzero diagonal"); return -1; }
   }
+  {
+    // the Gauss-Seidel and patch colourings treat the nonzero pattern as an undirected graph: with a
+    // nonsymmetric pattern two coupled rows could share a colour (a silent data race), so refuse it
+    long long bad = 0;
+#pragma omp parallel for schedule(static) reduction(+ : bad)
+    for (int i = 0; i < n; ++i)
+      for (int q = A.ia[i]; q < A.ia[i + 1]; ++q) {
+        const int j = A.ja[q];
+        if (j == i || A.a[q] == 0.0) continue;
+        const int* lo = A.ja.data() + A.ia[j];
+        const int* hi = A.ja.data() + A.ia[j + 1];
+        const int* it = std::lower_bound(lo, hi, i);
+        if (it == hi || *it != i || A.a[it - A.ja.data()] == 0.0) ++bad;
+      }
+    if (bad) {
+      set_error("setup: the nonzero pattern is not symmetric (" + std::to_string(bad) + " entries a_ij != 0 with a_ji == 0); "
+                "the multicolour smoothers need a structurally symmetric matrix");
+      return -1;
+    }
+  }
   if (part) {
     if (nparts < 1) { set_error("setup: nparts < 1"); return -1; }
     for (int i = 0; i < n; ++i)
@@ -116,7 +145,7 @@ int mamg_setup_partitioned(const mamg_params* p, int32_t n, const int32_t* indpt
   }
   mamg_handle h = new mamg_handle_s();
   std::string err;
-  if (!build_hierarchy(*p, std::move(A), idofs, n_idofs, part, nparts, h->H, err)) {
+  if (!build_hierarchy(*p, std::move(A), seeds.data(), (int)seeds.size(), part, nparts, h->H, err)) {
     delete h;
     set_error("AMG levels failed to set up: " + err);
     return -3;
@@ -173,7 +202,7 @@ int mamg_level_info(mamg_handle h, int32_t level, int64_t info[12]) {
   info[8] = row_entries;
   info[9] = inv_entries;
   info[10] = L->P.nnz();
-  info[11] = 0;
+  info[11] = L->nnz_structural;
   info[0] = L->A.n;
   info[1] = L->A.nnz();
   info[2] = L->nc;

@@ -38,6 +38,7 @@ struct SchwarzPatches {
 
 struct Level {
   Csr A;                       // natural ordering
+  int64_t nnz_structural = 0;  // entries before explicit zeros were dropped (setup.cpp)
   std::vector<int> agg;        // size n; coarse index or -1 (row left out of every aggregate)
   int nc = 0;                  // number of aggregates == rows of next level
   std::vector<int> color;      // multicolour GS colour of every row

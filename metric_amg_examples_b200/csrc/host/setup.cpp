@@ -262,6 +262,11 @@ void csr_multiply(const Csr& A, const Csr& B, Csr& C) {
       C.ia[i + 1] = (int)acc.size();
     }
   }
+  {
+    long long tot = 0;
+    for (int i = 0; i < A.n; ++i) tot += C.ia[i + 1];
+    if (tot > 0x7fffffffLL) throw std::runtime_error("sparse product has " + std::to_string(tot) + " entries: exceeds int32 indexing");
+  }
   for (int i = 0; i < A.n; ++i) C.ia[i + 1] += C.ia[i];
   C.ja.resize(C.ia[A.n]);
   C.a.resize(C.ia[A.n]);
@@ -406,6 +411,11 @@ void schwarz_patches(const Csr& A, const int* seeds, int nseeds, int maxlvl, int
     }
   }
   out.max_size = max_size;
+  {
+    long long tot = 0;
+    for (int s = 0; s < nseeds; ++s) tot += out.ptr[s + 1];
+    if (tot > 0x7fffffffLL) throw std::runtime_error("Schwarz patches: " + std::to_string(tot) + " patch dofs exceed int32 indexing");
+  }
   for (int s = 0; s < nseeds; ++s) out.ptr[s + 1] += out.ptr[s];
   out.dofs.reserve(out.ptr[nseeds]);
   for (int t = 0; t < nthreads; ++t) out.dofs.insert(out.dofs.end(), part[t].begin(), part[t].end());
@@ -528,8 +538,12 @@ bool build_hierarchy(const mamg_params& prm, Csr&& A0, const int* idofs, int n_i
     return false;
   }
   const int max_levels = std::max(1, prm.max_levels);
-  // MAMG_DROP_ZEROS=1 (default off until verified on the device): store no explicit zeros on any level
-  const bool drop_zeros = getenv("MAMG_DROP_ZEROS") && atoi(getenv("MAMG_DROP_ZEROS")) != 0;
+  // Store no explicit zeros on any level (MAMG_DROP_ZEROS=0 keeps the caller's full pattern): a +0*x
+  // term never changes a sum, aggregation / colouring / patch search ignore zero couplings anyway, and
+  // on the Kuhn-mesh P1 systems up to half of the stored entries are exact zeros.  nnz_structural
+  // remembers the pattern that was handed in / that the Galerkin product produced.
+  const bool drop_zeros = !(getenv("MAMG_DROP_ZEROS") && atoi(getenv("MAMG_DROP_ZEROS")) == 0);
+  H.lv[0].nnz_structural = H.lv[0].A.nnz();
   if (drop_zeros) csr_drop_zeros(H.lv[0].A);
   const bool timing = getenv("MAMG_SETUP_TIMING") != nullptr;   // per-phase seconds on stderr
   auto tp = std::chrono::steady_clock::now();
@@ -577,6 +591,7 @@ bool build_hierarchy(const mamg_params& prm, Csr&& A0, const int* idofs, int n_i
     } else {
       galerkin_ua(H.lv[l].A, H.lv[l].agg, H.lv[l].nc, H.lv[l + 1].A);
     }
+    H.lv[l + 1].nnz_structural = H.lv[l + 1].A.nnz();
     if (drop_zeros) csr_drop_zeros(H.lv[l + 1].A);
     lap("galerkin", l);
     if (!H.lv[l].part.empty()) {   // a coarse row belongs to the part of its members

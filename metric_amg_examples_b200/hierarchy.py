@@ -117,7 +117,8 @@ class Hierarchy:
         info = (C.c_int64 * 12)()
         check(lib.mamg_level_info(self._h, level, info))
         keys = ["rows", "nnz", "n_aggregates", "n_colors", "n_patches", "n_patch_entries",
-                "n_patch_colors", "max_patch_size", "patch_row_entries", "patch_inv_entries", "nnz_P"]
+                "n_patch_colors", "max_patch_size", "patch_row_entries", "patch_inv_entries", "nnz_P",
+                "nnz_structural"]
         return dict(zip(keys, [int(x) for x in info]))
 
     def export_level(self, level):
@@ -207,6 +208,11 @@ class Hierarchy:
 
     def set_stream(self, stream):
         check(lib.mamg_set_stream(self._h, C.c_void_p(stream) if stream else None))
+
+    def set_cycle(self, cycle_type):
+        """Switch V_CYCLE / W_CYCLE on the existing hierarchy (host and device)."""
+        check(lib.mamg_set_cycle(self._h, int(cycle_type)))
+        self.params.cycle_type = int(cycle_type)
 
     def release_host(self):
         """Free the host copy of the level matrices (after to_device); export() is no longer possible."""

@@ -19,3 +19,15 @@ def pytest_configure(config):
 def have_gpu():
     import torch
     return torch.cuda.is_available()
+
+
+def pytest_collection_modifyitems(config, items):
+    """`pytest tests` on a box without a CUDA device skips the gpu-marked tests instead of failing
+    them with 'no CUDA device' (the product path has no CPU fallback to run them on)."""
+    import torch
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device: gpu-marked tests run on the B200 box")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)

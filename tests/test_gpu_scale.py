@@ -1,0 +1,135 @@
+"""Oracle parity at the sizes and kernel variants that bench.py actually runs.
+
+The small cases of test_gpu_parity.py never reach the code paths that carry the bytes of the
+benchmark: levels of >= 32 k rows (the wide row kernels), a long stack of per-level kernels above
+the persistent tail, CUDA-graph replay of a > 1000-node cycle.  Here every BASELINE config is run at
+the reference's own refinements (src/bidomain_2d.py:168 n = 32..256, src/emi_2d.py:190 n = 64..512)
+and the 3-D systems at sizes whose finest level has > 32 k rows; the CPU oracle finishes each in
+seconds.  Tolerances are north_star's: apply 1e-10 relative, iteration counts +-1, first residuals.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import metric_amg_examples_b200 as mamg
+from metric_amg_examples_b200 import haznics_compat as haznics, params, problems
+from oracle import Oracle
+
+pytestmark = pytest.mark.gpu
+
+APPLY_TOL = 1e-10
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def rel(a, b):
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def check_against_oracle(system, prm, tol, relative=False, threads=0):
+    H = mamg.Hierarchy(system.A, prm, system.interface_dofs)
+    H.to_device(0)
+    orc = Oracle(H.export(), "multicolor")
+    orc.set_threads(threads)
+    rng = np.random.default_rng(21)
+    r = rng.standard_normal(system.ndofs)
+    assert rel(H.apply(r), orc.apply(r)) < APPLY_TOL
+    # every kernel class on the biggest levels: SpMV and one smoothing application
+    for l in range(min(2, H.num_levels - 1)):
+        nl = H.level_info(l)["rows"]
+        x, b = rng.standard_normal(nl), rng.standard_normal(nl)
+        assert rel(H.spmv(x, l), orc.spmv(x, l)) < 1e-13
+        assert rel(H.smooth(b, x, l), orc.smooth(b, x, l)) < 1e-11
+        assert rel(H.smooth(b, x, l, post=True), orc.smooth(b, x, l, post=True)) < 1e-11
+    b, xt = system.random_rhs(0)
+    x, info = H.pcg(b, tolerance=tol, relative=relative, maxiter=500)
+    xo, ref = orc.pcg(b, tolerance=tol, relative=relative, maxiter=500)
+    assert abs(info["niters"] - ref["niters"]) <= 1, (info["niters"], ref["niters"])
+    k = min(info["niters"], ref["niters"], 6)
+    assert np.allclose(info["residuals"][:k + 1], ref["residuals"][:k + 1], rtol=1e-8)
+    assert rel(x, xo) < 1e-6
+    return H, orc, info
+
+
+@pytest.mark.parametrize("n", [32, 64, 128, 256])
+def test_c1_bidomain2d_all_refinements(n):
+    """BASELINE configs[0]: bidomain_2d.py -nrefs 4 -gamma 1e3 -precond metric_mono (W-cycle,
+    Schwarz on level 0, absolute tolerance 1e-8: src/bidomain_2d.py:168,201-205)."""
+    check_against_oracle(problems.bidomain_system(2, n, gamma=1e3), params.parameters_metric_schwarz, 1e-8)
+
+
+@pytest.mark.parametrize("n", [64, 128, 256, 512])
+def test_c2_emi2d_refinements(n):
+    """BASELINE configs[1]: emi_2d.py -gamma 1e6 with the inline default parameters
+    (src/emi_2d.py:190,207-211; tolerance 1e-10 absolute)."""
+    check_against_oracle(problems.emi_system(2, n, gamma=1e6), params.default_metric_parameters, 1e-10)
+
+
+@pytest.mark.parametrize("cycle", ["V", "W"])
+def test_c3_bidomain3d_wide_kernels(cycle):
+    """bidomain_3d n=32 (71 874 dofs): level 0 and level 1 have >= 32 k rows, so the wide row kernels
+    the benchmark uses, the <24,4> Schwarz fast path and a non-tail stack of levels are compared."""
+    prm = dict(params.parameters_metric_schwarz,
+               cycle_type=haznics.V_CYCLE if cycle == "V" else haznics.W_CYCLE)
+    H, _, _ = check_against_oracle(problems.bidomain_system(3, 32, gamma=1e4), prm, 1e-8, relative=True)
+    assert H.level_info(0)["rows"] >= 32768 and H.level_info(1)["rows"] >= 32768
+
+
+def test_c4_emi3d_general_schwarz_at_scale():
+    """emi_3d n=40 (70 602 dofs), both interface sides seeded (src/emi_3d.py:134-138), 2-ring patches
+    of up to 100 dofs (general Schwarz kernel)."""
+    H, _, _ = check_against_oracle(problems.emi_system(3, 40, gamma=1e6), params.default_metric_parameters, 1e-10)
+    assert H.level_info(0)["max_patch_size"] > 32
+
+
+ENV_CASES = [
+    {"MAMG_UNROLL": "1"}, {"MAMG_UNROLL": "2"}, {"MAMG_UNROLL": "4"},
+    {"MAMG_LANES": "2"}, {"MAMG_LANES": "4"}, {"MAMG_LANES": "8"}, {"MAMG_LANES": "16"}, {"MAMG_LANES": "32"},
+    {"MAMG_SCHWARZ_GENERAL": "1"}, {"MAMG_GRAPH": "0"}, {"MAMG_TAIL_ROWS": "0"}, {"MAMG_DROP_ZEROS": "1"},
+    {"MAMG_DROP_ZEROS": "0"}, {"MAMG_SW_DEDUP": "0"}, {"MAMG_ROWS": "csr"}, {"MAMG_ROWS": "sell"},
+    {"MAMG_PCG_CHECK": "1"}, {"MAMG_PCG_CHECK": "8"},
+]
+
+
+@pytest.mark.parametrize("env", ENV_CASES, ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()))
+def test_env_variants_match_oracle(env, monkeypatch):
+    """Every tuning switch selects another kernel variant of the same arithmetic."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    check_against_oracle(problems.bidomain_system(3, 20, gamma=1e4), params.parameters_metric_schwarz, 1e-8)
+    if "MAMG_SCHWARZ_GENERAL" in env or "MAMG_DROP_ZEROS" in env or "MAMG_ROWS" in env:
+        check_against_oracle(problems.emi_system(3, 16, gamma=1e6), params.default_metric_parameters, 1e-10)
+
+
+def test_properties_at_bench_like_size():
+    """bidomain_3d n=64 (549 250 dofs; the oracle still finishes in seconds): apply parity on a hierarchy
+    with five levels above 32 k rows, graph replay equals the eager launch sequence bit for bit."""
+    system = problems.bidomain_system(3, 64, gamma=1e4)
+    prm = dict(params.parameters_metric_schwarz, cycle_type=haznics.V_CYCLE)
+    H = mamg.Hierarchy(system.A, prm, system.interface_dofs).to_device(0)
+    orc = Oracle(H.export(), "multicolor")
+    orc.set_threads(0)
+    r = np.random.default_rng(5).standard_normal(system.ndofs)
+    z1 = H.apply(r)     # first call captures the graph
+    z2 = H.apply(r)     # replay
+    assert np.array_equal(z1, z2)
+    assert rel(z1, orc.apply(r)) < APPLY_TOL
+    b, xt = system.random_rhs(3)
+    x, info = H.pcg(b, tolerance=1e-8, relative=True, maxiter=200)
+    _, ref = orc.pcg(b, tolerance=1e-8, relative=True, maxiter=200)
+    assert abs(info["niters"] - ref["niters"]) <= 1
+    assert np.linalg.norm(system.A @ x - b) <= 1e-6 * np.linalg.norm(b)
+
+
+def test_multi_gpu_parity_under_torchrun():
+    """tests/dist_check.py (apply/PCG parity with the oracle, all ranks bit-identical) on 2 GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tests", "dist_check.py")]
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-4000:]
+    assert "FAIL" not in p.stdout

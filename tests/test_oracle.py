@@ -179,17 +179,30 @@ def test_oracle_reproduces_golden(path):
 
 
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(HERE, "golden", "*.npz"))))
-def test_setup_reproduces_golden_hierarchy(path):
-    """The host setup is deterministic: re-building the case gives the frozen hierarchy."""
+def test_setup_reproduces_golden_hierarchy(path, monkeypatch):
+    """The host setup is deterministic: re-building the case gives the frozen hierarchy.  The fixtures
+    were frozen with the caller's full pattern (MAMG_DROP_ZEROS=0); the default setup stores the same
+    hierarchy without its explicit zeros (the diagonal always stays)."""
     name = os.path.basename(path)[:-4]
     z = np.load(path)
     system, prm, _ = make_golden.CASES[name]()
+    monkeypatch.setenv("MAMG_DROP_ZEROS", "0")
     ex = mamg.Hierarchy(system.A, prm, system.interface_dofs).export()
     assert len(ex["levels"]) == int(z["nlevels"])
     for l, L in enumerate(ex["levels"]):
         for k in ("indptr", "indices", "agg", "color", "patch_ptr", "patch_dofs", "patch_color"):
             assert np.array_equal(L[k], z[f"L{l}_{k}"]), (l, k)
         assert np.allclose(L["data"], z[f"L{l}_data"], rtol=1e-13, atol=0)
+    monkeypatch.delenv("MAMG_DROP_ZEROS")
+    lean = mamg.Hierarchy(system.A, prm, system.interface_dofs).export()
+    for l, L in enumerate(lean["levels"]):
+        ip, ix, dv = z[f"L{l}_indptr"], z[f"L{l}_indices"], z[f"L{l}_data"]
+        rows = np.repeat(np.arange(len(ip) - 1), np.diff(ip))
+        keep = (dv != 0.0) | (ix == rows)
+        assert np.array_equal(L["indices"], ix[keep]) and np.allclose(L["data"], dv[keep], rtol=1e-13, atol=0)
+        assert np.array_equal(np.diff(L["indptr"]), np.bincount(rows[keep], minlength=len(ip) - 1))
+        for k in ("agg", "color", "patch_ptr", "patch_dofs", "patch_color"):
+            assert np.array_equal(L[k], z[f"L{l}_{k}"]), (l, k)
 
 
 def test_krylov_solvers_against_scipy():
@@ -225,16 +238,18 @@ def test_krylov_solvers_against_scipy():
 
 
 def test_dropping_explicit_zeros_is_bit_neutral(monkeypatch):
-    """MAMG_DROP_ZEROS=1 (default off until verified on the device) removes the exact zeros of the P1
+    """Dropping explicit zeros (the default; MAMG_DROP_ZEROS=0 keeps them) removes the exact zeros of the P1
     pattern from every level: same aggregates, colours and patches, about half the stored entries for
     EMI-3D, and bit-identical cycle outputs and residual histories in both smoother orders."""
     s = problems.emi_system(3, 12, gamma=1e6)
     b, _ = s.random_rhs(0)
     r = np.random.default_rng(0).standard_normal(s.ndofs)
-    monkeypatch.delenv("MAMG_DROP_ZEROS", raising=False)
+    monkeypatch.setenv("MAMG_DROP_ZEROS", "0")
     full = mamg.Hierarchy(s.A, params.default_metric_parameters, s.interface_dofs).export()
-    monkeypatch.setenv("MAMG_DROP_ZEROS", "1")
-    lean = mamg.Hierarchy(s.A, params.default_metric_parameters, s.interface_dofs).export()
+    monkeypatch.delenv("MAMG_DROP_ZEROS", raising=False)
+    Hl = mamg.Hierarchy(s.A, params.default_metric_parameters, s.interface_dofs)
+    lean = Hl.export()
+    assert Hl.level_info(0)["nnz_structural"] == len(full["levels"][0]["data"]) > Hl.level_info(0)["nnz"]
     nnz = lambda ex: sum(len(L["data"]) for L in ex["levels"])
     assert nnz(lean) < 0.6 * nnz(full)
     for F, Z in zip(full["levels"], lean["levels"]):
