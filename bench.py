@@ -400,6 +400,10 @@ def run_mamg(a):
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s",
                      "avg_launch_ms": dom_ms / max(dom_launches, 1)},
         "kernels": kernels,
+        "schwarz_blobs": {k: H.stats(0)[k] for k in ("n_patches", "unique_blobs", "schwarz_sweep_bytes",
+                                                      "schwarz_sweep_bytes_stored_factors", "schwarz_fast_path")},
+        "sell": [{"rows": H.stats(l)["rows"], "nnz_stored": H.stats(l)["nnz_stored"], "slots": H.stats(l)["sell_slots"]}
+                 for l in range(min(H.num_levels, 4))],
         "gs_ms_by_level": [round(float(v), 2) for v in prof_lv[:, 1]],
         "level_rows": [H.level_info(l)["rows"] for l in range(H.num_levels)],
         "host": {"assemble_s": round(t_asm, 2), "setup_s": round(t_setup, 2), "upload_s": round(t_upload, 2),

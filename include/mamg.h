@@ -201,6 +201,14 @@ int mamg_schwarz_sweep_bytes(mamg_handle h, int32_t level, int64_t* bytes);
  * inside a timed region. */
 int mamg_profile(mamg_handle h, int32_t on, double* ms_per_class, int64_t* launches_per_class);
 int mamg_cycle_bytes(mamg_handle h, int64_t* bytes);
+/* device-side statistics of one level (SURVEY 8b `mamg_stats`): out[0]=rows out[1]=stored nnz
+ * out[2]=structural nnz (before zero dropping) out[3]=sliced-ELL entry slots (padding included)
+ * out[4]=device bytes of the whole handle out[5]=Schwarz patches out[6]=unique stored patch blobs
+ * out[7]=algorithmic bytes of one Schwarz sweep (shared blobs once per colour) out[8]=the same with
+ * every patch owning its data (SURVEY 8d stored-factor model) out[9]=GS colours out[10]=patch colours
+ * out[11]=1 if the level runs inside the persistent tail kernel out[12]=1 sliced-ELL row kernels
+ * out[13]=1 CSR entries kept on the device out[14]=row blocks (parts) out[15]=1 Schwarz fast path */
+int mamg_stats(mamg_handle h, int32_t level, int64_t out[16]);
 
 /* ---- synthetic systems of BASELINE.json's configs: P1 on UnitSquare/UnitCube
  *      (right-diagonal / 6-tet Kuhn split, lexicographic dofs), the matrices the

@@ -385,7 +385,7 @@ static void upload_hierarchy(const Hierarchy& H, DeviceState& D) {
       dl.cptr = upload(D, cptr);
       dl.cidx = upload(D, cidx);
     }
-    if (hl.sw.npatch() > 0) schwarz_upload(hl, dl.nb, iperm[l], dl.ia, dl.ja, dl.a, ia, ja, dl.sw, [&](size_t bytes) {
+    if (hl.sw.npatch() > 0) schwarz_upload(hl, dl.nb, iperm[l], dl.ia, dl.ja, dl.a, ia, ja, a, dl.sw, [&](size_t bytes) {
       void* p = nullptr;
       CUDA_OK(cudaMalloc(&p, bytes ? bytes : 1));
       D.allocs.push_back(p);
@@ -1563,6 +1563,31 @@ int mamg_schwarz_sweep_bytes(mamg_handle h, int32_t level, int64_t* bytes) {
   if (!D || !bytes) return -1;
   if (level < 0 || level >= (int)D->lv.size()) { set_error("level out of range"); return -1; }
   *bytes = D->lv[level].sw.alg_bytes;
+  return 0;
+}
+
+int mamg_stats(mamg_handle h, int32_t level, int64_t out[16]) {
+  DeviceState* D = get_dev(h);
+  if (!D || !out) return -1;
+  if (level < 0 || level >= (int)D->lv.size()) { set_error("level out of range"); return -1; }
+  const DLevel& l = D->lv[level];
+  for (int k = 0; k < 16; ++k) out[k] = 0;
+  out[0] = l.n;
+  out[1] = l.nnz;
+  out[2] = h->H.lv[level].nnz_structural;
+  out[3] = l.sell_slots;
+  out[4] = D->dev_bytes;
+  out[5] = l.sw.npatch;
+  out[6] = l.sw.nuniq;
+  out[7] = l.sw.alg_bytes;
+  out[8] = l.sw.alg_bytes_stored;
+  out[9] = l.ncolors;
+  out[10] = l.sw.ncolors;
+  out[11] = (D->tail_k0 >= 0 && level >= D->tail_k0) ? 1 : 0;
+  out[12] = l.use_sell ? 1 : 0;
+  out[13] = l.has_csr ? 1 : 0;
+  out[14] = l.nb;
+  out[15] = l.sw.fast ? 1 : 0;
   return 0;
 }
 

@@ -29,6 +29,8 @@
 #include <cstring>
 #include <functional>
 #include <numeric>
+#include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../host/hierarchy.h"
@@ -72,6 +74,12 @@ struct DSchwarz {
   int* nbrp = nullptr;         // [np][nbq][32] neighbourhood list, padded with a valid index
   double* vt = nullptr;        // [np][srow][32] entry e of row k; 0 padding
   uint32_t* ct4 = nullptr;     // [np][sq][32] four 8-bit local columns per word; 255 = zero slot
+  // de-duplication: patches whose blocks, off-patch values and local columns are bit-identical (most
+  // patches of a uniform mesh with constant coefficients) share one stored blob; pinv / vt / ct4 (and
+  // lcol on the general path) are indexed by the unique id, which keeps them L2-resident
+  int nuniq = 0;
+  int* uid = nullptr;          // [np] unique blob of every patch (fast path)
+  long long* inv_off = nullptr;  // [nuniq] offset of the packed inverse of a unique blob
   // patches sorted by (conflict colour, block of the seed): cb_ptr[c*nb + b] .. [c*nb + b + 1]
   int nb = 1;
   std::vector<int> cb_ptr;     // host: size ncolors*nb + 1
@@ -80,7 +88,8 @@ struct DSchwarz {
   // another part's row block) are exchanged; xoff[c*nb + b] .. delimit them inside xidx
   std::vector<int> xoff;
   int* xidx = nullptr;
-  long long alg_bytes = 0;     // algorithmic bytes of one sweep over all patches
+  long long alg_bytes = 0;     // algorithmic bytes of one sweep over all patches (shared blobs once per colour)
+  long long alg_bytes_stored = 0;  // the same with every patch owning its data (SURVEY 8d "stored factors")
 };
 
 __device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }  // i >= j
@@ -88,12 +97,13 @@ __device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }
 // ---- setup: packed inverse of every A_BB -------------------------------------------------------
 template <int T>
 __global__ void __launch_bounds__(T)
-schwarz_invert_kernel(int npatch, const SwPatch* __restrict__ pat, const int* __restrict__ pidx,
+schwarz_invert_kernel(int nuniq, const int* __restrict__ rep, const long long* __restrict__ inv_off,
+                      const SwPatch* __restrict__ pat, const int* __restrict__ pidx,
                       const int* __restrict__ ia, const int* __restrict__ ja,
                       const double* __restrict__ a, double* __restrict__ pinv, int max_size) {
   extern __shared__ double smem[];
-  const int patch = blockIdx.x;
-  if (patch >= npatch) return;
+  if ((int)blockIdx.x >= nuniq) return;
+  const int patch = rep[blockIdx.x];   // the representative patch of unique blob blockIdx.x
   const int q0 = pat[patch].q0, s = pat[patch].s;
   double* Lm = smem;                                                  // packed lower triangle
   double* col = Lm + (size_t)max_size * (max_size + 1) / 2;           // s scratch
@@ -150,7 +160,7 @@ schwarz_invert_kernel(int npatch, const SwPatch* __restrict__ pat, const int* __
     for (int c = tid; c <= i; c += T) Lm[tri(i, c)] = col[c];
     __syncthreads();
   }
-  double* out = pinv + pat[patch].i0;
+  double* out = pinv + inv_off[blockIdx.x];
   for (int k = tid; k < s * (s + 1) / 2; k += T) out[k] = Lm[k];
 }
 
@@ -272,22 +282,86 @@ schwarz_apply_kernel(int p0, int p1, const SwPatch* __restrict__ pat, const int*
 // ---- fast path -----------------------------------------------------------------------------------
 // setup: build vt / ct4 of one patch from the level CSR (one warp per patch, lane = patch row)
 __global__ void __launch_bounds__(256)
-schwarz_blob_kernel(int np, const SwPatch* __restrict__ pat, const int* __restrict__ pidx,
-                    const int* __restrict__ nbr, const int* __restrict__ ia, const int* __restrict__ ja,
-                    const double* __restrict__ a, int srow, int sq, int nbq, int* __restrict__ pidx32,
-                    int* __restrict__ nbrp, double* __restrict__ vt, uint32_t* __restrict__ ct4,
-                    const SwProfile prof, int vstride) {
+schwarz_index_kernel(int np, const SwPatch* __restrict__ pat, const int* __restrict__ pidx,
+                     const int* __restrict__ nbr, int nbq, int* __restrict__ pidx32, int* __restrict__ nbrp) {
+  // per-patch index data of the fast path: row ids (lane = patch row) and the padded neighbour list
   const int patch = blockIdx.x * 8 + threadIdx.x / 32, lane = threadIdx.x % 32;
   if (patch >= np) return;
   const SwPatch P = pat[patch];
   const size_t pp = (size_t)patch;
-  const int row = lane < P.s ? pidx[P.q0 + lane] : -1;
-  pidx32[pp * 32 + lane] = row;
+  pidx32[pp * 32 + lane] = lane < P.s ? pidx[P.q0 + lane] : -1;
   const int* nb = nbr + P.n0;
   for (int j = 0; j < nbq; ++j) {
     const int q = j * 32 + lane;
     nbrp[(pp * nbq + j) * 32 + lane] = q < P.nn ? nb[q] : 0;   // padding: any valid row id (never referenced)
   }
+}
+
+// 128-bit signature of everything the stored blob of a patch depends on: its size and, row by row in
+// lane order, every matrix entry as (inside the patch: local row | outside: position in the neighbour
+// list, value bits).  Equal signatures <=> bit-identical A_BB, off-patch values and local columns.
+struct SwSig { unsigned long long a, b; };
+__device__ __forceinline__ unsigned long long sw_mix(unsigned long long h, unsigned long long v, unsigned long long m) {
+  h ^= v + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2);
+  h *= m;
+  h ^= h >> 29;
+  return h;
+}
+__global__ void __launch_bounds__(256)
+schwarz_sig_kernel(int np, const SwPatch* __restrict__ pat, const int* __restrict__ pidx,
+                   const int* __restrict__ nbr, const int* __restrict__ ia, const int* __restrict__ ja,
+                   const double* __restrict__ a, SwSig* __restrict__ sig) {
+  const int patch = blockIdx.x * 8 + threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (patch >= np) return;
+  const SwPatch P = pat[patch];
+  const int row = lane < P.s ? pidx[P.q0 + lane] : -1;
+  const int* nb = nbr + P.n0;
+  const int r0 = row >= 0 ? ia[row] : 0, len = row >= 0 ? ia[row + 1] - r0 : 0;
+  int maxlen = len;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
+  unsigned long long h1 = 0x243f6a8885a308d3ULL + lane, h2 = 0x13198a2e03707344ULL ^ ((unsigned long long)lane << 32);
+  for (int e = 0; e < maxlen; ++e) {
+    const bool on = e < len;
+    const int col = on ? ja[r0 + e] : -2;
+    long long code = -1;
+    if (on && P.nn > 0) {
+      int lo = 0, hi = P.nn - 1;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (nb[mid] < col) lo = mid + 1; else hi = mid; }
+      if (nb[lo] == col) code = (2LL << 32) | lo;
+    }
+    for (int t = 0; t < 32; ++t) {   // inside the patch: which lane owns that row
+      const int rt = __shfl_sync(0xffffffffu, row, t);
+      if (on && code < 0 && rt == col) code = (1LL << 32) | t;
+    }
+    if (on) {
+      const unsigned long long vb = (unsigned long long)__double_as_longlong(a[r0 + e]);
+      h1 = sw_mix(sw_mix(h1, (unsigned long long)code, 0xff51afd7ed558ccdULL), vb, 0xff51afd7ed558ccdULL);
+      h2 = sw_mix(sw_mix(h2, vb, 0xc4ceb9fe1a85ec53ULL), (unsigned long long)code, 0xc4ceb9fe1a85ec53ULL);
+    }
+  }
+  unsigned long long H1 = sw_mix(0x452821e638d01377ULL, (unsigned long long)P.s, 0xff51afd7ed558ccdULL);
+  unsigned long long H2 = sw_mix(0xbe5466cf34e90c6cULL, (unsigned long long)P.s, 0xc4ceb9fe1a85ec53ULL);
+  for (int t = 0; t < 32; ++t) {
+    H1 = sw_mix(H1, __shfl_sync(0xffffffffu, h1, t), 0xff51afd7ed558ccdULL);
+    H2 = sw_mix(H2, __shfl_sync(0xffffffffu, h2, t), 0xc4ceb9fe1a85ec53ULL);
+  }
+  if (lane == 0) { sig[patch].a = H1; sig[patch].b = H2; }
+}
+
+// setup: build vt / ct4 of unique blob u from the level CSR (one warp per blob, lane = row of its
+// representative patch)
+__global__ void __launch_bounds__(256)
+schwarz_blob_kernel(int nuniq, const int* __restrict__ rep, const SwPatch* __restrict__ pat, const int* __restrict__ pidx,
+                    const int* __restrict__ nbr, const int* __restrict__ ia, const int* __restrict__ ja,
+                    const double* __restrict__ a, int srow, int sq, double* __restrict__ vt, uint32_t* __restrict__ ct4,
+                    const SwProfile prof, int vstride) {
+  const int u = blockIdx.x * 8 + threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (u >= nuniq) return;
+  const SwPatch P = pat[rep[u]];
+  const size_t pp = (size_t)u;
+  const int row = lane < P.s ? pidx[P.q0 + lane] : -1;
+  const int* nb = nbr + P.n0;
   // off-patch entries of this lane's row, compacted to the front (columns not found in the list of
   // outside neighbours belong to the patch itself and live in the stored inverse)
   const int r0 = row >= 0 ? ia[row] : 0, len = row >= 0 ? ia[row + 1] - r0 : 0;
@@ -327,9 +401,10 @@ constexpr int kSwFastSlot = 256 + 528 + 32;  // doubles per patch slot: xs[256],
 template <int SR, int NBQ>
 __global__ void __launch_bounds__(kSwFastWarps * 32, (SR <= 24 && NBQ <= 4) ? MAMG_SW_MINB24 : MAMG_SW_MINB)
 schwarz_fast_kernel(int p0, int p1, const int* __restrict__ pidx32, const int* __restrict__ nbrp,
+                    const int* __restrict__ uid, const long long* __restrict__ inv_off,
                     const double* __restrict__ vt, const uint32_t* __restrict__ ct4,
                     const double* __restrict__ pinv, const double* __restrict__ b, double* x, int srow,
-                    int sq, int nbq, int inv_stride, int smax, const SwProfile prof, int vstride) {
+                    int sq, int nbq, int smax, const SwProfile prof, int vstride) {
   extern __shared__ __align__(16) double smem[];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int patch = p0 + blockIdx.x * kSwFastWarps + warp;
@@ -338,6 +413,7 @@ schwarz_fast_kernel(int p0, int p1, const int* __restrict__ pidx32, const int* _
   double* Inv = xs + 256;
   double* rhs = Inv + 528;
   const size_t pp = (size_t)patch;
+  const size_t uu = (size_t)uid[patch];   // the stored blob this patch shares with its look-alikes
   // ---- wave 1 ----
   const int my = pidx32[pp * 32 + lane];
   int nb[NBQ];
@@ -345,19 +421,19 @@ schwarz_fast_kernel(int p0, int p1, const int* __restrict__ pidx32, const int* _
   for (int j = 0; j < NBQ; ++j) nb[j] = j < nbq ? ld_stream(nbrp + (pp * nbq + j) * 32 + lane) : 0;
   const int s = __popc(__ballot_sync(0xffffffffu, my >= 0));     // dofs of this patch
   {
-    const double* src = pinv + pp * inv_stride;
+    const double* src = pinv + inv_off[uu];
     const int nch = (s * (s + 1) / 2 + 1) / 2;                  // 16-byte chunks of its packed inverse
     for (int k = lane; k < nch; k += 32) cp_async16(Inv + 2 * k, src + 2 * k);
   }
   double v[SR];
   {
-    const double* vp = vt + pp * vstride + lane;
+    const double* vp = vt + uu * vstride + lane;
 #pragma unroll
     for (int e = 0; e < SR; ++e) v[e] = (e < srow && lane < prof.cnt[e]) ? ld_stream(vp + prof.off[e]) : 0.0;
   }
   uint32_t c4[SR / 4];
   {
-    const uint32_t* cp = ct4 + (pp * sq) * 32 + lane;
+    const uint32_t* cp = ct4 + (uu * sq) * 32 + lane;
 #pragma unroll
     for (int q = 0; q < SR / 4; ++q) c4[q] = q < sq ? ld_stream(cp + q * 32) : 0xffffffffu;
   }
@@ -391,7 +467,7 @@ schwarz_fast_kernel(int p0, int p1, const int* __restrict__ pidx32, const int* _
 // `alloc(bytes)` returns tracked device memory; pia/pja are the permuted CSR of the level.
 inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iperm, const int* d_ia,
                            const int* d_ja, const double* d_a, const std::vector<int>& pia,
-                           const std::vector<int>& pja, DSchwarz& d,
+                           const std::vector<int>& pja, const std::vector<double>& pa, DSchwarz& d,
                            const std::function<void*(size_t)>& alloc) {
   const SwPatch zero = {0, 0, 0, 0, 0, 0};
   const SchwarzPatches& sw = hl.sw;
@@ -476,8 +552,7 @@ inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iper
   }
   d.prof = prof;
   d.vstride = prof.off[32];
-  long long tot_e = 0, tot_i = 0, tot_val = 0;
-  long long tot_n = 0, tot_q = 0;
+  long long tot_val = 0, tot_n = 0, tot_q = 0, tot_tri = 0;
   int max_nbr = 0;
   for (int k = 0; k < np; ++k) {
     const int p = order[k];
@@ -486,15 +561,11 @@ inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iper
     pat[k].s = s;
     pat[k].n0 = (int)tot_n;
     pat[k].nn = nn[k];
-    pat[k].e0 = tot_e;
-    pat[k].i0 = fast_shape ? (long long)k * 528 : tot_i;
     tot_q += s;
     tot_n += nn[k];
-    tot_e += ((long long)s * srow + 7) / 8 * 8;                 // 16-byte aligned uint16 segments
     tot_val += ne[k];
-    tot_i += fast_shape ? 528 : ((long long)s * (s + 1) / 2 + 1) / 2 * 2;   // 16-byte aligned inverses
+    tot_tri += (long long)s * (s + 1) / 2;
     max_nbr = std::max(max_nbr, nn[k]);
-
   }
   d.qoff.resize(np + 1);
   for (int k = 0; k < np; ++k) d.qoff[k] = pat[k].q0;
@@ -505,10 +576,18 @@ inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iper
   std::vector<int> nbr((size_t)tot_n);
   if (nb > 64) throw std::runtime_error("more than 64 parts are not supported by the Schwarz exchange lists");
   std::vector<unsigned long long> readers(nb > 1 ? n : 0, 0ull);
-  std::vector<uint16_t> lcol(fast_shape ? 8 : (size_t)tot_e + 8, 0);
+  // general path: host signature of what the stored inverse and the local columns depend on (size, row
+  // lengths, local column of every entry, value of every entry inside the patch)
+  std::vector<unsigned long long> sigA(np, 0), sigB(np, 0);
+  auto mix = [](unsigned long long h, unsigned long long v, unsigned long long m) {
+    h ^= v + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2);
+    h *= m;
+    h ^= h >> 29;
+    return h;
+  };
 #pragma omp parallel
   {
-    std::vector<int> mark(n, -1), pos(n, 0), list;
+    std::vector<int> mark(n, -1), pos(n, 0), lidx(n, -1), list;
 #pragma omp for schedule(dynamic, 2048)
     for (int k = 0; k < np; ++k) {
       const int p = order[k];
@@ -533,22 +612,32 @@ inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iper
           readers[j] |= bit;
         }
       }
-      uint16_t* out = fast_shape ? nullptr : &lcol[(size_t)pat[k].e0];
-      for (int q = 0; q < s && !fast_shape; ++q) {
-        const int i = pidx[pat[k].q0 + q];
-        for (int e = pia[i]; e < pia[i + 1]; ++e) out[(size_t)q * srow + (e - pia[i])] = (uint16_t)pos[pja[e]];
+      if (!fast_shape) {
+        for (int q = 0; q < s; ++q) lidx[pidx[pat[k].q0 + q]] = q;
+        unsigned long long h1 = mix(0x452821e638d01377ULL, (unsigned long long)s, 0xff51afd7ed558ccdULL);
+        unsigned long long h2 = mix(0xbe5466cf34e90c6cULL, (unsigned long long)s, 0xc4ceb9fe1a85ec53ULL);
+        for (int q = 0; q < s; ++q) {
+          const int i = pidx[pat[k].q0 + q];
+          h1 = mix(h1, (unsigned long long)(pia[i + 1] - pia[i]), 0xff51afd7ed558ccdULL);
+          for (int e = pia[i]; e < pia[i + 1]; ++e) {
+            const int j = pja[e];
+            const int lj = lidx[j];
+            const bool inside = lj >= 0 && lj < s && pidx[pat[k].q0 + lj] == j;
+            unsigned long long code = (unsigned long long)pos[j] | (inside ? ((unsigned long long)(lj + 1) << 32) : 0ull);
+            unsigned long long vb = 0;
+            if (inside) std::memcpy(&vb, &pa[e], 8);
+            h1 = mix(mix(h1, code, 0xff51afd7ed558ccdULL), vb, 0xff51afd7ed558ccdULL);
+            h2 = mix(mix(h2, vb, 0xc4ceb9fe1a85ec53ULL), code, 0xc4ceb9fe1a85ec53ULL);
+          }
+        }
+        sigA[k] = h1;
+        sigB[k] = h2;
       }
     }
   }
-  // per sweep: values + local columns of the row entries, neighbour list + gathered x, packed
-  // inverse, (idx, row start, row offset, b, x update) per patch dof, patch descriptor
-  d.alg_bytes = 10 * tot_val + 12 * tot_n + 8 * tot_i + (12 + 8 + 16) * tot_q + 32LL * np;
-  if (fast_shape)  // values + 8-bit local columns, neighbour list + gathered x, packed inverse, (idx, b, x) per dof
-    d.alg_bytes = 9 * tot_val + 12 * tot_n + 4 * [&] { long long t = 0; for (int k = 0; k < np; ++k) t += (long long)pat[k].s * (pat[k].s + 1); return t; }() + (4 + 8 + 8) * tot_q;
   const size_t tri_max = (size_t)d.max_size * (d.max_size + 1) / 2;
   d.smem_setup = (tri_max + d.max_size) * sizeof(double) + (size_t)d.max_size * sizeof(int);
   d.warps = d.max_size <= 32 ? 1 : (d.max_size <= 96 ? 2 : 4);
-  d.ppc = d.warps == 1 ? 4 : 1;
   const SwLayout lay = {d.max_size, d.max_nbr, d.srow};
   d.ppc = d.warps == 1 ? (lay.total_d() * 8 * 4 <= 100 * 1024 ? 4 : 2) : 1;
   d.smem_apply = (size_t)d.ppc * lay.total_d() * sizeof(double);
@@ -559,7 +648,10 @@ inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iper
     if (bytes) cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice);
     return p;
   };
-  d.pat = (SwPatch*)up(pat.data(), pat.size() * sizeof(SwPatch));
+  auto sync_or_throw = [](const char* what) {
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) throw std::runtime_error(std::string(what) + " failed: " + cudaGetErrorString(e));
+  };
   if (nb > 1) {
     std::vector<int> xidx;
     d.xoff.assign(sw.ncolors * nb + 1, 0);
@@ -577,32 +669,101 @@ inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iper
     d.xidx = (int*)up(xidx.data(), xidx.size() * sizeof(int));
   }
   d.pidx = (int*)up(pidx.data(), pidx.size() * sizeof(int));
-  d.prow = (int*)up(prow.data(), prow.size() * sizeof(int));
-  d.plen = (int*)up(plen.data(), plen.size() * sizeof(int));
   d.nbr = (int*)up(nbr.data(), nbr.size() * sizeof(int));
-  d.lcol = (uint16_t*)up(lcol.data(), lcol.size() * sizeof(uint16_t));
+  // ---- de-duplication: group the patches by signature (order of first appearance) -----------------
+  const char* nodedup = getenv("MAMG_SW_DEDUP");
+  const bool dedup = !(nodedup && atoi(nodedup) == 0);
+  SwPatch* d_pat_tmp = nullptr;
+  if (fast_shape) {
+    // offsets e0 / i0 are not used by the fast path: upload the descriptors now, hash on the device
+    d.pat = (SwPatch*)up(pat.data(), pat.size() * sizeof(SwPatch));
+    if (dedup) {
+      SwSig* d_sig = nullptr;
+      if (cudaMalloc(&d_sig, sizeof(SwSig) * (size_t)np) != cudaSuccess) throw std::runtime_error("Schwarz signatures: out of device memory");
+      schwarz_sig_kernel<<<(np + 7) / 8, 256>>>(np, d.pat, d.pidx, d.nbr, d_ia, d_ja, d_a, d_sig);
+      sync_or_throw("Schwarz signature kernel");
+      std::vector<SwSig> hs(np);
+      cudaMemcpy(hs.data(), d_sig, sizeof(SwSig) * (size_t)np, cudaMemcpyDeviceToHost);
+      cudaFree(d_sig);
+      for (int k = 0; k < np; ++k) { sigA[k] = hs[k].a; sigB[k] = hs[k].b; }
+    }
+  }
+  (void)d_pat_tmp;
+  std::vector<int> uid(np), rep;
+  if (dedup) {
+    struct Key { unsigned long long a, b; bool operator==(const Key& o) const { return a == o.a && b == o.b; } };
+    struct KeyHash { size_t operator()(const Key& k) const { return (size_t)(k.a ^ (k.b * 0x9e3779b97f4a7c15ULL)); } };
+    std::unordered_map<Key, int, KeyHash> seen;
+    seen.reserve(1 << 16);
+    for (int k = 0; k < np; ++k) {
+      auto it = seen.find(Key{sigA[k], sigB[k]});
+      if (it == seen.end()) { seen.emplace(Key{sigA[k], sigB[k]}, (int)rep.size()); uid[k] = (int)rep.size(); rep.push_back(k); }
+      else uid[k] = it->second;
+    }
+  } else {
+    rep.resize(np);
+    std::iota(rep.begin(), rep.end(), 0);
+    uid = rep;
+  }
+  const int nu = (int)rep.size();
+  d.nuniq = nu;
+  // packed inverses (s(s+1)/2 doubles, 16-byte aligned) and, on the general path, the local columns of
+  // the unique blobs
+  std::vector<long long> inv_off(nu + 1, 0), e_off(nu + 1, 0);
+  for (int u = 0; u < nu; ++u) {
+    const long long s = pat[rep[u]].s;
+    inv_off[u + 1] = inv_off[u] + (s * (s + 1) / 2 + 1) / 2 * 2;
+    e_off[u + 1] = e_off[u] + (s * srow + 7) / 8 * 8;                 // 16-byte aligned uint16 segments
+  }
+  const long long tot_i = inv_off[nu], tot_e = fast_shape ? 0 : e_off[nu];
+  long long uniq_blob_bytes = 8 * tot_i;
+  if (!fast_shape) {
+    for (int k = 0; k < np; ++k) { pat[k].i0 = inv_off[uid[k]]; pat[k].e0 = e_off[uid[k]]; }
+    std::vector<uint16_t> lcol((size_t)tot_e + 8, 0);
+#pragma omp parallel
+    {
+      std::vector<int> pos(n, 0);
+#pragma omp for schedule(dynamic, 256)
+      for (int u = 0; u < nu; ++u) {
+        const int k = rep[u];
+        for (int j = 0; j < pat[k].nn; ++j) pos[nbr[pat[k].n0 + j]] = j;
+        uint16_t* out = &lcol[(size_t)e_off[u]];
+        for (int q = 0; q < pat[k].s; ++q) {
+          const int i = pidx[pat[k].q0 + q];
+          for (int e = pia[i]; e < pia[i + 1]; ++e) out[(size_t)q * srow + (e - pia[i])] = (uint16_t)pos[pja[e]];
+        }
+      }
+    }
+    d.pat = (SwPatch*)up(pat.data(), pat.size() * sizeof(SwPatch));
+    d.prow = (int*)up(prow.data(), prow.size() * sizeof(int));
+    d.plen = (int*)up(plen.data(), plen.size() * sizeof(int));
+    d.lcol = (uint16_t*)up(lcol.data(), lcol.size() * sizeof(uint16_t));
+    uniq_blob_bytes += 2 * tot_e;
+  }
+  int* d_rep = (int*)up(rep.data(), rep.size() * sizeof(int));
+  d.inv_off = (long long*)up(inv_off.data(), (size_t)nu * sizeof(long long));
   d.pinv = (double*)alloc(((size_t)tot_i + 2) * sizeof(double));
-  if (fast_shape) cudaMemset(d.pinv, 0, ((size_t)tot_i + 2) * sizeof(double));   // padding must be 0, not NaN bits
+  cudaMemset(d.pinv, 0, ((size_t)tot_i + 2) * sizeof(double));   // padding must be 0, not NaN bits
   constexpr int TS = 128;
   if (d.smem_setup > 48 * 1024)
     cudaFuncSetAttribute(schwarz_invert_kernel<TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_setup);
-  schwarz_invert_kernel<TS><<<np, TS, d.smem_setup>>>(np, d.pat, d.pidx, d_ia, d_ja, d_a, d.pinv, d.max_size);
-  cudaError_t e = cudaDeviceSynchronize();
-  if (e != cudaSuccess) throw std::runtime_error(std::string("Schwarz setup kernel failed: ") + cudaGetErrorString(e));
+  schwarz_invert_kernel<TS><<<nu, TS, d.smem_setup>>>(nu, d_rep, d.inv_off, d.pat, d.pidx, d_ia, d_ja, d_a, d.pinv, d.max_size);
+  sync_or_throw("Schwarz setup kernel");
   if (fast_shape) {
     d.fast = true;
     d.nbq = (max_nn + 31) / 32;
     d.sq = (srow + 3) / 4;
-    d.inv_stride = 528;
     d.sr_t = (srow <= 12 && d.nbq <= 1) ? 12 : ((srow <= 24 && d.nbq <= 4) ? 24 : 32);
+    d.uid = (int*)up(uid.data(), uid.size() * sizeof(int));
     d.pidx32 = (int*)alloc((size_t)np * 32 * sizeof(int));
     d.nbrp = (int*)alloc((size_t)np * d.nbq * 32 * sizeof(int));
-    d.vt = (double*)alloc(((size_t)np * d.vstride + 32) * sizeof(double));
-    d.ct4 = (uint32_t*)alloc((size_t)np * d.sq * 32 * sizeof(uint32_t));
-    schwarz_blob_kernel<<<(np + 7) / 8, 256>>>(np, d.pat, d.pidx, d.nbr, d_ia, d_ja, d_a, srow, d.sq, d.nbq,
-                                              d.pidx32, d.nbrp, d.vt, d.ct4, d.prof, d.vstride);
-    e = cudaDeviceSynchronize();
-    if (e != cudaSuccess) throw std::runtime_error(std::string("Schwarz blob kernel failed: ") + cudaGetErrorString(e));
+    d.vt = (double*)alloc(((size_t)nu * d.vstride + 32) * sizeof(double));
+    d.ct4 = (uint32_t*)alloc((size_t)nu * d.sq * 32 * sizeof(uint32_t));
+    schwarz_index_kernel<<<(np + 7) / 8, 256>>>(np, d.pat, d.pidx, d.nbr, d.nbq, d.pidx32, d.nbrp);
+    schwarz_blob_kernel<<<(nu + 7) / 8, 256>>>(nu, d_rep, d.pat, d.pidx, d.nbr, d_ia, d_ja, d_a, srow, d.sq,
+                                              d.vt, d.ct4, d.prof, d.vstride);
+    sync_or_throw("Schwarz blob kernel");
+    uniq_blob_bytes += (long long)nu * (8LL * d.vstride + 4LL * d.sq * 32);
     const int fsm = kSwFastWarps * kSwFastSlot * (int)sizeof(double);
     cudaFuncSetAttribute(schwarz_fast_kernel<12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm);
     cudaFuncSetAttribute(schwarz_fast_kernel<24, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm);
@@ -614,6 +775,17 @@ inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iper
     cudaFuncSetAttribute(schwarz_apply_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_apply);
     cudaFuncSetAttribute(schwarz_apply_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_apply);
   }
+  // Algorithmic bytes of one sweep.
+  //  stored-factor model (every patch owns its data): values + local columns of the row entries,
+  //  neighbour list + gathered x, packed inverse, (idx, row start, row length, b, x update) per patch dof
+  d.alg_bytes_stored = 10 * tot_val + 12 * tot_n + 8 * ((tot_tri + 1) / 2 * 2) + (12 + 8 + 16) * tot_q + 32LL * np;
+  if (fast_shape) d.alg_bytes_stored = 9 * tot_val + 12 * tot_n + 8 * tot_tri + (4 + 8 + 8) * tot_q;
+  //  with shared blobs: the per-patch index data, the gathered x, b and the x update stay per patch; the
+  //  blobs are counted once per colour launch (they are what a launch has to bring in at least once);
+  //  the general path still streams the row values of every patch from the level CSR
+  d.alg_bytes = 12 * tot_n + (fast_shape ? (4 + 8 + 8) : (12 + 8 + 16)) * tot_q + (fast_shape ? 4LL : 32LL) * np +
+                (fast_shape ? 0 : 8 * tot_val) + (long long)sw.ncolors * uniq_blob_bytes;
+  if (nu == np) d.alg_bytes = d.alg_bytes_stored;
 }
 
 // patches [p0, p1) of one conflict colour (they commute, so they run concurrently)
@@ -622,7 +794,7 @@ inline void schwarz_range_launch(const DSchwarz& d, int p0, int p1, const double
   if (d.fast) {
     const int g = (p1 - p0 + kSwFastWarps - 1) / kSwFastWarps;
     const size_t sm = (size_t)kSwFastWarps * kSwFastSlot * sizeof(double);
-#define MAMG_SWF_ARGS p0, p1, d.pidx32, d.nbrp, d.vt, d.ct4, d.pinv, b, x, d.srow, d.sq, d.nbq, d.inv_stride, d.max_size, d.prof, d.vstride
+#define MAMG_SWF_ARGS p0, p1, d.pidx32, d.nbrp, d.uid, d.inv_off, d.vt, d.ct4, d.pinv, b, x, d.srow, d.sq, d.nbq, d.max_size, d.prof, d.vstride
     if (d.sr_t == 12) schwarz_fast_kernel<12, 1><<<g, kSwFastWarps * 32, sm, stream>>>(MAMG_SWF_ARGS);
     else if (d.sr_t == 24) schwarz_fast_kernel<24, 4><<<g, kSwFastWarps * 32, sm, stream>>>(MAMG_SWF_ARGS);
     else schwarz_fast_kernel<32, 8><<<g, kSwFastWarps * 32, sm, stream>>>(MAMG_SWF_ARGS);

@@ -239,6 +239,17 @@ class Hierarchy:
         check(lib.mamg_schwarz_sweep_bytes(self._h, level, C.byref(v)))
         return v.value
 
+    STAT_KEYS = ["rows", "nnz_stored", "nnz_structural", "sell_slots", "device_bytes", "n_patches", "unique_blobs",
+                 "schwarz_sweep_bytes", "schwarz_sweep_bytes_stored_factors", "n_colors", "n_patch_colors", "in_tail",
+                 "sell", "csr_kept", "row_blocks", "schwarz_fast_path"]
+
+    def stats(self, level=0):
+        """Device-side statistics of one level (mamg_stats)."""
+        self._require_device()
+        out = (C.c_int64 * 16)()
+        check(lib.mamg_stats(self._h, int(level), out))
+        return dict(zip(self.STAT_KEYS, [int(v) for v in out]))
+
     def profile_start(self):
         check(lib.mamg_profile(self._h, 1, None, None))
 
