@@ -92,6 +92,40 @@ int mamg_setup_partitioned(const mamg_params* p, int32_t n, const int32_t* indpt
                            const double* data, int32_t n_idofs, const int32_t* idofs, const int32_t* part,
                            int32_t nparts, mamg_handle* out);
 int mamg_part_export(mamg_handle h, int32_t level, int32_t* part);
+
+/* ---- import of an externally built hierarchy (north_star: "the AMG setup ... may remain the
+ *      reference's HAZmath CPU setup exported once per problem, so that apply is compared on an
+ *      identical hierarchy").  One record per level, finest first, natural ordering, the same arrays
+ *      mamg_level_export / mamg_schwarz_export / mamg_prolongator_export / mamg_part_export hand out
+ *      (so export -> import is a round trip).  Pointers that do not apply may be NULL: agg on the
+ *      coarsest level, gs_skip / patch_* without Schwarz patches, P_* for unsmoothed aggregation,
+ *      part for an unpartitioned hierarchy, color (then the library colours the level itself).
+ *      The colourings are validated (rows / patches of one colour must not couple); the caller's arrays
+ *      are copied.  coarse_inv = dense row-major inverse of the coarsest operator or NULL (computed). */
+typedef struct mamg_level_arrays {
+  int32_t n;                    /* rows of A_l */
+  int32_t n_aggregates;         /* rows of A_{l+1}; 0 on the coarsest level */
+  int32_t n_colors;             /* Gauss-Seidel colours (0 with color == NULL) */
+  int32_t n_patches;            /* Schwarz patches on this level */
+  int32_t n_patch_colors;
+  int32_t reserved;
+  const int32_t* indptr;        /* CSR of A_l */
+  const int32_t* indices;
+  const double*  data;
+  const int32_t* agg;           /* [n] aggregate of every row, -1 = none */
+  const int32_t* color;         /* [n] */
+  const uint8_t* gs_skip;       /* [n] 1 = smoothed by Schwarz only */
+  const int32_t* patch_ptr;     /* [n_patches + 1] */
+  const int32_t* patch_dofs;
+  const int32_t* patch_seed;    /* [n_patches] */
+  const int32_t* patch_color;   /* [n_patches] */
+  const int32_t* P_indptr;      /* smoothed prolongator (SA_AMG), n x n_aggregates */
+  const int32_t* P_indices;
+  const double*  P_data;
+  const int32_t* part;          /* [n] owner part */
+} mamg_level_arrays;
+int mamg_import_hierarchy(const mamg_params* p, int32_t nlevels, const mamg_level_arrays* levels,
+                          const double* coarse_inv, int32_t nparts, mamg_handle* out);
 int mamg_destroy(mamg_handle h);
 
 /* ---- hierarchy introspection / export (natural ordering) so that the CPU oracle

@@ -24,6 +24,13 @@ class MamgParams(C.Structure):
     _fields_ = PARAM_FIELDS
 
 
+class MamgLevelArrays(C.Structure):
+    """mamg_level_arrays of include/mamg.h (mamg_import_hierarchy)."""
+    _fields_ = [(k, C.c_int32) for k in ("n", "n_aggregates", "n_colors", "n_patches", "n_patch_colors", "reserved")] + \
+               [(k, C.c_void_p) for k in ("indptr", "indices", "data", "agg", "color", "gs_skip", "patch_ptr", "patch_dofs",
+                                          "patch_seed", "patch_color", "P_indptr", "P_indices", "P_data", "part")]
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
@@ -52,6 +59,7 @@ def _load():
         "mamg_setup": (i32, [C.POINTER(MamgParams), i32, vp, vp, vp, i32, vp, C.POINTER(vp)]),
         "mamg_setup_partitioned": (i32, [C.POINTER(MamgParams), i32, vp, vp, vp, i32, vp, vp, i32, C.POINTER(vp)]),
         "mamg_part_export": (i32, [vp, i32, vp]),
+        "mamg_import_hierarchy": (i32, [C.POINTER(MamgParams), i32, C.POINTER(MamgLevelArrays), vp, i32, C.POINTER(vp)]),
         "mamg_destroy": (i32, [vp]),
         "mamg_num_levels": (i32, [vp, pi32]),
         "mamg_level_info": (i32, [vp, i32, pi64]),

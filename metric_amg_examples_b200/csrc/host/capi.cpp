@@ -339,3 +339,153 @@ int mamg_assemble_emi(int32_t dim, int32_t ncell, double kappa1, double kappa2, 
 }
 
 }  // extern "C"
+
+// ---- import of an externally produced hierarchy -----------------------------------------------
+namespace {
+bool fail(const std::string& msg) { set_error("import_hierarchy: " + msg); return false; }
+
+bool import_level(const mamg_level_arrays& in, int l, bool last, Level& L) {
+  const std::string at = " (level " + std::to_string(l) + ")";
+  if (in.n <= 0 || !in.indptr || !in.indices || !in.data) return fail("missing matrix" + at);
+  const int n = in.n;
+  if (in.indptr[0] != 0) return fail("indptr[0] != 0" + at);
+  for (int i = 0; i < n; ++i)
+    if (in.indptr[i + 1] < in.indptr[i]) return fail("indptr not monotone" + at);
+  const int nnz = in.indptr[n];
+  L.A.n = L.A.m = n;
+  L.A.ia.assign(in.indptr, in.indptr + n + 1);
+  L.A.ja.assign(in.indices, in.indices + nnz);
+  L.A.a.assign(in.data, in.data + nnz);
+  L.nnz_structural = nnz;
+  for (int i = 0; i < n; ++i) {
+    bool diag = false;
+    for (int q = L.A.ia[i]; q < L.A.ia[i + 1]; ++q) {
+      const int j = L.A.ja[q];
+      if (j < 0 || j >= n) return fail("column index out of range" + at);
+      if (q > L.A.ia[i] && j <= L.A.ja[q - 1]) return fail("columns must be strictly ascending inside a row" + at);
+      diag |= j == i && L.A.a[q] != 0.0;
+    }
+    if (!diag) return fail("row " + std::to_string(i) + " has no nonzero diagonal" + at);
+  }
+  if (!last) {
+    if (!in.agg || in.n_aggregates <= 0) return fail("aggregates missing on a non-coarsest level" + at);
+    L.agg.assign(in.agg, in.agg + n);
+    L.nc = in.n_aggregates;
+    std::vector<char> hit(L.nc, 0);
+    for (int i = 0; i < n; ++i) {
+      if (L.agg[i] < -1 || L.agg[i] >= L.nc) return fail("aggregate id out of range" + at);
+      if (L.agg[i] >= 0) hit[L.agg[i]] = 1;
+    }
+    for (int I = 0; I < L.nc; ++I)
+      if (!hit[I]) return fail("aggregate " + std::to_string(I) + " is empty" + at);
+  }
+  if (in.n_patches > 0) {
+    if (!in.patch_ptr || !in.patch_dofs || !in.patch_color) return fail("patch arrays missing" + at);
+    SchwarzPatches& s = L.sw;
+    s.ptr.assign(in.patch_ptr, in.patch_ptr + in.n_patches + 1);
+    if (s.ptr[0] != 0) return fail("patch_ptr[0] != 0" + at);
+    for (int p = 0; p < in.n_patches; ++p)
+      if (s.ptr[p + 1] <= s.ptr[p]) return fail("empty patch" + at);
+    s.dofs.assign(in.patch_dofs, in.patch_dofs + s.ptr[in.n_patches]);
+    s.color.assign(in.patch_color, in.patch_color + in.n_patches);
+    s.seed.resize(in.n_patches);
+    s.ncolors = in.n_patch_colors;
+    s.max_size = 0;
+    for (int p = 0; p < in.n_patches; ++p) {
+      s.max_size = std::max(s.max_size, s.ptr[p + 1] - s.ptr[p]);
+      if (s.color[p] < 0 || s.color[p] >= s.ncolors) return fail("patch colour out of range" + at);
+      for (int q = s.ptr[p]; q < s.ptr[p + 1]; ++q) {
+        if (s.dofs[q] < 0 || s.dofs[q] >= n) return fail("patch dof out of range" + at);
+        if (q > s.ptr[p] && s.dofs[q] <= s.dofs[q - 1]) return fail("patch dofs must be strictly ascending" + at);
+      }
+      s.seed[p] = in.patch_seed ? in.patch_seed[p] : s.dofs[s.ptr[p]];
+      if (s.seed[p] < 0 || s.seed[p] >= n) return fail("patch seed out of range" + at);
+    }
+    // patches of one colour are solved concurrently: none may share a dof with, or be coupled to, another
+    // patch of its colour (owner[j] = the patch of the colour under test that has j among its dofs)
+    std::vector<std::vector<int>> by_color(s.ncolors);
+    for (int p = 0; p < in.n_patches; ++p) by_color[s.color[p]].push_back(p);
+    std::vector<int> owner(n, -1);
+    for (int c = 0; c < s.ncolors; ++c) {
+      for (int p : by_color[c])
+        for (int q = s.ptr[p]; q < s.ptr[p + 1]; ++q) {
+          if (owner[s.dofs[q]] >= 0) return fail("patches " + std::to_string(owner[s.dofs[q]]) + " and " + std::to_string(p) + " of one colour share a dof" + at);
+          owner[s.dofs[q]] = p;
+        }
+      for (int p : by_color[c])
+        for (int q = s.ptr[p]; q < s.ptr[p + 1]; ++q) {
+          const int i = s.dofs[q];
+          for (int e = L.A.ia[i]; e < L.A.ia[i + 1]; ++e) {
+            if (L.A.a[e] == 0.0) continue;
+            const int o = owner[L.A.ja[e]];
+            if (o >= 0 && o != p) return fail("patches " + std::to_string(o) + " and " + std::to_string(p) + " of one colour are coupled" + at);
+          }
+        }
+      for (int p : by_color[c])
+        for (int q = s.ptr[p]; q < s.ptr[p + 1]; ++q) owner[s.dofs[q]] = -1;
+    }
+    if (!in.gs_skip) return fail("gs_skip missing on a Schwarz level" + at);
+  }
+  if (in.gs_skip && (in.n_patches > 0)) L.gs_skip.assign(in.gs_skip, in.gs_skip + n);
+  if (!last) {
+    if (in.color) {
+      L.color.assign(in.color, in.color + n);
+      L.ncolors = in.n_colors;
+      for (int i = 0; i < n; ++i) {
+        if (L.color[i] < 0 || L.color[i] >= L.ncolors) return fail("row colour out of range" + at);
+        if (!L.gs_skip.empty() && L.gs_skip[i]) continue;
+        for (int q = L.A.ia[i]; q < L.A.ia[i + 1]; ++q) {
+          const int j = L.A.ja[q];
+          if (j == i || L.A.a[q] == 0.0 || (!L.gs_skip.empty() && L.gs_skip[j])) continue;
+          if (L.color[j] == L.color[i]) return fail("rows " + std::to_string(i) + " and " + std::to_string(j) + " are coupled and share a colour" + at);
+        }
+      }
+    } else {
+      multicolor_greedy(L.A, L.gs_skip, L.color, L.ncolors);
+    }
+  }
+  if (in.P_indptr && !last) {
+    if (!in.P_indices || !in.P_data) return fail("prolongator arrays missing" + at);
+    L.P.n = n;
+    L.P.m = L.nc;
+    L.P.ia.assign(in.P_indptr, in.P_indptr + n + 1);
+    L.P.ja.assign(in.P_indices, in.P_indices + L.P.ia[n]);
+    L.P.a.assign(in.P_data, in.P_data + L.P.ia[n]);
+    for (int j : L.P.ja)
+      if (j < 0 || j >= L.nc) return fail("prolongator column out of range" + at);
+    csr_transpose(L.P, L.R);
+  }
+  if (in.part) L.part.assign(in.part, in.part + n);
+  return true;
+}
+}  // namespace
+
+extern "C" int mamg_import_hierarchy(const mamg_params* p, int32_t nlevels, const mamg_level_arrays* levels,
+                                     const double* coarse_inv, int32_t nparts, mamg_handle* out) {
+  MAMG_TRY
+  if (!p || !levels || !out || nlevels < 1) { set_error("import_hierarchy: NULL argument or no levels"); return -1; }
+  mamg_handle h = new mamg_handle_s();
+  Hierarchy& H = h->H;
+  H.prm = *p;
+  H.nparts = std::max(1, nparts);
+  H.lv.resize(nlevels);
+  for (int l = 0; l < nlevels; ++l) {
+    if (!import_level(levels[l], l, l == nlevels - 1, H.lv[l])) { delete h; return -1; }
+    if (l > 0 && H.lv[l].A.n != H.lv[l - 1].nc) {
+      delete h;
+      set_error("import_hierarchy: level " + std::to_string(l) + " has " + std::to_string(levels[l].n) + " rows but level " +
+                std::to_string(l - 1) + " has " + std::to_string(levels[l - 1].n_aggregates) + " aggregates");
+      return -1;
+    }
+    if (H.nparts > 1 && H.lv[l].part.empty()) { delete h; set_error("import_hierarchy: nparts > 1 needs part[] on every level"); return -1; }
+    for (int v : H.lv[l].part)
+      if (v < 0 || v >= H.nparts) { delete h; set_error("import_hierarchy: part id out of range"); return -1; }
+  }
+  const int nc = H.lv.back().A.n;
+  if (nc > 8192) { delete h; set_error("import_hierarchy: coarsest level has more than 8192 rows"); return -1; }
+  if (coarse_inv) H.coarse_inv.assign(coarse_inv, coarse_inv + (size_t)nc * nc);
+  else if (!dense_inverse(H.lv.back().A, H.coarse_inv)) { delete h; set_error("import_hierarchy: coarsest operator is singular"); return -1; }
+  *out = h;
+  return 0;
+  MAMG_CATCH
+}

@@ -92,6 +92,62 @@ class Hierarchy:
         self.on_device = False
         self.device = None
 
+    @classmethod
+    def from_export(cls, hier, parameters=None, recolor=False):
+        """Build a handle from an exported hierarchy (the dict `export()` returns, a golden fixture, or the
+        arrays of an external CPU setup such as HAZmath's): mamg_import_hierarchy.  `parameters` overrides
+        hier["params"]; recolor=True lets the library compute the Gauss-Seidel colouring itself."""
+        from ._capi import MamgLevelArrays
+        self = cls.__new__(cls)
+        prm = parameters if parameters is not None else hier["params"]
+        self.params = to_struct(prm)
+        levels = hier["levels"]
+        recs = (MamgLevelArrays * len(levels))()
+        keep = []
+
+        def arr(L, key, dtype):
+            if key not in L or L[key] is None:
+                return None
+            a = np.ascontiguousarray(L[key], dtype=dtype)
+            keep.append(a)
+            return a.ctypes.data_as(C.c_void_p)
+
+        nparts = 1
+        for l, L in enumerate(levels):
+            r = recs[l]
+            last = l == len(levels) - 1
+            r.n = int(L["n"])
+            r.n_aggregates = 0 if last else int(L["n_aggregates"])
+            npatch = len(L["patch_ptr"]) - 1 if "patch_ptr" in L and L["patch_ptr"] is not None else 0
+            r.n_patches = npatch
+            r.n_patch_colors = int(L.get("n_patch_colors", 0)) if npatch else 0
+            r.indptr, r.indices, r.data = arr(L, "indptr", np.int32), arr(L, "indices", np.int32), arr(L, "data", np.float64)
+            r.agg = None if last else arr(L, "agg", np.int32)
+            if not recolor and not last:
+                r.color, r.n_colors = arr(L, "color", np.int32), int(L["n_colors"])
+            r.gs_skip = arr(L, "gs_skip", np.uint8) if npatch else None
+            if npatch:
+                r.patch_ptr, r.patch_dofs = arr(L, "patch_ptr", np.int32), arr(L, "patch_dofs", np.int32)
+                r.patch_seed, r.patch_color = arr(L, "patch_seed", np.int32), arr(L, "patch_color", np.int32)
+            if "P_indptr" in L:
+                r.P_indptr, r.P_indices, r.P_data = arr(L, "P_indptr", np.int32), arr(L, "P_indices", np.int32), arr(L, "P_data", np.float64)
+            if "part" in L and L["part"] is not None and np.asarray(L["part"]).max(initial=0) > 0:
+                nparts = max(nparts, int(np.asarray(L["part"]).max()) + 1)
+        if nparts > 1:
+            for l, L in enumerate(levels):
+                recs[l].part = arr(L, "part", np.int32)
+        inv = hier.get("coarse_inv")
+        inv = np.ascontiguousarray(inv, np.float64) if inv is not None else None
+        h = C.c_void_p()
+        check(lib.mamg_import_hierarchy(C.byref(self.params), len(levels), recs, ptr(inv), nparts, C.byref(h)))
+        self._h = h
+        self.n = int(levels[0]["n"])
+        self.nparts = nparts
+        self.idofs = np.zeros(0, np.int32)
+        self.on_device = False
+        self.device = None
+        return self
+
     def __del__(self):
         h = getattr(self, "_h", None)
         if h:

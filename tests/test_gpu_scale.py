@@ -133,3 +133,24 @@ def test_multi_gpu_parity_under_torchrun():
     p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     assert p.returncode == 0, p.stdout[-4000:]
     assert "FAIL" not in p.stdout
+
+
+def test_imported_hierarchy_on_device():
+    """mamg_import_hierarchy: a hierarchy that comes in through the import door (here: the arrays of a
+    golden fixture and of an export) is applied on the device exactly like the one the library built."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_golden
+    z = np.load(os.path.join(ROOT, "tests", "golden", "bidomain3d_n8_g1e4.npz"))
+    hier = make_golden.unflatten(z)
+    H = mamg.Hierarchy.from_export(hier).to_device(0)
+    assert rel(H.apply(z["r"]), z["z_multicolor"]) < APPLY_TOL
+    _, info = H.pcg(z["b"], tolerance=float(z["tol"]), maxiter=500)
+    want = z["residuals_multicolor"]
+    assert abs(len(info["residuals"]) - len(want)) <= 1
+    s = problems.emi_system(3, 16, gamma=1e6)
+    H0 = mamg.Hierarchy(s.A, params.default_metric_parameters, s.interface_dofs)
+    H1 = mamg.Hierarchy.from_export(H0.export())
+    H0.to_device(0)
+    H1.to_device(0)
+    r = np.random.default_rng(1).standard_normal(s.ndofs)
+    assert np.array_equal(H0.apply(r), H1.apply(r))

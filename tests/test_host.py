@@ -3,6 +3,7 @@
 import ctypes as C
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -319,3 +320,63 @@ def test_params_struct_layout_matches_ctypes(tmp_path):
     got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     assert got[0] == C.sizeof(_capi.MamgParams)
     assert got[1:] == [getattr(_capi.MamgParams, n).offset for n in names]
+
+
+def test_import_hierarchy_round_trip():
+    """mamg_import_hierarchy: export -> import -> export is the identity, for UA with Schwarz
+    patches, SA with stored prolongators and a partitioned hierarchy; and the golden fixtures (an
+    'externally produced' hierarchy as far as the library is concerned) import as they are."""
+    import glob
+    from metric_amg_examples_b200 import haznics_compat as hz
+    cases = [
+        (problems.bidomain_system(2, 16, gamma=1e3), params.parameters_metric_schwarz, True, None),
+        (problems.emi_system(3, 8, gamma=1e6), params.default_metric_parameters, True, 2),
+        (problems.bidomain_system(2, 12, gamma=10.0),
+         dict(params.parameters_standard, AMG_type=hz.SA_AMG, cycle_type=hz.V_CYCLE, coarse_dof=40, max_aggregation=8), False, None),
+    ]
+    for s, prm, metric, nparts in cases:
+        part = problems.slab_partition(s, nparts) if nparts else None
+        H = mamg.Hierarchy(s.A, prm, s.interface_dofs if metric else None, part=part)
+        ex = H.export()
+        H2 = mamg.Hierarchy.from_export(ex)
+        ex2 = H2.export()
+        assert len(ex2["levels"]) == len(ex["levels"]) and H2.nparts == H.nparts
+        for L, M in zip(ex["levels"], ex2["levels"]):
+            for k in L:
+                if isinstance(L[k], np.ndarray):
+                    assert np.array_equal(L[k], M[k]), k
+                else:
+                    assert L[k] == M[k], k
+        assert np.array_equal(ex["coarse_inv"], ex2["coarse_inv"])
+        # the library recolours when no colouring is handed over, with the same greedy rule
+        ex3 = mamg.Hierarchy.from_export(ex, recolor=True).export()
+        assert all(np.array_equal(L["color"], M["color"]) for L, M in zip(ex["levels"][:-1], ex3["levels"][:-1]))
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import make_golden
+    for path in sorted(glob.glob(os.path.join(here, "golden", "*.npz"))):
+        hier = make_golden.unflatten(np.load(path))
+        Hg = mamg.Hierarchy.from_export(hier)
+        assert Hg.num_levels == len(hier["levels"])
+
+
+def test_import_hierarchy_rejects_bad_input():
+    s = problems.bidomain_system(2, 12, gamma=1e3)
+    ex = mamg.Hierarchy(s.A, params.parameters_metric_schwarz, s.interface_dofs).export()
+    import copy
+    bad = copy.deepcopy(ex)
+    bad["levels"][1]["color"][:] = 0          # coupled rows in one colour: a data race on the device
+    with pytest.raises(_capi.MamgError, match="share a colour"):
+        mamg.Hierarchy.from_export(bad)
+    bad = copy.deepcopy(ex)
+    bad["levels"][0]["patch_color"][:] = 0    # overlapping patches in one colour
+    with pytest.raises(_capi.MamgError, match="one colour"):
+        mamg.Hierarchy.from_export(bad)
+    bad = copy.deepcopy(ex)
+    bad["levels"][0]["agg"][0] = 10 ** 6
+    with pytest.raises(_capi.MamgError, match="aggregate id"):
+        mamg.Hierarchy.from_export(bad)
+    bad = copy.deepcopy(ex)
+    bad["levels"] = bad["levels"][:1] + bad["levels"][2:]
+    with pytest.raises(_capi.MamgError, match="aggregates"):
+        mamg.Hierarchy.from_export(bad)
