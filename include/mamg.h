@@ -189,6 +189,12 @@ int mamg_sync(mamg_handle h);
  *      on_device = 1: r, z are device pointers in the caller's (natural) dof order,
  *      the call is asynchronous on the handle's stream. */
 int mamg_apply(mamg_handle h, const double* r, double* z, int32_t on_device);
+/* The block variant R.T * Minv * R of src/utils.py:45-53 (xii.ReductionOperator concatenates the
+ * block_vec, .T splits the result) without the concatenated copies: the nblocks (<= 8) blocks of the
+ * block_vec are handed over as they are; sizes[] are their lengths (sum = matrix size).  With
+ * on_device = 1 the boundary gather / scatter kernels address the blocks by offsets. */
+int mamg_apply_blocks(mamg_handle h, int32_t nblocks, const int32_t* sizes, const double* const* r_blocks,
+                      double* const* z_blocks, int32_t on_device);
 
 /* y = A_level x on the device copy of the hierarchy (natural order, host or device
  * arrays as for mamg_apply); what dolfin's A*x (PETSc MatMult) does in the Krylov
@@ -210,6 +216,12 @@ int mamg_smooth(mamg_handle h, int32_t level, const double* b, double* x, int32_
 int mamg_pcg(mamg_handle h, const double* b, double* x, double tolerance, int32_t relative,
              int32_t maxiter, int32_t use_initial_guess, int32_t on_device, int32_t* niters,
              double* residuals, double* alphas, double* betas);
+/* the same solve on a block system (ConjGrad(AA, precond=R.T*Minv*R) * bb of src/emi_2d.py:207-212):
+ * right-hand side and solution as block_vec blocks, see mamg_apply_blocks */
+int mamg_pcg_blocks(mamg_handle h, int32_t nblocks, const int32_t* sizes, const double* const* b_blocks,
+                    double* const* x_blocks, double tolerance, int32_t relative, int32_t maxiter,
+                    int32_t use_initial_guess, int32_t on_device, int32_t* niters, double* residuals,
+                    double* alphas, double* betas);
 /* preconditioned MINRES / restarted right-preconditioned GMRES with the same surface
  * (block.iterative.MinRes / LGMRES share ConjGrad's constructor upstream). */
 int mamg_minres(mamg_handle h, const double* b, double* x, double tolerance, int32_t relative,

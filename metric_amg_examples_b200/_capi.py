@@ -80,6 +80,8 @@ def _load():
         "mamg_sync": (i32, [vp]),
         "mamg_release_host": (i32, [vp]),
         "mamg_apply": (i32, [vp, vp, vp, i32]),
+        "mamg_apply_blocks": (i32, [vp, i32, vp, vp, vp, i32]),
+        "mamg_pcg_blocks": (i32, [vp, i32, vp, vp, vp, dbl, i32, i32, i32, i32, pi32, vp, vp, vp]),
         "mamg_spmv": (i32, [vp, i32, vp, vp, i32]),
         "mamg_smooth": (i32, [vp, i32, vp, vp, i32, i32]),
         "mamg_pcg": (i32, [vp, vp, vp, dbl, i32, i32, i32, i32, pi32, vp, vp, vp]),

@@ -92,7 +92,23 @@ class block_mul(block_base):
         for op in ops:
             self.chain.extend(op.chain if isinstance(op, block_mul) else [op])
 
+    def _reduced_precond(self):
+        """Minv if this is R.T * Minv * R with a device preconditioner (src/utils.py:53), else None."""
+        if len(self.chain) != 3:
+            return None
+        Rt, M, R = self.chain
+        if (hasattr(M, "hierarchy") and isinstance(R, ReductionOperator) and isinstance(Rt, block_transpose)
+                and Rt.A is R):
+            return M
+        return None
+
     def matvec(self, b):
+        M = self._reduced_precond()
+        if M is not None and isinstance(b, block_vec) and len(b) == len(self.chain[2].sizes):
+            # the block variant of the preconditioner: the blocks go to the device as they are and are
+            # addressed by offsets there (mamg_apply_blocks) -- no concatenate / split copies
+            M._ensure_device()
+            return block_vec(M.hierarchy.apply_blocks(list(b)))
         for op in reversed(self.chain):
             b = op.matvec(b) if isinstance(op, block_base) else op * b
         return b

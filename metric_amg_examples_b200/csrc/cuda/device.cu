@@ -745,7 +745,7 @@ static void smooth(DeviceState& D, int lev, const double* b, double* x, bool pos
           const int p0 = l.sw.cb_ptr[c * snb + blk], p1 = l.sw.cb_ptr[c * snb + blk + 1];
           if (p1 == p0) continue;
           KScope ks(D, K_SCHWARZ);
-          schwarz_range_launch(l.sw, p0, p1, l.a, b, x, D.stream);
+          schwarz_range_launch(l.sw, p0, p1, l.a, b, x, D.stream, c * snb + blk);
         }
         if (D.world > 1 && snb > 1) {
           // the other ranks receive the just-updated dofs that they read in later colours (or that
@@ -911,6 +911,19 @@ static void k_gather(DeviceState& D, int n, const int* map, const double* in, do
   KScope ks(D, K_VEC);
   gather_kernel<<<cdiv(n, kBlock), kBlock, 0, D.stream>>>(n, map, in, out);
 }
+// boundary gathers: a flat natural-order vector, or the blocks of a block_vec addressed by offsets
+static void k_gather_in(DeviceState& D, int n, const int* perm, const double* flat, const BlockPtrs* blocks, double* out) {
+  if (!blocks) { k_gather(D, n, perm, flat, out); return; }
+  if (n == 0) return;
+  KScope ks(D, K_VEC);
+  gather_blocks_kernel<<<cdiv(n, kBlock), kBlock, 0, D.stream>>>(n, perm, *blocks, out);
+}
+static void k_scatter_out(DeviceState& D, int n, const int* iperm, const double* in, double* flat, const BlockPtrs* blocks) {
+  if (!blocks) { k_gather(D, n, iperm, in, flat); return; }
+  if (n == 0) return;
+  KScope ks(D, K_VEC);
+  scatter_blocks_kernel<<<cdiv(n, kBlock), kBlock, 0, D.stream>>>(n, iperm, in, *blocks);
+}
 static void k_copy(DeviceState& D, int n, const double* in, double* out) {
   if (n == 0) return;
   KScope ks(D, K_VEC);
@@ -1029,15 +1042,15 @@ static void read_scalars(DeviceState& D, int count) {
 // (HAZmath linear_stop_type 1, src/input_metric.dat:54)
 static int pcg_device(DeviceState& D, const double* b_nat, double* x_nat, double tol, int stop,
                       int maxiter, bool use_guess, int* niters, double* residuals, double* alphas,
-                      double* betas) {
+                      double* betas, const BlockPtrs* b_blocks = nullptr, const BlockPtrs* x_blocks = nullptr) {
   DLevel& l0 = D.lv[0];
   const int n = l0.n;
   double *b = D.w[0], *x = D.w[1], *r = D.w[2], *z = D.w[3], *d = D.w[4], *q = D.w[5];
   const int vgrid = cdiv(n, kBlock);
   const int rgrid = red_grid(D, n);
-  k_gather(D, n, l0.perm, b_nat, b);
+  k_gather_in(D, n, l0.perm, b_nat, b_blocks, b);
   if (use_guess) {
-    k_gather(D, n, l0.perm, x_nat, x);
+    k_gather_in(D, n, l0.perm, x_nat, x_blocks, x);
     k_spmv(D, l0, x, b, r, true);
   } else {
     k_fill(D, n, x, 0.0);
@@ -1092,7 +1105,7 @@ static int pcg_device(DeviceState& D, const double* b_nat, double* x_nat, double
     if (residuals) residuals[it] = res;
     if (!(rz >= 0.0) || !std::isfinite(D.h_scal[2])) { status = 1; break; }  // "ConjGrad breakdown"
   }
-  k_gather(D, n, l0.iperm, x, x_nat);
+  k_scatter_out(D, n, l0.iperm, x, x_nat, x_blocks);
   *niters = it;
   return status;
 }
@@ -1425,6 +1438,85 @@ int mamg_apply(mamg_handle h, const double* r, double* z, int32_t on_device) {
   k_gather(*D, l0.n, l0.iperm, D->w[3], zout);
   io.out(z, l0.n, D->io_b);
   CUDA_OK(cudaGetLastError());
+  return 0;
+  MAMG_CATCH
+}
+
+// block_vec entry points: sizes[] are the block lengths (sum = rows of level 0, at most 8 blocks)
+static bool make_blocks(DeviceState& D, int32_t nblocks, const int32_t* sizes, const double* const* ptrs, BlockPtrs& B) {
+  if (nblocks < 1 || nblocks > 8 || !sizes || !ptrs) { set_error("blocks: between 1 and 8 blocks"); return false; }
+  B.nb = nblocks;
+  long long off = 0;
+  for (int q = 0; q < nblocks; ++q) {
+    if (sizes[q] < 0 || !ptrs[q]) { set_error("blocks: negative size or NULL block"); return false; }
+    B.off[q] = (int)off;
+    B.p[q] = const_cast<double*>(ptrs[q]);
+    off += sizes[q];
+  }
+  for (int q = nblocks; q < 9; ++q) B.off[q] = (int)off;
+  for (int q = nblocks; q < 8; ++q) B.p[q] = nullptr;
+  if (off != D.lv[0].n) { set_error("blocks: the block sizes do not add up to the matrix size"); return false; }
+  return true;
+}
+
+int mamg_apply_blocks(mamg_handle h, int32_t nblocks, const int32_t* sizes, const double* const* r_blocks,
+                      double* const* z_blocks, int32_t on_device) {
+  MAMG_TRY
+  DeviceState* D = get_dev(h);
+  if (!D) return -1;
+  BlockPtrs R, Z;
+  if (!make_blocks(*D, nblocks, sizes, r_blocks, R) || !make_blocks(*D, nblocks, sizes, z_blocks, Z)) return -1;
+  DLevel& l0 = D->lv[0];
+  if (!on_device) {   // host blocks: stage them side by side (the concatenation happens inside the H2D copies)
+    for (int q = 0; q < nblocks; ++q)
+      CUDA_OK(cudaMemcpyAsync(D->io_a + R.off[q], r_blocks[q], sizeof(double) * sizes[q], cudaMemcpyHostToDevice, D->stream));
+    k_gather(*D, l0.n, l0.perm, D->io_a, D->w[2]);
+  } else {
+    k_gather_in(*D, l0.n, l0.perm, nullptr, &R, D->w[2]);
+  }
+  apply_permuted(*D, D->w[2], D->w[3]);
+  if (!on_device) {
+    k_gather(*D, l0.n, l0.iperm, D->w[3], D->io_b);
+    for (int q = 0; q < nblocks; ++q)
+      CUDA_OK(cudaMemcpyAsync(z_blocks[q], D->io_b + Z.off[q], sizeof(double) * sizes[q], cudaMemcpyDeviceToHost, D->stream));
+    CUDA_OK(cudaStreamSynchronize(D->stream));
+  } else {
+    k_scatter_out(*D, l0.n, l0.iperm, D->w[3], nullptr, &Z);
+  }
+  CUDA_OK(cudaGetLastError());
+  return 0;
+  MAMG_CATCH
+}
+
+int mamg_pcg_blocks(mamg_handle h, int32_t nblocks, const int32_t* sizes, const double* const* b_blocks,
+                    double* const* x_blocks, double tolerance, int32_t relative, int32_t maxiter,
+                    int32_t use_initial_guess, int32_t on_device, int32_t* niters, double* residuals,
+                    double* alphas, double* betas) {
+  MAMG_TRY
+  DeviceState* D = get_dev(h);
+  if (!D) return -1;
+  if (!niters) { set_error("pcg_blocks: NULL argument"); return -1; }
+  BlockPtrs Bb, Xb;
+  if (!make_blocks(*D, nblocks, sizes, b_blocks, Bb) || !make_blocks(*D, nblocks, sizes, x_blocks, Xb)) return -1;
+  DLevel& l0 = D->lv[0];
+  int it = 0, st = 0;
+  if (!on_device) {
+    for (int q = 0; q < nblocks; ++q) {
+      CUDA_OK(cudaMemcpyAsync(D->io_a + Bb.off[q], b_blocks[q], sizeof(double) * sizes[q], cudaMemcpyHostToDevice, D->stream));
+      if (use_initial_guess)
+        CUDA_OK(cudaMemcpyAsync(D->io_b + Xb.off[q], x_blocks[q], sizeof(double) * sizes[q], cudaMemcpyHostToDevice, D->stream));
+    }
+    st = pcg_device(*D, D->io_a, D->io_b, tolerance, relative, maxiter, use_initial_guess != 0, &it, residuals, alphas, betas);
+    for (int q = 0; q < nblocks; ++q)
+      CUDA_OK(cudaMemcpyAsync(x_blocks[q], D->io_b + Xb.off[q], sizeof(double) * sizes[q], cudaMemcpyDeviceToHost, D->stream));
+  } else {
+    st = pcg_device(*D, nullptr, nullptr, tolerance, relative, maxiter, use_initial_guess != 0, &it, residuals, alphas, betas, &Bb, &Xb);
+  }
+  CUDA_OK(cudaStreamSynchronize(D->stream));
+  CUDA_OK(cudaGetLastError());
+  *niters = it;
+  (void)l0;
+  if (st) { set_error("ConjGrad breakdown (r.Br < 0 or d.Ad == 0)"); return 1; }
   return 0;
   MAMG_CATCH
 }

@@ -429,6 +429,38 @@ copy_kernel(int n, const double* __restrict__ in, double* __restrict__ out) {
   if (i < n) out[i] = in[i];
 }
 
+// block_vec <-> monolithic vector on the device (xii.ReductionOperator / ii_convert of vectors,
+// src/utils.py:48-53): the blocks stay where the caller has them, the boundary gather / scatter
+// finds the block of a monolithic index from the offsets -- no concatenated copy is ever made
+struct BlockPtrs {
+  int nb;
+  int off[9];           // off[b] .. off[b+1]: monolithic range of block b
+  double* p[8];
+};
+__device__ __forceinline__ int block_of(const BlockPtrs& B, int j) {
+  int bk = 0;
+#pragma unroll
+  for (int q = 1; q < 8; ++q) bk += (q < B.nb && j >= B.off[q]) ? 1 : 0;
+  return bk;
+}
+// out[i] = blocks[map[i]]   (map = perm: permuted <- natural)
+__global__ void __launch_bounds__(kBlock)
+gather_blocks_kernel(int n, const int* __restrict__ map, const BlockPtrs B, double* __restrict__ out) {
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  const int j = map[i];
+  const int bk = block_of(B, j);
+  out[i] = B.p[bk][j - B.off[bk]];
+}
+// blocks[j] = in[map[j]]    (map = iperm: natural -> permuted)
+__global__ void __launch_bounds__(kBlock)
+scatter_blocks_kernel(int n, const int* __restrict__ map, const double* __restrict__ in, const BlockPtrs B) {
+  const int j = blockIdx.x * kBlock + threadIdx.x;
+  if (j >= n) return;
+  const int bk = block_of(B, j);
+  B.p[bk][j - B.off[bk]] = in[map[j]];
+}
+
 // out[0] = u.v     (K10 dots, fixed-order reduction)
 __global__ void __launch_bounds__(kBlock)
 dot_kernel(int n, const double* __restrict__ u, const double* __restrict__ v, double* partial,

@@ -55,6 +55,16 @@ struct SwProfile {
   int cnt[32];
 };
 
+// Grouped path: up to 32 patches that share one stored blob are solved together, LANE = PATCH.
+struct SwGroup { int uid; int cnt; };      // patches gpatch[32 g .. 32 g + cnt)
+struct SwBlob {                            // what the patches of one signature have in common
+  int s, nn;                               // dofs, neighbours outside the patch
+  int rp0;                                 // first entry of its row pointer (s + 1 ints) in bl_rowptr
+  int e0;                                  // first off-patch entry in bl_col / bl_val
+  long long iv0;                           // its full inverse in inv_full: [c][kpad], kpad = s rounded up to 4
+  int kpad, pad_;
+};
+
 struct DSchwarz {
   int npatch = 0, ncolors = 0, max_size = 0, max_nbr = 0, srow = 1, warps = 1, ppc = 1;
   size_t smem_apply = 0, smem_setup = 0;
@@ -80,6 +90,18 @@ struct DSchwarz {
   int nuniq = 0;
   int* uid = nullptr;          // [np] unique blob of every patch (fast path)
   long long* inv_off = nullptr;  // [nuniq] offset of the packed inverse of a unique blob
+  // grouped path (schwarz_group_kernel): chosen when the patches of a colour mostly share their blobs
+  bool grouped = false;
+  int ngroups = 0, g_nn_max = 0, g_s_max = 0;
+  size_t smem_group = 0;
+  SwGroup* groups = nullptr;
+  int* gpatch = nullptr;         // [ngroups][32] patch numbers
+  SwBlob* blobs = nullptr;
+  int* bl_rowptr = nullptr;
+  uint16_t* bl_col = nullptr;
+  double* bl_val = nullptr;
+  double* inv_full = nullptr;
+  std::vector<int> gb_ptr;       // host: groups of (colour c, block b) are gb_ptr[c*nb + b] .. [c*nb + b + 1]
   // patches sorted by (conflict colour, block of the seed): cb_ptr[c*nb + b] .. [c*nb + b + 1]
   int nb = 1;
   std::vector<int> cb_ptr;     // host: size ncolors*nb + 1
@@ -174,7 +196,7 @@ struct SwLayout {
   __host__ __device__ size_t inv_d() const { return ((size_t)max_size * (max_size + 1) / 2 + 2) & ~(size_t)1; }
   __host__ __device__ size_t ls_d() const { return ((ent() + 8) * 2 + 15) / 16 * 2; }  // doubles holding the uint16 columns
   __host__ __device__ size_t as_d() const { return (ent() + 1) & ~(size_t)1; }
-  __host__ __device__ size_t xs_d() const { return ((size_t)max_nbr + 1) & ~(size_t)1; }
+  __host__ __device__ size_t xs_d() const { return ((size_t)max_nbr + 2) & ~(size_t)1; }
   __host__ __device__ size_t rhs_d() const { return ((size_t)max_size + 1) & ~(size_t)1; }
   __host__ __device__ size_t int_d() const { return (3 * (size_t)max_size + 4) / 2 + 1; }
   __host__ __device__ size_t total_d() const { return (inv_d() + ls_d() + as_d() + xs_d() + rhs_d() + int_d() + 1) & ~(size_t)1; }
@@ -238,6 +260,7 @@ schwarz_apply_kernel(int p0, int p1, const SwPatch* __restrict__ pat, const int*
       cp_async8(rhs + k, b + i);
     }
     for (int j = tid; j < P.nn; j += T) cp_async8(xs + j, x + nbr[P.n0 + j]);
+    if (tid == 0) xs[P.nn] = 0.0;   // the slot every entry inside the patch points to (its coupling lives in the inverse)
   }
   if (WPP == 1) __syncwarp(); else __syncthreads();
   if (active) {
@@ -274,7 +297,7 @@ schwarz_apply_kernel(int p0, int p1, const SwPatch* __restrict__ pat, const int*
         d += Inv[ad] * rhs[c];
         if (c >= k) a2 += c + 1;
       }
-      x[idx[k]] += d;
+      x[idx[k]] = d;   // x_B = A_BB^{-1} (b_B - A_{B,out} x_out)
     }
   }
 }
@@ -462,6 +485,109 @@ schwarz_fast_kernel(int p0, int p1, const int* __restrict__ pidx32, const int* _
   if (my >= 0) x[my] = d;   // x_B = A_BB^{-1} (b_B - A_{B,out} x_out)
 }
 
+// ---- grouped path ----------------------------------------------------------------------------------
+// On a uniform mesh with constant coefficients almost all patches of a conflict colour are translates
+// of one another: same A_BB, same off-patch values, same local sparsity (one stored blob, see the
+// signatures below).  Solving 32 such patches together with LANE = PATCH turns every irregular access
+// of the per-patch kernels into a regular one: the blob's entries (value, local column) and the
+// inverse are warp-uniform (one broadcast load each, L1-resident), the gathered x values sit in shared
+// memory as xs[neighbour][patch] so that a warp reads 32 consecutive doubles (no bank conflicts, where
+// the per-patch kernels pay 3-6-way conflicts on every random xs[col] read), and the dense inverse is
+// applied as a register-tiled (4 rows x 32 patches) small GEMM instead of a packed symmetric mat-vec
+// with conflicting triangular addresses.  Global accesses keep their per-patch coalesced form: phase 1
+// (lane = neighbour / row) stages x on the neighbourhoods and b through a transposing shared-memory
+// store, phase 3 writes x_B back the same way.
+//   x_B = A_BB^{-1} (b_B - A_{B,out} x_out)   for the patches gpatch[32 g ...] of group g
+constexpr int kSwGroupLd = 33;   // leading dimension of the [entry][patch] shared arrays (odd: conflict-free transposes)
+__global__ void __launch_bounds__(256)
+schwarz_group_kernel(int g0, const SwGroup* __restrict__ groups, const int* __restrict__ gpatch,
+                     const SwPatch* __restrict__ pat, const int* __restrict__ pidx, const int* __restrict__ nbr,
+                     const SwBlob* __restrict__ blobs, const int* __restrict__ bl_rowptr,
+                     const uint16_t* __restrict__ bl_col, const double* __restrict__ bl_val,
+                     const double* __restrict__ inv_full, const double* __restrict__ b, double* x,
+                     int nn_max, int s_max) {
+  extern __shared__ __align__(16) double smem[];
+  constexpr int LD = kSwGroupLd;
+  double* xs = smem;                          // [nn_max][LD]  x on the outside neighbours
+  double* bs = xs + (size_t)nn_max * LD;      // [s_max][LD]   b_B, finally the new x_B
+  double* ds = bs + (size_t)s_max * LD;       // [s_max][LD]   the residual b_B - A_{B,out} x_out
+  __shared__ int q0s[32], n0s[32];
+  const int grp = g0 + blockIdx.x;
+  const SwGroup G = groups[grp];
+  const SwBlob B = blobs[G.uid];
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (threadIdx.x < 32) {
+    const int p = (int)threadIdx.x < G.cnt ? gpatch[(size_t)grp * 32 + threadIdx.x] : -1;
+    q0s[threadIdx.x] = p >= 0 ? pat[p].q0 : 0;
+    n0s[threadIdx.x] = p >= 0 ? pat[p].n0 : 0;
+  }
+  __syncthreads();
+  // phase 1: stage x on the neighbourhoods and b (per patch coalesced, transposed into [entry][patch])
+  for (int g = warp; g < G.cnt; g += 8) {
+    const int* nb = nbr + n0s[g];
+    for (int j = lane; j < B.nn; j += 32) xs[j * LD + g] = x[nb[j]];
+    const int* pi = pidx + q0s[g];
+    for (int k = lane; k < B.s; k += 32) bs[k * LD + g] = b[pi[k]];
+  }
+  __syncthreads();
+  if (lane < G.cnt) {
+    // phase 2a: residual rows (warp-uniform entries, lane = patch)
+    const int* rp = bl_rowptr + B.rp0;
+    const uint16_t* bc = bl_col + B.e0;
+    const double* bv = bl_val + B.e0;
+    for (int k = warp; k < B.s; k += 8) {
+      double acc = bs[k * LD + lane];
+      const int e1 = rp[k + 1];
+      for (int e = rp[k]; e < e1; ++e) acc -= __ldg(bv + e) * xs[(int)__ldg(bc + e) * LD + lane];
+      ds[k * LD + lane] = acc;
+    }
+  }
+  __syncthreads();
+  if (lane < G.cnt) {
+    // phase 2b: x_B = A_BB^{-1} r, 4 rows per thread (inverse stored [c][kpad]: two broadcast 128-bit loads per c)
+    const double* iv = inv_full + B.iv0;
+    for (int k0 = warp * 4; k0 < B.s; k0 += 32) {
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      const double* ivk = iv + k0;
+#pragma unroll 2
+      for (int c = 0; c < B.s; ++c) {
+        const double r = ds[c * LD + lane];
+        const double2 u = __ldg(reinterpret_cast<const double2*>(ivk + (size_t)c * B.kpad));
+        const double2 v = __ldg(reinterpret_cast<const double2*>(ivk + (size_t)c * B.kpad) + 1);
+        a0 += u.x * r;
+        a1 += u.y * r;
+        a2 += v.x * r;
+        a3 += v.y * r;
+      }
+      bs[k0 * LD + lane] = a0;
+      if (k0 + 1 < B.s) bs[(k0 + 1) * LD + lane] = a1;
+      if (k0 + 2 < B.s) bs[(k0 + 2) * LD + lane] = a2;
+      if (k0 + 3 < B.s) bs[(k0 + 3) * LD + lane] = a3;
+    }
+  }
+  __syncthreads();
+  // phase 3: write x_B back (per patch coalesced)
+  for (int g = warp; g < G.cnt; g += 8) {
+    const int* pi = pidx + q0s[g];
+    for (int k = lane; k < B.s; k += 32) x[pi[k]] = bs[k * LD + g];
+  }
+}
+
+// full inverse [c][kpad] of every unique blob from its packed lower triangle
+__global__ void __launch_bounds__(256)
+schwarz_expand_inverse_kernel(int nuniq, const SwBlob* __restrict__ blobs, const long long* __restrict__ inv_off,
+                              const double* __restrict__ pinv, double* __restrict__ inv_full) {
+  const int u = blockIdx.x;
+  if (u >= nuniq) return;
+  const SwBlob B = blobs[u];
+  const double* src = pinv + inv_off[u];
+  double* dst = inv_full + B.iv0;
+  for (int t = threadIdx.x; t < B.s * B.kpad; t += blockDim.x) {
+    const int c = t / B.kpad, k = t % B.kpad;
+    dst[t] = k < B.s ? src[k >= c ? tri(k, c) : tri(c, k)] : 0.0;
+  }
+}
+
 // Host side: reorder the patches by colour, translate to the permuted numbering, build the
 // neighbourhood lists and local columns, upload, invert on the device.
 // `alloc(bytes)` returns tracked device memory; pia/pja are the permuted CSR of the level.
@@ -530,7 +656,10 @@ inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iper
   // (and the neighbours outside the patch) are kept -- about a quarter less traffic per patch
   const int srow = fast_shape ? max_rowlen_out : (max_rowlen | 1);   // general path: odd row stride (conflict-free)
   d.srow = srow;
-  if (fast_shape) { nn = nn_out; ne = ne_out; }
+  // every path uses x_B + A_BB^{-1}(b - A x)_B = A_BB^{-1}(b_B - A_{B,out} x_out): only the neighbours outside the
+  // patch are gathered, the couplings inside the patch live in the stored inverse
+  nn = nn_out;
+  if (fast_shape) ne = ne_out;
   std::vector<int> dord(sw.dofs.size());   // sorted position -> position inside sw.dofs (identity on the general path)
   std::iota(dord.begin(), dord.end(), 0);
   SwProfile prof;
@@ -593,8 +722,7 @@ inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iper
       const int p = order[k];
       const int s = pat[k].s;
       list.clear();
-      if (fast_shape)   // the patch's own dofs are never gathered on the fast path
-        for (int q = 0; q < s; ++q) mark[iperm[sw.dofs[dord[sw.ptr[p] + q]]]] = k;
+      for (int q = 0; q < s; ++q) mark[iperm[sw.dofs[dord[sw.ptr[p] + q]]]] = k;   // the patch's own dofs are never gathered
       for (int q = 0; q < s; ++q) {
         const int i = iperm[sw.dofs[dord[sw.ptr[p] + q]]];
         pidx[pat[k].q0 + q] = i;
@@ -623,9 +751,9 @@ inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iper
             const int j = pja[e];
             const int lj = lidx[j];
             const bool inside = lj >= 0 && lj < s && pidx[pat[k].q0 + lj] == j;
-            unsigned long long code = (unsigned long long)pos[j] | (inside ? ((unsigned long long)(lj + 1) << 32) : 0ull);
+            unsigned long long code = inside ? ((unsigned long long)(lj + 1) << 32) : (unsigned long long)pos[j];
             unsigned long long vb = 0;
-            if (inside) std::memcpy(&vb, &pa[e], 8);
+            std::memcpy(&vb, &pa[e], 8);
             h1 = mix(mix(h1, code, 0xff51afd7ed558ccdULL), vb, 0xff51afd7ed558ccdULL);
             h2 = mix(mix(h2, vb, 0xc4ceb9fe1a85ec53ULL), code, 0xc4ceb9fe1a85ec53ULL);
           }
@@ -726,6 +854,7 @@ inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iper
 #pragma omp for schedule(dynamic, 256)
       for (int u = 0; u < nu; ++u) {
         const int k = rep[u];
+        for (int q = 0; q < pat[k].s; ++q) pos[pidx[pat[k].q0 + q]] = pat[k].nn;   // inside the patch: the zero slot
         for (int j = 0; j < pat[k].nn; ++j) pos[nbr[pat[k].n0 + j]] = j;
         uint16_t* out = &lcol[(size_t)e_off[u]];
         for (int q = 0; q < pat[k].s; ++q) {
@@ -769,6 +898,84 @@ inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iper
     cudaFuncSetAttribute(schwarz_fast_kernel<24, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm);
     cudaFuncSetAttribute(schwarz_fast_kernel<32, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm);
   }
+  // ---- grouped path: patches of one (colour, block) that share a blob, 32 at a time --------------
+  {
+    const char* genv = getenv("MAMG_SW_GROUP");
+    const bool want = dedup && !(genv && atoi(genv) == 0);
+    std::vector<SwGroup> groups;
+    std::vector<int> gpatch;
+    d.gb_ptr.assign(sw.ncolors * nb + 1, 0);
+    if (want) {
+      std::vector<std::pair<int, int>> bucket;
+      for (int kb = 0; kb < sw.ncolors * nb; ++kb) {
+        bucket.clear();
+        for (int k = d.cb_ptr[kb]; k < d.cb_ptr[kb + 1]; ++k) bucket.emplace_back(uid[k], k);
+        std::stable_sort(bucket.begin(), bucket.end(),
+                         [](const std::pair<int, int>& a, const std::pair<int, int>& b2) { return a.first < b2.first; });
+        for (size_t i = 0; i < bucket.size();) {
+          size_t j = i;
+          while (j < bucket.size() && bucket[j].first == bucket[i].first && j - i < 32) ++j;
+          groups.push_back(SwGroup{bucket[i].first, (int)(j - i)});
+          for (size_t t = i; t < i + 32; ++t) gpatch.push_back(t < j ? bucket[t].second : -1);
+          i = j;
+        }
+        d.gb_ptr[kb + 1] = (int)groups.size();
+      }
+    }
+    // worth it when the lanes are mostly busy (average group at least a quarter full); MAMG_SW_GROUP=2 forces it
+    const bool use = want && !groups.empty() && ((double)np / (double)groups.size() >= 8.0 || (genv && atoi(genv) == 2));
+    if (use) {
+      std::vector<SwBlob> blobs(nu);
+      std::vector<int> rowptr;
+      std::vector<uint16_t> bcol;
+      std::vector<double> bval;
+      long long iv_tot = 0;
+      int nn_max = 1, s_max = 1;
+      std::vector<int> pos(n, -1);
+      for (int u = 0; u < nu; ++u) {
+        const int k = rep[u];
+        SwBlob& B = blobs[u];
+        B.s = pat[k].s;
+        B.nn = pat[k].nn;
+        B.rp0 = (int)rowptr.size();
+        B.e0 = (int)bcol.size();
+        B.kpad = (B.s + 3) & ~3;
+        B.pad_ = 0;
+        B.iv0 = iv_tot;
+        iv_tot += (long long)B.s * B.kpad;
+        nn_max = std::max(nn_max, B.nn);
+        s_max = std::max(s_max, B.kpad);
+        for (int j = 0; j < B.nn; ++j) pos[nbr[pat[k].n0 + j]] = j;
+        for (int q = 0; q < B.s; ++q) {
+          const int i = pidx[pat[k].q0 + q];
+          rowptr.push_back((int)bcol.size() - B.e0);
+          for (int e = pia[i]; e < pia[i + 1]; ++e)
+            if (pos[pja[e]] >= 0) { bcol.push_back((uint16_t)pos[pja[e]]); bval.push_back(pa[e]); }
+        }
+        rowptr.push_back((int)bcol.size() - B.e0);
+        for (int j = 0; j < B.nn; ++j) pos[nbr[pat[k].n0 + j]] = -1;
+      }
+      d.g_nn_max = nn_max;
+      d.g_s_max = s_max;
+      d.smem_group = ((size_t)nn_max + 2 * (size_t)s_max) * kSwGroupLd * sizeof(double);
+      if (d.smem_group <= 200 * 1024) {
+        d.grouped = true;
+        d.ngroups = (int)groups.size();
+        d.groups = (SwGroup*)up(groups.data(), groups.size() * sizeof(SwGroup));
+        d.gpatch = (int*)up(gpatch.data(), gpatch.size() * sizeof(int));
+        d.blobs = (SwBlob*)up(blobs.data(), blobs.size() * sizeof(SwBlob));
+        d.bl_rowptr = (int*)up(rowptr.data(), rowptr.size() * sizeof(int));
+        d.bl_col = (uint16_t*)up(bcol.data(), bcol.size() * sizeof(uint16_t));
+        d.bl_val = (double*)up(bval.data(), bval.size() * sizeof(double));
+        d.inv_full = (double*)alloc(((size_t)iv_tot + 2) * sizeof(double));
+        if (fast_shape && !d.pat) d.pat = (SwPatch*)up(pat.data(), pat.size() * sizeof(SwPatch));
+        schwarz_expand_inverse_kernel<<<nu, 256>>>(nu, d.blobs, d.inv_off, d.pinv, d.inv_full);
+        sync_or_throw("Schwarz inverse expansion");
+        if (d.smem_group > 48 * 1024)
+          cudaFuncSetAttribute(schwarz_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_group);
+      }
+    }
+  }
   if (d.smem_apply > 48 * 1024) {
     cudaFuncSetAttribute(schwarz_apply_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_apply);
     cudaFuncSetAttribute(schwarz_apply_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_apply);
@@ -790,7 +997,15 @@ inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iper
 
 // patches [p0, p1) of one conflict colour (they commute, so they run concurrently)
 inline void schwarz_range_launch(const DSchwarz& d, int p0, int p1, const double* a, const double* b, double* x,
-                                 cudaStream_t stream) {
+                                 cudaStream_t stream, int kb = -1) {
+  if (d.grouped && kb >= 0) {   // (colour, block) kb: its groups of look-alike patches
+    const int g0 = d.gb_ptr[kb], g1 = d.gb_ptr[kb + 1];
+    if (g1 > g0)
+      schwarz_group_kernel<<<g1 - g0, 256, d.smem_group, stream>>>(g0, d.groups, d.gpatch, d.pat, d.pidx, d.nbr, d.blobs,
+                                                                  d.bl_rowptr, d.bl_col, d.bl_val, d.inv_full, b, x,
+                                                                  d.g_nn_max, d.g_s_max);
+    return;
+  }
   if (d.fast) {
     const int g = (p1 - p0 + kSwFastWarps - 1) / kSwFastWarps;
     const size_t sm = (size_t)kSwFastWarps * kSwFastSlot * sizeof(double);

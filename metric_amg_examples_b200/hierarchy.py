@@ -362,6 +362,65 @@ class Hierarchy:
         self._check_len(r, self.n)
         return self._vec_call(lib.mamg_apply, [r], self.n)
 
+    def _block_args(self, blocks, writable=False):
+        """(nblocks, sizes, pointer array, on_device, kept-alive arrays) of a list of per-field vectors."""
+        dev = self._is_torch_cuda(blocks[0])
+        if dev:
+            import torch
+            vs = [v.contiguous() for v in blocks]
+            for v in vs:
+                if v.dtype != torch.float64 or not v.is_cuda:
+                    raise TypeError("device blocks must be float64 CUDA tensors")
+            ptrs = (C.c_void_p * len(vs))(*[v.data_ptr() for v in vs])
+        else:
+            vs = [np.array(v, np.float64, copy=True) if writable else as_f64(v) for v in blocks]
+            ptrs = (C.c_void_p * len(vs))(*[v.ctypes.data for v in vs])
+        sizes = (C.c_int32 * len(vs))(*[int(v.shape[0]) for v in vs])
+        if sum(sizes) != self.n:
+            raise ValueError(f"block sizes {list(sizes)} do not add up to {self.n}")
+        return len(vs), sizes, ptrs, dev, vs
+
+    def apply_blocks(self, r_blocks):
+        """z = B r for a block_vec r (the R.T * Minv * R of src/utils.py:53) without concatenating the
+        blocks: mamg_apply_blocks addresses them by offsets in its boundary kernels."""
+        self._require_device()
+        nb, sizes, rp, dev, rs = self._block_args(r_blocks)
+        if dev:
+            import torch
+            zs = [torch.empty_like(v) for v in rs]
+            torch.cuda.current_stream(rs[0].device).synchronize()
+            zp = (C.c_void_p * nb)(*[v.data_ptr() for v in zs])
+        else:
+            zs = [np.empty_like(v) for v in rs]
+            zp = (C.c_void_p * nb)(*[v.ctypes.data for v in zs])
+        check(lib.mamg_apply_blocks(self._h, nb, sizes, rp, zp, int(dev)))
+        if dev:
+            check(lib.mamg_sync(self._h))
+        return zs
+
+    def pcg_blocks(self, b_blocks, x0_blocks=None, tolerance=1e-8, relative=False, maxiter=500):
+        """cbc.block ConjGrad on a block system: right-hand side and solution as lists of blocks."""
+        self._require_device()
+        nb, sizes, bp, dev, bs = self._block_args(b_blocks)
+        if dev:
+            import torch
+            xs = [torch.zeros_like(v) for v in bs] if x0_blocks is None else [v.clone().contiguous() for v in x0_blocks]
+            torch.cuda.current_stream(bs[0].device).synchronize()
+            xp = (C.c_void_p * nb)(*[v.data_ptr() for v in xs])
+        else:
+            xs = [np.zeros_like(v) for v in bs] if x0_blocks is None else [np.array(v, np.float64, copy=True) for v in x0_blocks]
+            xp = (C.c_void_p * nb)(*[v.ctypes.data for v in xs])
+        res = np.zeros(maxiter + 1, np.float64)
+        al = np.zeros(max(maxiter, 1), np.float64)
+        be = np.zeros(max(maxiter, 1), np.float64)
+        nit = C.c_int32()
+        rc = lib.mamg_pcg_blocks(self._h, nb, sizes, bp, xp, tolerance, int(relative), maxiter, int(x0_blocks is not None),
+                                 int(dev), C.byref(nit), ptr(res), ptr(al), ptr(be))
+        check(rc, allow=(1,))
+        k = nit.value
+        return xs, {"niters": k, "residuals": res[:k + 1].tolist(), "alphas": al[:k].tolist(),
+                    "betas": be[:k].tolist(), "breakdown": rc == 1}
+
     def spmv(self, x, level=0):
         n = self.level_info(level)["rows"]
         self._check_len(x, n)

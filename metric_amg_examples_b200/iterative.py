@@ -129,9 +129,19 @@ class ConjGrad(_Iterative):
     """block.iterative.ConjGrad (preconditioned CG)."""
 
     def _solve_fused(self, Minv, blocked, b):
+        Minv._ensure_device()
+        if blocked and isinstance(b, block_vec):
+            # block system: the blocks cross the ABI as they are (mamg_pcg_blocks), no concatenated copy
+            x0 = list(self.initial_guess) if self.initial_guess is not None else None
+            xs, info = Minv.hierarchy.pcg_blocks(list(b), x0_blocks=x0, tolerance=self.tolerance,
+                                                 relative=self.relativeconv, maxiter=self.maxiter)
+            self.residuals, self.alphas, self.betas = info["residuals"], info["alphas"], info["betas"]
+            if info["breakdown"] and self.show:
+                print("ConjGrad breakdown")
+            self.converged = self.residuals[-1] <= self._threshold()
+            return block_vec(xs)
         bm = self._mono_vec(b, blocked)
         x0 = self._mono_vec(self.initial_guess, blocked) if self.initial_guess is not None else None
-        Minv._ensure_device()
         x, info = Minv.hierarchy.pcg(bm, x0=x0, tolerance=self.tolerance, relative=self.relativeconv,
                                      maxiter=self.maxiter)
         self.residuals, self.alphas, self.betas = info["residuals"], info["alphas"], info["betas"]

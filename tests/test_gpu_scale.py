@@ -89,7 +89,7 @@ ENV_CASES = [
     {"MAMG_LANES": "2"}, {"MAMG_LANES": "4"}, {"MAMG_LANES": "8"}, {"MAMG_LANES": "16"}, {"MAMG_LANES": "32"},
     {"MAMG_SCHWARZ_GENERAL": "1"}, {"MAMG_GRAPH": "0"}, {"MAMG_TAIL_ROWS": "0"}, {"MAMG_DROP_ZEROS": "1"},
     {"MAMG_DROP_ZEROS": "0"}, {"MAMG_SW_DEDUP": "0"}, {"MAMG_ROWS": "csr"}, {"MAMG_ROWS": "sell"},
-    {"MAMG_PCG_CHECK": "1"}, {"MAMG_PCG_CHECK": "8"},
+    {"MAMG_SW_GROUP": "0"}, {"MAMG_SW_GROUP": "2"}, {"MAMG_SW_GROUP": "2", "MAMG_SCHWARZ_GENERAL": "1"},
 ]
 
 
@@ -99,7 +99,8 @@ def test_env_variants_match_oracle(env, monkeypatch):
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     check_against_oracle(problems.bidomain_system(3, 20, gamma=1e4), params.parameters_metric_schwarz, 1e-8)
-    if "MAMG_SCHWARZ_GENERAL" in env or "MAMG_DROP_ZEROS" in env or "MAMG_ROWS" in env:
+    if "MAMG_SCHWARZ_GENERAL" in env or "MAMG_DROP_ZEROS" in env or "MAMG_ROWS" in env or "MAMG_SW_GROUP" in env \
+            or "MAMG_SW_DEDUP" in env:
         check_against_oracle(problems.emi_system(3, 16, gamma=1e6), params.default_metric_parameters, 1e-10)
 
 
@@ -154,3 +155,32 @@ def test_imported_hierarchy_on_device():
     H1.to_device(0)
     r = np.random.default_rng(1).standard_normal(s.ndofs)
     assert np.array_equal(H0.apply(r), H1.apply(r))
+
+
+def test_block_vec_of_device_tensors_is_addressed_by_offsets():
+    """R.T * Minv * R and the block ConjGrad on a block_vec of CUDA tensors (mamg_apply_blocks /
+    mamg_pcg_blocks): same numbers as the monolithic calls, no concatenated copy on either side."""
+    import torch
+    from metric_amg_examples_b200 import utils
+    from metric_amg_examples_b200.block import block_vec, split_blocks
+    from metric_amg_examples_b200.iterative import ConjGrad
+    e = problems.emi_system(2, 64, gamma=1e4)
+    n0 = e.W[0].dim()
+    AA = split_blocks(e.A, [w.dim() for w in e.W])
+    Bblk = utils.get_hazmath_metric_precond(AA, e.W, None, interface_dofs=e.interface_dofs)
+    Minv = Bblk.chain[1]
+    r = np.random.default_rng(2).standard_normal(e.ndofs)
+    z_mono = Minv.hierarchy.to_device(0).apply(r)
+    rb = block_vec([torch.from_numpy(r[:n0]).cuda(), torch.from_numpy(r[n0:]).cuda()])
+    zb = Bblk * rb
+    assert isinstance(zb, block_vec) and zb[0].is_cuda and len(zb[0]) == n0
+    assert np.array_equal(np.concatenate([v.cpu().numpy() for v in zb]), z_mono)
+    zh = Bblk * block_vec([r[:n0], r[n0:]])
+    assert np.array_equal(np.concatenate(list(zh)), z_mono)
+    b, xt = e.random_rhs(5)
+    x_mono, info_mono = Minv.hierarchy.pcg(b, tolerance=1e-10, maxiter=500)
+    inv = ConjGrad(AA, precond=Bblk, tolerance=1e-10, show=0, maxiter=500)
+    xb = inv * block_vec([torch.from_numpy(b[:n0]).cuda(), torch.from_numpy(b[n0:]).cuda()])
+    assert inv.mode == "fused" and xb[0].is_cuda
+    assert np.array_equal(np.concatenate([v.cpu().numpy() for v in xb]), x_mono)
+    assert inv.residuals == info_mono["residuals"]
