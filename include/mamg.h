@@ -253,8 +253,11 @@ int mamg_cycle_bytes(mamg_handle h, int64_t* bytes);
  * out[7]=algorithmic bytes of one Schwarz sweep (shared blobs once per colour) out[8]=the same with
  * every patch owning its data (SURVEY 8d stored-factor model) out[9]=GS colours out[10]=patch colours
  * out[11]=1 if the level runs inside the persistent tail kernel out[12]=1 sliced-ELL row kernels
- * out[13]=1 CSR entries kept on the device out[14]=row blocks (parts) out[15]=1 Schwarz fast path */
-int mamg_stats(mamg_handle h, int32_t level, int64_t out[16]);
+ * out[13]=1 CSR entries kept on the device out[14]=row blocks (parts) out[15]=1 Schwarz fast path
+ * out[16]=1 grouped Schwarz kernel in use out[17]=groups of look-alike patches out[18]=its shared
+ * memory per CTA out[19]/out[20]=largest neighbourhood / padded patch size of a group
+ * out[21]=patches solved by the grouped kernel out[22]=largest patch out[23] reserved */
+int mamg_stats(mamg_handle h, int32_t level, int64_t out[24]);
 
 /* ---- synthetic systems of BASELINE.json's configs: P1 on UnitSquare/UnitCube
  *      (right-diagonal / 6-tet Kuhn split, lexicographic dofs), the matrices the

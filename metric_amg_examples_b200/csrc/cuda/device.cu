@@ -63,6 +63,15 @@ struct DLevel {
   SellView S;
   bool use_sell = false, has_csr = true;
   int64_t sell_slots = 0;       // stored entry slots (padding included)
+  // multi-GPU halo lists of a row-distributed level (halo mode): the rows of MY blocks that a row of
+  // another rank couples to, per (colour, neighbour rank); colour == ncolors holds all colours together
+  std::vector<int> nbr_ranks;   // ranks that share a boundary with this rank on this level
+  std::vector<int> send_off;    // [(ncolors + 1) * nnb + 1] ranges inside d_send
+  int* d_send = nullptr;
+  bool rows_owned_only = false; // matrix rows (CSR / sliced ELL) are stored for this rank's blocks only
+  // transition to the replicated levels: the rows of the (replicated) coarse level below whose aggregates I own
+  int* d_own_coarse = nullptr;
+  int n_own_coarse = 0;
 };
 
 enum KClass { K_SPMV = 0, K_GS, K_SCHWARZ, K_RESTRICT, K_SCALE, K_PROLONG, K_COARSE, K_VEC, K_DOT, K_EXCH, K_NCLS };
@@ -108,6 +117,11 @@ struct DeviceState {
   unsigned int* push_ticket = nullptr;
   long long* d_phase = nullptr;      // exchanges so far (device counter; the same sequence on every rank)
   bool use_p2p = false;
+  // halo mode (default with several ranks and peer memory): matrices are stored for the owned rows only,
+  // a kernel's updates travel to the neighbour ranks that read them (index lists, neighbour-only flags),
+  // dots are per-rank partial sums combined in rank order.  MAMG_HALO=0: the round-1 scheme (every
+  // updated range all-gathered to every rank).
+  bool halo = false;
   size_t xcap = 0;
   long long xflip = 0;
   // L2 residency: the vector that a smoother / SpMV gathers from is marked "persisting" in a
@@ -218,6 +232,8 @@ static int pick_unroll(int n) {
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+constexpr size_t kArenaHead = 64 + 2 * 64 * 4;
+
 static bool rows_sell() {
   const char* env = getenv("MAMG_ROWS");   // "csr": the sub-warp-per-row CSR kernels of round 1 (kept for comparison)
   return !(env && std::string(env) == "csr");
@@ -253,6 +269,46 @@ static void build_sell(DeviceState& D, DLevel& dl, const std::vector<int>& ia) {
   dl.use_sell = true;
 }
 
+// Halo lists of a row-distributed level: my rows that a row of rank q couples to (the pattern is
+// symmetric -- validated at setup -- so these are my rows with a column owned by q), per colour.
+static void build_halo_lists(DeviceState& D, DLevel& dl, const std::vector<int>& ia, const std::vector<int>& ja) {
+  const int per = dl.nb / D.world, nc = dl.ncolors;
+  std::vector<int> rank_lo(D.world + 1);
+  for (int q = 0; q <= D.world; ++q) rank_lo[q] = dl.bc_ptr[q * per * nc];
+  const int lo = rank_lo[D.rank], hi = rank_lo[D.rank + 1];
+  auto owner = [&](int j) { return (int)(std::upper_bound(rank_lo.begin(), rank_lo.end(), j) - rank_lo.begin()) - 1; };
+  // colour of my row i: position inside its (block, colour) ranges
+  std::vector<std::vector<std::vector<int>>> lists(D.world, std::vector<std::vector<int>>(nc + 1));
+  std::vector<char> hit(D.world);
+  int kb = D.rank * per * nc;
+  for (int i = lo; i < hi; ++i) {
+    while (i >= dl.bc_ptr[kb + 1]) ++kb;
+    const int c = kb % nc;
+    std::fill(hit.begin(), hit.end(), 0);
+    for (int p = ia[i]; p < ia[i + 1]; ++p) {
+      const int j = ja[p];
+      if (j >= lo && j < hi) continue;
+      const int q = owner(j);
+      if (!hit[q]) { hit[q] = 1; lists[q][c].push_back(i); lists[q][nc].push_back(i); }
+    }
+  }
+  dl.nbr_ranks.clear();
+  for (int q = 0; q < D.world; ++q)
+    if (q != D.rank && !lists[q][nc].empty()) dl.nbr_ranks.push_back(q);
+  // the neighbour relation must be symmetric across ranks; it is, because the pattern is symmetric
+  const int nnb = (int)dl.nbr_ranks.size();
+  if (nnb > 8) throw std::runtime_error("more than 8 neighbour ranks on a level: use MAMG_HALO=0");
+  std::vector<int> flat;
+  dl.send_off.assign((size_t)(nc + 1) * nnb + 1, 0);
+  for (int c = 0; c <= nc; ++c)
+    for (int k = 0; k < nnb; ++k) {
+      const std::vector<int>& v = lists[dl.nbr_ranks[k]][c];
+      flat.insert(flat.end(), v.begin(), v.end());
+      dl.send_off[(size_t)c * nnb + k + 1] = (int)flat.size();
+    }
+  dl.d_send = upload(D, flat);
+}
+
 // ------------------------------------------------------------------------------------------
 // upload: colour-permute every level (rows of one colour contiguous, stable inside a colour)
 // ------------------------------------------------------------------------------------------
@@ -286,14 +342,14 @@ static void upload_hierarchy(const Hierarchy& H, DeviceState& D) {
   }
   size_t max_n = 0;
   {
-    size_t need = 64;
+    size_t need = kArenaHead;
     for (int l = 0; l < L; ++l) need += 3 * (size_t)H.lv[l].A.n + 6;
     need += 10 * ((size_t)H.lv[0].A.n + 2) + 2 * (size_t)H.lv[0].A.n + 8;
     D.arena = dalloc<double>(D, need);
     D.arena_doubles = need;
     CUDA_OK(cudaMemset(D.arena, 0, need * sizeof(double)));
   }
-  size_t arena_used = 64;   // the first 64 doubles hold the per-rank arrival flags
+  size_t arena_used = kArenaHead;   // 64 arrival flags, then two banks of 64 x 4 all-reduce slots
   auto carve = [&](size_t count) {
     double* p = D.arena + arena_used;
     arena_used += (count + 1) & ~(size_t)1;
@@ -310,14 +366,26 @@ static void upload_hierarchy(const Hierarchy& H, DeviceState& D) {
     dl.nc = hl.nc;
     dl.lanes = pick_lanes(n ? (double)dl.nnz / n : 1.0);
     dl.unroll = pick_unroll(n);
-    std::vector<int> ia(n + 1, 0), ja(dl.nnz);
+    // halo mode: a rank stores the matrix rows of its own blocks only (levels with Schwarz patches keep all
+    // rows: the patch setup reads the rows of every patch dof, which straddle the cuts)
+    int row_lo = 0, row_hi = n;
+    if (D.halo && D.world > 1 && dl.nb > 1 && hl.sw.npatch() == 0) {
+      const int per = dl.nb / D.world;
+      row_lo = dl.bc_ptr[D.rank * per * dl.ncolors];
+      row_hi = dl.bc_ptr[(D.rank + 1) * per * dl.ncolors];
+      dl.rows_owned_only = true;
+    }
+    std::vector<int> ia(n + 1, 0);
+    for (int i = 0; i < n; ++i)
+      ia[i + 1] = ia[i] + ((i >= row_lo && i < row_hi) ? hl.A.ia[perm[l][i] + 1] - hl.A.ia[perm[l][i]] : 0);
+    dl.nnz = ia[n];
+    std::vector<int> ja(dl.nnz);
     std::vector<double> a(dl.nnz), invd(n, 1.0);
-    for (int i = 0; i < n; ++i) ia[i + 1] = ia[i] + (hl.A.ia[perm[l][i] + 1] - hl.A.ia[perm[l][i]]);
 #pragma omp parallel
     {
       std::vector<std::pair<int, double>> buf;
 #pragma omp for schedule(static)
-      for (int i = 0; i < n; ++i) {
+      for (int i = row_lo; i < row_hi; ++i) {
         const int o = perm[l][i];
         const int p0 = hl.A.ia[o], cnt = hl.A.ia[o + 1] - p0;
         buf.resize(cnt);
@@ -335,6 +403,7 @@ static void upload_hierarchy(const Hierarchy& H, DeviceState& D) {
     dl.ja = upload(D, ja);
     dl.a = upload(D, a);
     dl.invd = upload(D, invd);
+    if (D.halo && D.world > 1 && dl.nb > 1) build_halo_lists(D, dl, ia, ja);
     dl.perm = upload(D, perm[l]);
     dl.iperm = upload(D, iperm[l]);
     dl.x_own = dl.x = carve(n);
@@ -384,6 +453,18 @@ static void upload_hierarchy(const Hierarchy& H, DeviceState& D) {
       dl.agg = upload(D, agg);
       dl.cptr = upload(D, cptr);
       dl.cidx = upload(D, cidx);
+      if (D.halo && D.world > 1 && dl.nb > 1 && D.lv[l + 1].nb == 1) {
+        // first replicated level below a distributed one: the coarse rows whose aggregates sit in my blocks
+        const int per = dl.nb / D.world;
+        const int lo = dl.bc_ptr[D.rank * per * dl.ncolors], hi = dl.bc_ptr[(D.rank + 1) * per * dl.ncolors];
+        std::vector<int> mine;
+        for (int i = lo; i < hi; ++i)
+          if (agg[i] >= 0) mine.push_back(agg[i]);
+        std::sort(mine.begin(), mine.end());
+        mine.erase(std::unique(mine.begin(), mine.end()), mine.end());
+        dl.n_own_coarse = (int)mine.size();
+        dl.d_own_coarse = upload(D, mine);
+      }
     }
     if (hl.sw.npatch() > 0) schwarz_upload(hl, dl.nb, iperm[l], dl.ia, dl.ja, dl.a, ia, ja, a, dl.sw, [&](size_t bytes) {
       void* p = nullptr;
@@ -1658,12 +1739,12 @@ int mamg_schwarz_sweep_bytes(mamg_handle h, int32_t level, int64_t* bytes) {
   return 0;
 }
 
-int mamg_stats(mamg_handle h, int32_t level, int64_t out[16]) {
+int mamg_stats(mamg_handle h, int32_t level, int64_t out[24]) {
   DeviceState* D = get_dev(h);
   if (!D || !out) return -1;
   if (level < 0 || level >= (int)D->lv.size()) { set_error("level out of range"); return -1; }
   const DLevel& l = D->lv[level];
-  for (int k = 0; k < 16; ++k) out[k] = 0;
+  for (int k = 0; k < 24; ++k) out[k] = 0;
   out[0] = l.n;
   out[1] = l.nnz;
   out[2] = h->H.lv[level].nnz_structural;
@@ -1680,6 +1761,13 @@ int mamg_stats(mamg_handle h, int32_t level, int64_t out[16]) {
   out[13] = l.has_csr ? 1 : 0;
   out[14] = l.nb;
   out[15] = l.sw.fast ? 1 : 0;
+  out[16] = l.sw.grouped ? 1 : 0;
+  out[17] = l.sw.ngroups;
+  out[18] = (int64_t)l.sw.smem_group;
+  out[19] = l.sw.g_nn_max;
+  out[20] = l.sw.g_s_max;
+  out[21] = l.sw.grouped_patches;
+  out[22] = l.sw.max_size;
   return 0;
 }
 

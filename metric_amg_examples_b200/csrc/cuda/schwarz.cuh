@@ -102,6 +102,10 @@ struct DSchwarz {
   double* bl_val = nullptr;
   double* inv_full = nullptr;
   std::vector<int> gb_ptr;       // host: groups of (colour c, block b) are gb_ptr[c*nb + b] .. [c*nb + b + 1]
+  // patches whose blob is too rare inside their (colour, block) to fill a group keep the per-patch kernels
+  std::vector<int> lo_ptr;       // host: their positions lo_ptr[c*nb + b] .. in `leftover`
+  int* leftover = nullptr;       // device: patch numbers
+  long long grouped_patches = 0;
   // patches sorted by (conflict colour, block of the seed): cb_ptr[c*nb + b] .. [c*nb + b + 1]
   int nb = 1;
   std::vector<int> cb_ptr;     // host: size ncolors*nb + 1
@@ -225,12 +229,13 @@ schwarz_apply_kernel(int p0, int p1, const SwPatch* __restrict__ pat, const int*
                      const int* __restrict__ prow, const int* __restrict__ plen,
                      const int* __restrict__ nbr, const uint16_t* __restrict__ lcol,
                      const double* __restrict__ pinv, const double* __restrict__ a,
-                     const double* __restrict__ b, double* x, SwLayout lay) {
+                     const double* __restrict__ b, double* x, SwLayout lay, const int* __restrict__ plist) {
   constexpr int T = WPP * 32;  // threads per patch
   extern __shared__ __align__(16) double smem[];
   const int slot = threadIdx.x / T;
   const int tid = threadIdx.x % T;
-  const int patch = p0 + blockIdx.x * PPC + slot;
+  const int pos = p0 + blockIdx.x * PPC + slot;   // position in the range, or in the list of leftover patches
+  const int patch = (plist != nullptr && pos < p1) ? plist[pos] : pos;
   const int S = lay.srow;
   double* Inv = smem + slot * lay.total_d();
   uint16_t* Ls = reinterpret_cast<uint16_t*>(Inv + lay.inv_d());
@@ -240,7 +245,7 @@ schwarz_apply_kernel(int p0, int p1, const SwPatch* __restrict__ pat, const int*
   int* idx = reinterpret_cast<int*>(rhs + lay.rhs_d());   // s
   int* rst = idx + lay.max_size;                           // s
   int* rln = rst + lay.max_size;                           // s
-  const bool active = patch < p1;   // uniform per warp when PPC > 1 (WPP == 1)
+  const bool active = pos < p1;   // uniform per warp when PPC > 1 (WPP == 1)
   SwPatch P;
   P.s = 0;
   if (active) {
@@ -427,11 +432,12 @@ schwarz_fast_kernel(int p0, int p1, const int* __restrict__ pidx32, const int* _
                     const int* __restrict__ uid, const long long* __restrict__ inv_off,
                     const double* __restrict__ vt, const uint32_t* __restrict__ ct4,
                     const double* __restrict__ pinv, const double* __restrict__ b, double* x, int srow,
-                    int sq, int nbq, int smax, const SwProfile prof, int vstride) {
+                    int sq, int nbq, int smax, const SwProfile prof, int vstride, const int* __restrict__ plist) {
   extern __shared__ __align__(16) double smem[];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int patch = p0 + blockIdx.x * kSwFastWarps + warp;
-  if (patch >= p1) return;
+  const int pos = p0 + blockIdx.x * kSwFastWarps + warp;   // position in the range, or in the list of leftover patches
+  if (pos >= p1) return;
+  const int patch = plist != nullptr ? plist[pos] : pos;
   double* xs = smem + warp * kSwFastSlot;
   double* Inv = xs + 256;
   double* rhs = Inv + 528;
@@ -523,11 +529,49 @@ schwarz_group_kernel(int g0, const SwGroup* __restrict__ groups, const int* __re
   }
   __syncthreads();
   // phase 1: stage x on the neighbourhoods and b (per patch coalesced, transposed into [entry][patch])
-  for (int g = warp; g < G.cnt; g += 8) {
-    const int* nb = nbr + n0s[g];
-    for (int j = lane; j < B.nn; j += 32) xs[j * LD + g] = x[nb[j]];
-    const int* pi = pidx + q0s[g];
-    for (int k = lane; k < B.s; k += 32) bs[k * LD + g] = b[pi[k]];
+  // (a warp stages its up to 4 patches side by side, two 32-entry chunks each: 8 index loads, then 8
+  // gathers in flight per lane -- the two dependent global round trips are paid once per 64 entries)
+  {
+    int n0w[4], q0w[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int g = warp + 8 * u;
+      n0w[u] = g < G.cnt ? n0s[g] : -1;
+      q0w[u] = g < G.cnt ? q0s[g] : -1;
+    }
+    for (int j0 = 0; j0 < B.nn; j0 += 64) {
+      int id[4][2];
+      double xv[4][2];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          const int j = j0 + 32 * v + lane;
+          id[u][v] = (n0w[u] >= 0 && j < B.nn) ? nbr[n0w[u] + j] : -1;
+        }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 2; ++v) xv[u][v] = id[u][v] >= 0 ? x[id[u][v]] : 0.0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          const int j = j0 + 32 * v + lane;
+          if (id[u][v] >= 0) xs[j * LD + warp + 8 * u] = xv[u][v];
+        }
+    }
+    for (int k0 = 0; k0 < B.s; k0 += 32) {
+      int id[4];
+      double bv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) id[u] = (q0w[u] >= 0 && k0 + lane < B.s) ? pidx[q0w[u] + k0 + lane] : -1;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) bv[u] = id[u] >= 0 ? b[id[u]] : 0.0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (id[u] >= 0) bs[(k0 + lane) * LD + warp + 8 * u] = bv[u];
+    }
   }
   __syncthreads();
   if (lane < G.cnt) {
@@ -903,8 +947,12 @@ inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iper
     const char* genv = getenv("MAMG_SW_GROUP");
     const bool want = dedup && !(genv && atoi(genv) == 0);
     std::vector<SwGroup> groups;
-    std::vector<int> gpatch;
+    std::vector<int> gpatch, leftover;
     d.gb_ptr.assign(sw.ncolors * nb + 1, 0);
+    d.lo_ptr.assign(sw.ncolors * nb + 1, 0);
+    const bool force = genv && atoi(genv) == 2;   // MAMG_SW_GROUP=2: group everything (tests)
+    const int min_fill = force ? 1 : 8;           // a group below a quarter of the lanes is not worth a CTA
+    long long grouped_patches = 0;
     if (want) {
       std::vector<std::pair<int, int>> bucket;
       for (int kb = 0; kb < sw.ncolors * nb; ++kb) {
@@ -915,15 +963,22 @@ inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iper
         for (size_t i = 0; i < bucket.size();) {
           size_t j = i;
           while (j < bucket.size() && bucket[j].first == bucket[i].first && j - i < 32) ++j;
-          groups.push_back(SwGroup{bucket[i].first, (int)(j - i)});
-          for (size_t t = i; t < i + 32; ++t) gpatch.push_back(t < j ? bucket[t].second : -1);
+          if ((int)(j - i) >= min_fill) {
+            groups.push_back(SwGroup{bucket[i].first, (int)(j - i)});
+            for (size_t t = i; t < i + 32; ++t) gpatch.push_back(t < j ? bucket[t].second : -1);
+            grouped_patches += (long long)(j - i);
+          } else {
+            for (size_t t = i; t < j; ++t) leftover.push_back(bucket[t].second);
+          }
           i = j;
         }
+        std::sort(leftover.begin() + d.lo_ptr[kb], leftover.end());   // the rare ones in patch order (locality)
         d.gb_ptr[kb + 1] = (int)groups.size();
+        d.lo_ptr[kb + 1] = (int)leftover.size();
       }
     }
-    // worth it when the lanes are mostly busy (average group at least a quarter full); MAMG_SW_GROUP=2 forces it
-    const bool use = want && !groups.empty() && ((double)np / (double)groups.size() >= 8.0 || (genv && atoi(genv) == 2));
+    // the grouped kernel pays when most patches find company
+    const bool use = want && !groups.empty() && (force || 2 * grouped_patches >= (long long)np);
     if (use) {
       std::vector<SwBlob> blobs(nu);
       std::vector<int> rowptr;
@@ -960,6 +1015,8 @@ inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iper
       d.smem_group = ((size_t)nn_max + 2 * (size_t)s_max) * kSwGroupLd * sizeof(double);
       if (d.smem_group <= 200 * 1024) {
         d.grouped = true;
+        d.grouped_patches = grouped_patches;
+        d.leftover = (int*)up(leftover.data(), leftover.size() * sizeof(int));
         d.ngroups = (int)groups.size();
         d.groups = (SwGroup*)up(groups.data(), groups.size() * sizeof(SwGroup));
         d.gpatch = (int*)up(gpatch.data(), gpatch.size() * sizeof(int));
@@ -998,18 +1055,22 @@ inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iper
 // patches [p0, p1) of one conflict colour (they commute, so they run concurrently)
 inline void schwarz_range_launch(const DSchwarz& d, int p0, int p1, const double* a, const double* b, double* x,
                                  cudaStream_t stream, int kb = -1) {
-  if (d.grouped && kb >= 0) {   // (colour, block) kb: its groups of look-alike patches
+  const int* plist = nullptr;
+  if (d.grouped && kb >= 0) {   // (colour, block) kb: its groups of look-alike patches, then the rare ones one by one
     const int g0 = d.gb_ptr[kb], g1 = d.gb_ptr[kb + 1];
     if (g1 > g0)
       schwarz_group_kernel<<<g1 - g0, 256, d.smem_group, stream>>>(g0, d.groups, d.gpatch, d.pat, d.pidx, d.nbr, d.blobs,
                                                                   d.bl_rowptr, d.bl_col, d.bl_val, d.inv_full, b, x,
                                                                   d.g_nn_max, d.g_s_max);
-    return;
+    p0 = d.lo_ptr[kb];
+    p1 = d.lo_ptr[kb + 1];
+    if (p1 == p0) return;
+    plist = d.leftover;
   }
   if (d.fast) {
     const int g = (p1 - p0 + kSwFastWarps - 1) / kSwFastWarps;
     const size_t sm = (size_t)kSwFastWarps * kSwFastSlot * sizeof(double);
-#define MAMG_SWF_ARGS p0, p1, d.pidx32, d.nbrp, d.uid, d.inv_off, d.vt, d.ct4, d.pinv, b, x, d.srow, d.sq, d.nbq, d.max_size, d.prof, d.vstride
+#define MAMG_SWF_ARGS p0, p1, d.pidx32, d.nbrp, d.uid, d.inv_off, d.vt, d.ct4, d.pinv, b, x, d.srow, d.sq, d.nbq, d.max_size, d.prof, d.vstride, plist
     if (d.sr_t == 12) schwarz_fast_kernel<12, 1><<<g, kSwFastWarps * 32, sm, stream>>>(MAMG_SWF_ARGS);
     else if (d.sr_t == 24) schwarz_fast_kernel<24, 4><<<g, kSwFastWarps * 32, sm, stream>>>(MAMG_SWF_ARGS);
     else schwarz_fast_kernel<32, 8><<<g, kSwFastWarps * 32, sm, stream>>>(MAMG_SWF_ARGS);
@@ -1018,7 +1079,7 @@ inline void schwarz_range_launch(const DSchwarz& d, int p0, int p1, const double
   }
   const int grid = (p1 - p0 + d.ppc - 1) / d.ppc;
   const SwLayout lay = {d.max_size, d.max_nbr, d.srow};
-#define MAMG_SW_ARGS p0, p1, d.pat, d.pidx, d.prow, d.plen, d.nbr, d.lcol, d.pinv, a, b, x, lay
+#define MAMG_SW_ARGS p0, p1, d.pat, d.pidx, d.prow, d.plen, d.nbr, d.lcol, d.pinv, a, b, x, lay, plist
   if (d.warps == 1 && d.ppc == 4) schwarz_apply_kernel<1, 4><<<grid, 128, d.smem_apply, stream>>>(MAMG_SW_ARGS);
   else if (d.warps == 1) schwarz_apply_kernel<1, 2><<<grid, 64, d.smem_apply, stream>>>(MAMG_SW_ARGS);
   else if (d.warps == 2) schwarz_apply_kernel<2, 1><<<grid, 64, d.smem_apply, stream>>>(MAMG_SW_ARGS);

@@ -297,12 +297,14 @@ class Hierarchy:
 
     STAT_KEYS = ["rows", "nnz_stored", "nnz_structural", "sell_slots", "device_bytes", "n_patches", "unique_blobs",
                  "schwarz_sweep_bytes", "schwarz_sweep_bytes_stored_factors", "n_colors", "n_patch_colors", "in_tail",
-                 "sell", "csr_kept", "row_blocks", "schwarz_fast_path"]
+                 "sell", "csr_kept", "row_blocks", "schwarz_fast_path", "schwarz_grouped", "schwarz_groups",
+                 "schwarz_group_smem", "schwarz_group_nn_max", "schwarz_group_s_max", "schwarz_grouped_patches",
+                 "max_patch_size", "reserved"]
 
     def stats(self, level=0):
         """Device-side statistics of one level (mamg_stats)."""
         self._require_device()
-        out = (C.c_int64 * 16)()
+        out = (C.c_int64 * 24)()
         check(lib.mamg_stats(self._h, int(level), out))
         return dict(zip(self.STAT_KEYS, [int(v) for v in out]))
 
