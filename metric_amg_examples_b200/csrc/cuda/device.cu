@@ -106,6 +106,7 @@ struct DeviceState {
   int rank = 0, world = 1;
   ncclComm_t comm = nullptr;
   int64_t collectives = 0;
+  int64_t exch_bytes = 0;     // bytes this rank stored into peers (halo mode)
   double* xbuf = nullptr;     // staging for the Schwarz patch-dof exchange
   // Every vector that is ever exchanged between ranks lives in ONE allocation (the arena) that is
   // shared with the peer processes through CUDA IPC: the owner of a row range stores it straight
@@ -671,6 +672,194 @@ static void push_ranges(DeviceState& D, const double* v, const PushRanges& R) {
   KScope ks(D, K_EXCH);
   push_kernel<<<grid, kBlock, 0, D.stream>>>(R, voff, D.d_peer_arena, D.rank, D.world, D.push_ticket, D.d_phase);
   ++D.collectives;
+}
+
+// ---- halo mode ---------------------------------------------------------------------------------------
+// One exchange = the boundary rows of this rank (index list per neighbour) stored straight into the
+// neighbours' vectors, then a flag handshake with THOSE neighbours only: ranks that share no boundary
+// on the level neither send nor wait.  Every rank executes the same sequence of exchanges, so the
+// exchange number (d_phase) is a global clock; a flag holds the number of the last exchange its owner
+// finished sending, and flags only grow.
+struct HaloPush { int nn; int peer[8]; int beg[8]; int cnt[8]; };
+
+__global__ void __launch_bounds__(kBlock)
+halo_push_kernel(HaloPush P, const int* __restrict__ send, long long voff, double* const* __restrict__ peers, int me,
+                 unsigned int* ticket, long long* phase_ctr) {
+  const double* mine = peers[me] + voff;
+  for (int k = 0; k < P.nn; ++k) {
+    double* dst = peers[P.peer[k]] + voff;
+    const int* idx = send + P.beg[k];
+    for (int t = blockIdx.x * kBlock + threadIdx.x; t < P.cnt[k]; t += gridDim.x * kBlock) {
+      const int i = idx[t];
+      dst[i] = mine[i];
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  __shared__ long long phase_s;
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicInc(ticket, gridDim.x - 1);
+    last = t == gridDim.x - 1;
+    if (last) {
+      phase_s = *reinterpret_cast<volatile long long*>(phase_ctr) + 1;
+      __threadfence_system();
+      for (int k = 0; k < P.nn; ++k) reinterpret_cast<volatile long long*>(peers[P.peer[k]])[me] = phase_s;
+    }
+  }
+  __syncthreads();
+  if (!last) return;
+  const long long phase = phase_s;
+  if ((int)threadIdx.x < P.nn) {
+    const volatile long long* flag = reinterpret_cast<const volatile long long*>(peers[me]) + P.peer[threadIdx.x];
+    const long long t0 = clock64();
+    while (*flag < phase) {
+      if (clock64() - t0 > 200000000000LL) { printf("mamg: rank %d: neighbour %d never reached exchange %lld\n", me, P.peer[threadIdx.x], phase); __trap(); }
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *phase_ctr = phase;
+}
+
+// listed entries of a vector to EVERY peer, all-rank handshake (the right-hand side of the first
+// replicated level: each rank contributes the coarse rows whose aggregates it owns)
+__global__ void __launch_bounds__(kBlock)
+list_push_all_kernel(int cnt, const int* __restrict__ idx, long long voff, double* const* __restrict__ peers, int me, int world,
+                     unsigned int* ticket, long long* phase_ctr) {
+  const double* mine = peers[me] + voff;
+  for (int t = blockIdx.x * kBlock + threadIdx.x; t < cnt; t += gridDim.x * kBlock) {
+    const int i = idx[t];
+    const double val = mine[i];
+    for (int q = 0; q < world; ++q)
+      if (q != me) peers[q][voff + i] = val;
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  __shared__ long long phase_s;
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicInc(ticket, gridDim.x - 1);
+    last = t == gridDim.x - 1;
+    if (last) {
+      phase_s = *reinterpret_cast<volatile long long*>(phase_ctr) + 1;
+      __threadfence_system();
+      for (int q = 0; q < world; ++q)
+        if (q != me) reinterpret_cast<volatile long long*>(peers[q])[me] = phase_s;
+    }
+  }
+  __syncthreads();
+  if (!last) return;
+  const long long phase = phase_s;
+  if ((int)threadIdx.x < world && (int)threadIdx.x != me) {
+    const volatile long long* flag = reinterpret_cast<const volatile long long*>(peers[me]) + threadIdx.x;
+    const long long t0 = clock64();
+    while (*flag < phase) {
+      if (clock64() - t0 > 200000000000LL) { printf("mamg: rank %d: peer %d never reached exchange %lld\n", me, (int)threadIdx.x, phase); __trap(); }
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *phase_ctr = phase;
+}
+
+// All-reduce of up to 4 scalars in fixed rank order (identical bits on every rank), then the scalar
+// post-processing that the single-GPU reduction kernels do in their finishing block.
+//   op 1  coarse scaling: v = sc+8:  v[0] = e.r, v[1] = e.Ae summed, v[2] = min(v[0]/v[1], 1)
+//   op 2  CG step length: v = sc+1:  v[0] = d.q summed, sc[2] = sc[0] / sc[1]
+//   op 3  CG r.z (v = sc+5: r.z, r.r): sc[3] = r.z; sc[4] = sc[3]/sc[0] unless first; sc[0] = sc[3]
+//   op 0  plain sum of `count` values at v
+// Slots: two banks (exchange number parity) of 64 ranks x 4 doubles behind the 64 flags of the arena.
+__global__ void __launch_bounds__(64)
+allreduce_kernel(int count, double* v, int op, int first, double* sc, double* const* __restrict__ peers, int me, int world,
+                 long long* phase_ctr) {
+  __shared__ long long phase_s;
+  if (threadIdx.x == 0) phase_s = *reinterpret_cast<volatile long long*>(phase_ctr) + 1;
+  __syncthreads();
+  const long long phase = phase_s;
+  const int bank = 64 + (int)(phase & 1) * 256;
+  const int q = threadIdx.x;
+  if (q < world && q != me) {
+    for (int k = 0; k < count; ++k) reinterpret_cast<volatile double*>(peers[q])[bank + me * 4 + k] = v[k];
+    __threadfence_system();
+    reinterpret_cast<volatile long long*>(peers[q])[me] = phase;
+    const volatile long long* flag = reinterpret_cast<const volatile long long*>(peers[me]) + q;
+    const long long t0 = clock64();
+    while (*flag < phase) {
+      if (clock64() - t0 > 200000000000LL) { printf("mamg: rank %d: peer %d never reached all-reduce %lld\n", me, q, phase); __trap(); }
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const volatile double* slots = reinterpret_cast<const volatile double*>(peers[me]) + bank;
+    for (int k = 0; k < count; ++k) {
+      double acc = 0.0;
+      for (int r = 0; r < world; ++r) acc += (r == me) ? v[k] : slots[r * 4 + k];
+      v[k] = acc;
+    }
+    if (op == 1) { const double al = v[0] / v[1]; v[2] = (al < 1.0) ? al : 1.0; }
+    else if (op == 2) sc[2] = sc[0] / sc[1];
+    else if (op == 3) { sc[3] = sc[5]; if (!first) sc[4] = sc[3] / sc[0]; sc[0] = sc[3]; }
+    *phase_ctr = phase;
+  }
+}
+
+// partial sums over rows [lo, hi): out[0] = u.v, out[1] = u.u   (no post-processing; the all-reduce does it)
+__global__ void __launch_bounds__(kBlock)
+dot2_range_kernel(int lo, int hi, const double* __restrict__ u, const double* __restrict__ v, double* partial,
+                  unsigned int* ticket, double* out) {
+  double acc[2] = {0.0, 0.0};
+  for (int i = lo + blockIdx.x * kBlock + threadIdx.x; i < hi; i += gridDim.x * kBlock) {
+    const double ui = u[i];
+    acc[0] += ui * v[i];
+    acc[1] += ui * ui;
+  }
+  block_reduce_finish<2>(acc, partial, ticket, out);
+}
+// x += alpha d, r -= alpha q and d = z + beta d on a row range
+__global__ void __launch_bounds__(kBlock)
+pcg_update_range_kernel(int lo, int hi, const double* __restrict__ sc, const double* __restrict__ d,
+                        const double* __restrict__ q, double* __restrict__ x, double* __restrict__ r) {
+  const int i = lo + blockIdx.x * kBlock + threadIdx.x;
+  if (i >= hi) return;
+  const double al = sc[2];
+  x[i] += al * d[i];
+  r[i] -= al * q[i];
+}
+__global__ void __launch_bounds__(kBlock)
+pcg_dir_range_kernel(int lo, int hi, const double* __restrict__ sc, const double* __restrict__ z, double* __restrict__ d) {
+  const int i = lo + blockIdx.x * kBlock + threadIdx.x;
+  if (i >= hi) return;
+  d[i] = z[i] + sc[4] * d[i];
+}
+
+static void halo_exchange(DeviceState& D, const DLevel& l, const double* v, int c) {
+  // c in [0, ncolors): the rows of that colour; c < 0: all boundary rows
+  if (!(v >= D.arena && v < D.arena + D.arena_doubles)) throw std::runtime_error("halo exchange of a vector outside the peer arena");
+  const int nnb = (int)l.nbr_ranks.size();
+  HaloPush P;
+  P.nn = nnb;
+  const int cc = c >= 0 ? c : l.ncolors;
+  int total = 0;
+  for (int k = 0; k < nnb; ++k) {
+    P.peer[k] = l.nbr_ranks[k];
+    P.beg[k] = l.send_off[(size_t)cc * nnb + k];
+    P.cnt[k] = l.send_off[(size_t)cc * nnb + k + 1] - P.beg[k];
+    total = std::max(total, P.cnt[k]);
+  }
+  const int grid = std::max(1, std::min(D.red_blocks, cdiv(std::max(total, 1), kBlock)));
+  KScope ks(D, K_EXCH);
+  halo_push_kernel<<<grid, kBlock, 0, D.stream>>>(P, l.d_send, v - D.arena, D.d_peer_arena, D.rank, D.push_ticket, D.d_phase);
+  ++D.collectives;
+  D.exch_bytes += 8LL * [&] { long long t = 0; for (int k = 0; k < nnb; ++k) t += P.cnt[k]; return t; }();
+}
+
+static void allreduce(DeviceState& D, int count, double* v, int op, int first) {
+  KScope ks(D, K_EXCH);
+  allreduce_kernel<<<1, 64, 0, D.stream>>>(count, v, op, first, D.scal, D.d_peer_arena, D.rank, D.world, D.d_phase);
+  ++D.collectives;
+  D.exch_bytes += 8LL * count * (D.world - 1);
 }
 
 // Peer stores of exchange k+1 may land while the receiver is still busy with work it queued after

@@ -92,7 +92,7 @@ struct DSchwarz {
   long long* inv_off = nullptr;  // [nuniq] offset of the packed inverse of a unique blob
   // grouped path (schwarz_group_kernel): chosen when the patches of a colour mostly share their blobs
   bool grouped = false;
-  int ngroups = 0, g_nn_max = 0, g_s_max = 0;
+  int ngroups = 0, g_nn_max = 0, g_s_max = 0, g_ne_max = 0, g_xs_rows = 0;
   size_t smem_group = 0;
   SwGroup* groups = nullptr;
   int* gpatch = nullptr;         // [ngroups][32] patch numbers
@@ -505,18 +505,22 @@ schwarz_fast_kernel(int p0, int p1, const int* __restrict__ pidx32, const int* _
 // store, phase 3 writes x_B back the same way.
 //   x_B = A_BB^{-1} (b_B - A_{B,out} x_out)   for the patches gpatch[32 g ...] of group g
 constexpr int kSwGroupLd = 33;   // leading dimension of the [entry][patch] shared arrays (odd: conflict-free transposes)
+constexpr int kSwGroupInvSmem = 2048;   // doubles: inverses up to this size are staged in shared memory
 __global__ void __launch_bounds__(256)
 schwarz_group_kernel(int g0, const SwGroup* __restrict__ groups, const int* __restrict__ gpatch,
                      const SwPatch* __restrict__ pat, const int* __restrict__ pidx, const int* __restrict__ nbr,
                      const SwBlob* __restrict__ blobs, const int* __restrict__ bl_rowptr,
                      const uint16_t* __restrict__ bl_col, const double* __restrict__ bl_val,
                      const double* __restrict__ inv_full, const double* __restrict__ b, double* x,
-                     int nn_max, int s_max) {
+                     int xs_rows, int s_max, int ne_max, int inv_smem) {
   extern __shared__ __align__(16) double smem[];
   constexpr int LD = kSwGroupLd;
-  double* xs = smem;                          // [nn_max][LD]  x on the outside neighbours
-  double* bs = xs + (size_t)nn_max * LD;      // [s_max][LD]   b_B, finally the new x_B
-  double* ds = bs + (size_t)s_max * LD;       // [s_max][LD]   the residual b_B - A_{B,out} x_out
+  double* sinv = smem;                        // [inv_smem]     the blob's inverse when it fits (16-byte aligned: 128-bit reads)
+  double* xs = sinv + inv_smem;               // [xs_rows][LD]  x on the outside neighbours; finally the new x_B
+  double* bs = xs + (size_t)xs_rows * LD;     // [s_max][LD]    b_B, then the residual b_B - A_{B,out} x_out
+  double* sval = bs + (size_t)s_max * LD;     // [ne_max]       the blob's off-patch values ...
+  int* srp = reinterpret_cast<int*>(sval + ne_max);              // [s_max + 1]  ... row pointer ...
+  uint16_t* scol = reinterpret_cast<uint16_t*>(srp + s_max + 2); // [ne_max]     ... and local columns
   __shared__ int q0s[32], n0s[32];
   const int grp = g0 + blockIdx.x;
   const SwGroup G = groups[grp];
@@ -527,10 +531,18 @@ schwarz_group_kernel(int g0, const SwGroup* __restrict__ groups, const int* __re
     q0s[threadIdx.x] = p >= 0 ? pat[p].q0 : 0;
     n0s[threadIdx.x] = p >= 0 ? pat[p].n0 : 0;
   }
+  // the blob (shared by all patches of the group, L2-resident) into shared memory: afterwards every
+  // warp-uniform read of the compute phases is a shared-memory broadcast instead of an L2 round trip
+  const int ne = bl_rowptr[B.rp0 + B.s];
+  for (int e = threadIdx.x; e < ne; e += 256) { sval[e] = __ldg(bl_val + B.e0 + e); scol[e] = __ldg(bl_col + B.e0 + e); }
+  for (int k = threadIdx.x; k <= B.s; k += 256) srp[k] = __ldg(bl_rowptr + B.rp0 + k);
+  const bool inv_staged = B.s * B.kpad <= inv_smem;
+  if (inv_staged)
+    for (int t = threadIdx.x; t < B.s * B.kpad; t += 256) sinv[t] = __ldg(inv_full + B.iv0 + t);
   __syncthreads();
-  // phase 1: stage x on the neighbourhoods and b (per patch coalesced, transposed into [entry][patch])
-  // (a warp stages its up to 4 patches side by side, two 32-entry chunks each: 8 index loads, then 8
-  // gathers in flight per lane -- the two dependent global round trips are paid once per 64 entries)
+  // phase 1: stage x on the neighbourhoods and b (per patch coalesced, transposed into [entry][patch]).
+  // A warp stages its up to 4 patches side by side, two 32-entry chunks each: 8 index loads, then 8
+  // gathers in flight per lane -- the two dependent global round trips are paid once per 64 entries.
   {
     int n0w[4], q0w[4];
 #pragma unroll
@@ -575,45 +587,43 @@ schwarz_group_kernel(int g0, const SwGroup* __restrict__ groups, const int* __re
   }
   __syncthreads();
   if (lane < G.cnt) {
-    // phase 2a: residual rows (warp-uniform entries, lane = patch)
-    const int* rp = bl_rowptr + B.rp0;
-    const uint16_t* bc = bl_col + B.e0;
-    const double* bv = bl_val + B.e0;
+    // phase 2a: residual rows in place (blob entries are shared-memory broadcasts, lane = patch)
     for (int k = warp; k < B.s; k += 8) {
       double acc = bs[k * LD + lane];
-      const int e1 = rp[k + 1];
-      for (int e = rp[k]; e < e1; ++e) acc -= __ldg(bv + e) * xs[(int)__ldg(bc + e) * LD + lane];
-      ds[k * LD + lane] = acc;
+      const int e1 = srp[k + 1];
+#pragma unroll 4
+      for (int e = srp[k]; e < e1; ++e) acc -= sval[e] * xs[(int)scol[e] * LD + lane];
+      bs[k * LD + lane] = acc;
     }
   }
-  __syncthreads();
+  __syncthreads();   // every residual is complete and xs is free: the new x_B goes there
   if (lane < G.cnt) {
     // phase 2b: x_B = A_BB^{-1} r, 4 rows per thread (inverse stored [c][kpad]: two broadcast 128-bit loads per c)
-    const double* iv = inv_full + B.iv0;
+    const double* iv = inv_staged ? sinv : inv_full + B.iv0;
     for (int k0 = warp * 4; k0 < B.s; k0 += 32) {
       double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
       const double* ivk = iv + k0;
-#pragma unroll 2
+#pragma unroll 4
       for (int c = 0; c < B.s; ++c) {
-        const double r = ds[c * LD + lane];
-        const double2 u = __ldg(reinterpret_cast<const double2*>(ivk + (size_t)c * B.kpad));
-        const double2 v = __ldg(reinterpret_cast<const double2*>(ivk + (size_t)c * B.kpad) + 1);
+        const double r = bs[c * LD + lane];
+        const double2 u = *reinterpret_cast<const double2*>(ivk + (size_t)c * B.kpad);
+        const double2 v = *(reinterpret_cast<const double2*>(ivk + (size_t)c * B.kpad) + 1);
         a0 += u.x * r;
         a1 += u.y * r;
         a2 += v.x * r;
         a3 += v.y * r;
       }
-      bs[k0 * LD + lane] = a0;
-      if (k0 + 1 < B.s) bs[(k0 + 1) * LD + lane] = a1;
-      if (k0 + 2 < B.s) bs[(k0 + 2) * LD + lane] = a2;
-      if (k0 + 3 < B.s) bs[(k0 + 3) * LD + lane] = a3;
+      xs[k0 * LD + lane] = a0;
+      if (k0 + 1 < B.s) xs[(k0 + 1) * LD + lane] = a1;
+      if (k0 + 2 < B.s) xs[(k0 + 2) * LD + lane] = a2;
+      if (k0 + 3 < B.s) xs[(k0 + 3) * LD + lane] = a3;
     }
   }
   __syncthreads();
   // phase 3: write x_B back (per patch coalesced)
   for (int g = warp; g < G.cnt; g += 8) {
     const int* pi = pidx + q0s[g];
-    for (int k = lane; k < B.s; k += 32) x[pi[k]] = bs[k * LD + g];
+    for (int k = lane; k < B.s; k += 32) x[pi[k]] = xs[k * LD + g];
   }
 }
 
@@ -985,7 +995,7 @@ inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iper
       std::vector<uint16_t> bcol;
       std::vector<double> bval;
       long long iv_tot = 0;
-      int nn_max = 1, s_max = 1;
+      int nn_max = 1, s_max = 1, ne_max = 1;
       std::vector<int> pos(n, -1);
       for (int u = 0; u < nu; ++u) {
         const int k = rep[u];
@@ -1008,11 +1018,16 @@ inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iper
             if (pos[pja[e]] >= 0) { bcol.push_back((uint16_t)pos[pja[e]]); bval.push_back(pa[e]); }
         }
         rowptr.push_back((int)bcol.size() - B.e0);
+        ne_max = std::max(ne_max, (int)bcol.size() - B.e0);
         for (int j = 0; j < B.nn; ++j) pos[nbr[pat[k].n0 + j]] = -1;
       }
       d.g_nn_max = nn_max;
       d.g_s_max = s_max;
-      d.smem_group = ((size_t)nn_max + 2 * (size_t)s_max) * kSwGroupLd * sizeof(double);
+      d.g_ne_max = (ne_max + 3) & ~3;
+      d.g_xs_rows = std::max(nn_max, s_max);
+      d.smem_group = ((size_t)d.g_xs_rows + (size_t)s_max) * kSwGroupLd * sizeof(double) +
+                     ((size_t)d.g_ne_max + kSwGroupInvSmem) * sizeof(double) + ((size_t)s_max + 2) * sizeof(int) +
+                     (size_t)d.g_ne_max * sizeof(uint16_t) + 16;
       if (d.smem_group <= 200 * 1024) {
         d.grouped = true;
         d.grouped_patches = grouped_patches;
@@ -1028,8 +1043,11 @@ inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iper
         if (fast_shape && !d.pat) d.pat = (SwPatch*)up(pat.data(), pat.size() * sizeof(SwPatch));
         schwarz_expand_inverse_kernel<<<nu, 256>>>(nu, d.blobs, d.inv_off, d.pinv, d.inv_full);
         sync_or_throw("Schwarz inverse expansion");
-        if (d.smem_group > 48 * 1024)
-          cudaFuncSetAttribute(schwarz_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_group);
+        // always opt in (the kernel also has static shared memory; the opt-in value is per function, so keep
+        // the largest request of all hierarchies of this process)
+        static size_t opted = 0;
+        opted = std::max(opted, d.smem_group);
+        cudaFuncSetAttribute(schwarz_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)opted);
       }
     }
   }
@@ -1061,7 +1079,7 @@ inline void schwarz_range_launch(const DSchwarz& d, int p0, int p1, const double
     if (g1 > g0)
       schwarz_group_kernel<<<g1 - g0, 256, d.smem_group, stream>>>(g0, d.groups, d.gpatch, d.pat, d.pidx, d.nbr, d.blobs,
                                                                   d.bl_rowptr, d.bl_col, d.bl_val, d.inv_full, b, x,
-                                                                  d.g_nn_max, d.g_s_max);
+                                                                  d.g_xs_rows, d.g_s_max, d.g_ne_max, kSwGroupInvSmem);
     p0 = d.lo_ptr[kb];
     p1 = d.lo_ptr[kb + 1];
     if (p1 == p0) return;
