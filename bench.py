@@ -228,7 +228,7 @@ def run_mamg(a):
         conc = int(max(1, min(world, free_t.item() * 0.7 // need)))
         for r0 in range(0, world, conc):
             if r0 <= rank < r0 + conc:
-                H.to_device(local, stream.cuda_stream)
+                H.to_device(local, stream.cuda_stream, rank=rank, world=world)
             dist.barrier()
         H.dist_init()
     else:

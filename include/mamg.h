@@ -152,6 +152,12 @@ int mamg_setup_seconds(mamg_handle h, double* seconds);
  *      stream = a cudaStream_t cast to void* the library launches on (NULL: the
  *      library creates its own non-blocking stream). Fails if no CUDA device. */
 int mamg_to_device(mamg_handle h, int32_t device, void* stream);
+/* Multi-GPU upload: the rank and world size are known when the hierarchy goes to the device, so that
+ * rank r stores only the matrix rows of its own parts on the row-distributed levels ("halo mode":
+ * device memory and upload time divide by the number of ranks; kernels' updates travel as halo index
+ * lists to the neighbour ranks only).  mamg_dist_init / mamg_dist_peers follow as before.
+ * MAMG_HALO=0 keeps the round-1 scheme (whole hierarchy on every rank, updated ranges all-gathered). */
+int mamg_to_device_dist(mamg_handle h, int32_t device, void* stream, int32_t rank, int32_t world);
 int mamg_set_stream(mamg_handle h, void* stream);
 
 /* ---- multi-GPU, one process per GPU (torch.distributed / torchrun launches the ranks).

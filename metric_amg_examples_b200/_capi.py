@@ -69,6 +69,7 @@ def _load():
         "mamg_coarse_export": (i32, [vp, vp]),
         "mamg_setup_seconds": (i32, [vp, pdbl]),
         "mamg_to_device": (i32, [vp, i32, vp]),
+        "mamg_to_device_dist": (i32, [vp, i32, vp, i32, i32]),
         "mamg_set_stream": (i32, [vp, vp]),
         "mamg_nccl_unique_id": (i32, [vp]),
         "mamg_dist_init": (i32, [vp, i32, i32, vp]),

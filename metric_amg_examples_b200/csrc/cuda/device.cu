@@ -874,8 +874,25 @@ static void barrier_only(DeviceState& D) {
   push_ranges(D, D.arena + 64, R);
 }
 
+static bool halo_on(const DeviceState& D, const DLevel& l) { return D.halo && D.world > 1 && l.nb > 1; }
+
+// every rank's own row blocks of v to every peer (the complete vector everywhere): API boundaries, and
+// the whole exchange scheme of the round-1 mode
+static void allgather_own(DeviceState& D, const DLevel& l, double* v) {
+  const int per = l.nb / D.world;
+  if (per > 8) throw std::runtime_error("more than 8 row blocks per rank");
+  PushRanges R;
+  R.n = 0;
+  for (int b = D.rank * per; b < (D.rank + 1) * per; ++b) {
+    const int r0 = l.bc_ptr[b * l.ncolors], r1 = l.bc_ptr[(b + 1) * l.ncolors];
+    if (r1 > r0) { R.beg[R.n] = r0; R.len[R.n] = r1 - r0; ++R.n; }
+  }
+  push_ranges(D, v, R);
+}
+
 static void exchange(DeviceState& D, const DLevel& l, double* v, int c) {
   if (D.world == 1 || !is_dist(D, l)) return;
+  if (D.halo) { halo_exchange(D, l, v, c); return; }
   const int per = l.nb / D.world;
   if (D.use_p2p && per <= 8 && v >= D.arena && v < D.arena + D.arena_doubles) {
     PushRanges R;
@@ -902,10 +919,13 @@ static void exchange(DeviceState& D, const DLevel& l, double* v, int c) {
 // CTAs that cover the slices overlapping rows [r0, r1)
 static int sell_grid(int r0, int r1) { return cdiv((r1 + 31) / 32 - r0 / 32, kSellWarps); }
 
-static void k_spmv(DeviceState& D, const DLevel& l, const double* x, const double* b, double* y, bool resid) {
+// complete = true: the result is made complete on every rank (all-gather of the owned rows); halo-aware
+// callers that only need their own rows pass false
+static void k_spmv(DeviceState& D, const DLevel& l, const double* x, const double* b, double* y, bool resid,
+                   bool complete = true) {
   if (l.n == 0) return;
   const int r0 = own_lo(D, l), r1 = own_hi(D, l);
-  if (is_dist(D, l)) barrier_only(D);   // y may still be in local use on a peer (Krylov vector updates)
+  if (is_dist(D, l) && complete) barrier_only(D);   // y may still be in local use on a peer (Krylov vector updates)
   if (r1 > r0 && l.use_sell) {
     const int grid = sell_grid(r0, r1);
     KScope ks(D, K_SPMV);
@@ -918,7 +938,9 @@ static void k_spmv(DeviceState& D, const DLevel& l, const double* x, const doubl
       if (resid) spmv_kernel<LN, UN, true><<<grid, kBlock, 0, D.stream>>>(r0, r1, l.ia, l.ja, l.a, x, b, y);
       else spmv_kernel<LN, UN, false><<<grid, kBlock, 0, D.stream>>>(r0, r1, l.ia, l.ja, l.a, x, b, y)));
   }
-  exchange(D, l, y, -1);
+  if (D.world > 1 && is_dist(D, l) && complete) {
+    if (D.halo) allgather_own(D, l, y); else exchange(D, l, y, -1);
+  }
 }
 
 static void k_gs_color(DeviceState& D, const DLevel& l, int c, const double* b, double* x, double omega) {
@@ -957,6 +979,14 @@ static void k_jacobi(DeviceState& D, DLevel& l, const double* b, double* x, doub
     if (l.use_sell) sell_jacobi_kernel<<<sell_grid(r0, r1), kBlock, 0, D.stream>>>(r0, r1, l.S, l.invd, l.skip, b, x, l.t, w);
     else LANES_SWITCH(l.lanes,
       jacobi_kernel<LN><<<grid, kBlock, 0, D.stream>>>(r0, r1, l.ia, l.ja, l.a, l.invd, l.skip, b, x, l.t, w));
+  }
+  if (halo_on(D, l)) {   // new iterate on the owned rows, then its boundary rows to the neighbours
+    if (r1 > r0) {
+      KScope ks(D, K_VEC);
+      copy_kernel<<<cdiv(r1 - r0, kBlock), kBlock, 0, D.stream>>>(r1 - r0, l.t + r0, x + r0);
+    }
+    halo_exchange(D, l, x, -1);
+    return;
   }
   exchange(D, l, l.t, -1);
   {
@@ -1079,11 +1109,28 @@ static void k_resid_restrict(DeviceState& D, int lev) {
     // t = b - A x on the fine rows this rank owns (aggregates never cross parts, so the members of the
     // coarse rows [c0, c1) are among them), streamed once in layout order; then the aggregate sums
     const int r0 = own_lo(D, f), r1 = own_hi(D, f);
-    const bool all = !(is_dist(D, f) && D.world > 1) || !(is_dist(D, c));
+    const bool all = !(is_dist(D, f) && D.world > 1) || (!is_dist(D, c) && !halo_on(D, f));
     const int a0 = all ? 0 : r0, a1 = all ? f.n : r1;
     if (a1 > a0) {
       KScope ks(D, K_RESTRICT);
       sell_spmv_kernel<true><<<sell_grid(a0, a1), kBlock, 0, D.stream>>>(a0, a1, f.S, f.x, f.b, f.t);
+    }
+    if (halo_on(D, f) && !is_dist(D, c)) {
+      // first replicated level: every rank sums the aggregates it owns, then the entries travel to all peers
+      k_fill(D, c.n, c.x, 0.0);
+      if (f.n_own_coarse > 0) {
+        KScope ks(D, K_RESTRICT);
+        agg_sum_list_kernel<<<cdiv(f.n_own_coarse, kBlock), kBlock, 0, D.stream>>>(f.n_own_coarse, f.d_own_coarse, f.cptr, f.cidx, f.t, c.b);
+      }
+      {
+        const int grid = std::max(1, std::min(D.red_blocks, cdiv(std::max(f.n_own_coarse, 1), kBlock)));
+        KScope ks(D, K_EXCH);
+        list_push_all_kernel<<<grid, kBlock, 0, D.stream>>>(f.n_own_coarse, f.d_own_coarse, c.b - D.arena, D.d_peer_arena, D.rank, D.world,
+                                                           D.push_ticket, D.d_phase);
+        ++D.collectives;
+        D.exch_bytes += 8LL * f.n_own_coarse * (D.world - 1);
+      }
+      return;
     }
     if (c1 > c0) {
       KScope ks(D, K_RESTRICT);
@@ -1097,7 +1144,8 @@ static void k_resid_restrict(DeviceState& D, int lev) {
   }
   if (is_dist(D, c) && D.world > 1) {
     k_fill(D, c.n, c.x, 0.0);   // before the barrier of the exchange: afterwards peers push into c.x
-    exchange(D, c, c.b, -1);
+    if (D.halo) barrier_only(D);   // the coarse right-hand side is only needed on the owned rows
+    else exchange(D, c, c.b, -1);
   }
 }
 
@@ -1107,6 +1155,16 @@ static int red_grid(const DeviceState& D, long long threads) {
 
 static void k_scale_dots(DeviceState& D, int lev) {
   DLevel& c = D.lv[lev];
+  if (halo_on(D, c)) {   // partial e.r and e.A_c e over the owned rows, combined in rank order
+    const int r0 = own_lo(D, c), r1 = own_hi(D, c);
+    if (!c.use_sell) throw std::runtime_error("halo mode needs the sliced-ELL row kernels (MAMG_ROWS=sell)");
+    {
+      KScope ks(D, K_SCALE);
+      sell_scale_dots_range_kernel<<<red_grid(D, std::max(r1 - r0, 1)), kBlock, 0, D.stream>>>(r0, r1, c.S, c.x, c.b, D.partial, D.ticket, D.scal + 8);
+    }
+    allreduce(D, 2, D.scal + 8, 1, 0);
+    return;
+  }
   if (is_dist(D, c) && D.world > 1) {   // t = A_c e on the owned rows, all-gather, then the two dots on complete vectors
     k_spmv(D, c, c.x, nullptr, c.t, false);
     KScope ks(D, K_SCALE);
@@ -1278,6 +1336,13 @@ static void apply_permuted_raw(DeviceState& D, const double* r, double* z) {
   set_l2_window(D, nullptr, 0);
 }
 
+// z = B r with z complete on every rank (API boundary, MINRES / GMRES): in halo mode the cycle leaves z
+// valid on the owned rows and their halo only
+static void apply_complete(DeviceState& D, const double* r, double* z) {
+  apply_permuted(D, r, z);
+  if (halo_on(D, D.lv[0])) allgather_own(D, D.lv[0], z);
+}
+
 struct IoVec {  // natural-order vector handed over the ABI (host or device memory)
   DeviceState& D;
   bool on_device;
@@ -1326,12 +1391,18 @@ static int pcg_device(DeviceState& D, const double* b_nat, double* x_nat, double
     k_fill(D, n, x, 0.0);
     k_copy(D, n, b, r);
   }
-  apply_permuted(D, r, z);
-  k_copy(D, n, z, d);
-  {
+  const bool halo = halo_on(D, l0);
+  const int lo = halo ? own_lo(D, l0) : 0, hi = halo ? own_hi(D, l0) : n;
+  if (halo && !l0.use_sell) throw std::runtime_error("halo mode needs the sliced-ELL row kernels (MAMG_ROWS=sell)");
+  auto rz_dots = [&](int first) {
     KScope ks(D, K_DOT);
-    pcg_rz_kernel<<<rgrid, kBlock, 0, D.stream>>>(n, r, z, D.partial, D.ticket, D.scal, 1);
-  }
+    if (!halo) { pcg_rz_kernel<<<rgrid, kBlock, 0, D.stream>>>(n, r, z, D.partial, D.ticket, D.scal, first); return; }
+    dot2_range_kernel<<<red_grid(D, std::max(hi - lo, 1)), kBlock, 0, D.stream>>>(lo, hi, r, z, D.partial, D.ticket, D.scal + 5);
+  };
+  apply_permuted(D, r, z);
+  k_copy(D, n, z, d);   // owned rows and halo of z are valid, hence of d
+  rz_dots(1);
+  if (halo) allreduce(D, 2, D.scal + 5, 3, 1);
   read_scalars(D, 8);
   double rz = D.h_scal[0];
   int it = 0, status = 0;
@@ -1339,7 +1410,13 @@ static int pcg_device(DeviceState& D, const double* b_nat, double* x_nat, double
   if (residuals) residuals[0] = res;
   double target = stop != 0 ? tol * res : tol;
   while (res > target && it < maxiter) {
-    if (is_dist(D, l0) && D.world > 1) {   // q = A d on the owned rows, all-gather, then d.q on complete vectors
+    if (halo) {   // q = A d and the partial d.q on the owned rows (d is current on the halo), combined in rank order
+      {
+        KScope ks(D, K_SPMV);
+        sell_spmv_dot_range_kernel<<<red_grid(D, std::max(hi - lo, 1)), kBlock, 0, D.stream>>>(lo, hi, l0.S, d, q, D.partial, D.ticket, D.scal + 1);
+      }
+      allreduce(D, 1, D.scal + 1, 2, 0);
+    } else if (is_dist(D, l0) && D.world > 1) {   // q = A d on the owned rows, all-gather, then d.q on complete vectors
       k_spmv(D, l0, d, nullptr, q, false);
       KScope ks(D, K_DOT);
       pcg_dq_kernel<<<rgrid, kBlock, 0, D.stream>>>(n, d, q, D.partial, D.ticket, D.scal);
@@ -1353,16 +1430,23 @@ static int pcg_device(DeviceState& D, const double* b_nat, double* x_nat, double
           spmv_dot_kernel<LN, UN><<<sgrid, kBlock, 0, D.stream>>>(n, l0.ia, l0.ja, l0.a, d, q, D.partial, D.ticket, D.scal)));
       }
     }
-    {
+    if (halo) {
+      KScope ks(D, K_VEC);
+      if (hi > lo) pcg_update_range_kernel<<<cdiv(hi - lo, kBlock), kBlock, 0, D.stream>>>(lo, hi, D.scal, d, q, x, r);
+    } else {
       KScope ks(D, K_VEC);
       pcg_update_kernel<<<vgrid, kBlock, 0, D.stream>>>(n, D.scal, d, q, x, r);
     }
     apply_permuted(D, r, z);
-    {
-      KScope ks(D, K_DOT);
-      pcg_rz_kernel<<<rgrid, kBlock, 0, D.stream>>>(n, r, z, D.partial, D.ticket, D.scal, 0);
-    }
-    {
+    rz_dots(0);
+    if (halo) {
+      allreduce(D, 2, D.scal + 5, 3, 0);
+      {
+        KScope ks(D, K_VEC);
+        if (hi > lo) pcg_dir_range_kernel<<<cdiv(hi - lo, kBlock), kBlock, 0, D.stream>>>(lo, hi, D.scal, z, d);
+      }
+      halo_exchange(D, l0, d, -1);   // the next SpMV reads d on the halo
+    } else {
       KScope ks(D, K_VEC);
       pcg_dir_kernel<<<vgrid, kBlock, 0, D.stream>>>(n, D.scal, z, d);
     }
@@ -1375,6 +1459,7 @@ static int pcg_device(DeviceState& D, const double* b_nat, double* x_nat, double
     if (residuals) residuals[it] = res;
     if (!(rz >= 0.0) || !std::isfinite(D.h_scal[2])) { status = 1; break; }  // "ConjGrad breakdown"
   }
+  if (halo) allgather_own(D, l0, x);   // the caller gets the complete solution on every rank
   k_scatter_out(D, n, l0.iperm, x, x_nat, x_blocks);
   *niters = it;
   return status;
@@ -1409,7 +1494,7 @@ static int minres_device(DeviceState& D, const double* b_nat, double* x_nat, dou
   k_fill(D, n, x, 0.0);
   k_fill(D, n, w, 0.0);
   k_fill(D, n, w2, 0.0);
-  apply_permuted(D, r1, y);
+  apply_complete(D, r1, y);
   double beta1 = k_dot(D, n, r1, y);
   if (!(beta1 >= 0.0)) return 1;
   beta1 = std::sqrt(beta1);
@@ -1426,7 +1511,7 @@ static int minres_device(DeviceState& D, const double* b_nat, double* x_nat, dou
     k_axpby(D, n, -alfa / beta, r2, 1.0, y);
     std::swap(r1, r2);                                   // r1 = r2
     k_copy(D, n, y, r2);                                 // r2 = y
-    apply_permuted(D, r2, y);                            // y = B r2
+    apply_complete(D, r2, y);                            // y = B r2
     oldb = beta;
     const double b2 = k_dot(D, n, r2, y);
     if (!(b2 >= 0.0)) { *niters = it; return 1; }
@@ -1479,7 +1564,7 @@ static int gmres_device(DeviceState& D, const double* b_nat, double* x_nat, doub
     g[0] = rn;
     int j = 0;
     for (; j < m && it < maxiter && rn > target; ++j) {
-      apply_permuted(D, D.basis[j], z);                   // z = B v_j
+      apply_complete(D, D.basis[j], z);                   // z = B v_j
       k_spmv(D, l0, z, nullptr, wv, false);               // w = A z
       for (int i = 0; i <= j; ++i) {
         const double h = k_dot(D, n, wv, D.basis[i]);
@@ -1513,7 +1598,7 @@ static int gmres_device(DeviceState& D, const double* b_nat, double* x_nat, doub
     }
     k_fill(D, n, u, 0.0);
     for (int i = 0; i < j; ++i) k_axpby(D, n, yv[i], D.basis[i], 1.0, u);
-    apply_permuted(D, u, z);
+    apply_complete(D, u, z);
     k_axpby(D, n, 1.0, z, 1.0, x);
     k_spmv(D, l0, x, b, r, true);                         // true residual for the restart
     rn = std::sqrt(k_dot(D, n, r, r));
@@ -1536,7 +1621,16 @@ using namespace mamg;
 
 extern "C" {
 
-int mamg_to_device(mamg_handle h, int32_t device, void* stream) {
+static int to_device_impl(mamg_handle h, int32_t device, void* stream, int32_t rank, int32_t world);
+
+int mamg_to_device(mamg_handle h, int32_t device, void* stream) { return to_device_impl(h, device, stream, 0, 1); }
+
+int mamg_to_device_dist(mamg_handle h, int32_t device, void* stream, int32_t rank, int32_t world) {
+  if (world < 1 || rank < 0 || rank >= world) { set_error("to_device_dist: bad rank/world"); return -1; }
+  return to_device_impl(h, device, stream, rank, world);
+}
+
+static int to_device_impl(mamg_handle h, int32_t device, void* stream, int32_t rank, int32_t world) {
   MAMG_TRY
   if (!h) { set_error("NULL handle"); return -1; }
   int ndev = 0;
@@ -1552,6 +1646,22 @@ int mamg_to_device(mamg_handle h, int32_t device, void* stream) {
   DeviceState* D = new DeviceState();
   D->device = device;
   D->prm = h->H.prm;
+  if (world > 1) {
+    if (h->H.nparts % world != 0) {
+      delete D;
+      set_error("to_device_dist: the hierarchy has " + std::to_string(h->H.nparts) + " parts, not a multiple of world size " + std::to_string(world));
+      return -1;
+    }
+    D->rank = rank;
+    D->world = world;
+    const char* eh = getenv("MAMG_HALO");
+    const char* ep = getenv("MAMG_P2P");
+    bool sa = false;
+    for (const Level& L : h->H.lv) sa |= L.P.n > 0;
+    // halo mode needs the peer-memory exchange and the sliced-ELL kernels; smoothed prolongators reach
+    // across the parts, so SA hierarchies keep the all-gather scheme
+    D->halo = !(eh && atoi(eh) == 0) && !(ep && atoi(ep) == 0) && rows_sell() && !sa;
+  }
   { const char* g = getenv("MAMG_GRAPH"); if (g) D->use_graph = atoi(g) != 0; }
   { const char* g = getenv("MAMG_GRAPH_DIST"); if (g) D->graph_dist = atoi(g) != 0; }
   {
@@ -1623,6 +1733,11 @@ int mamg_dist_init(mamg_handle h, int32_t rank, int32_t world, const void* uniqu
   DeviceState* D = get_dev(h);
   if (!D) return -1;
   if (world < 1 || rank < 0 || rank >= world) { set_error("dist_init: bad rank/world"); return -1; }
+  if (D->world > 1 && (D->world != world || D->rank != rank)) {
+    set_error("dist_init: rank/world differ from the ones the hierarchy was uploaded for (mamg_to_device_dist)");
+    return -1;
+  }
+  if (world > 1 && D->world == 1 && !getenv("MAMG_HALO_ALLOW_LATE")) D->halo = false;   // uploaded without a rank: round-1 scheme
   if (world > 64) { set_error("dist_init: at most 64 ranks (the arrival flags occupy the first 64 slots of the vector arena; CUDA IPC peers are single-node anyway)"); return -1; }
   if (h->H.nparts % world != 0) {
     set_error("dist_init: the hierarchy has " + std::to_string(h->H.nparts) + " parts, not a multiple of world size " + std::to_string(world));
@@ -1704,7 +1819,7 @@ int mamg_apply(mamg_handle h, const double* r, double* z, int32_t on_device) {
   const double* rin = io.in(r, l0.n, D->io_a);
   double* zout = io.out_ptr(z, D->io_b);
   k_gather(*D, l0.n, l0.perm, rin, D->w[2]);
-  apply_permuted(*D, D->w[2], D->w[3]);
+  apply_complete(*D, D->w[2], D->w[3]);
   k_gather(*D, l0.n, l0.iperm, D->w[3], zout);
   io.out(z, l0.n, D->io_b);
   CUDA_OK(cudaGetLastError());
@@ -1744,7 +1859,7 @@ int mamg_apply_blocks(mamg_handle h, int32_t nblocks, const int32_t* sizes, cons
   } else {
     k_gather_in(*D, l0.n, l0.perm, nullptr, &R, D->w[2]);
   }
-  apply_permuted(*D, D->w[2], D->w[3]);
+  apply_complete(*D, D->w[2], D->w[3]);
   if (!on_device) {
     k_gather(*D, l0.n, l0.iperm, D->w[3], D->io_b);
     for (int q = 0; q < nblocks; ++q)
@@ -1822,6 +1937,7 @@ int mamg_smooth(mamg_handle h, int32_t level, const double* b, double* x, int32_
   k_gather(*D, l.n, l.perm, xin, l.x_own);
   if (is_dist(*D, l)) barrier_only(*D);
   smooth(*D, level, l.b_own, l.x_own, post != 0);
+  if (halo_on(*D, l)) allgather_own(*D, l, l.x_own);
   double* xout = io.out_ptr(x, D->io_b);
   k_gather(*D, l.n, l.iperm, l.x_own, xout);
   io.out(x, l.n, D->io_b);

@@ -197,4 +197,46 @@ agg_sum_kernel(int c0, int c1, const int* __restrict__ cptr, const int* __restri
   xc[I] = 0.0;
 }
 
+// the same sums for a list of coarse rows (first replicated level below a row-distributed one: every
+// rank sums the aggregates it owns)
+__global__ void __launch_bounds__(kBlock)
+agg_sum_list_kernel(int cnt, const int* __restrict__ rows, const int* __restrict__ cptr, const int* __restrict__ cidx,
+                    const double* __restrict__ t, double* __restrict__ bc) {
+  const int q = blockIdx.x * kBlock + threadIdx.x;
+  if (q >= cnt) return;
+  const int I = rows[q];
+  double acc = 0.0;
+  for (int p = cptr[I]; p < cptr[I + 1]; ++p) acc += t[cidx[p]];
+  bc[I] = acc;
+}
+
+// ---- row-range variants for a row-distributed level (halo mode): partial sums over the rows [r0, r1)
+//      this rank owns; the all-reduce kernel combines them in rank order and post-processes the scalars
+__global__ void __launch_bounds__(kBlock)
+sell_spmv_dot_range_kernel(int r0, int r1, const SellView S, const double* __restrict__ d, double* __restrict__ q,
+                           double* partial, unsigned int* ticket, double* out) {
+  const int lane = threadIdx.x % 32;
+  const int s0 = r0 / 32, s1 = (r1 + 31) / 32;
+  double v[1] = {0.0};
+  for (int slice = s0 + blockIdx.x * kSellWarps + threadIdx.x / 32; slice < s1; slice += gridDim.x * kSellWarps) {
+    const double s = sell_row_dot(S, slice, lane, d);
+    const int row = slice * 32 + lane;
+    if (row >= r0 && row < r1) { q[row] = s; v[0] += s * d[row]; }
+  }
+  block_reduce_finish<1>(v, partial, ticket, out);
+}
+__global__ void __launch_bounds__(kBlock)
+sell_scale_dots_range_kernel(int r0, int r1, const SellView S, const double* __restrict__ e, const double* __restrict__ r,
+                             double* partial, unsigned int* ticket, double* out) {
+  const int lane = threadIdx.x % 32;
+  const int s0 = r0 / 32, s1 = (r1 + 31) / 32;
+  double v[2] = {0.0, 0.0};
+  for (int slice = s0 + blockIdx.x * kSellWarps + threadIdx.x / 32; slice < s1; slice += gridDim.x * kSellWarps) {
+    const double s = sell_row_dot(S, slice, lane, e);
+    const int row = slice * 32 + lane;
+    if (row >= r0 && row < r1) { const double ei = e[row]; v[0] += ei * r[row]; v[1] += ei * s; }
+  }
+  block_reduce_finish<2>(v, partial, ticket, out);
+}
+
 }  // namespace mamg

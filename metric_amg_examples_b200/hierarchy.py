@@ -69,6 +69,23 @@ def owned_blocks(nparts, rank, world):
     return range(rank * per, (rank + 1) * per)
 
 
+def halo_send_rows(level, nparts, rank, world):
+    """Host-side mirror of build_halo_lists() in device.cu for one exported level: {neighbour rank: rows
+    (natural numbering) of `rank`'s parts that a row of the neighbour couples to}.  The device code relies
+    on this relation being symmetric (a rank waits for exactly the ranks it sends to)."""
+    per = nparts // world
+    owner = np.asarray(level["part"]) // per
+    indptr, indices, data = level["indptr"], level["indices"], level["data"]
+    rows = np.repeat(np.arange(level["n"]), np.diff(indptr))
+    mine = owner[rows] == rank
+    other = owner[indices] != rank
+    out = {}
+    sel = mine & other
+    for q in np.unique(owner[indices[sel]]):
+        out[int(q)] = np.unique(rows[sel & (owner[indices] == q)])
+    return out
+
+
 class Hierarchy:
     """Owns one metric-AMG hierarchy (host) and, after to_device(), its copy on one B200."""
 
@@ -223,8 +240,13 @@ class Hierarchy:
         return v.value
 
     # ---- device ------------------------------------------------------------------------------
-    def to_device(self, device=0, stream=None):
-        check(lib.mamg_to_device(self._h, int(device), C.c_void_p(stream) if stream else None))
+    def to_device(self, device=0, stream=None, rank=None, world=None):
+        """Upload to one GPU.  With rank/world (one process per GPU) the rank keeps only the matrix rows of
+        its own parts on the row-distributed levels (mamg_to_device_dist); dist_init() follows."""
+        if world is not None and world > 1:
+            check(lib.mamg_to_device_dist(self._h, int(device), C.c_void_p(stream) if stream else None, int(rank), int(world)))
+        else:
+            check(lib.mamg_to_device(self._h, int(device), C.c_void_p(stream) if stream else None))
         self.on_device = True
         self.device = int(device)
         return self

@@ -38,7 +38,7 @@ def main():
         nparts = 4 if world in (1, 2, 4) else world
         part = problems.slab_partition(s, nparts, axis=0 if name.endswith("strips") else None)
         H = mamg.Hierarchy(s.A, prm, s.interface_dofs, part=part)
-        H.to_device(local)
+        H.to_device(local, rank=rank, world=world)   # halo mode unless MAMG_HALO=0
         H.dist_init()
         r = np.random.default_rng(0).standard_normal(s.ndofs)
         H.collective_count(reset=True)
@@ -58,7 +58,7 @@ def main():
             _, ref = orc.pcg(b, tolerance=tol, maxiter=500)
             good = err < 1e-10 and abs(info["niters"] - ref["niters"]) <= 1 and \
                 np.linalg.norm(x - xt) / np.linalg.norm(xt) < 1e-6 and (world == 1 or ncoll > 0)
-            print(f"[dist_check] {name}: world={world} nparts={nparts} apply rel err {err:.2e}, iters {info['niters']} "
+            print(f"[dist_check] {name}: halo={os.environ.get('MAMG_HALO', '1')} world={world} nparts={nparts} dev_GB={H.device_bytes() / 1e9:.3f} apply rel err {err:.2e}, iters {info['niters']} "
                   f"(oracle {ref['niters']}), collectives per apply {ncoll}, {'OK' if good else 'FAIL'}", flush=True)
             ok &= good
         ok &= same

@@ -71,6 +71,18 @@ def _worker(rank, world, port, out):
         assert np.array_equal(Hx.export()["levels"][1]["part"][X0["agg"][ok]], X0["part"][ok])
         hx = hashlib.sha256(np.ascontiguousarray(X0["color"]).tobytes() + np.ascontiguousarray(X0["patch_color"]).tobytes())
         assert len(set(allgather_bytes(hx.digest(), None))) == 1
+        # halo mode: a rank waits for exactly the ranks it sends to, so the neighbour relation of the halo
+        # lists must be symmetric on every level; what rank r sends to q is what q's rows read from r
+        from metric_amg_examples_b200.hierarchy import halo_send_rows
+        import pickle
+        for L in Hx.export()["levels"][:3]:
+            send = halo_send_rows(L, nparts, rank, world)
+            blob = pickle.dumps({q: len(v) for q, v in send.items()})
+            blob = blob + bytes(256 - len(blob))
+            tables = [pickle.loads(t) for t in allgather_bytes(blob, None)]
+            for q, cnt in tables[rank].items():
+                assert rank in tables[q] and cnt > 0, "halo neighbour relation is not symmetric"
+            assert set(send) <= {rank - 1, rank + 1}, "x-strips: only the adjacent ranks are neighbours"
         out[rank] = 1
     finally:
         dist.destroy_process_group()

@@ -124,14 +124,17 @@ def test_properties_at_bench_like_size():
     assert np.linalg.norm(system.A @ x - b) <= 1e-6 * np.linalg.norm(b)
 
 
-def test_multi_gpu_parity_under_torchrun():
-    """tests/dist_check.py (apply/PCG parity with the oracle, all ranks bit-identical) on 2 GPUs."""
+@pytest.mark.parametrize("halo", ["1", "0"])
+def test_multi_gpu_parity_under_torchrun(halo):
+    """tests/dist_check.py (apply/PCG parity with the oracle, all ranks bit-identical) on 2 GPUs, in halo
+    mode (partitioned matrices, neighbour-only halo exchange) and in the all-gather mode of round 1."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
            "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tests", "dist_check.py")]
-    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900,
+                       env=dict(os.environ, MAMG_HALO=halo))
     assert p.returncode == 0, p.stdout[-4000:]
     assert "FAIL" not in p.stdout
 
