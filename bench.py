@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="mamg", choices=["mamg", "reference"])
-    ap.add_argument("--workload", default="bidomain_3d", choices=["bidomain_2d", "bidomain_3d", "emi_2d", "emi_3d"])
+    ap.add_argument("--workload", default="emi_3d", choices=["bidomain_2d", "bidomain_3d", "emi_2d", "emi_3d"])
     ap.add_argument("-n", type=int, default=None, help="cells per direction (default: the BASELINE config size)")
     ap.add_argument("--gamma", type=float, default=1e4)
     ap.add_argument("--cycle", default="V", choices=["V", "W"])
@@ -108,10 +108,11 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def class_bytes(H, niters, cycle_applies):
+def class_bytes(H):
     """Algorithmic bytes per kernel class (fp64 values, int32 columns, every vector
-    counted once per kernel) for `cycle_applies` V-cycle applies plus `niters` CG iterations,
-    counted from the rows each launch really processes."""
+    counted once per kernel), counted from the rows each launch really processes.  Returns
+    f(niters, cycle_applies) -> {class: bytes} for that many V-cycle applies plus CG iterations (the
+    level data is read here, while the host copy of the hierarchy still exists)."""
     import numpy as np
     import ctypes as C
     from metric_amg_examples_b200._capi import lib, ptr
@@ -151,14 +152,17 @@ def class_bytes(H, niters, cycle_applies):
         out["prolong"] += 4 * n + 16 * int(inagg.sum()) + 8 * nc
     ncst = infos[-1]["rows"]
     out["coarse"] += 8 * ncst * ncst + 16 * ncst
-    for k in out:
-        out[k] *= cycle_applies
     n0, nnz0 = infos[0]["rows"], infos[0]["nnz"]
-    out["spmv"] += niters * (12 * nnz0 + 4 * (n0 + 1) + 24 * n0)
-    out["dot"] += (niters + 1) * 16 * n0
-    # pcg update (48 n) + direction (24 n) per iteration, zero-fill of z per apply, gathers/copies at both ends
-    out["vector"] += niters * 72 * n0 + cycle_applies * 8 * n0 + 5 * 20 * n0
-    return out
+    per_apply = out
+
+    def finish(niters, cycle_applies):
+        res = {k: v * cycle_applies for k, v in per_apply.items()}
+        res["spmv"] += niters * (12 * nnz0 + 4 * (n0 + 1) + 24 * n0)
+        res["dot"] += (niters + 1) * 16 * n0
+        # pcg update (48 n) + direction (24 n) per iteration, zero-fill of z per apply, gathers/copies at both ends
+        res["vector"] += niters * 72 * n0 + cycle_applies * 8 * n0 + 5 * 20 * n0
+        return res
+    return finish
 
 
 def host_copies(world):
@@ -192,48 +196,55 @@ def run_mamg(a):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n = a.n or DEFAULT_N[a.workload]
     note = ""
-    if True:
-        # refuse rather than drive the host out of memory or silently run another workload: setup + upload
-        # temporaries per DOF, one copy per rank that builds the hierarchy
-        import psutil
-        dim = int(a.workload[-2])
-        ndof_est = 2 * (n + 1) ** dim if a.workload.startswith("bidomain") else (n + 1) ** (dim - 1) * (n + 2)
-        need = (3600.0 if a.workload.startswith("bidomain") else 1400.0) * ndof_est * host_copies(world)
-        avail = psutil.virtual_memory().available
-        if need > 0.9 * avail:
-            raise SystemExit(f"bench.py: {a.workload} n={n} on {world} rank(s) needs ~{need / 1e9:.0f} GB of host memory "
-                             f"for the setup, {avail / 1e9:.0f} GB available; the mesh is never reduced silently")
-    t0 = time.time()
-    system, prm = make_system(a.workload, n, a.gamma)
-    t_asm = time.time() - t0
-    prm["cycle_type"] = hz.V_CYCLE if a.cycle == "V" else hz.W_CYCLE
-    ndofs, nnz0 = system.ndofs, int(system.A.nnz)
-    b_host, x_true = system.random_rhs(0)       # the same system and right-hand side on every rank
-    part = problems_slab(system, world) if world > 1 else None
-    t0 = time.time()
-    B = metricAMG(system.A, system.W, idofs=system.interface_dofs, parameters=prm, device=local, part=part)
-    H = B.hierarchy
-    t_setup = time.time() - t0
-    stream = torch.cuda.Stream()
-    t0 = time.time()
+    # Host memory: every rank assembles the system and builds the hierarchy on the host (setup + upload
+    # temporaries per DOF below), uploads its share and frees the host copy.  The ranks do this in waves of
+    # as many ranks as the node's free memory takes; the mesh is never reduced silently.
+    import psutil
+    dim = int(a.workload[-2])
+    ndof_est = 2 * (n + 1) ** dim if a.workload.startswith("bidomain") else (n + 1) ** (dim - 1) * (n + 2)
+    need = (3600.0 if a.workload.startswith("bidomain") else 1400.0) * ndof_est
+    avail = float(psutil.virtual_memory().available)
     if world > 1:
-        B.A = None
-        system.A = None                          # the library has its own copy; free the scipy one
-        # the upload builds large host temporaries (permuted CSR, patch lists: ~1.2 KB per DOF): as many
-        # ranks at a time as the node's free memory allows
-        import psutil
-        need = 1200.0 * ndofs if a.workload.startswith("bidomain") else 500.0 * ndofs
-        free_t = torch.tensor([psutil.virtual_memory().available], dtype=torch.float64, device="cuda")
+        free_t = torch.tensor([avail], dtype=torch.float64, device="cuda")
         dist.all_reduce(free_t, op=dist.ReduceOp.MIN)
-        conc = int(max(1, min(world, free_t.item() * 0.7 // need)))
-        for r0 in range(0, world, conc):
-            if r0 <= rank < r0 + conc:
+        avail = float(free_t.item())
+    if need > 0.9 * avail:
+        raise SystemExit(f"bench.py: {a.workload} n={n} needs ~{need / 1e9:.0f} GB of host memory per rank for the setup, "
+                         f"{avail / 1e9:.0f} GB available; the mesh is never reduced silently")
+    conc = int(max(1, min(world, 0.9 * avail // need)))
+    stream = torch.cuda.Stream()
+    t_asm = t_setup = t_upload = 0.0
+    for w0 in range(0, world, conc):
+        if w0 <= rank < w0 + conc:
+            t0 = time.time()
+            system, prm = make_system(a.workload, n, a.gamma)
+            t_asm = time.time() - t0
+            prm["cycle_type"] = hz.V_CYCLE if a.cycle == "V" else hz.W_CYCLE
+            ndofs, nnz0 = system.ndofs, int(system.A.nnz)
+            b_host, x_true = system.random_rhs(0)       # the same system and right-hand side on every rank
+            part = problems_slab(system, world) if world > 1 else None
+            t0 = time.time()
+            B = metricAMG(system.A, system.W, idofs=system.interface_dofs, parameters=prm, device=local, part=part)
+            H = B.hierarchy
+            t_setup = time.time() - t0
+            t0 = time.time()
+            if world > 1:
+                B.A = None
+                system.A = None                      # the library has its own copy; free the scipy one
                 H.to_device(local, stream.cuda_stream, rank=rank, world=world)
+            else:
+                H.to_device(local, stream.cuda_stream)
+            t_upload = time.time() - t0
+            cb_of = class_bytes(H) if rank == 0 else None
+            nnz_levels = [[H.level_info(l)["nnz"], H.level_info(l)["nnz_structural"]] for l in range(min(H.num_levels, 4))]
+            if world > 1:
+                H.release_host()                     # the next wave needs the memory
+        if world > 1:
             dist.barrier()
+    if world > 1:
         H.dist_init()
-    else:
-        H.to_device(local, stream.cuda_stream)
-    t_upload = time.time() - t0
+    import resource
+    host_peak_gb = resource.getrusage(resource.RUSAGE_SELF).ru_maxrss / 1e6
     b_pin = torch.from_numpy(b_host).pin_memory()
     b_dev = b_pin.cuda(non_blocking=False)
 
@@ -322,8 +333,10 @@ def run_mamg(a):
         prof_lv = H.profile_levels()
         prof = H.profile_stop()
         ncoll = H.collective_count(reset=True)
+        H.exchange_bytes(reset=True)
         _, _ = solve_dev()
         ncoll = H.collective_count()
+        xbytes = H.exchange_bytes()
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -335,9 +348,12 @@ def run_mamg(a):
             dist.destroy_process_group()
         return
     nit = pinfo["niters"]
-    exch_mode = ("NCCL grouped broadcasts" if os.environ.get("MAMG_P2P", "1") == "0"
-                 else "peer-memory stores over NVLink fused with the flag barrier (CUDA IPC)")
-    cb = class_bytes(H, nit, nit + 1)
+    halo_mode = world > 1 and os.environ.get("MAMG_HALO", "1") != "0" and os.environ.get("MAMG_P2P", "1") != "0"
+    exch_mode = ("NCCL grouped broadcasts" if os.environ.get("MAMG_P2P", "1") == "0" else
+                 "halo index lists stored into the neighbour ranks' vectors over NVLink (CUDA IPC), neighbour-only flags, "
+                 "rank-ordered all-reduce of the dots" if halo_mode else
+                 "peer-memory stores over NVLink fused with the flag barrier (CUDA IPC), all-gather of the updated ranges")
+    cb = cb_of(nit, nit + 1)
     tot_ms = sum(v[0] for v in prof.values())
     dom = max(prof, key=lambda k: prof[k][0])
     peaks = {}
@@ -376,8 +392,9 @@ def run_mamg(a):
                    "precond": "metricAMG parameters_metric_schwarz" if a.workload.startswith("bidomain") else "metricAMG default_metric_parameters",
                    "cycle_type": a.cycle, "krylov": f"ConjGrad relativeconv tolerance={a.rtol:g}",
                    "levels": H.num_levels,
-                   "multi_gpu": (f"one system row-partitioned over {world} GPUs ({world} {'x-strips' if a.workload.startswith('emi') else 'z-slabs'}); updated row ranges "
-                                 f"exchanged by {exch_mode}, {ncoll} exchanges per solve; levels < "
+                   "multi_gpu": (f"one system row-partitioned over {world} GPUs ({world} {'x-strips' if a.workload.startswith('emi') else 'z-slabs'}), "
+                                 f"{'matrices stored per rank, ' if halo_mode else 'hierarchy replicated, '}"
+                                 f"exchange: {exch_mode}; {ncoll} exchanges and {xbytes / 1e6:.1f} MB sent per rank and solve; levels < "
                                  f"{os.environ.get('MAMG_DIST_MIN_ROWS', '1000000')} rows replicated")
                    if world > 1 else "single",
                    "l2_note": (f"level-0 matrix {12 * nnz0 / 1e9:.2f} GB and vectors {8 * ndofs / 1e6:.0f} MB each: "
@@ -389,7 +406,7 @@ def run_mamg(a):
         "spmv_hbm_frac": {"alg_GBs": kernels["spmv"]["alg_GBs"],
                           "of_nominal_8000": round((kernels["spmv"]["alg_GBs"] or 0) / 8000.0, 3),
                           "of_measured": round((kernels["spmv"]["alg_GBs"] or 0) / peak, 3)},
-        "nnz_stored_vs_structural": [[H.level_info(l)["nnz"], H.level_info(l)["nnz_structural"]] for l in range(min(H.num_levels, 4))],
+        "nnz_stored_vs_structural": nnz_levels,
         "e2e": {"value": ndofs * a.steps / e2e_s, "unit": "DOF/s", "h2d_bytes_per_step": 8 * ndofs,
                 "d2h_bytes_per_step": 8 * ndofs},
         "gpu_launches": int(launches),
@@ -407,7 +424,8 @@ def run_mamg(a):
         "gs_ms_by_level": [round(float(v), 2) for v in prof_lv[:, 1]],
         "level_rows": [H.level_info(l)["rows"] for l in range(H.num_levels)],
         "host": {"assemble_s": round(t_asm, 2), "setup_s": round(t_setup, 2), "upload_s": round(t_upload, 2),
-                 "device_GB": round(H.device_bytes() / 1e9, 2)},
+                 "device_GB": round(H.device_bytes() / 1e9, 2), "host_peak_GB": round(host_peak_gb, 1),
+                 "setup_waves": (world + conc - 1) // conc},
     }
     if not a.no_cpu_baseline and world == 1:
         out["cpu_baseline"] = cpu_sample(a, threads=1, ordering="natural", gpu_check=True)

@@ -171,6 +171,8 @@ int mamg_set_stream(mamg_handle h, void* stream);
 int mamg_nccl_unique_id(void* out128);
 int mamg_dist_init(mamg_handle h, int32_t rank, int32_t world, const void* unique_id128);
 int mamg_collective_count(mamg_handle h, int64_t* count, int32_t reset);
+/* bytes this rank has stored into peers' memory by halo pushes / all-reduces since the last reset (halo mode) */
+int mamg_exchange_bytes(mamg_handle h, int64_t* bytes, int32_t reset);
 /* Peer-memory exchange (same node, NVLink): every rank publishes the CUDA IPC handle of its vector
  * arena (mamg_ipc_handle, 64 bytes), the host side all-gathers them, mamg_dist_peers maps the peers'
  * arenas.  From then on the owner of a row range stores it directly into the peers' vectors and

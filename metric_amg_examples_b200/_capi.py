@@ -74,6 +74,7 @@ def _load():
         "mamg_nccl_unique_id": (i32, [vp]),
         "mamg_dist_init": (i32, [vp, i32, i32, vp]),
         "mamg_collective_count": (i32, [vp, pi64, i32]),
+        "mamg_exchange_bytes": (i32, [vp, pi64, i32]),
         "mamg_ipc_handle": (i32, [vp, vp]),
         "mamg_dist_peers": (i32, [vp, vp]),
         "mamg_device_bytes": (i32, [vp, pi64]),

@@ -241,12 +241,13 @@ static bool rows_sell() {
 }
 
 // sliced-ELL copy of a level, filled on the device from the permuted CSR that was just uploaded
-static void build_sell(DeviceState& D, DLevel& dl, const std::vector<int>& ia) {
+// (rows outside [row_lo, row_hi) -- the blocks of other ranks in halo mode -- get empty slices)
+static void build_sell(DeviceState& D, DLevel& dl, const std::vector<int>& ia, int row_lo, int row_hi) {
   const int n = dl.n, ns = (n + 31) / 32;
   std::vector<int> sp(ns + 1, 0);
   for (int s = 0; s < ns; ++s) {
     int w = 0;
-    for (int i = s * 32; i < std::min(n, s * 32 + 32); ++i) w = std::max(w, ia[i + 1] - ia[i]);
+    for (int i = std::max(s * 32, row_lo); i < std::min(std::min(n, s * 32 + 32), row_hi); ++i) w = std::max(w, ia[i + 1] - ia[i]);
     sp[s + 1] = w;
   }
   int64_t tot = 0;
@@ -260,7 +261,7 @@ static void build_sell(DeviceState& D, DLevel& dl, const std::vector<int>& ia) {
   double* val = dalloc<double>(D, (size_t)tot * 32 + 2);
   int* col = dalloc<int>(D, (size_t)tot * 32 + 4);
   if (ns > 0) {
-    sell_fill_kernel<<<(ns + kSellWarps - 1) / kSellWarps, kBlock>>>(n, dl.ia, dl.ja, dl.a, d_sp, val, col);
+    sell_fill_kernel<<<(ns + kSellWarps - 1) / kSellWarps, kBlock>>>(n, row_lo, row_hi, dl.ia, dl.ja, dl.a, d_sp, val, col);
     CUDA_OK(cudaGetLastError());
   }
   dl.S.sp = d_sp;
@@ -474,7 +475,15 @@ static void upload_hierarchy(const Hierarchy& H, DeviceState& D) {
       D.dev_bytes += (int64_t)bytes;
       return p;
     });
-    if (rows_sell()) build_sell(D, dl, ia);
+    if (rows_sell()) {
+      int slo = 0, shi = n;
+      if (D.halo && D.world > 1 && dl.nb > 1) {   // the row kernels only ever stream this rank's blocks
+        const int per = dl.nb / D.world;
+        slo = dl.bc_ptr[D.rank * per * dl.ncolors];
+        shi = dl.bc_ptr[(D.rank + 1) * per * dl.ncolors];
+      }
+      build_sell(D, dl, ia, slo, shi);
+    }
   }
   {
     size_t mx = 0;
@@ -1761,6 +1770,14 @@ int mamg_collective_count(mamg_handle h, int64_t* count, int32_t reset) {
   if (!D || !count) return -1;
   *count = D->collectives;
   if (reset) D->collectives = 0;
+  return 0;
+}
+
+int mamg_exchange_bytes(mamg_handle h, int64_t* bytes, int32_t reset) {
+  DeviceState* D = get_dev(h);
+  if (!D || !bytes) return -1;
+  *bytes = D->exch_bytes;
+  if (reset) D->exch_bytes = 0;
   return 0;
 }
 

@@ -82,12 +82,13 @@ __device__ __forceinline__ double sell_row_dot(const SellView& S, int slice, int
 
 // ---- build: fill slice arrays from the (permuted) CSR of the level; one warp per slice ---------
 __global__ void __launch_bounds__(kBlock)
-sell_fill_kernel(int n, const int* __restrict__ ia, const int* __restrict__ ja, const double* __restrict__ a,
-                 const int* __restrict__ sp, double* __restrict__ val, int* __restrict__ col) {
+sell_fill_kernel(int n, int row_lo, int row_hi, const int* __restrict__ ia, const int* __restrict__ ja,
+                 const double* __restrict__ a, const int* __restrict__ sp, double* __restrict__ val, int* __restrict__ col) {
   const int slice = blockIdx.x * kSellWarps + threadIdx.x / 32, lane = threadIdx.x % 32;
   if (slice * 32 >= n) return;
   const int row = slice * 32 + lane;
-  const int p0 = row < n ? ia[row] : 0, len = row < n ? ia[row + 1] - p0 : 0;
+  const bool mine = row < n && row >= row_lo && row < row_hi;
+  const int p0 = mine ? ia[row] : 0, len = mine ? ia[row + 1] - p0 : 0;
   const int s0 = sp[slice], W = sp[slice + 1] - s0;
   const size_t base = (size_t)s0 * 32;
   const int pad_col = row < n ? row : 0;

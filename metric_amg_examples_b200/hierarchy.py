@@ -284,6 +284,11 @@ class Hierarchy:
         check(lib.mamg_collective_count(self._h, C.byref(v), int(reset)))
         return v.value
 
+    def exchange_bytes(self, reset=False):
+        v = C.c_int64()
+        check(lib.mamg_exchange_bytes(self._h, C.byref(v), int(reset)))
+        return v.value
+
     def set_stream(self, stream):
         check(lib.mamg_set_stream(self._h, C.c_void_p(stream) if stream else None))
 
