@@ -255,6 +255,11 @@ int mamg_schwarz_sweep_bytes(mamg_handle h, int32_t level, int64_t* bytes);
  * inside a timed region. */
 int mamg_profile(mamg_handle h, int32_t on, double* ms_per_class, int64_t* launches_per_class);
 int mamg_cycle_bytes(mamg_handle h, int64_t* bytes);
+/* Static race check of the device layout (the colour correctness of SURVEY 5 is a data-race property):
+ * counts, over every launch the smoothers would issue, the rows of one Gauss-Seidel colour launch that
+ * couple to each other and the patches of one conflict colour that write or read a dof another patch of
+ * that launch writes.  Both counts must be 0.  Runs on the arrays the kernels stream. */
+int mamg_race_check(mamg_handle h, int64_t* gs_conflicts, int64_t* patch_conflicts, int64_t* launches_checked);
 /* device-side statistics of one level (SURVEY 8b `mamg_stats`): out[0]=rows out[1]=stored nnz
  * out[2]=structural nnz (before zero dropping) out[3]=sliced-ELL entry slots (padding included)
  * out[4]=device bytes of the whole handle out[5]=Schwarz patches out[6]=unique stored patch blobs
@@ -262,9 +267,7 @@ int mamg_cycle_bytes(mamg_handle h, int64_t* bytes);
  * every patch owning its data (SURVEY 8d stored-factor model) out[9]=GS colours out[10]=patch colours
  * out[11]=1 if the level runs inside the persistent tail kernel out[12]=1 sliced-ELL row kernels
  * out[13]=1 CSR entries kept on the device out[14]=row blocks (parts) out[15]=1 Schwarz fast path
- * out[16]=1 grouped Schwarz kernel in use out[17]=groups of look-alike patches out[18]=its shared
- * memory per CTA out[19]/out[20]=largest neighbourhood / padded patch size of a group
- * out[21]=patches solved by the grouped kernel out[22]=largest patch out[23] reserved */
+ * out[16]=largest patch out[17]=largest outside neighbourhood of a patch out[18..23] reserved */
 int mamg_stats(mamg_handle h, int32_t level, int64_t out[24]);
 
 /* ---- synthetic systems of BASELINE.json's configs: P1 on UnitSquare/UnitCube

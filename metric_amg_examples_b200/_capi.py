@@ -94,6 +94,7 @@ def _load():
         "mamg_profile_levels": (i32, [vp, vp, i32]),
         "mamg_schwarz_sweep_bytes": (i32, [vp, i32, pi64]),
         "mamg_cycle_bytes": (i32, [vp, pi64]),
+        "mamg_race_check": (i32, [vp, pi64, pi64, pi64]),
         "mamg_stats": (i32, [vp, i32, pi64]),
         "mamg_assemble_scalar": (i32, [i32, vp, vp, dbl, dbl, pi64, pi64, vp, vp, vp]),
         "mamg_assemble_bidomain": (i32, [i32, i32, dbl, dbl, dbl, pi64, pi64, vp, vp, vp]),

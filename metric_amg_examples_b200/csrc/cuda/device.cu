@@ -1054,7 +1054,7 @@ static void smooth(DeviceState& D, int lev, const double* b, double* x, bool pos
           const int p0 = l.sw.cb_ptr[c * snb + blk], p1 = l.sw.cb_ptr[c * snb + blk + 1];
           if (p1 == p0) continue;
           KScope ks(D, K_SCHWARZ);
-          schwarz_range_launch(l.sw, p0, p1, l.a, b, x, D.stream, c * snb + blk);
+          schwarz_range_launch(l.sw, p0, p1, l.a, b, x, D.stream);
         }
         if (D.world > 1 && snb > 1) {
           // the other ranks receive the just-updated dofs that they read in later colours (or that
@@ -1618,6 +1618,50 @@ static int gmres_device(DeviceState& D, const double* b_nat, double* x_nat, doub
   return 0;
 }
 
+// ---- static race check of the device layout ------------------------------------------------------------
+// compute-sanitizer is not available on the GPU pool this was developed on, and the correctness of the
+// coloured smoothers IS a data-race property: two rows (patches) that run in one launch must not couple.
+// These kernels verify exactly that on the arrays the kernels stream -- the permuted sliced-ELL / CSR rows
+// of every colour block and the patch lists -- and count the violations.
+__global__ void __launch_bounds__(kBlock)
+check_gs_color_kernel(int r0, int r1, const SellView S, const uint8_t* __restrict__ skip, unsigned long long* bad) {
+  const int lane = threadIdx.x % 32;
+  const int slice = r0 / 32 + blockIdx.x * kSellWarps + threadIdx.x / 32;
+  if (slice * 32 >= r1) return;
+  const int row = slice * 32 + lane;
+  if (row < r0 || row >= r1 || (skip != nullptr && skip[row])) return;
+  const int s0 = S.sp[slice], W = S.sp[slice + 1] - s0;
+  const size_t base = (size_t)s0 * 32;
+  for (int e = 0; e < W; ++e) {
+    const size_t pv = (e >> 1) < (W >> 1) ? base + (size_t)(e >> 1) * 64 + lane * 2 + (e & 1) : base + (size_t)(W >> 1) * 64 + lane;
+    const size_t pc = (e >> 2) < (W >> 2) ? base + (size_t)(e >> 2) * 128 + lane * 4 + (e & 3)
+                                          : base + (size_t)(W >> 2) * 128 + (size_t)(e - (W & ~3)) * 32 + lane;
+    const int j = S.col[pc];
+    // a row of the SAME launch (same colour range, smoothed) that this row reads with a nonzero weight
+    if (j != row && j >= r0 && j < r1 && S.val[pv] != 0.0 && !(skip != nullptr && skip[j])) atomicAdd(bad, 1ull);
+  }
+}
+// stamp[dof] = patch that writes it in this launch; then every patch checks its reads and writes
+__global__ void __launch_bounds__(kBlock)
+check_patch_stamp_kernel(int p0, int p1, const SwPatch* __restrict__ pat, const int* __restrict__ pidx, int* stamp,
+                         unsigned long long* bad) {
+  const int p = p0 + blockIdx.x * kBlock + threadIdx.x;
+  if (p >= p1) return;
+  for (int q = 0; q < pat[p].s; ++q)
+    if (atomicExch(stamp + pidx[pat[p].q0 + q], p) != -1) atomicAdd(bad, 1ull);   // two patches write one dof
+}
+__global__ void __launch_bounds__(kBlock)
+check_patch_reads_kernel(int p0, int p1, const SwPatch* __restrict__ pat, const int* __restrict__ pidx, const int* __restrict__ nbr,
+                         int* stamp, unsigned long long* bad, int clear) {
+  const int p = p0 + blockIdx.x * kBlock + threadIdx.x;
+  if (p >= p1) return;
+  if (clear) { for (int q = 0; q < pat[p].s; ++q) stamp[pidx[pat[p].q0 + q]] = -1; return; }
+  for (int j = 0; j < pat[p].nn; ++j) {
+    const int w = stamp[nbr[pat[p].n0 + j]];
+    if (w != -1 && w != p) atomicAdd(bad, 1ull);   // reads a dof another patch of the launch writes
+  }
+}
+
 }  // namespace mamg
 
 using namespace mamg;
@@ -2061,6 +2105,58 @@ int mamg_schwarz_sweep_bytes(mamg_handle h, int32_t level, int64_t* bytes) {
   return 0;
 }
 
+int mamg_race_check(mamg_handle h, int64_t* gs_conflicts, int64_t* patch_conflicts, int64_t* launches_checked) {
+  MAMG_TRY
+  DeviceState* D = get_dev(h);
+  if (!D || !gs_conflicts || !patch_conflicts) return -1;
+  CUDA_OK(cudaStreamSynchronize(D->stream));
+  unsigned long long* bad = nullptr;
+  CUDA_OK(cudaMalloc(&bad, 2 * sizeof(unsigned long long)));
+  CUDA_OK(cudaMemset(bad, 0, 2 * sizeof(unsigned long long)));
+  int64_t checked = 0;
+  for (DLevel& l : D->lv) {
+    if (l.use_sell && l.ncolors > 0 && &l != &D->lv.back()) {
+      for (int blk = 0; blk < l.nb; ++blk) {
+        if (l.rows_owned_only && (blk < blk_lo(*D, l) || blk >= blk_hi(*D, l))) continue;
+        for (int c = 0; c < l.ncolors; ++c) {
+          const int r0 = l.row0(blk, c), r1 = l.row1(blk, c);
+          if (r1 <= r0) continue;
+          if (!l.color_active.empty() && l.color_active[blk * l.ncolors + c] == 0) continue;
+          check_gs_color_kernel<<<sell_grid(r0, r1), kBlock, 0, D->stream>>>(r0, r1, l.S, l.skip, bad);
+          ++checked;
+        }
+      }
+    }
+    if (l.sw.npatch > 0) {
+      int* stamp = nullptr;
+      CUDA_OK(cudaMalloc(&stamp, sizeof(int) * (size_t)l.n));
+      CUDA_OK(cudaMemsetAsync(stamp, 0xff, sizeof(int) * (size_t)l.n, D->stream));
+      for (int kb = 0; kb + 1 < (int)l.sw.cb_ptr.size(); ++kb) {
+        // all blocks of one colour run concurrently on different ranks: check a colour as a whole
+        if (kb % l.sw.nb != 0) continue;
+        const int p0 = l.sw.cb_ptr[kb], p1 = l.sw.cb_ptr[kb + l.sw.nb];
+        if (p1 <= p0) continue;
+        const int g = cdiv(p1 - p0, kBlock);
+        check_patch_stamp_kernel<<<g, kBlock, 0, D->stream>>>(p0, p1, l.sw.pat, l.sw.pidx, stamp, bad + 1);
+        check_patch_reads_kernel<<<g, kBlock, 0, D->stream>>>(p0, p1, l.sw.pat, l.sw.pidx, l.sw.nbr, stamp, bad + 1, 0);
+        check_patch_reads_kernel<<<g, kBlock, 0, D->stream>>>(p0, p1, l.sw.pat, l.sw.pidx, l.sw.nbr, stamp, bad + 1, 1);
+        ++checked;
+      }
+      CUDA_OK(cudaStreamSynchronize(D->stream));
+      cudaFree(stamp);
+    }
+  }
+  unsigned long long hb[2] = {0, 0};
+  CUDA_OK(cudaMemcpyAsync(hb, bad, sizeof(hb), cudaMemcpyDeviceToHost, D->stream));
+  CUDA_OK(cudaStreamSynchronize(D->stream));
+  cudaFree(bad);
+  *gs_conflicts = (int64_t)hb[0];
+  *patch_conflicts = (int64_t)hb[1];
+  if (launches_checked) *launches_checked = checked;
+  return 0;
+  MAMG_CATCH
+}
+
 int mamg_stats(mamg_handle h, int32_t level, int64_t out[24]) {
   DeviceState* D = get_dev(h);
   if (!D || !out) return -1;
@@ -2083,13 +2179,8 @@ int mamg_stats(mamg_handle h, int32_t level, int64_t out[24]) {
   out[13] = l.has_csr ? 1 : 0;
   out[14] = l.nb;
   out[15] = l.sw.fast ? 1 : 0;
-  out[16] = l.sw.grouped ? 1 : 0;
-  out[17] = l.sw.ngroups;
-  out[18] = (int64_t)l.sw.smem_group;
-  out[19] = l.sw.g_nn_max;
-  out[20] = l.sw.g_s_max;
-  out[21] = l.sw.grouped_patches;
-  out[22] = l.sw.max_size;
+  out[16] = l.sw.max_size;
+  out[17] = l.sw.max_nbr;
   return 0;
 }
 

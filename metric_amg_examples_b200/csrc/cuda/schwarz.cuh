@@ -55,16 +55,6 @@ struct SwProfile {
   int cnt[32];
 };
 
-// Grouped path: up to 32 patches that share one stored blob are solved together, LANE = PATCH.
-struct SwGroup { int uid; int cnt; };      // patches gpatch[32 g .. 32 g + cnt)
-struct SwBlob {                            // what the patches of one signature have in common
-  int s, nn;                               // dofs, neighbours outside the patch
-  int rp0;                                 // first entry of its row pointer (s + 1 ints) in bl_rowptr
-  int e0;                                  // first off-patch entry in bl_col / bl_val
-  long long iv0;                           // its full inverse in inv_full: [c][kpad], kpad = s rounded up to 4
-  int kpad, pad_;
-};
-
 struct DSchwarz {
   int npatch = 0, ncolors = 0, max_size = 0, max_nbr = 0, srow = 1, warps = 1, ppc = 1;
   size_t smem_apply = 0, smem_setup = 0;
@@ -90,22 +80,6 @@ struct DSchwarz {
   int nuniq = 0;
   int* uid = nullptr;          // [np] unique blob of every patch (fast path)
   long long* inv_off = nullptr;  // [nuniq] offset of the packed inverse of a unique blob
-  // grouped path (schwarz_group_kernel): chosen when the patches of a colour mostly share their blobs
-  bool grouped = false;
-  int ngroups = 0, g_nn_max = 0, g_s_max = 0, g_ne_max = 0, g_xs_rows = 0;
-  size_t smem_group = 0;
-  SwGroup* groups = nullptr;
-  int* gpatch = nullptr;         // [ngroups][32] patch numbers
-  SwBlob* blobs = nullptr;
-  int* bl_rowptr = nullptr;
-  uint16_t* bl_col = nullptr;
-  double* bl_val = nullptr;
-  double* inv_full = nullptr;
-  std::vector<int> gb_ptr;       // host: groups of (colour c, block b) are gb_ptr[c*nb + b] .. [c*nb + b + 1]
-  // patches whose blob is too rare inside their (colour, block) to fill a group keep the per-patch kernels
-  std::vector<int> lo_ptr;       // host: their positions lo_ptr[c*nb + b] .. in `leftover`
-  int* leftover = nullptr;       // device: patch numbers
-  long long grouped_patches = 0;
   // patches sorted by (conflict colour, block of the seed): cb_ptr[c*nb + b] .. [c*nb + b + 1]
   int nb = 1;
   std::vector<int> cb_ptr;     // host: size ncolors*nb + 1
@@ -126,7 +100,7 @@ __global__ void __launch_bounds__(T)
 schwarz_invert_kernel(int nuniq, const int* __restrict__ rep, const long long* __restrict__ inv_off,
                       const SwPatch* __restrict__ pat, const int* __restrict__ pidx,
                       const int* __restrict__ ia, const int* __restrict__ ja,
-                      const double* __restrict__ a, double* __restrict__ pinv, int max_size) {
+                      const double* __restrict__ a, double* __restrict__ pinv, int max_size, int kpad_fixed) {
   extern __shared__ double smem[];
   if ((int)blockIdx.x >= nuniq) return;
   const int patch = rep[blockIdx.x];   // the representative patch of unique blob blockIdx.x
@@ -186,8 +160,15 @@ schwarz_invert_kernel(int nuniq, const int* __restrict__ rep, const long long* _
     for (int c = tid; c <= i; c += T) Lm[tri(i, c)] = col[c];
     __syncthreads();
   }
+  // stored FULL, column by column with the rows contiguous ([c][kpad], rows >= s zero): thread k of a patch
+  // reads entry (k, c) at c * kpad + k, so a warp-wide read is one contiguous run -- no triangular
+  // addressing, no bank conflicts, and (the blobs being shared) served from L1 / L2
+  const int kpad = kpad_fixed > 0 ? kpad_fixed : ((s + 3) & ~3);
   double* out = pinv + inv_off[blockIdx.x];
-  for (int k = tid; k < s * (s + 1) / 2; k += T) out[k] = Lm[k];
+  for (int t = tid; t < s * kpad; t += T) {
+    const int c = t / kpad, k = t % kpad;
+    out[t] = k < s ? Lm[k >= c ? tri(k, c) : tri(c, k)] : 0.0;
+  }
 }
 
 // ---- apply ---------------------------------------------------------------------------------------
@@ -197,13 +178,12 @@ schwarz_invert_kernel(int nuniq, const int* __restrict__ rep, const long long* _
 struct SwLayout {
   int max_size, max_nbr, srow;
   __host__ __device__ size_t ent() const { return (size_t)max_size * srow; }
-  __host__ __device__ size_t inv_d() const { return ((size_t)max_size * (max_size + 1) / 2 + 2) & ~(size_t)1; }
   __host__ __device__ size_t ls_d() const { return ((ent() + 8) * 2 + 15) / 16 * 2; }  // doubles holding the uint16 columns
   __host__ __device__ size_t as_d() const { return (ent() + 1) & ~(size_t)1; }
   __host__ __device__ size_t xs_d() const { return ((size_t)max_nbr + 2) & ~(size_t)1; }
   __host__ __device__ size_t rhs_d() const { return ((size_t)max_size + 1) & ~(size_t)1; }
   __host__ __device__ size_t int_d() const { return (3 * (size_t)max_size + 4) / 2 + 1; }
-  __host__ __device__ size_t total_d() const { return (inv_d() + ls_d() + as_d() + xs_d() + rhs_d() + int_d() + 1) & ~(size_t)1; }
+  __host__ __device__ size_t total_d() const { return (ls_d() + as_d() + xs_d() + rhs_d() + int_d() + 1) & ~(size_t)1; }
 };
 
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
@@ -229,31 +209,27 @@ schwarz_apply_kernel(int p0, int p1, const SwPatch* __restrict__ pat, const int*
                      const int* __restrict__ prow, const int* __restrict__ plen,
                      const int* __restrict__ nbr, const uint16_t* __restrict__ lcol,
                      const double* __restrict__ pinv, const double* __restrict__ a,
-                     const double* __restrict__ b, double* x, SwLayout lay, const int* __restrict__ plist) {
+                     const double* __restrict__ b, double* x, SwLayout lay) {
   constexpr int T = WPP * 32;  // threads per patch
   extern __shared__ __align__(16) double smem[];
   const int slot = threadIdx.x / T;
   const int tid = threadIdx.x % T;
-  const int pos = p0 + blockIdx.x * PPC + slot;   // position in the range, or in the list of leftover patches
-  const int patch = (plist != nullptr && pos < p1) ? plist[pos] : pos;
+  const int patch = p0 + blockIdx.x * PPC + slot;
   const int S = lay.srow;
-  double* Inv = smem + slot * lay.total_d();
-  uint16_t* Ls = reinterpret_cast<uint16_t*>(Inv + lay.inv_d());
-  double* As = Inv + lay.inv_d() + lay.ls_d();
+  double* base = smem + slot * lay.total_d();
+  uint16_t* Ls = reinterpret_cast<uint16_t*>(base);
+  double* As = base + lay.ls_d();
   double* xs = As + lay.as_d();
   double* rhs = xs + lay.xs_d();
   int* idx = reinterpret_cast<int*>(rhs + lay.rhs_d());   // s
   int* rst = idx + lay.max_size;                           // s
   int* rln = rst + lay.max_size;                           // s
-  const bool active = pos < p1;   // uniform per warp when PPC > 1 (WPP == 1)
+  const bool active = patch < p1;   // uniform per warp when PPC > 1 (WPP == 1)
   SwPatch P;
   P.s = 0;
   if (active) {
     P = pat[patch];
-    // wave 1: packed inverse and local columns (16-byte chunks; both segments are 16-byte aligned)
-    const double* src = pinv + P.i0;
-    const int nch = (P.s * (P.s + 1) / 2 + 1) / 2;
-    for (int k = tid; k < nch; k += T) cp_async16(Inv + 2 * k, src + 2 * k);
+    // wave 1: local columns (16-byte chunks; the segments are 16-byte aligned)
     const uint16_t* lsrc = lcol + P.e0;
     const int lch = (P.s * S + 7) / 8;
     for (int k = tid; k < lch; k += T) cp_async16(Ls + 8 * k, lsrc + 8 * k);
@@ -291,18 +267,20 @@ schwarz_apply_kernel(int p0, int p1, const SwPatch* __restrict__ pat, const int*
   }
   if (WPP == 1) __syncwarp(); else __syncthreads();
   if (active) {
-    // delta = A_BB^{-1} rhs with the packed symmetric inverse: entry (k,c) lives at tri(max,min);
-    // walk c with two running addresses (row part c <= k, column part c > k)
+    // x_B = A_BB^{-1} rhs with the blob's full inverse read straight from global memory ([c][kpad]: the
+    // threads of a warp read consecutive doubles; the blob is shared by the look-alike patches, so the
+    // reads hit L1 / L2), rhs[c] is a shared-memory broadcast
+    const int kpad = (P.s + 3) & ~3;
+    const double* iv = pinv + P.i0;
     for (int k = tid; k < P.s; k += T) {
-      double d = 0.0;
-      int a1 = k * (k + 1) / 2;   // (k, c) for c <= k
-      int a2 = a1 + k;            // (c, k) for c >= k, advanced by c + 1
-      for (int c = 0; c < P.s; ++c) {
-        const int ad = c <= k ? a1 + c : a2;
-        d += Inv[ad] * rhs[c];
-        if (c >= k) a2 += c + 1;
+      double d0 = 0.0, d1 = 0.0;
+      int c = 0;
+      for (; c + 1 < P.s; c += 2) {
+        d0 += __ldg(iv + (size_t)c * kpad + k) * rhs[c];
+        d1 += __ldg(iv + (size_t)(c + 1) * kpad + k) * rhs[c + 1];
       }
-      x[idx[k]] = d;   // x_B = A_BB^{-1} (b_B - A_{B,out} x_out)
+      if (c < P.s) d0 += __ldg(iv + (size_t)c * kpad + k) * rhs[c];
+      x[idx[k]] = d0 + d1;   // x_B = A_BB^{-1} (b_B - A_{B,out} x_out)
     }
   }
 }
@@ -415,13 +393,13 @@ schwarz_blob_kernel(int nuniq, const int* __restrict__ rep, const SwPatch* __res
 }
 
 #ifndef MAMG_SW_MINB24
-#define MAMG_SW_MINB24 3   // CTAs per SM for the <24,4> specialisation (78 registers, no spills)
+#define MAMG_SW_MINB24 4   // CTAs per SM for the <24,4> specialisation (64 registers, 4 bytes of spill; 16 KB of shared memory per CTA)
 #endif
 #ifndef MAMG_SW_MINB
 #define MAMG_SW_MINB 2   // CTAs per SM the fast kernel is compiled for (2: ~100 registers, 3: 80 with spills)
 #endif
 constexpr int kSwFastWarps = 8;     // patches per CTA
-constexpr int kSwFastSlot = 256 + 528 + 32;  // doubles per patch slot: xs[256], packed inverse (32*33/2), rhs[32]
+constexpr int kSwFastSlot = 256;  // doubles per patch slot: xs[256] (x on the outside neighbours + the zero slot)
 
 // apply: one warp per patch, lane k = patch row k.  Wave 1 loads everything addressed by the patch
 // number (row values, packed local columns, neighbour list, inverse via cp.async); wave 2 gathers
@@ -432,15 +410,12 @@ schwarz_fast_kernel(int p0, int p1, const int* __restrict__ pidx32, const int* _
                     const int* __restrict__ uid, const long long* __restrict__ inv_off,
                     const double* __restrict__ vt, const uint32_t* __restrict__ ct4,
                     const double* __restrict__ pinv, const double* __restrict__ b, double* x, int srow,
-                    int sq, int nbq, int smax, const SwProfile prof, int vstride, const int* __restrict__ plist) {
+                    int sq, int nbq, int smax, const SwProfile prof, int vstride) {
   extern __shared__ __align__(16) double smem[];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int pos = p0 + blockIdx.x * kSwFastWarps + warp;   // position in the range, or in the list of leftover patches
-  if (pos >= p1) return;
-  const int patch = plist != nullptr ? plist[pos] : pos;
+  const int patch = p0 + blockIdx.x * kSwFastWarps + warp;
+  if (patch >= p1) return;
   double* xs = smem + warp * kSwFastSlot;
-  double* Inv = xs + 256;
-  double* rhs = Inv + 528;
   const size_t pp = (size_t)patch;
   const size_t uu = (size_t)uid[patch];   // the stored blob this patch shares with its look-alikes
   // ---- wave 1 ----
@@ -449,11 +424,6 @@ schwarz_fast_kernel(int p0, int p1, const int* __restrict__ pidx32, const int* _
 #pragma unroll
   for (int j = 0; j < NBQ; ++j) nb[j] = j < nbq ? ld_stream(nbrp + (pp * nbq + j) * 32 + lane) : 0;
   const int s = __popc(__ballot_sync(0xffffffffu, my >= 0));     // dofs of this patch
-  {
-    const double* src = pinv + inv_off[uu];
-    const int nch = (s * (s + 1) / 2 + 1) / 2;                  // 16-byte chunks of its packed inverse
-    for (int k = lane; k < nch; k += 32) cp_async16(Inv + 2 * k, src + 2 * k);
-  }
   double v[SR];
   {
     const double* vp = vt + uu * vstride + lane;
@@ -476,170 +446,20 @@ schwarz_fast_kernel(int p0, int p1, const int* __restrict__ pidx32, const int* _
   double acc = 0.0;
 #pragma unroll
   for (int e = 0; e < SR; ++e) acc += v[e] * xs[(c4[e / 4] >> (8 * (e % 4))) & 255u];
-  rhs[lane] = my >= 0 ? bk - acc : 0.0;
-  cp_async_wait_all();
-  __syncwarp();
-  double d = 0.0;
-  const int base = lane * (lane + 1) / 2;
-#pragma unroll
-  for (int c = 0; c < 32; ++c) {
-    if (c < s && lane < s) {   // only the s x s part of the staged inverse is defined
-      const int ad = c <= lane ? base + c : c * (c + 1) / 2 + lane;
-      d += Inv[ad] * rhs[c];
-    }
+  // x_B = A_BB^{-1} rhs: the blob's full inverse is stored [c][32] (lane = row, rows >= s zero), so every
+  // step is one contiguous 256-byte read (L1 / L2 resident: the blob is shared by the look-alike patches)
+  // and the right-hand side travels by shuffle -- no staging, no triangular addresses, no shared memory
+  const double r = my >= 0 ? bk - acc : 0.0;
+  const double* ivp = pinv + inv_off[uu] + lane;
+  double d0 = 0.0, d1 = 0.0;
+  int c = 0;
+  for (; c + 1 < s; c += 2) {
+    const double i0 = __ldg(ivp + c * 32), i1 = __ldg(ivp + (c + 1) * 32);
+    d0 += i0 * __shfl_sync(0xffffffffu, r, c);
+    d1 += i1 * __shfl_sync(0xffffffffu, r, c + 1);
   }
-  if (my >= 0) x[my] = d;   // x_B = A_BB^{-1} (b_B - A_{B,out} x_out)
-}
-
-// ---- grouped path ----------------------------------------------------------------------------------
-// On a uniform mesh with constant coefficients almost all patches of a conflict colour are translates
-// of one another: same A_BB, same off-patch values, same local sparsity (one stored blob, see the
-// signatures below).  Solving 32 such patches together with LANE = PATCH turns every irregular access
-// of the per-patch kernels into a regular one: the blob's entries (value, local column) and the
-// inverse are warp-uniform (one broadcast load each, L1-resident), the gathered x values sit in shared
-// memory as xs[neighbour][patch] so that a warp reads 32 consecutive doubles (no bank conflicts, where
-// the per-patch kernels pay 3-6-way conflicts on every random xs[col] read), and the dense inverse is
-// applied as a register-tiled (4 rows x 32 patches) small GEMM instead of a packed symmetric mat-vec
-// with conflicting triangular addresses.  Global accesses keep their per-patch coalesced form: phase 1
-// (lane = neighbour / row) stages x on the neighbourhoods and b through a transposing shared-memory
-// store, phase 3 writes x_B back the same way.
-//   x_B = A_BB^{-1} (b_B - A_{B,out} x_out)   for the patches gpatch[32 g ...] of group g
-constexpr int kSwGroupLd = 33;   // leading dimension of the [entry][patch] shared arrays (odd: conflict-free transposes)
-constexpr int kSwGroupInvSmem = 2048;   // doubles: inverses up to this size are staged in shared memory
-__global__ void __launch_bounds__(256)
-schwarz_group_kernel(int g0, const SwGroup* __restrict__ groups, const int* __restrict__ gpatch,
-                     const SwPatch* __restrict__ pat, const int* __restrict__ pidx, const int* __restrict__ nbr,
-                     const SwBlob* __restrict__ blobs, const int* __restrict__ bl_rowptr,
-                     const uint16_t* __restrict__ bl_col, const double* __restrict__ bl_val,
-                     const double* __restrict__ inv_full, const double* __restrict__ b, double* x,
-                     int xs_rows, int s_max, int ne_max, int inv_smem) {
-  extern __shared__ __align__(16) double smem[];
-  constexpr int LD = kSwGroupLd;
-  double* sinv = smem;                        // [inv_smem]     the blob's inverse when it fits (16-byte aligned: 128-bit reads)
-  double* xs = sinv + inv_smem;               // [xs_rows][LD]  x on the outside neighbours; finally the new x_B
-  double* bs = xs + (size_t)xs_rows * LD;     // [s_max][LD]    b_B, then the residual b_B - A_{B,out} x_out
-  double* sval = bs + (size_t)s_max * LD;     // [ne_max]       the blob's off-patch values ...
-  int* srp = reinterpret_cast<int*>(sval + ne_max);              // [s_max + 1]  ... row pointer ...
-  uint16_t* scol = reinterpret_cast<uint16_t*>(srp + s_max + 2); // [ne_max]     ... and local columns
-  __shared__ int q0s[32], n0s[32];
-  const int grp = g0 + blockIdx.x;
-  const SwGroup G = groups[grp];
-  const SwBlob B = blobs[G.uid];
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  if (threadIdx.x < 32) {
-    const int p = (int)threadIdx.x < G.cnt ? gpatch[(size_t)grp * 32 + threadIdx.x] : -1;
-    q0s[threadIdx.x] = p >= 0 ? pat[p].q0 : 0;
-    n0s[threadIdx.x] = p >= 0 ? pat[p].n0 : 0;
-  }
-  // the blob (shared by all patches of the group, L2-resident) into shared memory: afterwards every
-  // warp-uniform read of the compute phases is a shared-memory broadcast instead of an L2 round trip
-  const int ne = bl_rowptr[B.rp0 + B.s];
-  for (int e = threadIdx.x; e < ne; e += 256) { sval[e] = __ldg(bl_val + B.e0 + e); scol[e] = __ldg(bl_col + B.e0 + e); }
-  for (int k = threadIdx.x; k <= B.s; k += 256) srp[k] = __ldg(bl_rowptr + B.rp0 + k);
-  const bool inv_staged = B.s * B.kpad <= inv_smem;
-  if (inv_staged)
-    for (int t = threadIdx.x; t < B.s * B.kpad; t += 256) sinv[t] = __ldg(inv_full + B.iv0 + t);
-  __syncthreads();
-  // phase 1: stage x on the neighbourhoods and b (per patch coalesced, transposed into [entry][patch]).
-  // A warp stages its up to 4 patches side by side, two 32-entry chunks each: 8 index loads, then 8
-  // gathers in flight per lane -- the two dependent global round trips are paid once per 64 entries.
-  {
-    int n0w[4], q0w[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int g = warp + 8 * u;
-      n0w[u] = g < G.cnt ? n0s[g] : -1;
-      q0w[u] = g < G.cnt ? q0s[g] : -1;
-    }
-    for (int j0 = 0; j0 < B.nn; j0 += 64) {
-      int id[4][2];
-      double xv[4][2];
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-#pragma unroll
-        for (int v = 0; v < 2; ++v) {
-          const int j = j0 + 32 * v + lane;
-          id[u][v] = (n0w[u] >= 0 && j < B.nn) ? nbr[n0w[u] + j] : -1;
-        }
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-#pragma unroll
-        for (int v = 0; v < 2; ++v) xv[u][v] = id[u][v] >= 0 ? x[id[u][v]] : 0.0;
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-#pragma unroll
-        for (int v = 0; v < 2; ++v) {
-          const int j = j0 + 32 * v + lane;
-          if (id[u][v] >= 0) xs[j * LD + warp + 8 * u] = xv[u][v];
-        }
-    }
-    for (int k0 = 0; k0 < B.s; k0 += 32) {
-      int id[4];
-      double bv[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) id[u] = (q0w[u] >= 0 && k0 + lane < B.s) ? pidx[q0w[u] + k0 + lane] : -1;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) bv[u] = id[u] >= 0 ? b[id[u]] : 0.0;
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (id[u] >= 0) bs[(k0 + lane) * LD + warp + 8 * u] = bv[u];
-    }
-  }
-  __syncthreads();
-  if (lane < G.cnt) {
-    // phase 2a: residual rows in place (blob entries are shared-memory broadcasts, lane = patch)
-    for (int k = warp; k < B.s; k += 8) {
-      double acc = bs[k * LD + lane];
-      const int e1 = srp[k + 1];
-#pragma unroll 4
-      for (int e = srp[k]; e < e1; ++e) acc -= sval[e] * xs[(int)scol[e] * LD + lane];
-      bs[k * LD + lane] = acc;
-    }
-  }
-  __syncthreads();   // every residual is complete and xs is free: the new x_B goes there
-  if (lane < G.cnt) {
-    // phase 2b: x_B = A_BB^{-1} r, 4 rows per thread (inverse stored [c][kpad]: two broadcast 128-bit loads per c)
-    const double* iv = inv_staged ? sinv : inv_full + B.iv0;
-    for (int k0 = warp * 4; k0 < B.s; k0 += 32) {
-      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-      const double* ivk = iv + k0;
-#pragma unroll 4
-      for (int c = 0; c < B.s; ++c) {
-        const double r = bs[c * LD + lane];
-        const double2 u = *reinterpret_cast<const double2*>(ivk + (size_t)c * B.kpad);
-        const double2 v = *(reinterpret_cast<const double2*>(ivk + (size_t)c * B.kpad) + 1);
-        a0 += u.x * r;
-        a1 += u.y * r;
-        a2 += v.x * r;
-        a3 += v.y * r;
-      }
-      xs[k0 * LD + lane] = a0;
-      if (k0 + 1 < B.s) xs[(k0 + 1) * LD + lane] = a1;
-      if (k0 + 2 < B.s) xs[(k0 + 2) * LD + lane] = a2;
-      if (k0 + 3 < B.s) xs[(k0 + 3) * LD + lane] = a3;
-    }
-  }
-  __syncthreads();
-  // phase 3: write x_B back (per patch coalesced)
-  for (int g = warp; g < G.cnt; g += 8) {
-    const int* pi = pidx + q0s[g];
-    for (int k = lane; k < B.s; k += 32) x[pi[k]] = xs[k * LD + g];
-  }
-}
-
-// full inverse [c][kpad] of every unique blob from its packed lower triangle
-__global__ void __launch_bounds__(256)
-schwarz_expand_inverse_kernel(int nuniq, const SwBlob* __restrict__ blobs, const long long* __restrict__ inv_off,
-                              const double* __restrict__ pinv, double* __restrict__ inv_full) {
-  const int u = blockIdx.x;
-  if (u >= nuniq) return;
-  const SwBlob B = blobs[u];
-  const double* src = pinv + inv_off[u];
-  double* dst = inv_full + B.iv0;
-  for (int t = threadIdx.x; t < B.s * B.kpad; t += blockDim.x) {
-    const int c = t / B.kpad, k = t % B.kpad;
-    dst[t] = k < B.s ? src[k >= c ? tri(k, c) : tri(c, k)] : 0.0;
-  }
+  if (c < s) d0 += __ldg(ivp + c * 32) * __shfl_sync(0xffffffffu, r, c);
+  if (my >= 0) x[my] = d0 + d1;   // x_B = A_BB^{-1} (b_B - A_{B,out} x_out)
 }
 
 // Host side: reorder the patches by colour, translate to the permuted numbering, build the
@@ -894,7 +714,7 @@ inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iper
   std::vector<long long> inv_off(nu + 1, 0), e_off(nu + 1, 0);
   for (int u = 0; u < nu; ++u) {
     const long long s = pat[rep[u]].s;
-    inv_off[u + 1] = inv_off[u] + (s * (s + 1) / 2 + 1) / 2 * 2;
+    inv_off[u + 1] = inv_off[u] + s * (fast_shape ? 32 : ((s + 3) & ~3LL));   // full inverse, [c][kpad]
     e_off[u + 1] = e_off[u] + (s * srow + 7) / 8 * 8;                 // 16-byte aligned uint16 segments
   }
   const long long tot_i = inv_off[nu], tot_e = fast_shape ? 0 : e_off[nu];
@@ -930,7 +750,8 @@ inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iper
   constexpr int TS = 128;
   if (d.smem_setup > 48 * 1024)
     cudaFuncSetAttribute(schwarz_invert_kernel<TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_setup);
-  schwarz_invert_kernel<TS><<<nu, TS, d.smem_setup>>>(nu, d_rep, d.inv_off, d.pat, d.pidx, d_ia, d_ja, d_a, d.pinv, d.max_size);
+  schwarz_invert_kernel<TS><<<nu, TS, d.smem_setup>>>(nu, d_rep, d.inv_off, d.pat, d.pidx, d_ia, d_ja, d_a, d.pinv, d.max_size,
+                                                      fast_shape ? 32 : 0);
   sync_or_throw("Schwarz setup kernel");
   if (fast_shape) {
     d.fast = true;
@@ -951,105 +772,6 @@ inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iper
     cudaFuncSetAttribute(schwarz_fast_kernel<12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm);
     cudaFuncSetAttribute(schwarz_fast_kernel<24, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm);
     cudaFuncSetAttribute(schwarz_fast_kernel<32, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm);
-  }
-  // ---- grouped path: patches of one (colour, block) that share a blob, 32 at a time --------------
-  {
-    const char* genv = getenv("MAMG_SW_GROUP");
-    const bool want = dedup && !(genv && atoi(genv) == 0);
-    std::vector<SwGroup> groups;
-    std::vector<int> gpatch, leftover;
-    d.gb_ptr.assign(sw.ncolors * nb + 1, 0);
-    d.lo_ptr.assign(sw.ncolors * nb + 1, 0);
-    const bool force = genv && atoi(genv) == 2;   // MAMG_SW_GROUP=2: group everything (tests)
-    const int min_fill = force ? 1 : 8;           // a group below a quarter of the lanes is not worth a CTA
-    long long grouped_patches = 0;
-    if (want) {
-      std::vector<std::pair<int, int>> bucket;
-      for (int kb = 0; kb < sw.ncolors * nb; ++kb) {
-        bucket.clear();
-        for (int k = d.cb_ptr[kb]; k < d.cb_ptr[kb + 1]; ++k) bucket.emplace_back(uid[k], k);
-        std::stable_sort(bucket.begin(), bucket.end(),
-                         [](const std::pair<int, int>& a, const std::pair<int, int>& b2) { return a.first < b2.first; });
-        for (size_t i = 0; i < bucket.size();) {
-          size_t j = i;
-          while (j < bucket.size() && bucket[j].first == bucket[i].first && j - i < 32) ++j;
-          if ((int)(j - i) >= min_fill) {
-            groups.push_back(SwGroup{bucket[i].first, (int)(j - i)});
-            for (size_t t = i; t < i + 32; ++t) gpatch.push_back(t < j ? bucket[t].second : -1);
-            grouped_patches += (long long)(j - i);
-          } else {
-            for (size_t t = i; t < j; ++t) leftover.push_back(bucket[t].second);
-          }
-          i = j;
-        }
-        std::sort(leftover.begin() + d.lo_ptr[kb], leftover.end());   // the rare ones in patch order (locality)
-        d.gb_ptr[kb + 1] = (int)groups.size();
-        d.lo_ptr[kb + 1] = (int)leftover.size();
-      }
-    }
-    // the grouped kernel pays when most patches find company
-    const bool use = want && !groups.empty() && (force || 2 * grouped_patches >= (long long)np);
-    if (use) {
-      std::vector<SwBlob> blobs(nu);
-      std::vector<int> rowptr;
-      std::vector<uint16_t> bcol;
-      std::vector<double> bval;
-      long long iv_tot = 0;
-      int nn_max = 1, s_max = 1, ne_max = 1;
-      std::vector<int> pos(n, -1);
-      for (int u = 0; u < nu; ++u) {
-        const int k = rep[u];
-        SwBlob& B = blobs[u];
-        B.s = pat[k].s;
-        B.nn = pat[k].nn;
-        B.rp0 = (int)rowptr.size();
-        B.e0 = (int)bcol.size();
-        B.kpad = (B.s + 3) & ~3;
-        B.pad_ = 0;
-        B.iv0 = iv_tot;
-        iv_tot += (long long)B.s * B.kpad;
-        nn_max = std::max(nn_max, B.nn);
-        s_max = std::max(s_max, B.kpad);
-        for (int j = 0; j < B.nn; ++j) pos[nbr[pat[k].n0 + j]] = j;
-        for (int q = 0; q < B.s; ++q) {
-          const int i = pidx[pat[k].q0 + q];
-          rowptr.push_back((int)bcol.size() - B.e0);
-          for (int e = pia[i]; e < pia[i + 1]; ++e)
-            if (pos[pja[e]] >= 0) { bcol.push_back((uint16_t)pos[pja[e]]); bval.push_back(pa[e]); }
-        }
-        rowptr.push_back((int)bcol.size() - B.e0);
-        ne_max = std::max(ne_max, (int)bcol.size() - B.e0);
-        for (int j = 0; j < B.nn; ++j) pos[nbr[pat[k].n0 + j]] = -1;
-      }
-      d.g_nn_max = nn_max;
-      d.g_s_max = s_max;
-      d.g_ne_max = (ne_max + 3) & ~3;
-      d.g_xs_rows = std::max(nn_max, s_max);
-      d.smem_group = ((size_t)d.g_xs_rows + (size_t)s_max) * kSwGroupLd * sizeof(double) +
-                     ((size_t)d.g_ne_max + kSwGroupInvSmem) * sizeof(double) + ((size_t)s_max + 2) * sizeof(int) +
-                     (size_t)d.g_ne_max * sizeof(uint16_t) + 16;
-      if (d.smem_group <= 200 * 1024) {
-        d.grouped = true;
-        d.grouped_patches = grouped_patches;
-        d.leftover = (int*)up(leftover.data(), leftover.size() * sizeof(int));
-        d.ngroups = (int)groups.size();
-        d.groups = (SwGroup*)up(groups.data(), groups.size() * sizeof(SwGroup));
-        d.gpatch = (int*)up(gpatch.data(), gpatch.size() * sizeof(int));
-        d.blobs = (SwBlob*)up(blobs.data(), blobs.size() * sizeof(SwBlob));
-        d.bl_rowptr = (int*)up(rowptr.data(), rowptr.size() * sizeof(int));
-        d.bl_col = (uint16_t*)up(bcol.data(), bcol.size() * sizeof(uint16_t));
-        d.bl_val = (double*)up(bval.data(), bval.size() * sizeof(double));
-        d.inv_full = (double*)alloc(((size_t)iv_tot + 2) * sizeof(double));
-        if (fast_shape && !d.pat) d.pat = (SwPatch*)up(pat.data(), pat.size() * sizeof(SwPatch));
-        schwarz_expand_inverse_kernel<<<nu, 256>>>(nu, d.blobs, d.inv_off, d.pinv, d.inv_full);
-        sync_or_throw("Schwarz inverse expansion");
-        // always opt in (the kernel also has static shared memory; the opt-in value is per function, so keep
-        // the largest request of all hierarchies of this process)
-        static size_t opted = 0;
-        opted = std::max(opted, d.smem_group);
-        cudaFuncSetAttribute(schwarz_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)opted);
-      }
-    }
   }
   if (d.smem_apply > 48 * 1024) {
     cudaFuncSetAttribute(schwarz_apply_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_apply);
@@ -1072,23 +794,11 @@ inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iper
 
 // patches [p0, p1) of one conflict colour (they commute, so they run concurrently)
 inline void schwarz_range_launch(const DSchwarz& d, int p0, int p1, const double* a, const double* b, double* x,
-                                 cudaStream_t stream, int kb = -1) {
-  const int* plist = nullptr;
-  if (d.grouped && kb >= 0) {   // (colour, block) kb: its groups of look-alike patches, then the rare ones one by one
-    const int g0 = d.gb_ptr[kb], g1 = d.gb_ptr[kb + 1];
-    if (g1 > g0)
-      schwarz_group_kernel<<<g1 - g0, 256, d.smem_group, stream>>>(g0, d.groups, d.gpatch, d.pat, d.pidx, d.nbr, d.blobs,
-                                                                  d.bl_rowptr, d.bl_col, d.bl_val, d.inv_full, b, x,
-                                                                  d.g_xs_rows, d.g_s_max, d.g_ne_max, kSwGroupInvSmem);
-    p0 = d.lo_ptr[kb];
-    p1 = d.lo_ptr[kb + 1];
-    if (p1 == p0) return;
-    plist = d.leftover;
-  }
+                                 cudaStream_t stream) {
   if (d.fast) {
     const int g = (p1 - p0 + kSwFastWarps - 1) / kSwFastWarps;
     const size_t sm = (size_t)kSwFastWarps * kSwFastSlot * sizeof(double);
-#define MAMG_SWF_ARGS p0, p1, d.pidx32, d.nbrp, d.uid, d.inv_off, d.vt, d.ct4, d.pinv, b, x, d.srow, d.sq, d.nbq, d.max_size, d.prof, d.vstride, plist
+#define MAMG_SWF_ARGS p0, p1, d.pidx32, d.nbrp, d.uid, d.inv_off, d.vt, d.ct4, d.pinv, b, x, d.srow, d.sq, d.nbq, d.max_size, d.prof, d.vstride
     if (d.sr_t == 12) schwarz_fast_kernel<12, 1><<<g, kSwFastWarps * 32, sm, stream>>>(MAMG_SWF_ARGS);
     else if (d.sr_t == 24) schwarz_fast_kernel<24, 4><<<g, kSwFastWarps * 32, sm, stream>>>(MAMG_SWF_ARGS);
     else schwarz_fast_kernel<32, 8><<<g, kSwFastWarps * 32, sm, stream>>>(MAMG_SWF_ARGS);
@@ -1097,7 +807,7 @@ inline void schwarz_range_launch(const DSchwarz& d, int p0, int p1, const double
   }
   const int grid = (p1 - p0 + d.ppc - 1) / d.ppc;
   const SwLayout lay = {d.max_size, d.max_nbr, d.srow};
-#define MAMG_SW_ARGS p0, p1, d.pat, d.pidx, d.prow, d.plen, d.nbr, d.lcol, d.pinv, a, b, x, lay, plist
+#define MAMG_SW_ARGS p0, p1, d.pat, d.pidx, d.prow, d.plen, d.nbr, d.lcol, d.pinv, a, b, x, lay
   if (d.warps == 1 && d.ppc == 4) schwarz_apply_kernel<1, 4><<<grid, 128, d.smem_apply, stream>>>(MAMG_SW_ARGS);
   else if (d.warps == 1) schwarz_apply_kernel<1, 2><<<grid, 64, d.smem_apply, stream>>>(MAMG_SW_ARGS);
   else if (d.warps == 2) schwarz_apply_kernel<2, 1><<<grid, 64, d.smem_apply, stream>>>(MAMG_SW_ARGS);

@@ -324,9 +324,7 @@ class Hierarchy:
 
     STAT_KEYS = ["rows", "nnz_stored", "nnz_structural", "sell_slots", "device_bytes", "n_patches", "unique_blobs",
                  "schwarz_sweep_bytes", "schwarz_sweep_bytes_stored_factors", "n_colors", "n_patch_colors", "in_tail",
-                 "sell", "csr_kept", "row_blocks", "schwarz_fast_path", "schwarz_grouped", "schwarz_groups",
-                 "schwarz_group_smem", "schwarz_group_nn_max", "schwarz_group_s_max", "schwarz_grouped_patches",
-                 "max_patch_size", "reserved"]
+                 "sell", "csr_kept", "row_blocks", "schwarz_fast_path", "max_patch_size", "max_patch_nbr"]
 
     def stats(self, level=0):
         """Device-side statistics of one level (mamg_stats)."""
@@ -334,6 +332,13 @@ class Hierarchy:
         out = (C.c_int64 * 24)()
         check(lib.mamg_stats(self._h, int(level), out))
         return dict(zip(self.STAT_KEYS, [int(v) for v in out]))
+
+    def race_check(self):
+        """(gs_conflicts, patch_conflicts, launches_checked) of the device layout: mamg_race_check."""
+        self._require_device()
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        check(lib.mamg_race_check(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
 
     def profile_start(self):
         check(lib.mamg_profile(self._h, 1, None, None))
