@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(T)
 schwarz_invert_kernel(int nuniq, const int* __restrict__ rep, const long long* __restrict__ inv_off,
                       const SwPatch* __restrict__ pat, const int* __restrict__ pidx,
                       const int* __restrict__ ia, const int* __restrict__ ja,
-                      const double* __restrict__ a, double* __restrict__ pinv, int max_size, int kpad_fixed) {
+                      const double* __restrict__ a, double* __restrict__ pinv, int max_size) {
   extern __shared__ double smem[];
   if ((int)blockIdx.x >= nuniq) return;
   const int patch = rep[blockIdx.x];   // the representative patch of unique blob blockIdx.x
@@ -160,15 +160,8 @@ schwarz_invert_kernel(int nuniq, const int* __restrict__ rep, const long long* _
     for (int c = tid; c <= i; c += T) Lm[tri(i, c)] = col[c];
     __syncthreads();
   }
-  // stored FULL, column by column with the rows contiguous ([c][kpad], rows >= s zero): thread k of a patch
-  // reads entry (k, c) at c * kpad + k, so a warp-wide read is one contiguous run -- no triangular
-  // addressing, no bank conflicts, and (the blobs being shared) served from L1 / L2
-  const int kpad = kpad_fixed > 0 ? kpad_fixed : ((s + 3) & ~3);
   double* out = pinv + inv_off[blockIdx.x];
-  for (int t = tid; t < s * kpad; t += T) {
-    const int c = t / kpad, k = t % kpad;
-    out[t] = k < s ? Lm[k >= c ? tri(k, c) : tri(c, k)] : 0.0;
-  }
+  for (int k = tid; k < s * (s + 1) / 2; k += T) out[k] = Lm[k];
 }
 
 // ---- apply ---------------------------------------------------------------------------------------
@@ -178,12 +171,13 @@ schwarz_invert_kernel(int nuniq, const int* __restrict__ rep, const long long* _
 struct SwLayout {
   int max_size, max_nbr, srow;
   __host__ __device__ size_t ent() const { return (size_t)max_size * srow; }
+  __host__ __device__ size_t inv_d() const { return ((size_t)max_size * (max_size + 1) / 2 + 2) & ~(size_t)1; }
   __host__ __device__ size_t ls_d() const { return ((ent() + 8) * 2 + 15) / 16 * 2; }  // doubles holding the uint16 columns
   __host__ __device__ size_t as_d() const { return (ent() + 1) & ~(size_t)1; }
   __host__ __device__ size_t xs_d() const { return ((size_t)max_nbr + 2) & ~(size_t)1; }
   __host__ __device__ size_t rhs_d() const { return ((size_t)max_size + 1) & ~(size_t)1; }
   __host__ __device__ size_t int_d() const { return (3 * (size_t)max_size + 4) / 2 + 1; }
-  __host__ __device__ size_t total_d() const { return (ls_d() + as_d() + xs_d() + rhs_d() + int_d() + 1) & ~(size_t)1; }
+  __host__ __device__ size_t total_d() const { return (inv_d() + ls_d() + as_d() + xs_d() + rhs_d() + int_d() + 1) & ~(size_t)1; }
 };
 
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
@@ -216,9 +210,9 @@ schwarz_apply_kernel(int p0, int p1, const SwPatch* __restrict__ pat, const int*
   const int tid = threadIdx.x % T;
   const int patch = p0 + blockIdx.x * PPC + slot;
   const int S = lay.srow;
-  double* base = smem + slot * lay.total_d();
-  uint16_t* Ls = reinterpret_cast<uint16_t*>(base);
-  double* As = base + lay.ls_d();
+  double* Inv = smem + slot * lay.total_d();
+  uint16_t* Ls = reinterpret_cast<uint16_t*>(Inv + lay.inv_d());
+  double* As = Inv + lay.inv_d() + lay.ls_d();
   double* xs = As + lay.as_d();
   double* rhs = xs + lay.xs_d();
   int* idx = reinterpret_cast<int*>(rhs + lay.rhs_d());   // s
@@ -229,7 +223,10 @@ schwarz_apply_kernel(int p0, int p1, const SwPatch* __restrict__ pat, const int*
   P.s = 0;
   if (active) {
     P = pat[patch];
-    // wave 1: local columns (16-byte chunks; the segments are 16-byte aligned)
+    // wave 1: packed inverse and local columns (16-byte chunks; both segments are 16-byte aligned)
+    const double* src = pinv + P.i0;
+    const int nch = (P.s * (P.s + 1) / 2 + 1) / 2;
+    for (int k = tid; k < nch; k += T) cp_async16(Inv + 2 * k, src + 2 * k);
     const uint16_t* lsrc = lcol + P.e0;
     const int lch = (P.s * S + 7) / 8;
     for (int k = tid; k < lch; k += T) cp_async16(Ls + 8 * k, lsrc + 8 * k);
@@ -267,20 +264,18 @@ schwarz_apply_kernel(int p0, int p1, const SwPatch* __restrict__ pat, const int*
   }
   if (WPP == 1) __syncwarp(); else __syncthreads();
   if (active) {
-    // x_B = A_BB^{-1} rhs with the blob's full inverse read straight from global memory ([c][kpad]: the
-    // threads of a warp read consecutive doubles; the blob is shared by the look-alike patches, so the
-    // reads hit L1 / L2), rhs[c] is a shared-memory broadcast
-    const int kpad = (P.s + 3) & ~3;
-    const double* iv = pinv + P.i0;
+    // delta = A_BB^{-1} rhs with the packed symmetric inverse: entry (k,c) lives at tri(max,min);
+    // walk c with two running addresses (row part c <= k, column part c > k)
     for (int k = tid; k < P.s; k += T) {
-      double d0 = 0.0, d1 = 0.0;
-      int c = 0;
-      for (; c + 1 < P.s; c += 2) {
-        d0 += __ldg(iv + (size_t)c * kpad + k) * rhs[c];
-        d1 += __ldg(iv + (size_t)(c + 1) * kpad + k) * rhs[c + 1];
+      double d = 0.0;
+      int a1 = k * (k + 1) / 2;   // (k, c) for c <= k
+      int a2 = a1 + k;            // (c, k) for c >= k, advanced by c + 1
+      for (int c = 0; c < P.s; ++c) {
+        const int ad = c <= k ? a1 + c : a2;
+        d += Inv[ad] * rhs[c];
+        if (c >= k) a2 += c + 1;
       }
-      if (c < P.s) d0 += __ldg(iv + (size_t)c * kpad + k) * rhs[c];
-      x[idx[k]] = d0 + d1;   // x_B = A_BB^{-1} (b_B - A_{B,out} x_out)
+      x[idx[k]] = d;   // x_B = A_BB^{-1} (b_B - A_{B,out} x_out)
     }
   }
 }
@@ -393,13 +388,13 @@ schwarz_blob_kernel(int nuniq, const int* __restrict__ rep, const SwPatch* __res
 }
 
 #ifndef MAMG_SW_MINB24
-#define MAMG_SW_MINB24 4   // CTAs per SM for the <24,4> specialisation (64 registers, 4 bytes of spill; 16 KB of shared memory per CTA)
+#define MAMG_SW_MINB24 3   // CTAs per SM for the <24,4> specialisation (78 registers, no spills)
 #endif
 #ifndef MAMG_SW_MINB
 #define MAMG_SW_MINB 2   // CTAs per SM the fast kernel is compiled for (2: ~100 registers, 3: 80 with spills)
 #endif
 constexpr int kSwFastWarps = 8;     // patches per CTA
-constexpr int kSwFastSlot = 256;  // doubles per patch slot: xs[256] (x on the outside neighbours + the zero slot)
+constexpr int kSwFastSlot = 256 + 528 + 32;  // doubles per patch slot: xs[256], packed inverse (32*33/2), rhs[32]
 
 // apply: one warp per patch, lane k = patch row k.  Wave 1 loads everything addressed by the patch
 // number (row values, packed local columns, neighbour list, inverse via cp.async); wave 2 gathers
@@ -416,6 +411,8 @@ schwarz_fast_kernel(int p0, int p1, const int* __restrict__ pidx32, const int* _
   const int patch = p0 + blockIdx.x * kSwFastWarps + warp;
   if (patch >= p1) return;
   double* xs = smem + warp * kSwFastSlot;
+  double* Inv = xs + 256;
+  double* rhs = Inv + 528;
   const size_t pp = (size_t)patch;
   const size_t uu = (size_t)uid[patch];   // the stored blob this patch shares with its look-alikes
   // ---- wave 1 ----
@@ -424,6 +421,11 @@ schwarz_fast_kernel(int p0, int p1, const int* __restrict__ pidx32, const int* _
 #pragma unroll
   for (int j = 0; j < NBQ; ++j) nb[j] = j < nbq ? ld_stream(nbrp + (pp * nbq + j) * 32 + lane) : 0;
   const int s = __popc(__ballot_sync(0xffffffffu, my >= 0));     // dofs of this patch
+  {
+    const double* src = pinv + inv_off[uu];
+    const int nch = (s * (s + 1) / 2 + 1) / 2;                  // 16-byte chunks of its packed inverse
+    for (int k = lane; k < nch; k += 32) cp_async16(Inv + 2 * k, src + 2 * k);
+  }
   double v[SR];
   {
     const double* vp = vt + uu * vstride + lane;
@@ -446,20 +448,19 @@ schwarz_fast_kernel(int p0, int p1, const int* __restrict__ pidx32, const int* _
   double acc = 0.0;
 #pragma unroll
   for (int e = 0; e < SR; ++e) acc += v[e] * xs[(c4[e / 4] >> (8 * (e % 4))) & 255u];
-  // x_B = A_BB^{-1} rhs: the blob's full inverse is stored [c][32] (lane = row, rows >= s zero), so every
-  // step is one contiguous 256-byte read (L1 / L2 resident: the blob is shared by the look-alike patches)
-  // and the right-hand side travels by shuffle -- no staging, no triangular addresses, no shared memory
-  const double r = my >= 0 ? bk - acc : 0.0;
-  const double* ivp = pinv + inv_off[uu] + lane;
-  double d0 = 0.0, d1 = 0.0;
-  int c = 0;
-  for (; c + 1 < s; c += 2) {
-    const double i0 = __ldg(ivp + c * 32), i1 = __ldg(ivp + (c + 1) * 32);
-    d0 += i0 * __shfl_sync(0xffffffffu, r, c);
-    d1 += i1 * __shfl_sync(0xffffffffu, r, c + 1);
+  rhs[lane] = my >= 0 ? bk - acc : 0.0;
+  cp_async_wait_all();
+  __syncwarp();
+  double d = 0.0;
+  const int base = lane * (lane + 1) / 2;
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    if (c < s && lane < s) {   // only the s x s part of the staged inverse is defined
+      const int ad = c <= lane ? base + c : c * (c + 1) / 2 + lane;
+      d += Inv[ad] * rhs[c];
+    }
   }
-  if (c < s) d0 += __ldg(ivp + c * 32) * __shfl_sync(0xffffffffu, r, c);
-  if (my >= 0) x[my] = d0 + d1;   // x_B = A_BB^{-1} (b_B - A_{B,out} x_out)
+  if (my >= 0) x[my] = d;   // x_B = A_BB^{-1} (b_B - A_{B,out} x_out)
 }
 
 // Host side: reorder the patches by colour, translate to the permuted numbering, build the
@@ -714,7 +715,7 @@ inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iper
   std::vector<long long> inv_off(nu + 1, 0), e_off(nu + 1, 0);
   for (int u = 0; u < nu; ++u) {
     const long long s = pat[rep[u]].s;
-    inv_off[u + 1] = inv_off[u] + s * (fast_shape ? 32 : ((s + 3) & ~3LL));   // full inverse, [c][kpad]
+    inv_off[u + 1] = inv_off[u] + (s * (s + 1) / 2 + 1) / 2 * 2;
     e_off[u + 1] = e_off[u] + (s * srow + 7) / 8 * 8;                 // 16-byte aligned uint16 segments
   }
   const long long tot_i = inv_off[nu], tot_e = fast_shape ? 0 : e_off[nu];
@@ -750,8 +751,7 @@ inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iper
   constexpr int TS = 128;
   if (d.smem_setup > 48 * 1024)
     cudaFuncSetAttribute(schwarz_invert_kernel<TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_setup);
-  schwarz_invert_kernel<TS><<<nu, TS, d.smem_setup>>>(nu, d_rep, d.inv_off, d.pat, d.pidx, d_ia, d_ja, d_a, d.pinv, d.max_size,
-                                                      fast_shape ? 32 : 0);
+  schwarz_invert_kernel<TS><<<nu, TS, d.smem_setup>>>(nu, d_rep, d.inv_off, d.pat, d.pidx, d_ia, d_ja, d_a, d.pinv, d.max_size);
   sync_or_throw("Schwarz setup kernel");
   if (fast_shape) {
     d.fast = true;
