@@ -273,6 +273,10 @@ static void build_sell(DeviceState& D, DLevel& dl, const std::vector<int>& ia, i
 
 // Halo lists of a row-distributed level: my rows that a row of rank q couples to (the pattern is
 // symmetric -- validated at setup -- so these are my rows with a column owned by q), per colour.
+// On a level with Schwarz patches the halo is deeper: a patch seeded in another rank's block gathers x up to
+// Schwarz_maxlvl + 1 rings into my block (dl.sw.readers) and reads b on its own dofs there (dl.sw.members),
+// so those rows travel with their colour as well; list ncolors + 1 holds the rows whose right-hand side the
+// other ranks' patches need.
 static void build_halo_lists(DeviceState& D, DLevel& dl, const std::vector<int>& ia, const std::vector<int>& ja) {
   const int per = dl.nb / D.world, nc = dl.ncolors;
   std::vector<int> rank_lo(D.world + 1);
@@ -280,29 +284,42 @@ static void build_halo_lists(DeviceState& D, DLevel& dl, const std::vector<int>&
   const int lo = rank_lo[D.rank], hi = rank_lo[D.rank + 1];
   auto owner = [&](int j) { return (int)(std::upper_bound(rank_lo.begin(), rank_lo.end(), j) - rank_lo.begin()) - 1; };
   // colour of my row i: position inside its (block, colour) ranges
-  std::vector<std::vector<std::vector<int>>> lists(D.world, std::vector<std::vector<int>>(nc + 1));
+  std::vector<std::vector<std::vector<int>>> lists(D.world, std::vector<std::vector<int>>(nc + 2));
   std::vector<char> hit(D.world);
+  const bool deep = !dl.sw.readers.empty();
   int kb = D.rank * per * nc;
   for (int i = lo; i < hi; ++i) {
     while (i >= dl.bc_ptr[kb + 1]) ++kb;
     const int c = kb % nc;
     std::fill(hit.begin(), hit.end(), 0);
+    auto add = [&](int q) {
+      if (q != D.rank && !hit[q]) { hit[q] = 1; lists[q][c].push_back(i); lists[q][nc].push_back(i); }
+    };
     for (int p = ia[i]; p < ia[i + 1]; ++p) {
       const int j = ja[p];
       if (j >= lo && j < hi) continue;
-      const int q = owner(j);
-      if (!hit[q]) { hit[q] = 1; lists[q][c].push_back(i); lists[q][nc].push_back(i); }
+      add(owner(j));
+    }
+    if (deep) {
+      const unsigned long long rd = dl.sw.readers[i] | dl.sw.members[i], mb = dl.sw.members[i];
+      for (int part = 0; part < dl.nb; ++part) {
+        if ((rd >> part) & 1ull) add(part / per);
+        if (((mb >> part) & 1ull) && part / per != D.rank) {
+          std::vector<int>& v = lists[part / per][nc + 1];
+          if (v.empty() || v.back() != i) v.push_back(i);
+        }
+      }
     }
   }
   dl.nbr_ranks.clear();
   for (int q = 0; q < D.world; ++q)
-    if (q != D.rank && !lists[q][nc].empty()) dl.nbr_ranks.push_back(q);
+    if (q != D.rank && (!lists[q][nc].empty() || !lists[q][nc + 1].empty())) dl.nbr_ranks.push_back(q);
   // the neighbour relation must be symmetric across ranks; it is, because the pattern is symmetric
   const int nnb = (int)dl.nbr_ranks.size();
   if (nnb > 8) throw std::runtime_error("more than 8 neighbour ranks on a level: use MAMG_HALO=0");
   std::vector<int> flat;
-  dl.send_off.assign((size_t)(nc + 1) * nnb + 1, 0);
-  for (int c = 0; c <= nc; ++c)
+  dl.send_off.assign((size_t)(nc + 2) * nnb + 1, 0);
+  for (int c = 0; c <= nc + 1; ++c)
     for (int k = 0; k < nnb; ++k) {
       const std::vector<int>& v = lists[dl.nbr_ranks[k]][c];
       flat.insert(flat.end(), v.begin(), v.end());
@@ -405,7 +422,6 @@ static void upload_hierarchy(const Hierarchy& H, DeviceState& D) {
     dl.ja = upload(D, ja);
     dl.a = upload(D, a);
     dl.invd = upload(D, invd);
-    if (D.halo && D.world > 1 && dl.nb > 1) build_halo_lists(D, dl, ia, ja);
     dl.perm = upload(D, perm[l]);
     dl.iperm = upload(D, iperm[l]);
     dl.x_own = dl.x = carve(n);
@@ -475,6 +491,7 @@ static void upload_hierarchy(const Hierarchy& H, DeviceState& D) {
       D.dev_bytes += (int64_t)bytes;
       return p;
     });
+    if (D.halo && D.world > 1 && dl.nb > 1) build_halo_lists(D, dl, ia, ja);
     if (rows_sell()) {
       int slo = 0, shi = n;
       if (D.halo && D.world > 1 && dl.nb > 1) {   // the row kernels only ever stream this rank's blocks
@@ -849,7 +866,7 @@ static void halo_exchange(DeviceState& D, const DLevel& l, const double* v, int 
   const int nnb = (int)l.nbr_ranks.size();
   HaloPush P;
   P.nn = nnb;
-  const int cc = c >= 0 ? c : l.ncolors;
+  const int cc = c >= 0 ? c : (c == -1 ? l.ncolors : l.ncolors + 1);   // -1: all boundary rows; -2: right-hand-side rows of foreign patches
   int total = 0;
   for (int k = 0; k < nnb; ++k) {
     P.peer[k] = l.nbr_ranks[k];
@@ -1338,6 +1355,8 @@ static void apply_permuted_raw(DeviceState& D, const double* r, double* z) {
   } else {
     k_fill(D, l0.n, z, 0.0);
     if (is_dist(D, l0)) barrier_only(D);   // peers push into z from the first colour on
+    // halo mode: the patches that straddle a cut read the right-hand side on dofs of the neighbour's block
+    if (halo_on(D, l0) && l0.sw.npatch > 0) halo_exchange(D, l0, r, -2);
     for (int it = 0; it < std::max(1, D.prm.maxit); ++it) cycle_level(D, 0);
   }
   l0.b = l0.b_own;
@@ -1348,6 +1367,10 @@ static void apply_permuted_raw(DeviceState& D, const double* r, double* z) {
 // z = B r with z complete on every rank (API boundary, MINRES / GMRES): in halo mode the cycle leaves z
 // valid on the owned rows and their halo only
 static void apply_complete(DeviceState& D, const double* r, double* z) {
+  if (halo_on(D, D.lv[0]) && !(r >= D.arena && r < D.arena + D.arena_doubles)) {
+    k_copy(D, D.lv[0].n, r, D.w[9]);   // a vector outside the peer arena (GMRES basis) cannot be exchanged
+    r = D.w[9];
+  }
   apply_permuted(D, r, z);
   if (halo_on(D, D.lv[0])) allgather_own(D, D.lv[0], z);
 }

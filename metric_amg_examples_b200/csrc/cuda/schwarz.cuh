@@ -88,6 +88,9 @@ struct DSchwarz {
   // another part's row block) are exchanged; xoff[c*nb + b] .. delimit them inside xidx
   std::vector<int> xoff;
   int* xidx = nullptr;
+  // host, permuted dof ids (only with nb > 1): bit p of readers[j] = a patch seeded in part p gathers x[j]
+  // (j outside that patch); bit p of members[j] = a patch seeded in part p contains j (reads b[j], writes x[j])
+  std::vector<unsigned long long> readers, members;
   long long alg_bytes = 0;     // algorithmic bytes of one sweep over all patches (shared blobs once per colour)
   long long alg_bytes_stored = 0;  // the same with every patch owning its data (SURVEY 8d "stored factors")
 };
@@ -579,7 +582,10 @@ inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iper
   d.max_nbr = max_nbr;
   std::vector<int> nbr((size_t)tot_n);
   if (nb > 64) throw std::runtime_error("more than 64 parts are not supported by the Schwarz exchange lists");
-  std::vector<unsigned long long> readers(nb > 1 ? n : 0, 0ull);
+  std::vector<unsigned long long>& readers = d.readers;
+  std::vector<unsigned long long>& members = d.members;
+  readers.assign(nb > 1 ? n : 0, 0ull);
+  members.assign(nb > 1 ? n : 0, 0ull);
   // general path: host signature of what the stored inverse and the local columns depend on (size, row
   // lengths, local column of every entry, value of every entry inside the patch)
   std::vector<unsigned long long> sigA(np, 0), sigB(np, 0);
@@ -613,6 +619,10 @@ inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iper
         for (int j : list) {
 #pragma omp atomic
           readers[j] |= bit;
+        }
+        for (int q = 0; q < s; ++q) {
+#pragma omp atomic
+          members[pidx[pat[k].q0 + q]] |= bit;
         }
       }
       if (!fast_shape) {
