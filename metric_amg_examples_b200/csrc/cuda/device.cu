@@ -72,6 +72,9 @@ struct DLevel {
   // transition to the replicated levels: the rows of the (replicated) coarse level below whose aggregates I own
   int* d_own_coarse = nullptr;
   int n_own_coarse = 0;
+  // Schwarz colours in halo mode: the dofs my patches of colour c updated that neighbour k gathers or owns
+  std::vector<int> sw_send_off;   // [ncolors_sw * nnb + 1]
+  int* d_sw_send = nullptr;
 };
 
 enum KClass { K_SPMV = 0, K_GS, K_SCHWARZ, K_RESTRICT, K_SCALE, K_PROLONG, K_COARSE, K_VEC, K_DOT, K_EXCH, K_NCLS };
@@ -326,6 +329,21 @@ static void build_halo_lists(DeviceState& D, DLevel& dl, const std::vector<int>&
       dl.send_off[(size_t)c * nnb + k + 1] = (int)flat.size();
     }
   dl.d_send = upload(D, flat);
+  if (deep) {
+    // per Schwarz colour and neighbour: the exported dofs (schwarz_upload's export lists) that neighbour needs
+    const DSchwarz& sw = dl.sw;
+    std::vector<int> sflat;
+    dl.sw_send_off.assign((size_t)sw.ncolors * nnb + 1, 0);
+    for (int c = 0; c < sw.ncolors; ++c)
+      for (int k = 0; k < nnb; ++k) {
+        unsigned long long rmask = 0;
+        for (int part = dl.nbr_ranks[k] * per; part < (dl.nbr_ranks[k] + 1) * per; ++part) rmask |= 1ull << part;
+        for (int q = sw.xoff[c * sw.nb + D.rank * per]; q < sw.xoff[c * sw.nb + (D.rank + 1) * per]; ++q)
+          if (sw.h_xmask[q] & rmask) sflat.push_back(sw.h_xidx[q]);
+        dl.sw_send_off[(size_t)c * nnb + k + 1] = (int)sflat.size();
+      }
+    dl.d_sw_send = upload(D, sflat);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -860,23 +878,25 @@ pcg_dir_range_kernel(int lo, int hi, const double* __restrict__ sc, const double
   d[i] = z[i] + sc[4] * d[i];
 }
 
-static void halo_exchange(DeviceState& D, const DLevel& l, const double* v, int c) {
-  // c in [0, ncolors): the rows of that colour; c < 0: all boundary rows
+static void halo_exchange(DeviceState& D, const DLevel& l, const double* v, int c, bool schwarz_color = false) {
+  // c in [0, ncolors): the rows of that colour; c = -1: all boundary rows; c = -2: right-hand-side rows of
+  // foreign patches; schwarz_color: c is a patch colour, the list holds the dofs my patches of it exported
   if (!(v >= D.arena && v < D.arena + D.arena_doubles)) throw std::runtime_error("halo exchange of a vector outside the peer arena");
   const int nnb = (int)l.nbr_ranks.size();
   HaloPush P;
   P.nn = nnb;
-  const int cc = c >= 0 ? c : (c == -1 ? l.ncolors : l.ncolors + 1);   // -1: all boundary rows; -2: right-hand-side rows of foreign patches
+  const int cc = schwarz_color ? c : (c >= 0 ? c : (c == -1 ? l.ncolors : l.ncolors + 1));
+  const std::vector<int>& off = schwarz_color ? l.sw_send_off : l.send_off;
   int total = 0;
   for (int k = 0; k < nnb; ++k) {
     P.peer[k] = l.nbr_ranks[k];
-    P.beg[k] = l.send_off[(size_t)cc * nnb + k];
-    P.cnt[k] = l.send_off[(size_t)cc * nnb + k + 1] - P.beg[k];
+    P.beg[k] = off[(size_t)cc * nnb + k];
+    P.cnt[k] = off[(size_t)cc * nnb + k + 1] - P.beg[k];
     total = std::max(total, P.cnt[k]);
   }
   const int grid = std::max(1, std::min(D.red_blocks, cdiv(std::max(total, 1), kBlock)));
   KScope ks(D, K_EXCH);
-  halo_push_kernel<<<grid, kBlock, 0, D.stream>>>(P, l.d_send, v - D.arena, D.d_peer_arena, D.rank, D.push_ticket, D.d_phase);
+  halo_push_kernel<<<grid, kBlock, 0, D.stream>>>(P, schwarz_color ? l.d_sw_send : l.d_send, v - D.arena, D.d_peer_arena, D.rank, D.push_ticket, D.d_phase);
   ++D.collectives;
   D.exch_bytes += 8LL * [&] { long long t = 0; for (int k = 0; k < nnb; ++k) t += P.cnt[k]; return t; }();
 }
@@ -1078,6 +1098,10 @@ static void smooth(DeviceState& D, int lev, const double* b, double* x, bool pos
           // sit in their row block); everything else travels once, at the end of the sweep
           const int qa = l.sw.xoff[c * snb], qb = l.sw.xoff[(c + 1) * snb];
           if (qb == qa) continue;
+          if (halo_on(D, l)) {   // straight into the vectors of the neighbours that gather or own those dofs
+            halo_exchange(D, l, x, c, true);
+            continue;
+          }
           const int mq0 = l.sw.xoff[c * snb + lo], mq1 = l.sw.xoff[c * snb + hi];
           double* xb = D.xbuf + (D.xflip++ & 1) * D.xcap;
           if (mq1 > mq0) {

@@ -91,6 +91,9 @@ struct DSchwarz {
   // host, permuted dof ids (only with nb > 1): bit p of readers[j] = a patch seeded in part p gathers x[j]
   // (j outside that patch); bit p of members[j] = a patch seeded in part p contains j (reads b[j], writes x[j])
   std::vector<unsigned long long> readers, members;
+  // host copies of the export lists: xidx and, per entry, the parts that need the value (gather it or own the row)
+  std::vector<int> h_xidx;
+  std::vector<unsigned long long> h_xmask;
   long long alg_bytes = 0;     // algorithmic bytes of one sweep over all patches (shared blobs once per colour)
   long long alg_bytes_stored = 0;  // the same with every patch owning its data (SURVEY 8d "stored factors")
 };
@@ -674,12 +677,14 @@ inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iper
         const int pp = hl.part[sw.seed[p]];
         for (int q = 0; q < pat[k].s; ++q) {
           const int nat = sw.dofs[dord[sw.ptr[p] + q]], dof = pidx[pat[k].q0 + q];
-          if ((readers[dof] & ~(1ull << pp)) || hl.part[nat] != pp) xidx.push_back(dof);
+          const unsigned long long need = (readers[dof] | (1ull << hl.part[nat])) & ~(1ull << pp);
+          if (need) { xidx.push_back(dof); d.h_xmask.push_back(need); }
         }
       }
       d.xoff[kb + 1] = (int)xidx.size();
     }
     d.xidx = (int*)up(xidx.data(), xidx.size() * sizeof(int));
+    d.h_xidx = xidx;
   }
   d.pidx = (int*)up(pidx.data(), pidx.size() * sizeof(int));
   d.nbr = (int*)up(nbr.data(), nbr.size() * sizeof(int));
