@@ -202,7 +202,7 @@ def run_mamg(a):
     import psutil
     dim = int(a.workload[-2])
     ndof_est = 2 * (n + 1) ** dim if a.workload.startswith("bidomain") else (n + 1) ** (dim - 1) * (n + 2)
-    need = (3600.0 if a.workload.startswith("bidomain") else 1400.0) * ndof_est
+    need = (3600.0 if a.workload.startswith("bidomain") else 650.0) * ndof_est   # measured peaks: emi_3d n=464 50.5 GB
     avail = float(psutil.virtual_memory().available)
     if world > 1:
         free_t = torch.tensor([avail], dtype=torch.float64, device="cuda")

@@ -140,7 +140,7 @@ struct DeviceState {
   // one apply is a fixed launch sequence: it is captured once per (input, output) pair into a
   // CUDA graph and replayed, which removes the host launch cost of the ~1000 small kernels of the
   // coarse levels (MAMG_GRAPH=0 disables; not used while profiling or for very long W sequences)
-  struct GraphEntry { const double* r; double* z; cudaGraphExec_t exec; int64_t launches; int64_t cls[K_NCLS]; };
+  struct GraphEntry { const double* r; double* z; cudaGraphExec_t exec; int64_t launches; int64_t cls[K_NCLS]; int64_t coll, xbytes; };
   std::vector<GraphEntry> graphs;
   bool use_graph = true;
   bool graph_dist = true;            // capture the cycle with several ranks too (MAMG_GRAPH_DIST=0 disables)
@@ -758,7 +758,7 @@ halo_push_kernel(HaloPush P, const int* __restrict__ send, long long voff, doubl
     const volatile long long* flag = reinterpret_cast<const volatile long long*>(peers[me]) + P.peer[threadIdx.x];
     const long long t0 = clock64();
     while (*flag < phase) {
-      if (clock64() - t0 > 200000000000LL) { printf("mamg: rank %d: neighbour %d never reached exchange %lld\n", me, P.peer[threadIdx.x], phase); __trap(); }
+      if (clock64() - t0 > 40000000000LL) { printf("mamg: rank %d: neighbour %d never reached exchange %lld\n", me, P.peer[threadIdx.x], phase); __trap(); }
     }
     __threadfence_system();
   }
@@ -799,7 +799,7 @@ list_push_all_kernel(int cnt, const int* __restrict__ idx, long long voff, doubl
     const volatile long long* flag = reinterpret_cast<const volatile long long*>(peers[me]) + threadIdx.x;
     const long long t0 = clock64();
     while (*flag < phase) {
-      if (clock64() - t0 > 200000000000LL) { printf("mamg: rank %d: peer %d never reached exchange %lld\n", me, (int)threadIdx.x, phase); __trap(); }
+      if (clock64() - t0 > 40000000000LL) { printf("mamg: rank %d: peer %d never reached exchange %lld\n", me, (int)threadIdx.x, phase); __trap(); }
     }
     __threadfence_system();
   }
@@ -830,7 +830,7 @@ allreduce_kernel(int count, double* v, int op, int first, double* sc, double* co
     const volatile long long* flag = reinterpret_cast<const volatile long long*>(peers[me]) + q;
     const long long t0 = clock64();
     while (*flag < phase) {
-      if (clock64() - t0 > 200000000000LL) { printf("mamg: rank %d: peer %d never reached all-reduce %lld\n", me, q, phase); __trap(); }
+      if (clock64() - t0 > 40000000000LL) { printf("mamg: rank %d: peer %d never reached all-reduce %lld\n", me, q, phase); __trap(); }
     }
     __threadfence_system();
   }
@@ -876,6 +876,38 @@ pcg_dir_range_kernel(int lo, int hi, const double* __restrict__ sc, const double
   const int i = lo + blockIdx.x * kBlock + threadIdx.x;
   if (i >= hi) return;
   d[i] = z[i] + sc[4] * d[i];
+}
+
+// descriptor of one halo exchange for a kernel that performs it in its last block (kernels.cuh: halo_tail)
+static HaloTail halo_tail_desc(DeviceState& D, const DLevel& l, const double* v, int c, bool schwarz_color = false) {
+  if (!(v >= D.arena && v < D.arena + D.arena_doubles)) throw std::runtime_error("halo exchange of a vector outside the peer arena");
+  const int nnb = (int)l.nbr_ranks.size();
+  HaloTail T;
+  std::memset(&T, 0, sizeof(T));
+  T.nn = nnb;
+  const int cc = schwarz_color ? c : (c >= 0 ? c : (c == -1 ? l.ncolors : l.ncolors + 1));
+  const std::vector<int>& off = schwarz_color ? l.sw_send_off : l.send_off;
+  long long bytes = 0;
+  for (int k = 0; k < nnb; ++k) {
+    T.peer[k] = l.nbr_ranks[k];
+    T.beg[k] = off[(size_t)cc * nnb + k];
+    T.cnt[k] = off[(size_t)cc * nnb + k + 1] - T.beg[k];
+    bytes += 8LL * T.cnt[k];
+  }
+  T.send = schwarz_color ? l.d_sw_send : l.d_send;
+  T.voff = v - D.arena;
+  T.peers = D.d_peer_arena;
+  T.me = D.rank;
+  T.ticket = D.push_ticket;
+  T.phase_ctr = D.d_phase;
+  ++D.collectives;
+  D.exch_bytes += bytes;
+  return T;
+}
+static HaloTail no_halo_tail() {
+  HaloTail T;
+  std::memset(&T, 0, sizeof(T));
+  return T;
 }
 
 static void halo_exchange(DeviceState& D, const DLevel& l, const double* v, int c, bool schwarz_color = false) {
@@ -994,20 +1026,26 @@ static void k_gs_color(DeviceState& D, const DLevel& l, int c, const double* b, 
   for (int blk = 0; blk < l.nb; ++blk)
     any |= l.row1(blk, c) > l.row0(blk, c) && (l.color_active.empty() || l.color_active[blk * l.ncolors + c] > 0);
   if (!any) return;   // every row of the colour belongs to Schwarz (same decision on every rank)
+  // halo mode: the launch of this rank's last active block of the colour also sends the boundary rows
+  int last_blk = -1;
+  if (halo_on(D, l) && l.use_sell)
+    for (int blk = blk_lo(D, l); blk < blk_hi(D, l); ++blk)
+      if (l.row1(blk, c) > l.row0(blk, c) && (l.color_active.empty() || l.color_active[blk * l.ncolors + c] > 0)) last_blk = blk;
   for (int blk = blk_lo(D, l); blk < blk_hi(D, l); ++blk) {
     const int r0 = l.row0(blk, c), r1 = l.row1(blk, c);
     if (r1 <= r0) continue;
     if (!l.color_active.empty() && l.color_active[blk * l.ncolors + c] == 0) continue;
     KScope ks(D, K_GS);
     if (l.use_sell) {
-      sell_gs_kernel<<<sell_grid(r0, r1), kBlock, 0, D.stream>>>(r0, r1, l.S, l.invd, l.skip, b, x, omega);
+      const HaloTail tail = blk == last_blk ? halo_tail_desc(D, l, x, c) : no_halo_tail();
+      sell_gs_kernel<<<sell_grid(r0, r1), kBlock, 0, D.stream>>>(r0, r1, l.S, l.invd, l.skip, b, x, omega, tail);
       continue;
     }
     const int grid = cdiv((long long)cdiv(r1 - r0, l.unroll) * l.lanes, kBlock);
     LANES_SWITCH(l.lanes, UNROLL_SWITCH(l.unroll,
       gs_color_kernel<LN, UN><<<grid, kBlock, 0, D.stream>>>(r0, r1, l.ia, l.ja, l.a, l.invd, l.skip, b, x, omega)));
   }
-  exchange(D, l, x, c);
+  if (last_blk < 0) exchange(D, l, x, c);   // not folded into a kernel of this rank: a push kernel of its own
 }
 
 static void gs_forward(DeviceState& D, const DLevel& l, const double* b, double* x, double w, int first = 0) {
@@ -1087,19 +1125,26 @@ static void smooth(DeviceState& D, int lev, const double* b, double* x, bool pos
       for (int cc = 0; cc < l.sw.ncolors; ++cc) {
         const int c = backward ? l.sw.ncolors - 1 - cc : cc;
         const int lo = snb > 1 ? D.rank * per : 0, hi = snb > 1 ? (D.rank + 1) * per : 1;
+        // halo mode: the dofs this colour's patches updated go straight into the vectors of the neighbours
+        // that gather or own them, sent by the last block of this rank's last patch launch of the colour
+        const bool xch = D.world > 1 && snb > 1 && l.sw.xoff[(c + 1) * snb] > l.sw.xoff[c * snb];
+        int last_blk = -1;
+        if (xch && halo_on(D, l))
+          for (int blk = lo; blk < hi; ++blk)
+            if (l.sw.cb_ptr[c * snb + blk + 1] > l.sw.cb_ptr[c * snb + blk]) last_blk = blk;
         for (int blk = lo; blk < hi; ++blk) {
           const int p0 = l.sw.cb_ptr[c * snb + blk], p1 = l.sw.cb_ptr[c * snb + blk + 1];
           if (p1 == p0) continue;
           KScope ks(D, K_SCHWARZ);
-          schwarz_range_launch(l.sw, p0, p1, l.a, b, x, D.stream);
+          schwarz_range_launch(l.sw, p0, p1, l.a, b, x, D.stream, blk == last_blk ? halo_tail_desc(D, l, x, c, true) : no_halo_tail());
         }
         if (D.world > 1 && snb > 1) {
           // the other ranks receive the just-updated dofs that they read in later colours (or that
           // sit in their row block); everything else travels once, at the end of the sweep
           const int qa = l.sw.xoff[c * snb], qb = l.sw.xoff[(c + 1) * snb];
           if (qb == qa) continue;
-          if (halo_on(D, l)) {   // straight into the vectors of the neighbours that gather or own those dofs
-            halo_exchange(D, l, x, c, true);
+          if (halo_on(D, l)) {
+            if (last_blk < 0) halo_exchange(D, l, x, c, true);   // no patch of mine in this colour: a push kernel of its own
             continue;
           }
           const int mq0 = l.sw.xoff[c * snb + lo], mq1 = l.sw.xoff[c * snb + hi];
@@ -1337,11 +1382,13 @@ static void apply_permuted(DeviceState& D, const double* r, double* z) {
     if (g.r == r && g.z == z) {
       CUDA_OK(cudaGraphLaunch(g.exec, D.stream));
       D.launches += g.launches;
+      D.collectives += g.coll;
+      D.exch_bytes += g.xbytes;
       for (int k = 0; k < K_NCLS; ++k) D.cls_launches[k] += g.cls[k];
       return;
     }
   // capture (nothing executes), instantiate, then launch through the cache on the next lookup
-  const int64_t l0 = D.launches;
+  const int64_t l0 = D.launches, coll0 = D.collectives, xb0 = D.exch_bytes;
   int64_t c0[K_NCLS];
   for (int k = 0; k < K_NCLS; ++k) c0[k] = D.cls_launches[k];
   cudaGraph_t graph = nullptr;
@@ -1361,6 +1408,10 @@ static void apply_permuted(DeviceState& D, const double* r, double* z) {
   e.r = r;
   e.z = z;
   e.launches = D.launches - l0;
+  e.coll = D.collectives - coll0;
+  e.xbytes = D.exch_bytes - xb0;
+  D.collectives = coll0;
+  D.exch_bytes = xb0;
   for (int k = 0; k < K_NCLS; ++k) { e.cls[k] = D.cls_launches[k] - c0[k]; D.cls_launches[k] = c0[k]; }
   D.launches = l0;
   CUDA_OK(cudaGraphInstantiate(&e.exec, graph, 0));

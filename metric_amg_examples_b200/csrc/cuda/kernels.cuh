@@ -11,6 +11,7 @@
 // rows fall in the same cache lines.
 #pragma once
 #include <cstdint>
+#include <cstdio>
 #include <cuda_runtime.h>
 
 namespace mamg {
@@ -71,6 +72,62 @@ __device__ __forceinline__ unsigned int ld_stream(const unsigned int* p) {
   return v;
 }
 #endif
+
+// ---- halo push folded into the producing kernel (multi-GPU halo mode) -----------------------------------
+// A smoother kernel that is followed by a halo exchange carries this descriptor: when its last block
+// retires (ticket), that block stores the listed boundary entries of the vector into the neighbour
+// ranks' copies, raises this rank's flag there and waits for theirs -- the exchange costs no launch of
+// its own.  nn = 0: no exchange.  See halo_push_kernel (device.cu) for the protocol.
+struct HaloTail {
+  int nn;
+  int peer[8], beg[8], cnt[8];
+  const int* send;
+  long long voff;
+  double* const* peers;
+  int me;
+  unsigned int* ticket;
+  long long* phase_ctr;
+};
+__device__ __forceinline__ void halo_tail(const HaloTail& T) {
+  if (T.nn == 0) return;   // kernel-uniform
+  __shared__ bool ht_last;
+  __shared__ long long ht_phase;
+  __threadfence();          // this block's updates are visible device-wide before it takes a ticket
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int nblk = gridDim.x;
+    ht_last = atomicInc(T.ticket, nblk - 1) == nblk - 1;
+  }
+  __syncthreads();
+  if (!ht_last) return;
+  __threadfence();
+  const double* mine = T.peers[T.me] + T.voff;
+  for (int k = 0; k < T.nn; ++k) {
+    double* dst = T.peers[T.peer[k]] + T.voff;
+    const int* idx = T.send + T.beg[k];
+    for (int t = threadIdx.x; t < T.cnt[k]; t += blockDim.x) {
+      const int i = idx[t];
+      dst[i] = __ldcg(mine + i);   // written by other blocks of this launch: read past this SM's L1
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ht_phase = *reinterpret_cast<volatile long long*>(T.phase_ctr) + 1;
+    for (int k = 0; k < T.nn; ++k) reinterpret_cast<volatile long long*>(T.peers[T.peer[k]])[T.me] = ht_phase;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < T.nn) {
+    const volatile long long* flag = reinterpret_cast<const volatile long long*>(T.peers[T.me]) + T.peer[threadIdx.x];
+    const long long t0 = clock64();
+    while (*flag < ht_phase) {
+      if (clock64() - t0 > 40000000000LL) { printf("mamg: rank %d: neighbour %d never reached exchange %lld\n", T.me, T.peer[threadIdx.x], ht_phase); __trap(); }
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *T.phase_ctr = ht_phase;
+}
 
 // Row dot product a_i . x by one sub-warp; the full sum is valid in lane 0 of the sub-warp.
 template <int LANES>

@@ -209,7 +209,7 @@ schwarz_apply_kernel(int p0, int p1, const SwPatch* __restrict__ pat, const int*
                      const int* __restrict__ prow, const int* __restrict__ plen,
                      const int* __restrict__ nbr, const uint16_t* __restrict__ lcol,
                      const double* __restrict__ pinv, const double* __restrict__ a,
-                     const double* __restrict__ b, double* x, SwLayout lay) {
+                     const double* __restrict__ b, double* x, SwLayout lay, const HaloTail tail) {
   constexpr int T = WPP * 32;  // threads per patch
   extern __shared__ __align__(16) double smem[];
   const int slot = threadIdx.x / T;
@@ -284,6 +284,7 @@ schwarz_apply_kernel(int p0, int p1, const SwPatch* __restrict__ pat, const int*
       x[idx[k]] = d;   // x_B = A_BB^{-1} (b_B - A_{B,out} x_out)
     }
   }
+  halo_tail(tail);   // multi-GPU halo mode: the last block sends the dofs this colour's patches updated to the neighbours
 }
 
 // ---- fast path -----------------------------------------------------------------------------------
@@ -406,16 +407,12 @@ constexpr int kSwFastSlot = 256 + 528 + 32;  // doubles per patch slot: xs[256],
 // number (row values, packed local columns, neighbour list, inverse via cp.async); wave 2 gathers
 // x on the neighbourhood.  All loops have compile-time bounds; padding multiplies by the zero slot.
 template <int SR, int NBQ>
-__global__ void __launch_bounds__(kSwFastWarps * 32, (SR <= 24 && NBQ <= 4) ? MAMG_SW_MINB24 : MAMG_SW_MINB)
-schwarz_fast_kernel(int p0, int p1, const int* __restrict__ pidx32, const int* __restrict__ nbrp,
-                    const int* __restrict__ uid, const long long* __restrict__ inv_off,
-                    const double* __restrict__ vt, const uint32_t* __restrict__ ct4,
-                    const double* __restrict__ pinv, const double* __restrict__ b, double* x, int srow,
-                    int sq, int nbq, int smax, const SwProfile prof, int vstride) {
-  extern __shared__ __align__(16) double smem[];
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int patch = p0 + blockIdx.x * kSwFastWarps + warp;
-  if (patch >= p1) return;
+__device__ __forceinline__ void
+schwarz_fast_patch(int patch, int warp, int lane, double* smem, const int* __restrict__ pidx32, const int* __restrict__ nbrp,
+                   const int* __restrict__ uid, const long long* __restrict__ inv_off,
+                   const double* __restrict__ vt, const uint32_t* __restrict__ ct4,
+                   const double* __restrict__ pinv, const double* __restrict__ b, double* x, int srow,
+                   int sq, int nbq, const SwProfile& prof, int vstride) {
   double* xs = smem + warp * kSwFastSlot;
   double* Inv = xs + 256;
   double* rhs = Inv + 528;
@@ -467,6 +464,21 @@ schwarz_fast_kernel(int p0, int p1, const int* __restrict__ pidx32, const int* _
     }
   }
   if (my >= 0) x[my] = d;   // x_B = A_BB^{-1} (b_B - A_{B,out} x_out)
+}
+
+template <int SR, int NBQ>
+__global__ void __launch_bounds__(kSwFastWarps * 32, (SR <= 24 && NBQ <= 4) ? MAMG_SW_MINB24 : MAMG_SW_MINB)
+schwarz_fast_kernel(int p0, int p1, const int* __restrict__ pidx32, const int* __restrict__ nbrp,
+                    const int* __restrict__ uid, const long long* __restrict__ inv_off,
+                    const double* __restrict__ vt, const uint32_t* __restrict__ ct4,
+                    const double* __restrict__ pinv, const double* __restrict__ b, double* x, int srow,
+                    int sq, int nbq, int smax, const SwProfile prof, int vstride, const HaloTail tail) {
+  extern __shared__ __align__(16) double smem[];
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int patch = p0 + blockIdx.x * kSwFastWarps + warp;
+  if (patch < p1)
+    schwarz_fast_patch<SR, NBQ>(patch, warp, lane, smem, pidx32, nbrp, uid, inv_off, vt, ct4, pinv, b, x, srow, sq, nbq, prof, vstride);
+  halo_tail(tail);   // multi-GPU halo mode: the last block sends the dofs this colour's patches updated to the neighbours
 }
 
 // Host side: reorder the patches by colour, translate to the permuted numbering, build the
@@ -809,11 +821,11 @@ inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iper
 
 // patches [p0, p1) of one conflict colour (they commute, so they run concurrently)
 inline void schwarz_range_launch(const DSchwarz& d, int p0, int p1, const double* a, const double* b, double* x,
-                                 cudaStream_t stream) {
+                                 cudaStream_t stream, const HaloTail& tail) {
   if (d.fast) {
     const int g = (p1 - p0 + kSwFastWarps - 1) / kSwFastWarps;
     const size_t sm = (size_t)kSwFastWarps * kSwFastSlot * sizeof(double);
-#define MAMG_SWF_ARGS p0, p1, d.pidx32, d.nbrp, d.uid, d.inv_off, d.vt, d.ct4, d.pinv, b, x, d.srow, d.sq, d.nbq, d.max_size, d.prof, d.vstride
+#define MAMG_SWF_ARGS p0, p1, d.pidx32, d.nbrp, d.uid, d.inv_off, d.vt, d.ct4, d.pinv, b, x, d.srow, d.sq, d.nbq, d.max_size, d.prof, d.vstride, tail
     if (d.sr_t == 12) schwarz_fast_kernel<12, 1><<<g, kSwFastWarps * 32, sm, stream>>>(MAMG_SWF_ARGS);
     else if (d.sr_t == 24) schwarz_fast_kernel<24, 4><<<g, kSwFastWarps * 32, sm, stream>>>(MAMG_SWF_ARGS);
     else schwarz_fast_kernel<32, 8><<<g, kSwFastWarps * 32, sm, stream>>>(MAMG_SWF_ARGS);
@@ -822,7 +834,7 @@ inline void schwarz_range_launch(const DSchwarz& d, int p0, int p1, const double
   }
   const int grid = (p1 - p0 + d.ppc - 1) / d.ppc;
   const SwLayout lay = {d.max_size, d.max_nbr, d.srow};
-#define MAMG_SW_ARGS p0, p1, d.pat, d.pidx, d.prow, d.plen, d.nbr, d.lcol, d.pinv, a, b, x, lay
+#define MAMG_SW_ARGS p0, p1, d.pat, d.pidx, d.prow, d.plen, d.nbr, d.lcol, d.pinv, a, b, x, lay, tail
   if (d.warps == 1 && d.ppc == 4) schwarz_apply_kernel<1, 4><<<grid, 128, d.smem_apply, stream>>>(MAMG_SW_ARGS);
   else if (d.warps == 1) schwarz_apply_kernel<1, 2><<<grid, 64, d.smem_apply, stream>>>(MAMG_SW_ARGS);
   else if (d.warps == 2) schwarz_apply_kernel<2, 1><<<grid, 64, d.smem_apply, stream>>>(MAMG_SW_ARGS);

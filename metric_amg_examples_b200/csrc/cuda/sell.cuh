@@ -135,17 +135,21 @@ sell_spmv_dot_kernel(const SellView S, const double* __restrict__ d, double* __r
 // ---- K6  one colour of Gauss-Seidel / SOR on rows [r0, r1): x_i += w (b_i - a_i . x) / a_ii -------
 __global__ void __launch_bounds__(kBlock)
 sell_gs_kernel(int r0, int r1, const SellView S, const double* __restrict__ invd,
-               const uint8_t* __restrict__ skip, const double* __restrict__ b, double* x, double omega) {
+               const uint8_t* __restrict__ skip, const double* __restrict__ b, double* x, double omega,
+               const HaloTail tail) {
   const int lane = threadIdx.x % 32;
   const int slice = r0 / 32 + blockIdx.x * kSellWarps + threadIdx.x / 32;
-  if (slice * 32 >= r1) return;
-  const int row = slice * 32 + lane;
-  const bool active = row >= r0 && row < r1 && !(skip != nullptr && skip[row]);
-  if (!__any_sync(0xffffffffu, active)) return;
-  // lanes of a slice that straddles the colour boundary (or Schwarz rows) compute and discard: the
-  // rows of one colour do not couple, so what they read is never what an active lane writes
-  const double s = sell_row_dot(S, slice, lane, x);
-  if (active) x[row] += omega * (b[row] - s) * invd[row];
+  if (slice * 32 < r1) {
+    const int row = slice * 32 + lane;
+    const bool active = row >= r0 && row < r1 && !(skip != nullptr && skip[row]);
+    if (__any_sync(0xffffffffu, active)) {
+      // lanes of a slice that straddles the colour boundary (or Schwarz rows) compute and discard: the
+      // rows of one colour do not couple, so what they read is never what an active lane writes
+      const double s = sell_row_dot(S, slice, lane, x);
+      if (active) x[row] += omega * (b[row] - s) * invd[row];
+    }
+  }
+  halo_tail(tail);   // multi-GPU halo mode: the last block sends this colour's boundary rows to the neighbours
 }
 
 // damped Jacobi, out of place
