@@ -904,6 +904,21 @@ static HaloTail halo_tail_desc(DeviceState& D, const DLevel& l, const double* v,
   D.exch_bytes += bytes;
   return T;
 }
+// entries one exchange of the level sends (largest neighbour list): the push is folded into the producing
+// kernel only when ONE block can send it quickly; long lists (the finest levels) get the full-grid push kernel
+static int halo_list_len(const DLevel& l, int c, bool schwarz_color = false) {
+  const int nnb = (int)l.nbr_ranks.size();
+  const int cc = schwarz_color ? c : (c >= 0 ? c : (c == -1 ? l.ncolors : l.ncolors + 1));
+  const std::vector<int>& off = schwarz_color ? l.sw_send_off : l.send_off;
+  int total = 0;
+  for (int k = 0; k < nnb; ++k) total = std::max(total, off[(size_t)cc * nnb + k + 1] - off[(size_t)cc * nnb + k]);
+  return total;
+}
+static int halo_fuse_max() {   // MAMG_HALO_FUSE_MAX: longest list a producing kernel sends itself (0: always a push kernel)
+  static const int v = getenv("MAMG_HALO_FUSE_MAX") ? atoi(getenv("MAMG_HALO_FUSE_MAX")) : 2048;
+  return v;
+}
+
 static HaloTail no_halo_tail() {
   HaloTail T;
   std::memset(&T, 0, sizeof(T));
@@ -1028,7 +1043,7 @@ static void k_gs_color(DeviceState& D, const DLevel& l, int c, const double* b, 
   if (!any) return;   // every row of the colour belongs to Schwarz (same decision on every rank)
   // halo mode: the launch of this rank's last active block of the colour also sends the boundary rows
   int last_blk = -1;
-  if (halo_on(D, l) && l.use_sell)
+  if (halo_on(D, l) && l.use_sell && halo_list_len(l, c) <= halo_fuse_max())
     for (int blk = blk_lo(D, l); blk < blk_hi(D, l); ++blk)
       if (l.row1(blk, c) > l.row0(blk, c) && (l.color_active.empty() || l.color_active[blk * l.ncolors + c] > 0)) last_blk = blk;
   for (int blk = blk_lo(D, l); blk < blk_hi(D, l); ++blk) {
@@ -1129,7 +1144,7 @@ static void smooth(DeviceState& D, int lev, const double* b, double* x, bool pos
         // that gather or own them, sent by the last block of this rank's last patch launch of the colour
         const bool xch = D.world > 1 && snb > 1 && l.sw.xoff[(c + 1) * snb] > l.sw.xoff[c * snb];
         int last_blk = -1;
-        if (xch && halo_on(D, l))
+        if (xch && halo_on(D, l) && halo_list_len(l, c, true) <= halo_fuse_max())
           for (int blk = lo; blk < hi; ++blk)
             if (l.sw.cb_ptr[c * snb + blk + 1] > l.sw.cb_ptr[c * snb + blk]) last_blk = blk;
         for (int blk = lo; blk < hi; ++blk) {

@@ -105,9 +105,15 @@ __device__ __forceinline__ void halo_tail(const HaloTail& T) {
   for (int k = 0; k < T.nn; ++k) {
     double* dst = T.peers[T.peer[k]] + T.voff;
     const int* idx = T.send + T.beg[k];
-    for (int t = threadIdx.x; t < T.cnt[k]; t += blockDim.x) {
-      const int i = idx[t];
-      dst[i] = __ldcg(mine + i);   // written by other blocks of this launch: read past this SM's L1
+    for (int t0 = threadIdx.x; t0 < T.cnt[k]; t0 += 4 * blockDim.x) {   // 4 entries in flight per thread
+      int i[4];
+      double v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const int t = t0 + u * blockDim.x; i[u] = t < T.cnt[k] ? idx[t] : -1; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = i[u] >= 0 ? __ldcg(mine + i[u]) : 0.0;   // written by other blocks: read past this SM's L1
+#pragma unroll
+      for (int u = 0; u < 4; ++u) if (i[u] >= 0) dst[i[u]] = v[u];
     }
   }
   __threadfence_system();
