@@ -101,6 +101,7 @@ struct DeviceState {
   int64_t dev_bytes = 0;
   double* w[10] = {nullptr};  // Krylov work vectors (level-0 size)
   std::vector<double*> basis; // GMRES Krylov basis, allocated on first use
+  double* hcoef = nullptr;    // GMRES: one column of the Hessenberg matrix on the device
   double *io_a = nullptr, *io_b = nullptr;  // staging for host-array calls
   std::vector<void*> allocs;
   mamg_params prm;
@@ -1603,6 +1604,22 @@ static double k_dot(DeviceState& D, int n, const double* u, const double* v) {
   return D.h_scal[16];
 }
 
+// dot product left on the device (no host round trip); read back later together with others
+static void k_dot_dev(DeviceState& D, int n, const double* u, const double* v, double* out_dev) {
+  KScope ks(D, K_DOT);
+  dot_kernel<<<red_grid(D, n), kBlock, 0, D.stream>>>(n, u, v, D.partial, D.ticket, out_dev);
+}
+static void k_axpy_dev(DeviceState& D, int n, const double* coef_dev, double scale, const double* x, double* y) {
+  if (n == 0) return;
+  KScope ks(D, K_VEC);
+  axpy_dev_kernel<<<cdiv(n, kBlock), kBlock, 0, D.stream>>>(n, coef_dev, scale, x, y);
+}
+static void read_dev(DeviceState& D, const double* dev, int count, double* host) {
+  CUDA_OK(cudaMemcpyAsync(D.h_scal, dev, sizeof(double) * count, cudaMemcpyDeviceToHost, D.stream));
+  CUDA_OK(cudaStreamSynchronize(D.stream));
+  for (int k = 0; k < count; ++k) host[k] = D.h_scal[k];
+}
+
 // Preconditioned MINRES (Paige-Saunders with an SPD preconditioner; the residual estimate phibar
 // is the B-norm of the residual, as in block.iterative.MinRes).  Permuted ordering.
 static int minres_device(DeviceState& D, const double* b_nat, double* x_nat, double tol, bool relative,
@@ -1629,13 +1646,18 @@ static int minres_device(DeviceState& D, const double* b_nat, double* x_nat, dou
     k_axpby(D, n, 1.0 / beta, y, 0.0, v);               // v = y / beta
     k_spmv(D, l0, v, nullptr, y, false);                 // y = A v
     if (it >= 2) k_axpby(D, n, -beta / oldb, r1, 1.0, y);
-    const double alfa = k_dot(D, n, v, y);
-    k_axpby(D, n, -alfa / beta, r2, 1.0, y);
+    // alfa = v.y stays on the device: the update y -= (alfa/beta) r2 reads it there, and the host fetches it
+    // together with beta^2 after the preconditioner apply -- one synchronisation per iteration
+    k_dot_dev(D, n, v, y, D.scal + 16);
+    k_axpy_dev(D, n, D.scal + 16, -1.0 / beta, r2, y);
     std::swap(r1, r2);                                   // r1 = r2
     k_copy(D, n, y, r2);                                 // r2 = y
     apply_complete(D, r2, y);                            // y = B r2
     oldb = beta;
-    const double b2 = k_dot(D, n, r2, y);
+    k_dot_dev(D, n, r2, y, D.scal + 17);
+    double ab[2];
+    read_dev(D, D.scal + 16, 2, ab);
+    const double alfa = ab[0], b2 = ab[1];
     if (!(b2 >= 0.0)) { *niters = it; return 1; }
     beta = std::sqrt(b2);
     const double oldeps = epsln;
@@ -1651,11 +1673,11 @@ static int minres_device(DeviceState& D, const double* b_nat, double* x_nat, dou
     // w1 = w2; w2 = w; w = (v - oldeps*w1 - delta*w2) / gamma
     std::swap(w1, w2);
     std::swap(w2, w);
-    k_axpby(D, n, 1.0 / gamma, v, 0.0, t);
-    k_axpby(D, n, -oldeps / gamma, w1, 1.0, t);
-    k_axpby(D, n, -delta / gamma, w2, 1.0, t);
+    {   // direction and iterate in one pass
+      KScope ks(D, K_VEC);
+      minres_update_kernel<<<cdiv(n, kBlock), kBlock, 0, D.stream>>>(n, 1.0 / gamma, oldeps, delta, phi, v, w1, w2, t, x);
+    }
     std::swap(w, t);
-    k_axpby(D, n, phi, w, 1.0, x);
     residuals[it] = phibar;
   }
   k_gather(D, n, l0.iperm, x, x_nat);
@@ -1669,7 +1691,7 @@ static int gmres_device(DeviceState& D, const double* b_nat, double* x_nat, doub
                         int maxiter, int m, int* niters, double* residuals) {
   DLevel& l0 = D.lv[0];
   const int n = l0.n;
-  if (m < 1) m = 30;
+  if (m < 1 || m > 30) m = 30;
   while ((int)D.basis.size() < m + 1) D.basis.push_back(dalloc<double>(D, n));
   double *b = D.w[0], *x = D.w[1], *r = D.w[2], *z = D.w[3], *wv = D.w[4], *u = D.w[5];
   k_gather(D, n, l0.perm, b_nat, b);
@@ -1688,12 +1710,19 @@ static int gmres_device(DeviceState& D, const double* b_nat, double* x_nat, doub
     for (; j < m && it < maxiter && rn > target; ++j) {
       apply_complete(D, D.basis[j], z);                   // z = B v_j
       k_spmv(D, l0, z, nullptr, wv, false);               // w = A z
+      // modified Gram-Schmidt with the coefficients left on the device: every projection reads its h_ij there,
+      // the host fetches the whole column (and ||w||^2) once per inner iteration
+      if (!D.hcoef) D.hcoef = dalloc<double>(D, 32);
+      if (j + 2 > 32) throw std::runtime_error("GMRES restart length above 30 is not supported");
       for (int i = 0; i <= j; ++i) {
-        const double h = k_dot(D, n, wv, D.basis[i]);
-        Hm[(size_t)i * m + j] = h;
-        k_axpby(D, n, -h, D.basis[i], 1.0, wv);
+        k_dot_dev(D, n, wv, D.basis[i], D.hcoef + i);
+        k_axpy_dev(D, n, D.hcoef + i, -1.0, D.basis[i], wv);
       }
-      const double hn = std::sqrt(k_dot(D, n, wv, wv));
+      k_dot_dev(D, n, wv, wv, D.hcoef + j + 1);
+      double col[32];
+      read_dev(D, D.hcoef, j + 2, col);
+      for (int i = 0; i <= j; ++i) Hm[(size_t)i * m + j] = col[i];
+      const double hn = std::sqrt(col[j + 1]);
       Hm[(size_t)(j + 1) * m + j] = hn;
       if (hn > 0.0) k_axpby(D, n, 1.0 / hn, wv, 0.0, D.basis[j + 1]);
       for (int i = 0; i < j; ++i) {

@@ -574,4 +574,23 @@ axpby_kernel(int n, double a, const double* __restrict__ x, double b, double* __
   if (i < n) y[i] = a * x[i] + b * y[i];
 }
 
+// ---- MINRES / GMRES vector kernels with device-resident coefficients (no host round trip per dot) ------
+// y += sign * coef[0] * scale * x
+__global__ void __launch_bounds__(kBlock)
+axpy_dev_kernel(int n, const double* __restrict__ coef, double scale, const double* __restrict__ x, double* __restrict__ y) {
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  if (i < n) y[i] += coef[0] * scale * x[i];
+}
+// MINRES direction and iterate in one pass: t = (v - oldeps*w1 - delta*w2) / gamma ; x += phi * t   (t becomes the new w)
+__global__ void __launch_bounds__(kBlock)
+minres_update_kernel(int n, double inv_gamma, double oldeps, double delta, double phi, const double* __restrict__ v,
+                     const double* __restrict__ w1, const double* __restrict__ w2, double* __restrict__ t,
+                     double* __restrict__ x) {
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  const double ti = ((v[i] * inv_gamma - (oldeps * inv_gamma) * w1[i]) - (delta * inv_gamma) * w2[i]);
+  t[i] = ti;
+  x[i] += phi * ti;
+}
+
 }  // namespace mamg

@@ -83,14 +83,21 @@ int mamg_setup_partitioned(const mamg_params* p, int32_t n, const int32_t* indpt
   Csr A;
   A.n = A.m = n;
   A.ia.assign(indptr, indptr + n + 1);
-  A.ja.assign(indices, indices + nnz);
-  A.a.assign(data, data + nnz);
-  bool canonical = true;   // columns strictly ascending inside every row (what PETSc / scipy hand over)
+  A.ja.resize(nnz);
+  A.a.resize(nnz);
+  // the copies and checks below walk 10^9 entries at the BASELINE sizes: all of them run on every core
+  long long bad_col = 0, unsorted = 0;
+#pragma omp parallel for schedule(static) reduction(+ : bad_col, unsorted)
   for (int i = 0; i < n; ++i)
-    for (int q = A.ia[i]; q < A.ia[i + 1]; ++q) {
-      if (A.ja[q] < 0 || A.ja[q] >= n) { set_error("setup: column index out of range"); return -1; }
-      if (q > A.ia[i] && A.ja[q] <= A.ja[q - 1]) canonical = false;
+    for (int q = indptr[i]; q < indptr[i + 1]; ++q) {
+      const int j = indices[q];
+      A.ja[q] = j;
+      A.a[q] = data[q];
+      if (j < 0 || j >= n) ++bad_col;
+      if (q > indptr[i] && j <= indices[q - 1]) ++unsorted;
     }
+  if (bad_col) { set_error("setup: column index out of range"); return -1; }
+  const bool canonical = unsorted == 0;   // columns strictly ascending inside every row (what PETSc / scipy hand over)
   if (!canonical) {
     // the aggregation and colouring break ties by position inside the row: sort the rows and add up
     // duplicate entries so that the hierarchy does not depend on the caller's storage order
@@ -113,11 +120,16 @@ int mamg_setup_partitioned(const mamg_params* p, int32_t n, const int32_t* indpt
     }
     A = std::move(B);
   }
-  for (int i = 0; i < n; ++i) {
-    bool has_diag = false;
-    for (int q = A.ia[i]; q < A.ia[i + 1]; ++q)
-      if (A.ja[q] == i && A.a[q] != 0.0) has_diag = true;
-    if (!has_diag) { set_error("setup: row " + std::to_string(i) + " has no nonzero diagonal"); return -1; }
+  {
+    int first_bad = n;
+#pragma omp parallel for schedule(static) reduction(min : first_bad)
+    for (int i = 0; i < n; ++i) {
+      bool has_diag = false;
+      for (int q = A.ia[i]; q < A.ia[i + 1]; ++q)
+        if (A.ja[q] == i && A.a[q] != 0.0) has_diag = true;
+      if (!has_diag) first_bad = std::min(first_bad, i);
+    }
+    if (first_bad < n) { set_error("setup: row " + std::to_string(first_bad) + " has no nonzero diagonal"); return -1; }
   }
   {
     // the Gauss-Seidel and patch colourings treat the nonzero pattern as an undirected graph: with a

@@ -202,18 +202,27 @@ void galerkin_ua(const Csr& A, const std::vector<int>& agg, int nc, Csr& Ac) {
 // the diagonals of the Kuhn mesh, eliminated Dirichlet couplings) contribute nothing to any sum and
 // the setup already ignores them.  Removing them is bit-neutral for every kernel.  The diagonal stays.
 void csr_drop_zeros(Csr& A) {
-  int k = 0;
-  for (int i = 0; i < A.n; ++i) {
-    const int p0 = A.ia[i], p1 = A.ia[i + 1];
-    A.ia[i] = k;
-    for (int p = p0; p < p1; ++p)
-      if (A.a[p] != 0.0 || A.ja[p] == i) { A.ja[k] = A.ja[p]; A.a[k] = A.a[p]; ++k; }
+  const int n = A.n;
+  std::vector<int> ia2(n + 1, 0);
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < n; ++i) {
+    int cnt = 0;
+    for (int p = A.ia[i]; p < A.ia[i + 1]; ++p) cnt += (A.a[p] != 0.0 || A.ja[p] == i);
+    ia2[i + 1] = cnt;
   }
-  A.ia[A.n] = k;
-  A.ja.resize(k);
-  A.a.resize(k);
-  A.ja.shrink_to_fit();
-  A.a.shrink_to_fit();
+  for (int i = 0; i < n; ++i) ia2[i + 1] += ia2[i];
+  if (ia2[n] == A.ia[n]) return;   // nothing to drop
+  std::vector<int> ja2(ia2[n]);
+  std::vector<double> a2(ia2[n]);
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < n; ++i) {
+    int k = ia2[i];
+    for (int p = A.ia[i]; p < A.ia[i + 1]; ++p)
+      if (A.a[p] != 0.0 || A.ja[p] == i) { ja2[k] = A.ja[p]; a2[k] = A.a[p]; ++k; }
+  }
+  A.ia.swap(ia2);
+  A.ja.swap(ja2);
+  A.a.swap(a2);
 }
 
 void csr_transpose(const Csr& A, Csr& At) {
