@@ -1054,7 +1054,8 @@ static void k_gs_color(DeviceState& D, const DLevel& l, int c, const double* b, 
     KScope ks(D, K_GS);
     if (l.use_sell) {
       const HaloTail tail = blk == last_blk ? halo_tail_desc(D, l, x, c) : no_halo_tail();
-      sell_gs_kernel<<<sell_grid(r0, r1), kBlock, 0, D.stream>>>(r0, r1, l.S, l.invd, l.skip, b, x, omega, tail);
+      if (tail.nn > 0) sell_gs_kernel<true><<<sell_grid(r0, r1), kBlock, 0, D.stream>>>(r0, r1, l.S, l.invd, l.skip, b, x, omega, tail);
+      else sell_gs_kernel<false><<<sell_grid(r0, r1), kBlock, 0, D.stream>>>(r0, r1, l.S, l.invd, l.skip, b, x, omega, tail);
       continue;
     }
     const int grid = cdiv((long long)cdiv(r1 - r0, l.unroll) * l.lanes, kBlock);

@@ -203,7 +203,7 @@ __device__ __forceinline__ void cp_async_wait_all() {
 // descriptor-addressed arrays, then the row values / x gathers they point to), so one warp has a
 // whole patch (~15 KB) in flight; the arithmetic then runs out of shared memory with one thread
 // per patch row (no shuffles) and a packed symmetric mat-vec.
-template <int WPP, int PPC>
+template <int WPP, int PPC, bool TAIL>
 __global__ void __launch_bounds__(WPP * PPC * 32)
 schwarz_apply_kernel(int p0, int p1, const SwPatch* __restrict__ pat, const int* __restrict__ pidx,
                      const int* __restrict__ prow, const int* __restrict__ plen,
@@ -284,7 +284,7 @@ schwarz_apply_kernel(int p0, int p1, const SwPatch* __restrict__ pat, const int*
       x[idx[k]] = d;   // x_B = A_BB^{-1} (b_B - A_{B,out} x_out)
     }
   }
-  halo_tail(tail);   // multi-GPU halo mode: the last block sends the dofs this colour's patches updated to the neighbours
+  if (TAIL) halo_tail(tail);   // multi-GPU halo mode: the last block sends the dofs this colour's patches updated to the neighbours
 }
 
 // ---- fast path -----------------------------------------------------------------------------------
@@ -466,7 +466,7 @@ schwarz_fast_patch(int patch, int warp, int lane, double* smem, const int* __res
   if (my >= 0) x[my] = d;   // x_B = A_BB^{-1} (b_B - A_{B,out} x_out)
 }
 
-template <int SR, int NBQ>
+template <int SR, int NBQ, bool TAIL>
 __global__ void __launch_bounds__(kSwFastWarps * 32, (SR <= 24 && NBQ <= 4) ? MAMG_SW_MINB24 : MAMG_SW_MINB)
 schwarz_fast_kernel(int p0, int p1, const int* __restrict__ pidx32, const int* __restrict__ nbrp,
                     const int* __restrict__ uid, const long long* __restrict__ inv_off,
@@ -478,7 +478,7 @@ schwarz_fast_kernel(int p0, int p1, const int* __restrict__ pidx32, const int* _
   const int patch = p0 + blockIdx.x * kSwFastWarps + warp;
   if (patch < p1)
     schwarz_fast_patch<SR, NBQ>(patch, warp, lane, smem, pidx32, nbrp, uid, inv_off, vt, ct4, pinv, b, x, srow, sq, nbq, prof, vstride);
-  halo_tail(tail);   // multi-GPU halo mode: the last block sends the dofs this colour's patches updated to the neighbours
+  if (TAIL) halo_tail(tail);   // multi-GPU halo mode: the last block sends the dofs this colour's patches updated to the neighbours
 }
 
 // Host side: reorder the patches by colour, translate to the permuted numbering, build the
@@ -796,15 +796,25 @@ inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iper
     sync_or_throw("Schwarz blob kernel");
     uniq_blob_bytes += (long long)nu * (8LL * d.vstride + 4LL * d.sq * 32);
     const int fsm = kSwFastWarps * kSwFastSlot * (int)sizeof(double);
-    cudaFuncSetAttribute(schwarz_fast_kernel<12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm);
-    cudaFuncSetAttribute(schwarz_fast_kernel<24, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm);
-    cudaFuncSetAttribute(schwarz_fast_kernel<32, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm);
+    cudaFuncSetAttribute(schwarz_fast_kernel<12, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm);
+    cudaFuncSetAttribute(schwarz_fast_kernel<24, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm);
+    cudaFuncSetAttribute(schwarz_fast_kernel<32, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm);
+    cudaFuncSetAttribute(schwarz_fast_kernel<12, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm);
+    cudaFuncSetAttribute(schwarz_fast_kernel<24, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm);
+    cudaFuncSetAttribute(schwarz_fast_kernel<32, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm);
   }
   if (d.smem_apply > 48 * 1024) {
-    cudaFuncSetAttribute(schwarz_apply_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_apply);
-    cudaFuncSetAttribute(schwarz_apply_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_apply);
-    cudaFuncSetAttribute(schwarz_apply_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_apply);
-    cudaFuncSetAttribute(schwarz_apply_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_apply);
+    // (the opt-in value is per function: keep the largest request of all hierarchies of this process)
+    static size_t opted = 0;
+    opted = std::max(opted, d.smem_apply);
+    cudaFuncSetAttribute(schwarz_apply_kernel<1, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)opted);
+    cudaFuncSetAttribute(schwarz_apply_kernel<1, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)opted);
+    cudaFuncSetAttribute(schwarz_apply_kernel<2, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)opted);
+    cudaFuncSetAttribute(schwarz_apply_kernel<4, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)opted);
+    cudaFuncSetAttribute(schwarz_apply_kernel<1, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)opted);
+    cudaFuncSetAttribute(schwarz_apply_kernel<1, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)opted);
+    cudaFuncSetAttribute(schwarz_apply_kernel<2, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)opted);
+    cudaFuncSetAttribute(schwarz_apply_kernel<4, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)opted);
   }
   // Algorithmic bytes of one sweep.
   //  stored-factor model (every patch owns its data): values + local columns of the row entries,
@@ -826,19 +836,31 @@ inline void schwarz_range_launch(const DSchwarz& d, int p0, int p1, const double
     const int g = (p1 - p0 + kSwFastWarps - 1) / kSwFastWarps;
     const size_t sm = (size_t)kSwFastWarps * kSwFastSlot * sizeof(double);
 #define MAMG_SWF_ARGS p0, p1, d.pidx32, d.nbrp, d.uid, d.inv_off, d.vt, d.ct4, d.pinv, b, x, d.srow, d.sq, d.nbq, d.max_size, d.prof, d.vstride, tail
-    if (d.sr_t == 12) schwarz_fast_kernel<12, 1><<<g, kSwFastWarps * 32, sm, stream>>>(MAMG_SWF_ARGS);
-    else if (d.sr_t == 24) schwarz_fast_kernel<24, 4><<<g, kSwFastWarps * 32, sm, stream>>>(MAMG_SWF_ARGS);
-    else schwarz_fast_kernel<32, 8><<<g, kSwFastWarps * 32, sm, stream>>>(MAMG_SWF_ARGS);
+#define MAMG_SWF_LAUNCH(SR, NBQ)                                                                         \
+    do {                                                                                                 \
+      if (tail.nn > 0) schwarz_fast_kernel<SR, NBQ, true><<<g, kSwFastWarps * 32, sm, stream>>>(MAMG_SWF_ARGS); \
+      else schwarz_fast_kernel<SR, NBQ, false><<<g, kSwFastWarps * 32, sm, stream>>>(MAMG_SWF_ARGS);      \
+    } while (0)
+    if (d.sr_t == 12) MAMG_SWF_LAUNCH(12, 1);
+    else if (d.sr_t == 24) MAMG_SWF_LAUNCH(24, 4);
+    else MAMG_SWF_LAUNCH(32, 8);
+#undef MAMG_SWF_LAUNCH
 #undef MAMG_SWF_ARGS
     return;
   }
   const int grid = (p1 - p0 + d.ppc - 1) / d.ppc;
   const SwLayout lay = {d.max_size, d.max_nbr, d.srow};
 #define MAMG_SW_ARGS p0, p1, d.pat, d.pidx, d.prow, d.plen, d.nbr, d.lcol, d.pinv, a, b, x, lay, tail
-  if (d.warps == 1 && d.ppc == 4) schwarz_apply_kernel<1, 4><<<grid, 128, d.smem_apply, stream>>>(MAMG_SW_ARGS);
-  else if (d.warps == 1) schwarz_apply_kernel<1, 2><<<grid, 64, d.smem_apply, stream>>>(MAMG_SW_ARGS);
-  else if (d.warps == 2) schwarz_apply_kernel<2, 1><<<grid, 64, d.smem_apply, stream>>>(MAMG_SW_ARGS);
-  else schwarz_apply_kernel<4, 1><<<grid, 128, d.smem_apply, stream>>>(MAMG_SW_ARGS);
+#define MAMG_SW_LAUNCH(WPP, PPC, THREADS)                                                                  \
+  do {                                                                                                     \
+    if (tail.nn > 0) schwarz_apply_kernel<WPP, PPC, true><<<grid, THREADS, d.smem_apply, stream>>>(MAMG_SW_ARGS); \
+    else schwarz_apply_kernel<WPP, PPC, false><<<grid, THREADS, d.smem_apply, stream>>>(MAMG_SW_ARGS);      \
+  } while (0)
+  if (d.warps == 1 && d.ppc == 4) MAMG_SW_LAUNCH(1, 4, 128);
+  else if (d.warps == 1) MAMG_SW_LAUNCH(1, 2, 64);
+  else if (d.warps == 2) MAMG_SW_LAUNCH(2, 1, 64);
+  else MAMG_SW_LAUNCH(4, 1, 128);
+#undef MAMG_SW_LAUNCH
 #undef MAMG_SW_ARGS
 }
 

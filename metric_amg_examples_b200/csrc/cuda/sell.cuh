@@ -133,6 +133,7 @@ sell_spmv_dot_kernel(const SellView S, const double* __restrict__ d, double* __r
 }
 
 // ---- K6  one colour of Gauss-Seidel / SOR on rows [r0, r1): x_i += w (b_i - a_i . x) / a_ii -------
+template <bool TAIL>
 __global__ void __launch_bounds__(kBlock)
 sell_gs_kernel(int r0, int r1, const SellView S, const double* __restrict__ invd,
                const uint8_t* __restrict__ skip, const double* __restrict__ b, double* x, double omega,
@@ -149,7 +150,7 @@ sell_gs_kernel(int r0, int r1, const SellView S, const double* __restrict__ invd
       if (active) x[row] += omega * (b[row] - s) * invd[row];
     }
   }
-  halo_tail(tail);   // multi-GPU halo mode: the last block sends this colour's boundary rows to the neighbours
+  if (TAIL) halo_tail(tail);   // multi-GPU halo mode: the last block sends this colour's boundary rows to the neighbours
 }
 
 // damped Jacobi, out of place
