@@ -11,8 +11,8 @@ E="python tools/dev_time.py --kind emi -n 200 --prm default_metric_parameters --
 $B > gpurun_out/${tag}_plain_b.log 2>&1 || { echo "plain bidomain run failed"; tail -5 gpurun_out/${tag}_plain_b.log; exit 1; }
 $E > gpurun_out/${tag}_plain_e.log 2>&1 || { echo "plain emi run failed"; tail -5 gpurun_out/${tag}_plain_e.log; exit 1; }
 tail -1 gpurun_out/${tag}_plain_b.log; tail -1 gpurun_out/${tag}_plain_e.log
-ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/${tag}_launches_b.csv $B > /dev/null 2>&1
-ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv --log-file gpurun_out/${tag}_launches_e.csv $E > /dev/null 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/${tag}_launches_b.csv $B > /dev/null 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/${tag}_launches_e.csv $E > /dev/null 2>&1
 F="ncu --set full --clock-control none --import-source on"
 $F -k regex:schwarz_fast -s 100 -c 2 -f -o gpurun_out/${tag}_schwarz_fast $B > /dev/null 2>&1
 $F -k regex:sell_gs -s 0 -c 3 -f -o gpurun_out/${tag}_sell_gs $B > /dev/null 2>&1
