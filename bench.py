@@ -120,6 +120,7 @@ def class_bytes(H):
     infos = [H.level_info(l) for l in range(L)]
     prm = H.params
     out = {k: 0.0 for k in H.KERNEL_CLASSES}
+    gs_lvl = []
     sgs = prm.smoother in (3, 6)
     for l in range(L - 1):
         n, nnz, nc = infos[l]["rows"], infos[l]["nnz"], infos[l + 1]["rows"]
@@ -139,6 +140,7 @@ def class_bytes(H):
         sweep_bw = sweep - (12 * nnz_last + 28 * n_last) if prm.smoother == 3 else sweep
         per_smooth = (sweep + sweep_bw) if sgs else sweep
         out["gs"] += per_smooth * (prm.presmooth_iter + prm.postsmooth_iter)
+        gs_lvl.append(per_smooth * (prm.presmooth_iter + prm.postsmooth_iter))
         if infos[l]["n_patches"]:
             # "Schwarz level-0 (stored factors)" -- every patch owns its inverse and its row values;
             # the shared-blob figure (what the kernel has to bring in at least once per launch) is kept beside it
@@ -164,6 +166,7 @@ def class_bytes(H):
         res["dot"] += (niters + 1) * 16 * n0
         # pcg update (48 n) + direction (24 n) per iteration, zero-fill of z per apply, gathers/copies at both ends
         res["vector"] += niters * 72 * n0 + cycle_applies * 8 * n0 + 5 * 20 * n0
+        res["gs_by_level"] = [v * cycle_applies for v in gs_lvl]
         return res
     return finish
 
@@ -368,6 +371,7 @@ def run_mamg(a):
     dom_ms, dom_launches = prof[dom]
     # with several ranks the smoothing / transfer / SpMV classes run on 1/world of the rows of the
     # distributed levels (per-rank numbers; small replicated levels make this a slight under-estimate)
+    gs_by_level = cb.pop("gs_by_level")
     share = {k: (1.0 / world if k in ("spmv", "gs", "schwarz", "schwarz_shared", "restrict", "scale", "prolong") else 1.0) for k in cb}
     achieved = cb[dom] * share[dom] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     kernels = {k: {"ms": round(prof[k][0], 3), "launches": prof[k][1], "share": round(prof[k][0] / tot_ms, 4),
@@ -401,7 +405,7 @@ def run_mamg(a):
                    "multi_gpu": (f"one system row-partitioned over {world} GPUs ({world} {'x-strips' if a.workload.startswith('emi') else 'z-slabs'}), "
                                  f"{'matrices stored per rank, ' if halo_mode else 'hierarchy replicated, '}"
                                  f"exchange: {exch_mode}; {ncoll} exchanges and {xbytes / 1e6:.1f} MB sent per rank and solve; levels < "
-                                 f"{os.environ.get('MAMG_DIST_MIN_ROWS', '1000000')} rows replicated")
+                                 f"{os.environ.get('MAMG_DIST_MIN_ROWS', '6000000' if halo_mode else '1000000')} rows replicated")
                    if world > 1 else "single",
                    "l2_note": (f"level-0 matrix {12 * nnz0 / 1e9:.2f} GB and vectors {8 * ndofs / 1e6:.0f} MB each: "
                                + ("larger than" if 12 * nnz0 > 126e6 else "NOT larger than") + " the 126 MB L2")},
@@ -433,6 +437,8 @@ def run_mamg(a):
         "sell": [{"rows": H.stats(l)["rows"], "nnz_stored": H.stats(l)["nnz_stored"], "slots": H.stats(l)["sell_slots"]}
                  for l in range(min(H.num_levels, 4))],
         "gs_ms_by_level": [round(float(v), 2) for v in prof_lv[:, 1]],
+        "gs_alg_GBs_by_level": [round(gs_by_level[l] / world / (float(prof_lv[l, 1]) * 1e-3) / 1e9, 1) if l < len(gs_by_level) and prof_lv[l, 1] > 0
+                                else None for l in range(min(H.num_levels, 8))],
         "level_rows": [H.level_info(l)["rows"] for l in range(H.num_levels)],
         "host": {"assemble_s": round(t_asm, 2), "setup_s": round(t_setup, 2), "upload_s": round(t_upload, 2),
                  "device_GB": round(H.device_bytes() / 1e9, 2), "host_peak_GB": round(host_peak_gb, 1),

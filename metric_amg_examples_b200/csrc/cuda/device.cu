@@ -219,11 +219,13 @@ static int pick_lanes(double avg) {
   return l;
 }
 
-static int dist_min_rows() {
+static int dist_min_rows(bool halo = false) {
   const char* env = getenv("MAMG_DIST_MIN_ROWS");
-  // smaller levels are executed redundantly by every rank (no communication); measured on 4 x B200 at
-  // 16 M DOFs: 1 M rows -> 994 ms per solve, 100 k rows -> 1076 ms (each exchange costs ~35 us of latency + skew)
-  return env ? atoi(env) : 1000000;
+  // smaller levels are executed redundantly by every rank (no communication).  Round-1 scheme, measured on
+  // 4 x B200 at 16 M DOFs: 1 M rows -> 994 ms per solve, 100 k rows -> 1076 ms (~35 us per exchange).  Halo mode:
+  // a level visit costs ~24 exchanges of ~12 us (measured at C4 on 2 GPUs), which a level of ~420 B/row of
+  // traffic per visit only wins back above ~5 M rows
+  return env ? atoi(env) : (halo ? 6000000 : 1000000);
 }
 
 static int pick_unroll(int n) {
@@ -367,7 +369,7 @@ static void upload_hierarchy(const Hierarchy& H, DeviceState& D) {
       dl.nb = 1;
     } else {
       dl.ncolors = hl.ncolors;
-      dl.nb = (H.nparts > 1 && !hl.part.empty() && n >= dist_min_rows()) ? H.nparts : 1;
+      dl.nb = (H.nparts > 1 && !hl.part.empty() && n >= dist_min_rows(D.halo && D.world > 1)) ? H.nparts : 1;
       const int nbc = dl.nb * dl.ncolors;
       auto key = [&](int i) { return (dl.nb > 1 ? hl.part[i] : 0) * dl.ncolors + hl.color[i]; };
       dl.bc_ptr.assign(nbc + 1, 0);
@@ -699,7 +701,7 @@ push_kernel(PushRanges R, long long voff, double* const* __restrict__ peers, int
     const volatile long long* flag = reinterpret_cast<const volatile long long*>(peers[me]) + threadIdx.x;
     const long long t0 = clock64();
     while (*flag < phase) {
-      if (clock64() - t0 > 20000000000LL) { printf("mamg: peer %d never reached exchange %lld\n", (int)threadIdx.x, phase); __trap(); }
+      if (clock64() - t0 > g_spin_limit) { printf("mamg: peer %d never reached exchange %lld\n", (int)threadIdx.x, phase); __trap(); }
     }
     __threadfence_system();
   }
@@ -759,7 +761,7 @@ halo_push_kernel(HaloPush P, const int* __restrict__ send, long long voff, doubl
     const volatile long long* flag = reinterpret_cast<const volatile long long*>(peers[me]) + P.peer[threadIdx.x];
     const long long t0 = clock64();
     while (*flag < phase) {
-      if (clock64() - t0 > 40000000000LL) { printf("mamg: rank %d: neighbour %d never reached exchange %lld\n", me, P.peer[threadIdx.x], phase); __trap(); }
+      if (clock64() - t0 > g_spin_limit) { printf("mamg: rank %d: neighbour %d never reached exchange %lld\n", me, P.peer[threadIdx.x], phase); __trap(); }
     }
     __threadfence_system();
   }
@@ -800,7 +802,7 @@ list_push_all_kernel(int cnt, const int* __restrict__ idx, long long voff, doubl
     const volatile long long* flag = reinterpret_cast<const volatile long long*>(peers[me]) + threadIdx.x;
     const long long t0 = clock64();
     while (*flag < phase) {
-      if (clock64() - t0 > 40000000000LL) { printf("mamg: rank %d: peer %d never reached exchange %lld\n", me, (int)threadIdx.x, phase); __trap(); }
+      if (clock64() - t0 > g_spin_limit) { printf("mamg: rank %d: peer %d never reached exchange %lld\n", me, (int)threadIdx.x, phase); __trap(); }
     }
     __threadfence_system();
   }
@@ -831,7 +833,7 @@ allreduce_kernel(int count, double* v, int op, int first, double* sc, double* co
     const volatile long long* flag = reinterpret_cast<const volatile long long*>(peers[me]) + q;
     const long long t0 = clock64();
     while (*flag < phase) {
-      if (clock64() - t0 > 40000000000LL) { printf("mamg: rank %d: peer %d never reached all-reduce %lld\n", me, q, phase); __trap(); }
+      if (clock64() - t0 > g_spin_limit) { printf("mamg: rank %d: peer %d never reached all-reduce %lld\n", me, q, phase); __trap(); }
     }
     __threadfence_system();
   }
@@ -1947,6 +1949,11 @@ int mamg_dist_init(mamg_handle h, int32_t rank, int32_t world, const void* uniqu
   }
   D->rank = rank;
   D->world = world;
+  {
+    const char* env = getenv("MAMG_PEER_TIMEOUT_S");
+    const long long limit = (long long)((env ? atof(env) : 60.0) * 2.0e9);
+    CUDA_OK(cudaMemcpyToSymbol(g_spin_limit, &limit, sizeof(limit)));
+  }
   drop_graphs(*D);
   return 0;
   MAMG_CATCH

@@ -78,6 +78,11 @@ __device__ __forceinline__ unsigned int ld_stream(const unsigned int* p) {
 // retires (ticket), that block stores the listed boundary entries of the vector into the neighbour
 // ranks' copies, raises this rank's flag there and waits for theirs -- the exchange costs no launch of
 // its own.  nn = 0: no exchange.  See halo_push_kernel (device.cu) for the protocol.
+// clock cycles a rank spins on a peer's flag before it gives up with a trap (a peer that never arrives would
+// otherwise hang the GPU).  MAMG_PEER_TIMEOUT_S (default 60 s at ~2 GHz) sets it at mamg_dist_init; benign skew
+// between ranks -- a rank that enters a solve seconds later because of host-side work -- stays far below it.
+__device__ long long g_spin_limit = 120000000000LL;
+
 struct HaloTail {
   int nn;
   int peer[8], beg[8], cnt[8];
@@ -127,7 +132,7 @@ __device__ __forceinline__ void halo_tail(const HaloTail& T) {
     const volatile long long* flag = reinterpret_cast<const volatile long long*>(T.peers[T.me]) + T.peer[threadIdx.x];
     const long long t0 = clock64();
     while (*flag < ht_phase) {
-      if (clock64() - t0 > 40000000000LL) { printf("mamg: rank %d: neighbour %d never reached exchange %lld\n", T.me, T.peer[threadIdx.x], ht_phase); __trap(); }
+      if (clock64() - t0 > g_spin_limit) { printf("mamg: rank %d: neighbour %d never reached exchange %lld\n", T.me, T.peer[threadIdx.x], ht_phase); __trap(); }
     }
     __threadfence_system();
   }

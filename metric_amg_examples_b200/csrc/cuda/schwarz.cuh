@@ -433,7 +433,7 @@ schwarz_fast_patch(int patch, int warp, int lane, double* smem, const int* __res
   {
     const double* vp = vt + uu * vstride + lane;
 #pragma unroll
-    for (int e = 0; e < SR; ++e) v[e] = lane < prof.cnt[e] ? ld_stream(vp + prof.off[e]) : 0.0;   // cnt[e] = 0 for e >= srow
+    for (int e = 0; e < SR; ++e) v[e] = (e < srow && lane < prof.cnt[e]) ? ld_stream(vp + prof.off[e]) : 0.0;
   }
   uint32_t c4[SR / 4];
   {
@@ -454,16 +454,14 @@ schwarz_fast_patch(int patch, int warp, int lane, double* smem, const int* __res
   rhs[lane] = my >= 0 ? bk - acc : 0.0;
   cp_async_wait_all();
   __syncwarp();
-  // packed symmetric mat-vec: entry (lane, c) sits at tri(max, min).  Lanes >= s run along on whatever the
-  // slot holds (their result is never stored), so the only test per step is the warp-uniform c < s
   double d = 0.0;
-  const double* row = Inv + lane * (lane + 1) / 2;   // (lane, c) for c <= lane
-  const double* colp = Inv + lane;                   // (c, lane) for c > lane, at c (c + 1) / 2
+  const int base = lane * (lane + 1) / 2;
 #pragma unroll
   for (int c = 0; c < 32; ++c) {
-    if (c >= s) break;
-    const double iv = c <= lane ? row[c] : colp[c * (c + 1) / 2];
-    d += iv * rhs[c];
+    if (c < s && lane < s) {   // only the s x s part of the staged inverse is defined
+      const int ad = c <= lane ? base + c : c * (c + 1) / 2 + lane;
+      d += Inv[ad] * rhs[c];
+    }
   }
   if (my >= 0) x[my] = d;   // x_B = A_BB^{-1} (b_B - A_{B,out} x_out)
 }

@@ -45,6 +45,9 @@ def main():
         z = H.apply(r)
         ncoll = H.collective_count()
         b, xt = s.random_rhs(1)
+        if rank == world - 1:
+            import time
+            time.sleep(1.5)   # injected skew: the last rank enters the solve late; its peers spin on its flags meanwhile
         x, info = H.pcg(b, tolerance=tol, maxiter=500)
         # every rank must hold the same result (vectors are complete on every rank)
         zt = torch.from_numpy(z).cuda()
