@@ -43,6 +43,7 @@ struct DLevel {
   int n = 0, nnz = 0, nc = 0, ncolors = 0, lanes = 8, unroll = 4;
   int *ia = nullptr, *ja = nullptr;
   double *a = nullptr, *invd = nullptr;
+  double* invl1 = nullptr;       // 1 / sum_j |a_ij| (SMOOTHER_L1DIAG only)
   uint8_t* skip = nullptr;
   int *agg = nullptr, *cptr = nullptr, *cidx = nullptr;
   double *x = nullptr, *b = nullptr, *t = nullptr;
@@ -421,6 +422,7 @@ static void upload_hierarchy(const Hierarchy& H, DeviceState& D) {
     dl.nnz = ia[n];
     std::vector<int> ja(dl.nnz);
     std::vector<double> a(dl.nnz), invd(n, 1.0);
+    std::vector<double> invl1(H.prm.smoother == MAMG_SMOOTHER_L1DIAG ? n : 0, 1.0);
 #pragma omp parallel
     {
       std::vector<std::pair<int, double>> buf;
@@ -432,17 +434,21 @@ static void upload_hierarchy(const Hierarchy& H, DeviceState& D) {
         for (int k = 0; k < cnt; ++k) buf[k] = {iperm[l][hl.A.ja[p0 + k]], hl.A.a[p0 + k]};
         std::sort(buf.begin(), buf.end(),
                   [](const std::pair<int, double>& u, const std::pair<int, double>& v) { return u.first < v.first; });
+        double l1 = 0.0;
         for (int k = 0; k < cnt; ++k) {
           ja[ia[i] + k] = buf[k].first;
           a[ia[i] + k] = buf[k].second;
+          l1 += std::fabs(buf[k].second);
           if (buf[k].first == i) invd[i] = 1.0 / buf[k].second;
         }
+        if (!invl1.empty()) invl1[i] = 1.0 / l1;
       }
     }
     dl.ia = upload(D, ia);
     dl.ja = upload(D, ja);
     dl.a = upload(D, a);
     dl.invd = upload(D, invd);
+    if (!invl1.empty()) dl.invl1 = upload(D, invl1);
     dl.perm = upload(D, perm[l]);
     dl.iperm = upload(D, iperm[l]);
     dl.x_own = dl.x = carve(n);
@@ -536,7 +542,7 @@ static void upload_hierarchy(const Hierarchy& H, DeviceState& D) {
     // persistent tail: the longest suffix of levels that are small, undistributed, plain UA levels
     const char* env = getenv("MAMG_TAIL_ROWS");
     const int tail_rows = env ? atoi(env) : 4096;
-    const bool smoother_ok = H.prm.smoother != MAMG_SMOOTHER_JACOBI;
+    const bool smoother_ok = H.prm.smoother != MAMG_SMOOTHER_JACOBI && H.prm.smoother != MAMG_SMOOTHER_L1DIAG;
     int k0 = L;
     while (k0 > 0) {
       const DLevel& dl = D.lv[k0 - 1];
@@ -1074,14 +1080,15 @@ static void gs_backward(DeviceState& D, const DLevel& l, const double* b, double
   for (int c = l.ncolors - 1 - skip_last; c >= 0; --c) k_gs_color(D, l, c, b, x, w);
 }
 
-static void k_jacobi(DeviceState& D, DLevel& l, const double* b, double* x, double w) {
+// damped Jacobi (invd = 1 / a_ii, weight w) or l1-Jacobi (SMOOTHER_L1DIAG: invd = 1 / sum_j |a_ij|, w = 1)
+static void k_jacobi(DeviceState& D, DLevel& l, const double* b, double* x, double w, const double* invd) {
   const int r0 = own_lo(D, l), r1 = own_hi(D, l);
   if (r1 > r0) {
     const int grid = cdiv((long long)(r1 - r0) * l.lanes, kBlock);
     KScope ks(D, K_GS);
-    if (l.use_sell) sell_jacobi_kernel<<<sell_grid(r0, r1), kBlock, 0, D.stream>>>(r0, r1, l.S, l.invd, l.skip, b, x, l.t, w);
+    if (l.use_sell) sell_jacobi_kernel<<<sell_grid(r0, r1), kBlock, 0, D.stream>>>(r0, r1, l.S, invd, l.skip, b, x, l.t, w);
     else LANES_SWITCH(l.lanes,
-      jacobi_kernel<LN><<<grid, kBlock, 0, D.stream>>>(r0, r1, l.ia, l.ja, l.a, l.invd, l.skip, b, x, l.t, w));
+      jacobi_kernel<LN><<<grid, kBlock, 0, D.stream>>>(r0, r1, l.ia, l.ja, l.a, invd, l.skip, b, x, l.t, w));
   }
   if (halo_on(D, l)) {   // new iterate on the owned rows, then its boundary rows to the neighbours
     if (r1 > r0) {
@@ -1112,7 +1119,8 @@ static void smooth(DeviceState& D, int lev, const double* b, double* x, bool pos
   auto point = [&]() {
     for (int it = 0; it < iters; ++it) {
       switch (P.smoother) {
-        case MAMG_SMOOTHER_JACOBI: k_jacobi(D, l, b, x, P.relaxation); break;
+        case MAMG_SMOOTHER_JACOBI: k_jacobi(D, l, b, x, P.relaxation, l.invd); break;
+        case MAMG_SMOOTHER_L1DIAG: k_jacobi(D, l, b, x, 1.0, l.invl1); break;
         case MAMG_SMOOTHER_GS:
           if (!post) gs_forward(D, l, b, x, 1.0); else gs_backward(D, l, b, x, 1.0);
           break;

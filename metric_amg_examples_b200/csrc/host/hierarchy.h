@@ -61,6 +61,9 @@ struct Hierarchy {
 // ---- setup pieces (each file states the reference lines it restates) -------
 void aggregate_hem(const Csr& A, const int* part, std::vector<int>& agg, int& nc);
 void aggregate_vmb(const Csr& A, const int* part, double strong, int max_agg, std::vector<int>& agg, int& nc);
+void aggregate_hec(const Csr& A, const int* part, int max_agg, std::vector<int>& agg, int& nc);
+void aggregate_mwm(const Csr& A, const int* part, std::vector<int>& agg, int& nc);
+void aggregate_mis(const Csr& A, const int* part, double strong, std::vector<int>& agg, int& nc);
 void galerkin_ua(const Csr& A, const std::vector<int>& agg, int nc, Csr& Ac);
 void csr_transpose(const Csr& A, Csr& At);
 void csr_drop_zeros(Csr& A);                              // removes exact zeros off the diagonal

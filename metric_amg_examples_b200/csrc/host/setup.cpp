@@ -77,6 +77,118 @@ void aggregate_hem(const Csr& A, const int* part, std::vector<int>& agg, int& nc
   }
 }
 
+// The remaining aggregation_type values of haznics (src/amg_parameters.py:16 lists VMB, MIS, MWM, HEC; HEM is
+// what the metric dicts use).  HAZmath's source is not available here, so these are the textbook algorithms
+// their names stand for, frozen like every other choice of this setup:
+//   HEC  heavy-edge coarsening: in natural order, a free row joins its heaviest neighbour -- a new pair if
+//        that neighbour is free, else the neighbour's aggregate while it has room (max_aggregation)
+//   MWM  maximal weighted matching: greedy over all couplings sorted by decreasing |a_ij| (ties: lower row,
+//        lower column first); leftovers join the aggregate of their heaviest matched neighbour
+//   MIS  aggregation around a greedy maximal independent set of the strong-coupling graph: every root
+//        takes its free strong neighbours, remaining rows join the root aggregate they are most strongly tied to
+void aggregate_hec(const Csr& A, const int* part, int max_agg, std::vector<int>& agg, int& nc) {
+  const int n = A.n;
+  agg.assign(n, -2);
+  nc = 0;
+  if (max_agg < 2) max_agg = 2;
+  std::vector<int> size;
+  for (int i = 0; i < n; ++i) {
+    if (agg[i] != -2) continue;
+    if (row_isolated(A, i)) { agg[i] = -1; continue; }
+    int best = -1;
+    double bw = 0.0;
+    for (int p = A.ia[i]; p < A.ia[i + 1]; ++p) {
+      const int j = A.ja[p];
+      if (j == i || agg[j] == -1 || (part && part[j] != part[i])) continue;
+      if (agg[j] >= 0 && size[agg[j]] >= max_agg) continue;
+      if (agg[j] == -2 && row_isolated(A, j)) continue;
+      const double w = std::fabs(A.a[p]);
+      if (w > bw) { bw = w; best = j; }
+    }
+    if (best < 0) { agg[i] = nc++; size.push_back(1); }
+    else if (agg[best] == -2) { agg[i] = agg[best] = nc++; size.push_back(2); }
+    else { agg[i] = agg[best]; ++size[agg[best]]; }
+  }
+}
+
+void aggregate_mwm(const Csr& A, const int* part, std::vector<int>& agg, int& nc) {
+  const int n = A.n;
+  agg.assign(n, -2);
+  nc = 0;
+  struct Edge { double w; int i, j; };
+  std::vector<Edge> edges;
+  for (int i = 0; i < n; ++i) {
+    if (row_isolated(A, i)) { agg[i] = -1; continue; }
+    for (int p = A.ia[i]; p < A.ia[i + 1]; ++p) {
+      const int j = A.ja[p];
+      if (j <= i || A.a[p] == 0.0 || (part && part[j] != part[i])) continue;
+      edges.push_back({std::fabs(A.a[p]), i, j});
+    }
+  }
+  std::stable_sort(edges.begin(), edges.end(), [](const Edge& a, const Edge& b) { return a.w > b.w; });
+  for (const Edge& e : edges)
+    if (agg[e.i] == -2 && agg[e.j] == -2) agg[e.i] = agg[e.j] = nc++;
+  std::vector<int> frozen(agg);
+  for (int i = 0; i < n; ++i) {
+    if (agg[i] != -2) continue;
+    int best = -1;
+    double bw = 0.0;
+    for (int p = A.ia[i]; p < A.ia[i + 1]; ++p) {
+      const int j = A.ja[p];
+      if (j == i || frozen[j] < 0 || (part && part[j] != part[i])) continue;
+      const double w = std::fabs(A.a[p]);
+      if (w > bw) { bw = w; best = j; }
+    }
+    agg[i] = best >= 0 ? frozen[best] : nc++;
+  }
+}
+
+void aggregate_mis(const Csr& A, const int* part, double strong, std::vector<int>& agg, int& nc) {
+  const int n = A.n;
+  std::vector<double> diag(n, 0.0);
+  for (int i = 0; i < n; ++i)
+    for (int p = A.ia[i]; p < A.ia[i + 1]; ++p)
+      if (A.ja[p] == i) diag[i] = A.a[p];
+  const double s2 = strong * strong;
+  auto is_strong = [&](int i, int p) {
+    const int j = A.ja[p];
+    if (j == i || A.a[p] == 0.0 || (part && part[j] != part[i])) return false;
+    return A.a[p] * A.a[p] >= s2 * std::fabs(diag[i] * diag[j]);
+  };
+  agg.assign(n, -2);
+  nc = 0;
+  std::vector<char> state(n, 0);   // 0 free, 1 root, 2 excluded
+  for (int i = 0; i < n; ++i) {
+    bool any = false;
+    for (int p = A.ia[i]; p < A.ia[i + 1] && !any; ++p) any = is_strong(i, p);
+    if (!any) { agg[i] = -1; state[i] = 2; }
+  }
+  for (int i = 0; i < n; ++i) {
+    if (state[i]) continue;
+    state[i] = 1;
+    agg[i] = nc;
+    for (int p = A.ia[i]; p < A.ia[i + 1]; ++p)
+      if (is_strong(i, p)) {
+        const int j = A.ja[p];
+        if (state[j] == 0) state[j] = 2;
+        if (agg[j] == -2) agg[j] = nc;
+      }
+    ++nc;
+  }
+  std::vector<int> frozen(agg);
+  for (int i = 0; i < n; ++i) {
+    if (agg[i] != -2) continue;
+    int best = -1;
+    double bw = 0.0;
+    for (int p = A.ia[i]; p < A.ia[i + 1]; ++p) {
+      if (!is_strong(i, p) || frozen[A.ja[p]] < 0) continue;
+      const double w = std::fabs(A.a[p]);
+      if (w > bw) { bw = w; best = A.ja[p]; }
+    }
+    agg[i] = best >= 0 ? frozen[best] : nc++;
+  }
+}
+
 void aggregate_vmb(const Csr& A, const int* part, double strong, int max_agg, std::vector<int>& agg, int& nc) {
   const int n = A.n;
   std::vector<double> diag(n, 0.0);
@@ -532,14 +644,14 @@ bool build_hierarchy(const mamg_params& prm, Csr&& A0, const int* idofs, int n_i
     err = "cycle_type: only V_CYCLE and W_CYCLE are implemented";
     return false;
   }
-  if (prm.aggregation_type != MAMG_HEM && prm.aggregation_type != MAMG_VMB) {
-    err = "aggregation_type: only HEM and VMB are implemented";
-    return false;
+  switch (prm.aggregation_type) {
+    case MAMG_HEM: case MAMG_VMB: case MAMG_HEC: case MAMG_MWM: case MAMG_MIS: break;
+    default: err = "aggregation_type: unknown value"; return false;
   }
   switch (prm.smoother) {
     case MAMG_SMOOTHER_JACOBI: case MAMG_SMOOTHER_GS: case MAMG_SMOOTHER_SGS:
-    case MAMG_SMOOTHER_SOR: case MAMG_SMOOTHER_SSOR: break;
-    default: err = "smoother: only JACOBI, GS, SGS, SOR, SSOR are implemented"; return false;
+    case MAMG_SMOOTHER_SOR: case MAMG_SMOOTHER_SSOR: case MAMG_SMOOTHER_L1DIAG: break;
+    default: err = "smoother: only JACOBI, GS, SGS, SOR, SSOR, L1DIAG are implemented"; return false;
   }
   if (prm.coarse_solver != MAMG_SOLVER_UMFPACK) { err = "coarse_solver: only 32 (direct) is implemented"; return false; }
   if (prm.Schwarz_levels > 0 && prm.Schwarz_blksolver != MAMG_SOLVER_UMFPACK) {
@@ -580,8 +692,13 @@ bool build_hierarchy(const mamg_params& prm, Csr&& A0, const int* idofs, int n_i
     }
     if (last) break;
     const int* lpart = L.part.empty() ? nullptr : L.part.data();
-    if (prm.aggregation_type == MAMG_HEM) aggregate_hem(L.A, lpart, L.agg, L.nc);
-    else aggregate_vmb(L.A, lpart, prm.strong_coupled, prm.max_aggregation, L.agg, L.nc);
+    switch (prm.aggregation_type) {
+      case MAMG_HEM: aggregate_hem(L.A, lpart, L.agg, L.nc); break;
+      case MAMG_HEC: aggregate_hec(L.A, lpart, prm.max_aggregation, L.agg, L.nc); break;
+      case MAMG_MWM: aggregate_mwm(L.A, lpart, L.agg, L.nc); break;
+      case MAMG_MIS: aggregate_mis(L.A, lpart, prm.strong_coupled, L.agg, L.nc); break;
+      default: aggregate_vmb(L.A, lpart, prm.strong_coupled, prm.max_aggregation, L.agg, L.nc);
+    }
     lap("aggregate", l);
     if (L.nc == 0 || L.nc >= n) {  // no coarsening possible: this level becomes the coarsest
       L.agg.clear(); L.nc = 0; L.sw = SchwarzPatches(); L.gs_skip.clear();

@@ -97,10 +97,10 @@ def to_struct(parameters=None):
         raise NotImplementedError(
             f"cycle_type={p.cycle_type}: only V_CYCLE and W_CYCLE are implemented (AMLI/ADD are not used "
             "by any reference configuration)")
-    if p.aggregation_type not in (haznics.VMB, haznics.HEM):
-        raise NotImplementedError(f"aggregation_type={p.aggregation_type}: only VMB and HEM are implemented")
+    if p.aggregation_type not in (haznics.VMB, haznics.MIS, haznics.MWM, haznics.HEC, haznics.HEM):
+        raise NotImplementedError(f"aggregation_type={p.aggregation_type}")
     if p.smoother not in (haznics.SMOOTHER_JACOBI, haznics.SMOOTHER_GS, haznics.SMOOTHER_SGS,
-                          haznics.SMOOTHER_SOR, haznics.SMOOTHER_SSOR):
+                          haznics.SMOOTHER_SOR, haznics.SMOOTHER_SSOR, haznics.SMOOTHER_L1DIAG):
         raise NotImplementedError(f"smoother={p.smoother}")
     if p.coarse_solver != haznics.SOLVER_UMFPACK:
         raise NotImplementedError("coarse_solver: only 32 (direct) is implemented")

@@ -34,7 +34,7 @@ static int omp_get_thread_num(void) { return 0; }
 static int omp_get_max_threads(void) { return 1; }
 #endif
 
-enum { UA_AMG = 1, V_CYCLE = 1, W_CYCLE = 2, SM_JACOBI = 1, SM_GS = 2, SM_SGS = 3, SM_SOR = 5, SM_SSOR = 6,
+enum { UA_AMG = 1, V_CYCLE = 1, W_CYCLE = 2, SM_JACOBI = 1, SM_GS = 2, SM_SGS = 3, SM_SOR = 5, SM_SSOR = 6, SM_L1DIAG = 10,
        SW_FORWARD = 1, SW_BACKWARD = 2, SW_SYMMETRIC = 3 };
 
 typedef struct {
@@ -251,6 +251,16 @@ static void jacobi(const orc_level* L, const double* b, double* x, double w) {
   memcpy(x, L->w, sizeof(double) * L->n);
 }
 
+/* l1-Jacobi (haznics SMOOTHER_L1DIAG): x += D_l1^{-1} (b - A x) with (D_l1)_ii = sum_j |a_ij|, all rows at once */
+static void jacobi_l1(const orc_level* L, const double* b, double* x) {
+  for (int i = 0; i < L->n; ++i) {
+    double l1 = 0.0;
+    for (int p = L->ia[i]; p < L->ia[i + 1]; ++p) l1 += fabs(L->a[p]);
+    L->w[i] = L->skip[i] ? x[i] : x[i] + (b[i] - row_dot(L, i, x)) * (1.0 / l1);
+  }
+  memcpy(x, L->w, sizeof(double) * L->n);
+}
+
 /* exact solve on one patch: x_B += A_BB^{-1} (b - A x)_B with the stored Cholesky factor */
 static void patch_solve(orc_hier* h, const orc_level* L, int p, const double* b, double* x) {
   const int q0 = L->pptr[p], s = L->pptr[p + 1] - q0;
@@ -304,6 +314,7 @@ static void smooth(orc_hier* h, int lev, const double* b, double* x, int post) {
       for (int it = 0; it < iters; ++it) {
         switch (h->smoother) {
           case SM_JACOBI: jacobi(L, b, x, h->relaxation); break;
+          case SM_L1DIAG: jacobi_l1(L, b, x); break;
           case SM_GS: gs_sweep(h, L, b, x, 1.0, post, 0); break;
           case SM_SOR: gs_sweep(h, L, b, x, h->relaxation, post, 0); break;
           case SM_SGS: gs_sweep(h, L, b, x, 1.0, 0, 0); gs_sweep(h, L, b, x, 1.0, 1, mc ? 1 : 0); break;

@@ -112,7 +112,7 @@ def test_pcg_relative_and_initial_guess(case):
 @pytest.mark.parametrize("cycle", [haznics.V_CYCLE, haznics.W_CYCLE])
 @pytest.mark.parametrize("smoother,relax", [(haznics.SMOOTHER_JACOBI, 0.6), (haznics.SMOOTHER_GS, 1.0),
                                             (haznics.SMOOTHER_SGS, 1.0), (haznics.SMOOTHER_SOR, 1.2),
-                                            (haznics.SMOOTHER_SSOR, 1.2)])
+                                            (haznics.SMOOTHER_SSOR, 1.2), (haznics.SMOOTHER_L1DIAG, 1.0)])
 def test_option_space(cycle, smoother, relax):
     system = problems.bidomain_system(2, 24, gamma=1e2)
     prm = dict(params.parameters_metric, cycle_type=cycle, smoother=smoother, relaxation=relax,

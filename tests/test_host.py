@@ -163,7 +163,9 @@ def test_parameter_translation():
     with pytest.raises(NotImplementedError):
         params.to_struct({"cycle_type": haznics.AMLI_CYCLE})
     with pytest.raises(NotImplementedError):
-        params.to_struct({"aggregation_type": haznics.MWM})
+        params.to_struct({"aggregation_type": 77})
+    with pytest.raises(NotImplementedError):
+        params.to_struct({"smoother": 4})
     with pytest.raises(NotImplementedError):
         params.to_struct({"coarse_solver": 0})
 
@@ -380,3 +382,30 @@ def test_import_hierarchy_rejects_bad_input():
     bad["levels"] = bad["levels"][:1] + bad["levels"][2:]
     with pytest.raises(_capi.MamgError, match="aggregates"):
         mamg.Hierarchy.from_export(bad)
+
+
+@pytest.mark.parametrize("agg", ["VMB", "MIS", "MWM", "HEC", "HEM"])
+def test_every_aggregation_type_builds_a_valid_hierarchy(agg):
+    """src/amg_parameters.py:16 lists VMB, MIS, MWM, HEC beside the HEM of the metric dicts: each gives aggregates
+    that cover every non-isolated row, a Galerkin coarse operator P'AP and a cycle under which the oracle's PCG
+    converges (the device path does not depend on how the aggregates were formed)."""
+    from oracle import Oracle
+    s = problems.bidomain_system(2, 24, gamma=1e2)
+    prm = dict(params.parameters_metric, aggregation_type=getattr(haznics, agg), strong_coupled=0.05, max_aggregation=6)
+    H = mamg.Hierarchy(s.A, prm, s.interface_dofs)
+    ex = H.export()
+    assert len(ex["levels"]) >= 3
+    for l in range(len(ex["levels"]) - 1):
+        L, Lc = ex["levels"][l], ex["levels"][l + 1]
+        A = sp.csr_matrix((L["data"], L["indices"], L["indptr"]), shape=(L["n"], L["n"]))
+        agg_map = L["agg"]
+        ok = agg_map >= 0
+        assert set(agg_map[ok]) == set(range(L["n_aggregates"])) and Lc["n"] == L["n_aggregates"] < L["n"]
+        P = sp.csr_matrix((np.ones(ok.sum()), (np.flatnonzero(ok), agg_map[ok])), shape=(L["n"], Lc["n"]))
+        Ac = sp.csr_matrix((Lc["data"], Lc["indices"], Lc["indptr"]), shape=(Lc["n"], Lc["n"]))
+        assert abs(P.T @ A @ P - Ac).max() <= 1e-12 * abs(Ac).max()
+        if agg in ("HEM", "MWM"):
+            assert np.bincount(agg_map[ok]).max() <= 3          # matchings: pairs (+ a leftover)
+    b, xt = s.random_rhs(0)
+    x, info = Oracle(ex, "multicolor").pcg(b, tolerance=1e-8, relative=True, maxiter=200)
+    assert info["niters"] < 60 and np.linalg.norm(x - xt) < 1e-5 * np.linalg.norm(xt)
