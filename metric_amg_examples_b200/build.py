@@ -11,7 +11,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-# experiment variants: MAMG_DEFS="-DMAMG_HINT=0 ..." MAMG_VARIANT=name -> libmamg_<name>.so (selected with MAMG_LIB)
+# experiment variants: MAMG_DEFS="-DMAMG_SW_MINB24=4 ..." MAMG_VARIANT=name -> libmamg_<name>.so (selected with MAMG_LIB)
 VARIANT = os.environ.get("MAMG_VARIANT", "")
 DEFS = os.environ.get("MAMG_DEFS", "").split()
 OUT = os.path.join(HERE, f"libmamg_{VARIANT}.so" if VARIANT else "libmamg.so")

@@ -35,43 +35,12 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// Streaming loads for data that is read exactly once per kernel (matrix values / columns, patch
-// blobs): no L1 allocation and evict-first in L2, so that the vectors that ARE re-read (x gathers)
-// keep the 126 MB L2 to themselves.
-#ifndef MAMG_HINT
-#define MAMG_HINT 0   // 0: plain loads, 1: L2 evict-first, 2: L2 evict-first + no L1 allocation
-#endif
-__device__ __forceinline__ unsigned long long stream_policy() {
-  unsigned long long pol;
-  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
-#if MAMG_HINT == 0
+// Loads of data that is read exactly once per kernel (matrix values / columns, patch index data) go
+// through the read-only path.  L2 evict-first / no-L1-allocate cache hints were measured in round 1 and
+// were slower than plain loads on B200 (the 126 MB L2 keeps the re-read vectors anyway); they are gone.
 __device__ __forceinline__ double ld_stream(const double* p) { return __ldg(p); }
 __device__ __forceinline__ int ld_stream(const int* p) { return __ldg(p); }
 __device__ __forceinline__ unsigned int ld_stream(const unsigned int* p) { return __ldg(p); }
-#else
-#if MAMG_HINT == 1
-#define MAMG_LD "ld.global.nc.L2::cache_hint"
-#else
-#define MAMG_LD "ld.global.nc.L1::no_allocate.L2::cache_hint"
-#endif
-__device__ __forceinline__ double ld_stream(const double* p) {
-  double v;
-  asm(MAMG_LD ".f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(stream_policy()));
-  return v;
-}
-__device__ __forceinline__ int ld_stream(const int* p) {
-  int v;
-  asm(MAMG_LD ".s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(stream_policy()));
-  return v;
-}
-__device__ __forceinline__ unsigned int ld_stream(const unsigned int* p) {
-  unsigned int v;
-  asm(MAMG_LD ".u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(stream_policy()));
-  return v;
-}
-#endif
 
 // ---- halo push folded into the producing kernel (multi-GPU halo mode) -----------------------------------
 // A smoother kernel that is followed by a halo exchange carries this descriptor: when its last block

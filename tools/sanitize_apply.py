@@ -1,4 +1,4 @@
-"""One small apply + PCG of every kernel family, for `compute-sanitizer --tool memcheck|racecheck`:
+"""One small apply + PCG of every kernel family, for `a sanitizer (compute-sanitizer is closed on the development pool)`:
 bidomain 3-D (SELL row kernels, Schwarz fast path, persistent tail) and EMI 3-D (general Schwarz
 kernel).  Checks the result against the oracle so that a sanitizer-clean run is also a correct one."""
 import os
