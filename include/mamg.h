@@ -162,12 +162,14 @@ int mamg_set_stream(mamg_handle h, void* stream);
 
 /* ---- multi-GPU, one process per GPU (torch.distributed / torchrun launches the ranks).
  *      Every rank calls mamg_setup_partitioned with the same matrix and partition and
- *      mamg_to_device on its GPU; rank 0 creates an NCCL id (mamg_nccl_unique_id, 128 bytes) that
- *      the host side broadcasts; then mamg_dist_init.  Afterwards apply / pcg run row-distributed
- *      on the levels with at least MAMG_DIST_MIN_ROWS (default 1 M) rows: rank r executes the rows of parts
- *      [r*P/world, (r+1)*P/world) and the updated ranges are all-gathered over NCCL; smaller levels
- *      are executed redundantly by every rank.  Vectors handed over the ABI are complete on every
- *      rank.  world == 1 is valid (a partitioned hierarchy on one GPU: same numbers, no NCCL). */
+ *      mamg_to_device_dist(rank, world) on its GPU; rank 0 creates an NCCL id (mamg_nccl_unique_id,
+ *      128 bytes) that the host side broadcasts; then mamg_dist_init and mamg_dist_peers.  Afterwards
+ *      apply / pcg run row-distributed on the levels with at least MAMG_DIST_MIN_ROWS rows: rank r
+ *      executes the rows of parts [r*P/world, (r+1)*P/world); in halo mode (default) it stores only
+ *      those rows and sends what its neighbours read (halo index lists over peer memory), dots are
+ *      rank-ordered all-reduces; smaller levels are executed redundantly by every rank.  Vectors
+ *      handed over the ABI are complete on every rank.  world == 1 is valid (a partitioned hierarchy
+ *      on one GPU: same numbers, no communication). */
 int mamg_nccl_unique_id(void* out128);
 int mamg_dist_init(mamg_handle h, int32_t rank, int32_t world, const void* unique_id128);
 int mamg_collective_count(mamg_handle h, int64_t* count, int32_t reset);

@@ -1,4 +1,5 @@
-// Device half of the C-ABI: upload of the hierarchy, the multigrid cycle, the Krylov loops.
+// Device half of the C-ABI: upload of the hierarchy (colour-permuted, sliced-ELL rows, shared Schwarz blobs),
+// the multigrid cycle, the Krylov loops, the multi-GPU exchange.
 //
 // Replaces, on one B200, what the reference runs on the CPU for every B*r inside
 // ConjGrad (src/bidomain_2d.py:205-206): haznics.apply_precond -> precond_amg -> mgcycle.
@@ -106,8 +107,10 @@ struct DeviceState {
   double *io_a = nullptr, *io_b = nullptr;  // staging for host-array calls
   std::vector<void*> allocs;
   mamg_params prm;
-  // multi-GPU (one process per GPU): every rank holds the hierarchy and complete vectors, executes
-  // the rows of its blocks on the distributed levels and all-gathers the updated ranges over NCCL
+  // multi-GPU (one process per GPU): rank r executes the rows of its blocks on the row-distributed levels.
+  // Halo mode (default): the matrices are stored per rank, vectors keep their global length and are valid on
+  // the owned rows + halo, updates travel as halo index lists to the neighbour ranks (peer memory, CUDA IPC).
+  // Round-1 mode (MAMG_HALO=0): hierarchy and vectors complete on every rank, updated ranges all-gathered.
   int rank = 0, world = 1;
   ncclComm_t comm = nullptr;
   int64_t collectives = 0;
