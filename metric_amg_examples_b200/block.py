@@ -163,6 +163,25 @@ class block_mat(block_base):
         return block_vec([np.zeros(k) for k in n])
 
 
+class block_diag_mat(block_base):
+    """xii.block_diag_mat([op_0, op_1, ...]): block i of the vector goes through operator i
+    (src/utils.py:12: the block-LU `diag` preconditioner)."""
+
+    def __init__(self, ops):
+        self.ops = list(ops)
+
+    def matvec(self, b):
+        if len(b) != len(self.ops):
+            raise ValueError(f"block_diag_mat of {len(self.ops)} blocks applied to a {len(b)}-block vector")
+        return block_vec([op * v if not isinstance(op, block_base) else op.matvec(v) for op, v in zip(self.ops, b)])
+
+    def transpmult(self, b):
+        return block_vec([op.transpmult(v) if isinstance(op, block_base) else op * v for op, v in zip(self.ops, b)])
+
+    def create_vec(self, dim=1):
+        return block_vec([op.create_vec(dim) for op in self.ops])
+
+
 def ii_convert(obj):
     """Collapse a block_mat to one monolithic CSR matrix / a block_vec to one vector, blocks
     concatenated in order (xii.ii_convert, src/bidomain_2d.py:178-179)."""

@@ -94,3 +94,48 @@ class metricAMG(_Precond):
                 idofs = np.flatnonzero(idofs)
         super().__init__(A, parameters if parameters is not None else default_metric_parameters,
                          idofs, device, part)
+
+
+class LU(block_base):
+    """block.algebraic.petsc.LU(A) as the reference uses it for the `diag` preconditioner
+    (src/utils.py:9-12: `xii.block_diag_mat([LU(A[i, i]) ...])`): the action of A^{-1} on one block.
+
+    There is no sparse direct factorisation on the device; the block is solved by CG on the device,
+    preconditioned with a plain UA-AMG V-cycle of the same library (mamg_pcg), to a relative residual of
+    `tolerance` (1e-12: exact as far as the outer Krylov iteration can tell).
+    A solve that does not reach the tolerance raises, it is never returned silently."""
+
+    def __init__(self, A, tolerance=1e-12, maxiter=500, device=0):
+        from . import haznics_compat as haznics
+        prm = dict(default_amg_parameters, cycle_type=haznics.V_CYCLE)
+        self.A = A
+        try:
+            self.hierarchy = Hierarchy(A, prm, None)
+        except MamgError as e:
+            raise RuntimeError(str(e)) from e
+        self.n = self.hierarchy.n
+        self.tolerance, self.maxiter, self._device = tolerance, maxiter, device
+        self.iterations = []
+
+    def matvec(self, b):
+        if not self.hierarchy.on_device:
+            self.hierarchy.to_device(self._device)
+        wrapped = isinstance(b, block_vec)
+        v = b[0] if wrapped else b
+        x, info = self.hierarchy.pcg(v, tolerance=self.tolerance, relative=True, maxiter=self.maxiter)
+        res = info["residuals"]
+        if res[0] > 0.0 and not res[-1] <= self.tolerance * res[0]:
+            raise RuntimeError(f"LU: the block solve stopped at a relative residual of {res[-1] / res[0]:.2e} "
+                               f"after {info['niters']} iterations")
+        self.iterations.append(info["niters"])
+        return block_vec([x]) if wrapped else x
+
+    def transpmult(self, b):   # the blocks are symmetric
+        return self.matvec(b)
+
+    @property
+    def T(self):
+        return self
+
+    def create_vec(self, dim=1):
+        return np.zeros(self.n)

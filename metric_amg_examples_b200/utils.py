@@ -6,8 +6,15 @@
 (src/bidomain_2d.py:203) works against this package.  `bcs` is accepted and unused, exactly as
 in the reference (src/utils.py:9,15,45,56).
 """
-from .block import ReductionOperator, ii_convert
-from .precond import AMG, metricAMG
+from .block import ReductionOperator, block_diag_mat, ii_convert
+from .precond import AMG, LU, metricAMG
+
+
+def get_block_diag_precond(A, W, bcs):
+    """src/utils.py:9-12 -- 'Exact blocks LU as preconditioner' (`-precond diag` of src/emi_2d.py:149):
+    block_diag_mat of one exact solve per diagonal block (see precond.LU for how the solve is done)."""
+    n, = set(A.blocks.shape)
+    return block_diag_mat([LU(A[i, i]) for i in range(n)])
 
 
 def get_hazmath_amg_precond(A, W, bcs, parameters=None, interface_dofs=None):

@@ -324,3 +324,33 @@ def test_metric_amg_without_interface_dofs():
     orc = Oracle(He.export(), "multicolor")
     r = np.random.default_rng(12).standard_normal(s.ndofs)
     assert rel(He.apply(r), orc.apply(r)) < APPLY_TOL
+
+
+def test_block_diag_precond_matches_exact_block_solves():
+    """`-precond diag` (src/emi_2d.py:149,181,209; src/utils.py:9-12): block_diag_mat of exact block solves.
+    The device realises each LU(A_ii) as an AMG-preconditioned CG to 1e-12; the outer ConjGrad must then take
+    the iterations it takes with a true sparse LU of the blocks (scipy splu, test side only)."""
+    import scipy.sparse.linalg as spla
+    from metric_amg_examples_b200 import utils
+    from metric_amg_examples_b200.block import block_vec, split_blocks
+    from metric_amg_examples_b200.iterative import ConjGrad
+    e = problems.emi_system(2, 32, gamma=1e2)
+    n0 = e.W[0].dim()
+    AA = split_blocks(e.A, [w.dim() for w in e.W])
+    be, xe = e.random_rhs(7)
+    bb = block_vec([be[:n0], be[n0:]])
+    BB = utils.get_block_diag_precond(AA, e.W, None)
+    inv = ConjGrad(AA, precond=BB, tolerance=1e-10, show=0, maxiter=500)
+    xb = inv * bb
+    assert inv.mode == "drop-in" and rel(np.concatenate(list(xb)), xe) < 1e-6
+    lus = [spla.splu(AA[i, i].tocsc()) for i in range(2)]
+
+    class Exact:
+        def __mul__(self, r):
+            return block_vec([lus[i].solve(np.asarray(r[i])) for i in range(2)])
+    ref = ConjGrad(AA, precond=Exact(), tolerance=1e-10, show=0, maxiter=500)
+    xr = ref * bb
+    assert abs(len(inv.residuals) - len(ref.residuals)) <= 1
+    assert np.allclose(inv.residuals[:5], ref.residuals[:5], rtol=1e-6)
+    assert rel(np.concatenate(list(xb)), np.concatenate(list(xr))) < 1e-7
+    assert all(k < 60 for op in BB.ops for k in op.iterations)
