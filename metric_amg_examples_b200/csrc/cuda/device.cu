@@ -8,6 +8,7 @@
 // solve on the coarsest level.  All scalars (alpha of the coarse scaling, alpha/beta of CG)
 // stay on the device, so one apply is a fixed launch sequence without host synchronisation.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -358,6 +359,16 @@ static void build_halo_lists(DeviceState& D, DLevel& dl, const std::vector<int>&
 // ------------------------------------------------------------------------------------------
 static void upload_hierarchy(const Hierarchy& H, DeviceState& D) {
   const int L = (int)H.lv.size();
+  // MAMG_SETUP_TIMING: per-phase host seconds of the upload on stderr (as build_hierarchy does for the setup)
+  const bool timing = getenv("MAMG_SETUP_TIMING") != nullptr;
+  auto tp = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what, int lev) {
+    if (!timing) return;
+    cudaDeviceSynchronize();
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[mamg upload] level %d %-14s %.3f s\n", lev, what, std::chrono::duration<double>(now - tp).count());
+    tp = now;
+  };
   D.lv.resize(L);
   std::vector<std::vector<int>> perm(L), iperm(L);
   for (int l = 0; l < L; ++l) {
@@ -384,6 +395,7 @@ static void upload_hierarchy(const Hierarchy& H, DeviceState& D) {
     }
     for (int i = 0; i < n; ++i) iperm[l][perm[l][i]] = i;
   }
+  lap("permutations", -1);
   size_t max_n = 0;
   {
     size_t need = kArenaHead;
@@ -447,6 +459,7 @@ static void upload_hierarchy(const Hierarchy& H, DeviceState& D) {
         if (!invl1.empty()) invl1[i] = 1.0 / l1;
       }
     }
+    lap("permute+sort", l);
     dl.ia = upload(D, ia);
     dl.ja = upload(D, ja);
     dl.a = upload(D, a);
@@ -457,6 +470,7 @@ static void upload_hierarchy(const Hierarchy& H, DeviceState& D) {
     dl.x_own = dl.x = carve(n);
     dl.b_own = dl.b = carve(n);
     dl.t = carve(n);
+    lap("h2d csr", l);
     if (!hl.gs_skip.empty()) {
       std::vector<uint8_t> sk(n);
       for (int i = 0; i < n; ++i) sk[i] = hl.gs_skip[perm[l][i]];
@@ -514,6 +528,7 @@ static void upload_hierarchy(const Hierarchy& H, DeviceState& D) {
         dl.d_own_coarse = upload(D, mine);
       }
     }
+    lap("agg+misc", l);
     if (hl.sw.npatch() > 0) schwarz_upload(hl, dl.nb, iperm[l], dl.ia, dl.ja, dl.a, ia, ja, a, dl.sw, [&](size_t bytes) {
       void* p = nullptr;
       CUDA_OK(cudaMalloc(&p, bytes ? bytes : 1));
@@ -521,6 +536,7 @@ static void upload_hierarchy(const Hierarchy& H, DeviceState& D) {
       D.dev_bytes += (int64_t)bytes;
       return p;
     });
+    lap("schwarz", l);
     if (D.halo && D.world > 1 && dl.nb > 1) build_halo_lists(D, dl, ia, ja);
     if (rows_sell()) {
       int slo = 0, shi = n;
@@ -531,6 +547,7 @@ static void upload_hierarchy(const Hierarchy& H, DeviceState& D) {
       }
       build_sell(D, dl, ia, slo, shi);
     }
+    lap("halo+sell", l);
   }
   {
     size_t mx = 0;
