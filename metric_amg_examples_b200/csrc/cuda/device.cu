@@ -194,8 +194,9 @@ static void dfree(DeviceState& D, T* p, size_t count) {
   cudaFree(p);
   D.dev_bytes -= (int64_t)(count * sizeof(T));
 }
-template <class T>
-static T* upload(DeviceState& D, const std::vector<T>& v) {
+template <class V>
+static typename V::value_type* upload(DeviceState& D, const V& v) {
+  using T = typename V::value_type;
   T* p = dalloc<T>(D, v.size());
   if (!v.empty()) CUDA_OK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
   return p;
@@ -288,7 +289,7 @@ static void build_sell(DeviceState& D, DLevel& dl, const std::vector<int>& ia, i
 // Schwarz_maxlvl + 1 rings into my block (dl.sw.readers) and reads b on its own dofs there (dl.sw.members),
 // so those rows travel with their colour as well; list ncolors + 1 holds the rows whose right-hand side the
 // other ranks' patches need.
-static void build_halo_lists(DeviceState& D, DLevel& dl, const std::vector<int>& ia, const std::vector<int>& ja) {
+static void build_halo_lists(DeviceState& D, DLevel& dl, const std::vector<int>& ia, const bigvec<int>& ja) {
   const int per = dl.nb / D.world, nc = dl.ncolors;
   std::vector<int> rank_lo(D.world + 1);
   for (int q = 0; q <= D.world; ++q) rank_lo[q] = dl.bc_ptr[q * per * nc];
@@ -435,8 +436,9 @@ static void upload_hierarchy(const Hierarchy& H, DeviceState& D) {
     for (int i = 0; i < n; ++i)
       ia[i + 1] = ia[i] + ((i >= row_lo && i < row_hi) ? hl.A.ia[perm[l][i] + 1] - hl.A.ia[perm[l][i]] : 0);
     dl.nnz = ia[n];
-    std::vector<int> ja(dl.nnz);
-    std::vector<double> a(dl.nnz), invd(n, 1.0);
+    bigvec<int> ja(dl.nnz);       // filled completely (in parallel) below: no value-initialising pass
+    bigvec<double> a(dl.nnz);
+    std::vector<double> invd(n, 1.0);
     std::vector<double> invl1(H.prm.smoother == MAMG_SMOOTHER_L1DIAG ? n : 0, 1.0);
 #pragma omp parallel
     {

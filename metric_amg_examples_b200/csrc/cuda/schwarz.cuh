@@ -486,7 +486,7 @@ schwarz_fast_kernel(int p0, int p1, const int* __restrict__ pidx32, const int* _
 // `alloc(bytes)` returns tracked device memory; pia/pja are the permuted CSR of the level.
 inline void schwarz_upload(const Level& hl, int nb, const std::vector<int>& iperm, const int* d_ia,
                            const int* d_ja, const double* d_a, const std::vector<int>& pia,
-                           const std::vector<int>& pja, const std::vector<double>& pa, DSchwarz& d,
+                           const bigvec<int>& pja, const bigvec<double>& pa, DSchwarz& d,
                            const std::function<void*(size_t)>& alloc) {
   const SwPatch zero = {0, 0, 0, 0, 0, 0};
   const SchwarzPatches& sw = hl.sw;

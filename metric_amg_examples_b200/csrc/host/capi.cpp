@@ -179,11 +179,11 @@ int mamg_release_host(mamg_handle h) {
   if (!h) { set_error("NULL handle"); return -1; }
   if (!h->dev) { set_error("release_host: hierarchy is not on a device yet"); return -1; }
   for (Level& L : h->H.lv) {
-    std::vector<int>().swap(L.A.ja);
-    std::vector<double>().swap(L.A.a);
+    bigvec<int>().swap(L.A.ja);
+    bigvec<double>().swap(L.A.a);
     std::vector<int>().swap(L.sw.dofs);
-    Csr().ia.swap(L.P.ia); std::vector<int>().swap(L.P.ja); std::vector<double>().swap(L.P.a);
-    std::vector<int>().swap(L.R.ja); std::vector<double>().swap(L.R.a);
+    Csr().ia.swap(L.P.ia); bigvec<int>().swap(L.P.ja); bigvec<double>().swap(L.P.a);
+    bigvec<int>().swap(L.R.ja); bigvec<double>().swap(L.R.a);
   }
   h->H.released = true;
   return 0;

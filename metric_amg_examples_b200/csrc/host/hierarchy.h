@@ -10,18 +10,35 @@
 #pragma once
 #include <cstdint>
 #include <stdexcept>
+#include <memory>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../../include/mamg.h"
 
 namespace mamg {
 
+// std::vector whose resize() leaves the new elements uninitialised: the entry arrays of the level matrices
+// hold up to 1.5e9 entries and are always filled completely (in parallel) right after they are sized, so a
+// value-initialising resize would be a single-threaded pass over 18 GB for nothing.
+template <class T>
+struct uninit_alloc : std::allocator<T> {
+  template <class U> struct rebind { using other = uninit_alloc<U>; };
+  template <class U, class... Args>
+  void construct(U* p, Args&&... args) {
+    if constexpr (sizeof...(Args) == 0) ::new (static_cast<void*>(p)) U;
+    else ::new (static_cast<void*>(p)) U(std::forward<Args>(args)...);
+  }
+};
+template <class T> using bigvec = std::vector<T, uninit_alloc<T>>;
+
 struct Csr {
   int n = 0;     // rows
   int m = 0;     // columns
-  std::vector<int> ia, ja;
-  std::vector<double> a;
+  std::vector<int> ia;
+  bigvec<int> ja;
+  bigvec<double> a;
   int nnz() const { return ia.empty() ? 0 : ia[n]; }
 };
 

@@ -324,8 +324,8 @@ void csr_drop_zeros(Csr& A) {
   }
   for (int i = 0; i < n; ++i) ia2[i + 1] += ia2[i];
   if (ia2[n] == A.ia[n]) return;   // nothing to drop
-  std::vector<int> ja2(ia2[n]);
-  std::vector<double> a2(ia2[n]);
+  bigvec<int> ja2(ia2[n]);
+  bigvec<double> a2(ia2[n]);
 #pragma omp parallel for schedule(static)
   for (int i = 0; i < n; ++i) {
     int k = ia2[i];
