@@ -34,7 +34,7 @@ enum {
   MAMG_SMOOTHER_SOR = 5, MAMG_SMOOTHER_SSOR = 6, MAMG_SMOOTHER_L1DIAG = 10,
   MAMG_VMB = 1, MAMG_MIS = 2, MAMG_MWM = 3, MAMG_HEC = 4, MAMG_HEM = 5,
   MAMG_SCHWARZ_FORWARD = 1, MAMG_SCHWARZ_BACKWARD = 2, MAMG_SCHWARZ_SYMMETRIC = 3,
-  MAMG_SOLVER_UMFPACK = 32,
+  MAMG_SOLVER_DEFAULT = 0, MAMG_SOLVER_VFGMRES = 4, MAMG_SOLVER_GCG = 5, MAMG_SOLVER_GCR = 6, MAMG_SOLVER_UMFPACK = 32,
   MAMG_OFF = 0, MAMG_ON = 1
 };
 
@@ -42,7 +42,7 @@ enum {
  * the dict keys (what haznics.param_amg_set_dict consumes upstream). */
 typedef struct mamg_params {
   int32_t AMG_type;          /* UA_AMG | SA_AMG */
-  int32_t cycle_type;        /* V_CYCLE | W_CYCLE */
+  int32_t cycle_type;        /* V_CYCLE | W_CYCLE | AMLI_CYCLE | NL_AMLI_CYCLE | ADD_CYCLE */
   int32_t max_levels;
   int32_t maxit;             /* cycles per apply */
   int32_t smoother;          /* SMOOTHER_* */
@@ -50,19 +50,22 @@ typedef struct mamg_params {
   int32_t presmooth_iter;
   int32_t postsmooth_iter;
   int32_t coarse_dof;
-  int32_t coarse_solver;     /* 32 = direct */
+  int32_t coarse_solver;     /* 32 = direct; 0 = HAZmath's iterative solve to tol*1e-4, served by the same
+                              * dense inverse (the exact solution the iteration converges to) */
   int32_t coarse_scaling;    /* ON | OFF */
   int32_t aggregation_type;  /* VMB | HEM | HEC */
   double  strong_coupled;
   int32_t max_aggregation;
-  int32_t amli_degree;
+  int32_t amli_degree;       /* degree of the AMLI polynomial (AMLI_CYCLE), at most 15 */
   int32_t Schwarz_levels;
   int32_t Schwarz_mmsize;
   int32_t Schwarz_maxlvl;
   int32_t Schwarz_type;      /* SCHWARZ_FORWARD | BACKWARD | SYMMETRIC */
-  int32_t Schwarz_blksolver; /* 32 = direct */
+  int32_t Schwarz_blksolver; /* 32 = direct; 0 = iterative upstream, served by the same block inverses */
   int32_t print_level;
-  int32_t reserved[8];
+  int32_t nl_amli_krylov_type; /* NL_AMLI_CYCLE: SOLVER_GCG (5) = flexible CG K-cycle, anything else GCR
+                                * (HAZmath's default branch); haznics.AMG_param() default 4 */
+  int32_t reserved[7];
 } mamg_params;
 
 typedef struct mamg_handle_s* mamg_handle;

@@ -16,7 +16,7 @@ PARAM_FIELDS = [
     ("strong_coupled", C.c_double), ("max_aggregation", C.c_int32), ("amli_degree", C.c_int32),
     ("Schwarz_levels", C.c_int32), ("Schwarz_mmsize", C.c_int32), ("Schwarz_maxlvl", C.c_int32),
     ("Schwarz_type", C.c_int32), ("Schwarz_blksolver", C.c_int32), ("print_level", C.c_int32),
-    ("reserved", C.c_int32 * 8),
+    ("nl_amli_krylov_type", C.c_int32), ("reserved", C.c_int32 * 7),
 ]
 
 

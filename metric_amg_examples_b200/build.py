@@ -73,7 +73,7 @@ def build(force=False, verbose=False):
         jobs.append([NVCC] + ARCH + flags + DEFS + ["-c", os.path.join(CSRC, s), "-o", o])
     with ThreadPoolExecutor(max_workers=4) as ex:
         list(ex.map(lambda c: _run(c, log), jobs))
-    _run([NVCC] + ARCH + ["-shared", "-o", OUT] + objs + ["-Xcompiler", "-fopenmp", "-lgomp", "-lnccl"], log)
+    _run([NVCC] + ARCH + ["-shared", "-o", OUT] + objs + ["-Xcompiler", "-fopenmp", "-lgomp", "-lnccl", "-ldl"], log)
     with open(os.path.join(OBJ, "build.log"), "w") as fh:
         fh.write("\n".join(log))
     with open(stamp, "w") as fh:

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include <nccl.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include "../host/handle.h"
 #include "kernels.cuh"
@@ -141,6 +142,11 @@ struct DeviceState {
   size_t l2_persist_bytes = 0;
   const void* l2_window = nullptr;
   int tail_k0 = -1;           // first level executed by the single-CTA tail kernel (-1: none)
+  // AMLI / nonlinear AMLI cycles: per level >= 1 three work vectors (saved right-hand side, first direction and
+  // its image) and 16 scalars of the K-cycle, allocated when such a cycle is first applied
+  std::vector<double*> kwork;
+  double* kscal = nullptr;
+  double amli_coef[16] = {0};
   TailArgs tail;
   size_t tail_smem = 0;
   // one apply is a fixed launch sequence: it is captured once per (input, output) pair into a
@@ -151,6 +157,23 @@ struct DeviceState {
   bool use_graph = true;
   bool graph_dist = true;            // capture the cycle with several ranks too (MAMG_GRAPH_DIST=0 disables)
   bool capturing = false;
+  bool nvtx = false;                 // MAMG_NVTX=1: NVTX ranges around applies, level visits and Krylov solves
+};
+
+// NVTX range on the host timeline (ncu --nvtx --nvtx-include "mamg:smooth L0/" selects the kernels launched inside;
+// during graph capture the ranges bracket the capture, not the replay)
+struct Nvtx {
+  bool on;
+  Nvtx(const DeviceState& D, const char* what, int level = -1) : on(D.nvtx) {
+    if (!on) return;
+    char buf[64];
+    if (level >= 0) snprintf(buf, sizeof buf, "mamg:%s L%d", what, level);
+    else snprintf(buf, sizeof buf, "mamg:%s", what);
+    nvtxRangePushA(buf);
+  }
+  ~Nvtx() { if (on) nvtxRangePop(); }
+  Nvtx(const Nvtx&) = delete;
+  Nvtx& operator=(const Nvtx&) = delete;
 };
 
 // Brackets one kernel launch: counts it and, in profiling mode, times it with a CUDA event pair
@@ -1133,6 +1156,7 @@ static void k_jacobi(DeviceState& D, DLevel& l, const double* b, double* x, doub
 // (src/utils.py:84); post-smoothing is its adjoint (point smoother first, reverse directions
 // for one-directional variants) so that the cycle stays symmetric.
 static void smooth(DeviceState& D, int lev, const double* b, double* x, bool post) {
+  Nvtx range(D, post ? "post-smooth" : "pre-smooth", lev);
   DLevel& l = D.lv[lev];
   D.cur_level = lev;
   set_l2_window(D, l.n >= (1 << 19) ? x : nullptr, l.n >= (1 << 19) ? sizeof(double) * (size_t)l.n : 0);
@@ -1240,6 +1264,7 @@ static void k_csr_apply(DeviceState& D, const DCsr& M, int r0, int r1, const dou
 }
 
 static void k_resid_restrict(DeviceState& D, int lev) {
+  Nvtx range(D, "residual+restrict", lev);
   D.cur_level = lev;
   DLevel& f = D.lv[lev];
   DLevel& c = D.lv[lev + 1];
@@ -1298,6 +1323,7 @@ static int red_grid(const DeviceState& D, long long threads) {
 }
 
 static void k_scale_dots(DeviceState& D, int lev) {
+  Nvtx range(D, "coarse scaling", lev);
   DLevel& c = D.lv[lev];
   if (halo_on(D, c)) {   // partial e.r and e.A_c e over the owned rows, combined in rank order
     const int r0 = own_lo(D, c), r1 = own_hi(D, c);
@@ -1326,6 +1352,7 @@ static void k_scale_dots(DeviceState& D, int lev) {
 }
 
 static void k_prolong(DeviceState& D, int lev, bool scaled) {
+  Nvtx range(D, "prolong", lev);
   DLevel& f = D.lv[lev];
   DLevel& c = D.lv[lev + 1];
   const int r0 = own_lo(D, f), r1 = own_hi(D, f);
@@ -1341,14 +1368,162 @@ static void k_prolong(DeviceState& D, int lev, bool scaled) {
 }
 
 static void k_coarse_solve(DeviceState& D) {
+  Nvtx range(D, "coarse solve");
   DLevel& c = D.lv.back();
   KScope ks(D, K_COARSE);
   dense_gemv_kernel<<<cdiv((long long)c.n * 32, kBlock), kBlock, 0, D.stream>>>(c.n, D.coarse_inv, c.b, c.x);
 }
 
+static void k_fill(DeviceState& D, int n, double* x, double v);
+static void k_copy(DeviceState& D, int n, const double* in, double* out);
+static void k_axpby(DeviceState& D, int n, double a, const double* x, double b, double* y);
+static void k_dot_dev(DeviceState& D, int n, const double* u, const double* v, double* out_dev);
+static void k_axpy_dev(DeviceState& D, int n, const double* coef_dev, double scale, const double* x, double* y);
+
+// ---- AMLI, nonlinear AMLI (K-cycle) and additive cycles -----------------------------------------------------
+// The remaining values of the reference's cycle_type key (src/amg_parameters.py:6,26,49,69).  They run the
+// per-level kernels down to the coarsest level (no persistent tail kernel) on one GPU and are not tuned:
+// no reference configuration selects them.
+
+// Coefficients q_0..q_degree of the AMLI polynomial: the polynomial of best uniform approximation to 1/t on
+// [lambda_min, lambda_max] = [1/2, 2] (HAZmath / FASP take lambda_max = 2, lambda_min = lambda_max / 4), built by
+// the three-term recurrence in the degree.
+static void amli_coefficients(int degree, double* coef) {
+  const double lmax = 2.0, lmin = 0.5;
+  const double mu0 = 1.0 / lmax, mu1 = 1.0 / lmin;
+  const double sq = std::sqrt(mu0) + std::sqrt(mu1);
+  const double c = sq * sq, a = 4.0 * mu0 * mu1 / c;
+  const double sk = std::sqrt(lmax / lmin), delta = (sk - 1.0) / (sk + 1.0), b = delta * delta;
+  double q[16][16] = {{0.0}};
+  q[0][0] = 0.5 * (mu0 + mu1);
+  q[1][0] = 0.5 * c;
+  q[1][1] = -mu0 * mu1;
+  for (int k = 2; k <= degree; ++k) {
+    q[k][0] = a - b * q[k - 2][0] + (1.0 + b) * q[k - 1][0];
+    for (int i = 1; i <= k - 2; ++i) q[k][i] = -b * q[k - 2][i] + (1.0 + b) * q[k - 1][i] - a * q[k - 1][i - 1];
+    q[k][k - 1] = (1.0 + b) * q[k - 1][k - 1] - a * q[k - 1][k - 2];
+    q[k][k] = -a * q[k - 1][k - 1];
+  }
+  for (int i = 0; i <= degree; ++i) coef[i] = q[degree][i];
+}
+
+static bool recursive_poly_cycle(const DeviceState& D) {
+  return D.prm.cycle_type == MAMG_AMLI_CYCLE || D.prm.cycle_type == MAMG_NL_AMLI_CYCLE;
+}
+
+// called outside stream capture (allocates)
+static void ensure_cycle_work(DeviceState& D) {
+  if (!recursive_poly_cycle(D)) return;
+  if (D.prm.amli_degree < 0 || D.prm.amli_degree > 15) throw std::runtime_error("amli_degree: 0..15");
+  amli_coefficients(D.prm.amli_degree, D.amli_coef);
+  if (!D.kwork.empty()) return;
+  const size_t L = D.lv.size();
+  D.kwork.assign(L, nullptr);
+  for (size_t l = 1; l < L; ++l) D.kwork[l] = dalloc<double>(D, 3 * (size_t)std::max(D.lv[l].n, 1));
+  D.kscal = dalloc<double>(D, 16 * L);
+  CUDA_OK(cudaMemset(D.kscal, 0, 16 * L * sizeof(double)));
+}
+
+static void coarse_correction_up(DeviceState& D, int lev) {
+  const bool scaled = D.prm.coarse_scaling == MAMG_ON;
+  if (scaled) k_scale_dots(D, lev + 1);
+  k_prolong(D, lev, scaled);
+  smooth(D, lev, D.lv[lev].b, D.lv[lev].x, true);
+}
+
+// AMLI-cycle (HAZmath / FASP amli() of mgcycle.c): the coarse correction is q(B_c A_c) B_c r_c with the coarse
+// cycle B_c, in Horner form: e = B_c r_c; degree times: rhs = A_c e + (q_{degree-i} / q_degree) r_c, e = B_c rhs;
+// then e *= q_degree and the usual scaling alpha = min(1, e.r_c / e.A_c e).
+static void cycle_amli(DeviceState& D, int lev) {
+  const int L = (int)D.lv.size();
+  if (lev == L - 1) { k_coarse_solve(D); return; }
+  DLevel& f = D.lv[lev];
+  DLevel& c = D.lv[lev + 1];
+  const int deg = D.prm.amli_degree;
+  const double* q = D.amli_coef;
+  double* rc = D.kwork[lev + 1];
+  smooth(D, lev, f.b, f.x, false);
+  k_resid_restrict(D, lev);   // c.b = R (b - A x), c.x = 0
+  k_copy(D, c.n, c.b, rc);
+  for (int i = 1; i <= deg; ++i) {
+    cycle_amli(D, lev + 1);
+    k_spmv(D, c, c.x, nullptr, c.b, false);
+    k_axpby(D, c.n, q[deg - i] / q[deg], rc, 1.0, c.b);
+    k_fill(D, c.n, c.x, 0.0);
+  }
+  cycle_amli(D, lev + 1);
+  k_axpby(D, c.n, 0.0, rc, q[deg], c.x);   // e *= q_degree
+  k_copy(D, c.n, rc, c.b);                 // the scaling reads the restricted residual
+  coarse_correction_up(D, lev);
+}
+
+static void cycle_nlamli(DeviceState& D, int lev);
+
+// K-cycle coarse correction (Notay & Vassilevski; HAZmath / FASP Kcycle_dcsr_pgcg / _pgcr): two steps of a Krylov
+// method on A_c x = b_c preconditioned by the nonlinear AMLI cycle of that level.  The launch sequence is fixed
+// (graph capture): the second step always runs, and kcycle_step2_kernel discards it on the device when the
+// first step already reduced the residual by the K-cycle tolerance 0.2 (where upstream returns early).
+static void kcycle(DeviceState& D, int lc) {
+  DLevel& c = D.lv[lc];
+  const int n = c.n;
+  double* bsave = D.kwork[lc];
+  double* c1 = bsave + n;
+  double* v1 = bsave + 2 * (size_t)n;
+  double* s = D.kscal + 16 * (size_t)lc;
+  const bool gcg = D.prm.nl_amli_krylov_type == MAMG_SOLVER_GCG;
+  k_copy(D, n, c.b, bsave);
+  k_dot_dev(D, n, c.b, c.b, s + 0);
+  cycle_nlamli(D, lc);                       // c.x (zero on entry) = B r
+  k_copy(D, n, c.x, c1);
+  k_spmv(D, c, c1, nullptr, v1, false);
+  k_dot_dev(D, n, gcg ? c1 : v1, v1, s + 1);
+  k_dot_dev(D, n, gcg ? c1 : v1, c.b, s + 2);
+  { KScope ks(D, K_VEC); kcycle_step1_kernel<<<1, 32, 0, D.stream>>>(s); }
+  k_axpy_dev(D, n, s + 3, -1.0, v1, c.b);    // r -= beta1 v1 (the residual lives in the level's right-hand side)
+  k_dot_dev(D, n, c.b, c.b, s + 4);
+  k_fill(D, n, c.x, 0.0);
+  cycle_nlamli(D, lc);                       // c.x = B r~
+  k_spmv(D, c, c.x, nullptr, c.t, false);
+  const double* w = gcg ? c.x : c.t;
+  k_dot_dev(D, n, w, v1, s + 5);
+  k_dot_dev(D, n, w, c.t, s + 6);
+  k_dot_dev(D, n, w, c.b, s + 7);
+  { KScope ks(D, K_VEC); kcycle_step2_kernel<<<1, 32, 0, D.stream>>>(s, 0.04); }
+  if (n > 0) { KScope ks(D, K_VEC); kcycle_combine_kernel<<<cdiv(n, kBlock), kBlock, 0, D.stream>>>(n, s + 8, c1, c.x); }
+  k_copy(D, n, bsave, c.b);
+}
+
+// nonlinear AMLI-cycle (HAZmath / FASP nl_amli() of mgcycle.c): every coarse problem but the last is handed to
+// the K-cycle, the coarsest one is solved directly.
+static void cycle_nlamli(DeviceState& D, int lev) {
+  const int L = (int)D.lv.size();
+  if (lev == L - 1) { k_coarse_solve(D); return; }
+  DLevel& f = D.lv[lev];
+  smooth(D, lev, f.b, f.x, false);
+  k_resid_restrict(D, lev);
+  if (lev + 1 == L - 1) k_coarse_solve(D);
+  else kcycle(D, lev + 1);
+  coarse_correction_up(D, lev);
+}
+
+// additive cycle: z = sum_l P_0..P_{l-1} S_l R_{l-1}..R_0 r, S_l = pre- then post-smoothing from a zero iterate,
+// exact solve on the coarsest level, no coarse scaling (the frozen choice of oracle/mamg_oracle.c cycle_add)
+static void cycle_additive(DeviceState& D) {
+  const int L = (int)D.lv.size();
+  for (int lev = 0; lev + 1 < L; ++lev) {
+    DLevel& f = D.lv[lev];
+    k_resid_restrict(D, lev);   // x = 0: restricts the right-hand side itself and zeroes the coarse iterate
+    smooth(D, lev, f.b, f.x, false);
+    smooth(D, lev, f.b, f.x, true);
+  }
+  k_coarse_solve(D);
+  for (int lev = L - 2; lev >= 0; --lev) k_prolong(D, lev, false);
+}
+
 static void cycle_level(DeviceState& D, int lev) {
   const int L = (int)D.lv.size();
   if (lev == D.tail_k0) {   // everything from here down runs inside one kernel
+    Nvtx range(D, "tail cycle", lev);
     D.cur_level = lev;
     TailArgs T = D.tail;
     T.top_reps = (lev > 0 && D.prm.cycle_type == MAMG_W_CYCLE) ? 2 : 1;
@@ -1410,10 +1585,12 @@ static void drop_graphs(DeviceState& D) {
 static int64_t apply_launch_estimate(const DeviceState& D) {
   // launches of one apply: ~ (4 colours sweeps + 4) per visit, visits doubling per level for W
   double visits = 1, total = 0;
+  const bool poly = recursive_poly_cycle(D);
   for (size_t l = 0; l + 1 < D.lv.size(); ++l) {
-    if ((int)l == D.tail_k0) { total += visits; break; }   // one kernel for everything below
-    total += visits * (4.0 * D.lv[l].ncolors + 4.0 * D.lv[l].sw.ncolors + 4.0);
-    if (D.prm.cycle_type == MAMG_W_CYCLE) visits *= 2;
+    if ((int)l == D.tail_k0 && !poly && D.prm.cycle_type != MAMG_ADD_CYCLE) { total += visits; break; }   // one kernel for everything below
+    total += visits * (4.0 * D.lv[l].ncolors + 4.0 * D.lv[l].sw.ncolors + (poly ? 24.0 : 4.0));
+    if (D.prm.cycle_type == MAMG_W_CYCLE || D.prm.cycle_type == MAMG_NL_AMLI_CYCLE) visits *= 2;
+    if (D.prm.cycle_type == MAMG_AMLI_CYCLE) visits *= D.prm.amli_degree + 1;
   }
   return (int64_t)total;
 }
@@ -1422,6 +1599,7 @@ static void apply_permuted_raw(DeviceState& D, const double* r, double* z);
 
 // z' = B r' in the permuted ordering of level 0 (both device arrays of size n0)
 static void apply_permuted(DeviceState& D, const double* r, double* z) {
+  ensure_cycle_work(D);
   // several ranks: only the peer-memory exchange is captured (its exchange counter lives on the device)
   if (!D.use_graph || D.prof_on || (D.world > 1 && !(D.use_p2p && D.graph_dist)) || apply_launch_estimate(D) > 60000) {
     apply_permuted_raw(D, r, z);
@@ -1471,6 +1649,7 @@ static void apply_permuted(DeviceState& D, const double* r, double* z) {
 }
 
 static void apply_permuted_raw(DeviceState& D, const double* r, double* z) {
+  Nvtx range(D, "apply");
   DLevel& l0 = D.lv[0];
   l0.b = const_cast<double*>(r);
   l0.x = z;
@@ -1481,7 +1660,19 @@ static void apply_permuted_raw(DeviceState& D, const double* r, double* z) {
     if (is_dist(D, l0)) barrier_only(D);   // peers push into z from the first colour on
     // halo mode: the patches that straddle a cut read the right-hand side on dofs of the neighbour's block
     if (halo_on(D, l0) && l0.sw.npatch > 0) halo_exchange(D, l0, r, -2);
-    for (int it = 0; it < std::max(1, D.prm.maxit); ++it) cycle_level(D, 0);
+    switch (D.prm.cycle_type) {
+      case MAMG_V_CYCLE: case MAMG_W_CYCLE:
+        for (int it = 0; it < std::max(1, D.prm.maxit); ++it) cycle_level(D, 0);
+        break;
+      case MAMG_AMLI_CYCLE: case MAMG_NL_AMLI_CYCLE: case MAMG_ADD_CYCLE:
+        if (D.world > 1) throw std::runtime_error("AMLI / NL_AMLI / ADD cycles run on one GPU (V_CYCLE and W_CYCLE are distributed)");
+        if (D.prm.cycle_type == MAMG_ADD_CYCLE) { cycle_additive(D); break; }
+        for (int it = 0; it < std::max(1, D.prm.maxit); ++it) {
+          if (D.prm.cycle_type == MAMG_AMLI_CYCLE) cycle_amli(D, 0); else cycle_nlamli(D, 0);
+        }
+        break;
+      default: throw std::runtime_error("cycle_type: unknown value");
+    }
   }
   l0.b = l0.b_own;
   l0.x = l0.x_own;
@@ -1534,6 +1725,7 @@ static void read_scalars(DeviceState& D, int count) {
 static int pcg_device(DeviceState& D, const double* b_nat, double* x_nat, double tol, int stop,
                       int maxiter, bool use_guess, int* niters, double* residuals, double* alphas,
                       double* betas, const BlockPtrs* b_blocks = nullptr, const BlockPtrs* x_blocks = nullptr) {
+  Nvtx range(D, "pcg");
   DLevel& l0 = D.lv[0];
   const int n = l0.n;
   double *b = D.w[0], *x = D.w[1], *r = D.w[2], *z = D.w[3], *d = D.w[4], *q = D.w[5];
@@ -1891,6 +2083,7 @@ static int to_device_impl(mamg_handle h, int32_t device, void* stream, int32_t r
     D->halo = !(eh && atoi(eh) == 0) && !(ep && atoi(ep) == 0) && rows_sell() && !sa;
   }
   { const char* g = getenv("MAMG_GRAPH"); if (g) D->use_graph = atoi(g) != 0; }
+  { const char* g = getenv("MAMG_NVTX"); D->nvtx = g && atoi(g) != 0; }
   { const char* g = getenv("MAMG_GRAPH_DIST"); if (g) D->graph_dist = atoi(g) != 0; }
   {
     const char* e2 = getenv("MAMG_L2_PERSIST_MB");   // 0 disables; default: what the device allows
@@ -2021,7 +2214,10 @@ int mamg_set_stream(mamg_handle h, void* stream) {
 int mamg_set_cycle(mamg_handle h, int32_t cycle_type) {
   MAMG_TRY
   if (!h) { set_error("NULL handle"); return -1; }
-  if (cycle_type != MAMG_V_CYCLE && cycle_type != MAMG_W_CYCLE) { set_error("set_cycle: only V_CYCLE and W_CYCLE"); return -1; }
+  if (cycle_type < MAMG_V_CYCLE || cycle_type > MAMG_ADD_CYCLE) { set_error("set_cycle: unknown cycle_type"); return -1; }
+  if (cycle_type == MAMG_ADD_CYCLE && h->H.prm.maxit > 1) { set_error("set_cycle: ADD_CYCLE is applied once per call (maxit 1)"); return -1; }
+  if (cycle_type == MAMG_AMLI_CYCLE && (h->H.prm.amli_degree < 0 || h->H.prm.amli_degree > 15)) { set_error("set_cycle: amli_degree 0..15"); return -1; }
+  if (cycle_type > MAMG_W_CYCLE && h->dev && h->dev->world > 1) { set_error("set_cycle: AMLI / NL_AMLI / ADD cycles run on one GPU"); return -1; }
   h->H.prm.cycle_type = cycle_type;
   if (h->dev) {
     cudaSetDevice(h->dev->device);

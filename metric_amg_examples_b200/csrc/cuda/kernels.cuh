@@ -567,4 +567,32 @@ minres_update_kernel(int n, double inv_gamma, double oldeps, double delta, doubl
   x[i] += phi * ti;
 }
 
+// ---- K-cycle scalars (nonlinear AMLI): s[0]=|b|^2 s[1]=rho1 s[2]=alpha1 s[3]=beta1 s[4]=|r~|^2 s[5]=gamma s[6]=alpha2
+// s[7]=rho2 s[8]=beta3 s[9]=beta4.  One thread; keeps every coefficient of the two-step Krylov update on the device.
+__global__ void kcycle_step1_kernel(double* s) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) s[3] = s[1] != 0.0 ? s[2] / s[1] : 0.0;
+}
+// x = beta3 c1 + beta4 c2; beta4 = 0 (and beta3 = beta1) when the first step already met the tolerance
+__global__ void kcycle_step2_kernel(double* s, double tol2) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double nb2 = s[0], rho1 = s[1], alpha1 = s[2], beta1 = s[3], nr2 = s[4], gamma = s[5], alpha2 = s[6], rho2 = s[7];
+  double beta3 = beta1, beta4 = 0.0;
+  if (!(nr2 < tol2 * nb2) && nb2 != 0.0) {
+    const double beta2 = alpha2 - gamma * gamma / rho1;
+    if (beta2 != 0.0 && rho1 != 0.0) {
+      beta3 = (alpha1 - gamma * rho2 / beta2) / rho1;
+      beta4 = rho2 / beta2;
+    }
+  }
+  s[8] = beta3;
+  s[9] = beta4;
+}
+__global__ void __launch_bounds__(kBlock)
+kcycle_combine_kernel(int n, const double* __restrict__ coef, const double* __restrict__ c1, double* __restrict__ x) {
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  const double b3 = coef[0], b4 = coef[1];
+  x[i] = b4 == 0.0 ? b3 * c1[i] : b3 * c1[i] + b4 * x[i];
+}
+
 }  // namespace mamg

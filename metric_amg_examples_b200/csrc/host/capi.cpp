@@ -51,6 +51,7 @@ int mamg_params_default(mamg_params* p) {
   p->Schwarz_type = MAMG_SCHWARZ_SYMMETRIC;
   p->Schwarz_blksolver = MAMG_SOLVER_UMFPACK;
   p->print_level = 0;
+  p->nl_amli_krylov_type = MAMG_SOLVER_VFGMRES;
   return 0;
 }
 

@@ -640,8 +640,15 @@ bool build_hierarchy(const mamg_params& prm, Csr&& A0, const int* idofs, int n_i
   H.lv[0].A = std::move(A0);
   if (part) H.lv[0].part.assign(part, part + H.lv[0].A.n);
   if (prm.AMG_type != MAMG_UA_AMG && prm.AMG_type != MAMG_SA_AMG) { err = "AMG_type: only UA_AMG and SA_AMG are implemented"; return false; }
-  if (prm.cycle_type != MAMG_V_CYCLE && prm.cycle_type != MAMG_W_CYCLE) {
-    err = "cycle_type: only V_CYCLE and W_CYCLE are implemented";
+  switch (prm.cycle_type) {
+    case MAMG_V_CYCLE: case MAMG_W_CYCLE: case MAMG_AMLI_CYCLE: case MAMG_NL_AMLI_CYCLE: break;
+    case MAMG_ADD_CYCLE:
+      if (prm.maxit > 1) { err = "cycle_type ADD_CYCLE: the additive cycle is applied once per call (maxit 1)"; return false; }
+      break;
+    default: err = "cycle_type: unknown value"; return false;
+  }
+  if (prm.cycle_type == MAMG_AMLI_CYCLE && (prm.amli_degree < 0 || prm.amli_degree > 15)) {
+    err = "amli_degree: 0..15";
     return false;
   }
   switch (prm.aggregation_type) {
@@ -653,9 +660,15 @@ bool build_hierarchy(const mamg_params& prm, Csr&& A0, const int* idofs, int n_i
     case MAMG_SMOOTHER_SOR: case MAMG_SMOOTHER_SSOR: case MAMG_SMOOTHER_L1DIAG: break;
     default: err = "smoother: only JACOBI, GS, SGS, SOR, SSOR, L1DIAG are implemented"; return false;
   }
-  if (prm.coarse_solver != MAMG_SOLVER_UMFPACK) { err = "coarse_solver: only 32 (direct) is implemented"; return false; }
-  if (prm.Schwarz_levels > 0 && prm.Schwarz_blksolver != MAMG_SOLVER_UMFPACK) {
-    err = "Schwarz_blksolver: only 32 (direct) is implemented";
+  // coarse_solver / Schwarz_blksolver 0 ("iterative", src/amg_parameters.py:14,43): upstream these iterate to
+  // tol*1e-4 on the coarsest operator / the patch blocks; the dense inverses used here are the limit of that
+  // iteration, so both values are served by the same path
+  if (prm.coarse_solver != MAMG_SOLVER_UMFPACK && prm.coarse_solver != MAMG_SOLVER_DEFAULT) {
+    err = "coarse_solver: 32 (direct) or 0 (iterative)";
+    return false;
+  }
+  if (prm.Schwarz_levels > 0 && prm.Schwarz_blksolver != MAMG_SOLVER_UMFPACK && prm.Schwarz_blksolver != MAMG_SOLVER_DEFAULT) {
+    err = "Schwarz_blksolver: 32 (direct) or 0 (iterative)";
     return false;
   }
   const int max_levels = std::max(1, prm.max_levels);

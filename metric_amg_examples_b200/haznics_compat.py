@@ -11,5 +11,5 @@ SMOOTHER_JACOBI, SMOOTHER_GS, SMOOTHER_SGS = 1, 2, 3
 SMOOTHER_SOR, SMOOTHER_SSOR, SMOOTHER_L1DIAG = 5, 6, 10
 VMB, MIS, MWM, HEC, HEM = 1, 2, 3, 4, 5
 SCHWARZ_FORWARD, SCHWARZ_BACKWARD, SCHWARZ_SYMMETRIC = 1, 2, 3
-SOLVER_UMFPACK = 32
+SOLVER_DEFAULT, SOLVER_VFGMRES, SOLVER_GCG, SOLVER_GCR, SOLVER_UMFPACK = 0, 4, 5, 6, 32
 OFF, ON = 0, 1

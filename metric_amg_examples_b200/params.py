@@ -4,7 +4,7 @@ The four dicts restate src/amg_parameters.py:3-89 key for key (values via the
 haznics-compatible constants); `default_metric_parameters` is the inline dict of
 src/utils.py:60-82 and `default_amg_parameters` the one of src/utils.py:20-38.
 `to_struct` plays the role of haznics.param_amg_set_dict: unknown keys warn,
-unsupported values raise NotImplementedError (never a silent fallback).
+values outside the implemented option space raise NotImplementedError (never a silent fallback).
 """
 import warnings
 
@@ -93,19 +93,24 @@ def to_struct(parameters=None):
         setattr(p, key, type(getattr(p, key))(val))
     if p.AMG_type not in (haznics.UA_AMG, haznics.SA_AMG):
         raise NotImplementedError(f"AMG_type={p.AMG_type}")
-    if p.cycle_type not in (haznics.V_CYCLE, haznics.W_CYCLE):
-        raise NotImplementedError(
-            f"cycle_type={p.cycle_type}: only V_CYCLE and W_CYCLE are implemented (AMLI/ADD are not used "
-            "by any reference configuration)")
+    if p.cycle_type not in (haznics.V_CYCLE, haznics.W_CYCLE, haznics.AMLI_CYCLE, haznics.NL_AMLI_CYCLE,
+                            haznics.ADD_CYCLE):
+        raise NotImplementedError(f"cycle_type={p.cycle_type}")
+    if p.cycle_type == haznics.ADD_CYCLE and p.maxit > 1:
+        raise NotImplementedError("ADD_CYCLE: the additive cycle is applied once per call (maxit 1)")
+    if p.cycle_type == haznics.AMLI_CYCLE and not 0 <= p.amli_degree <= 15:
+        raise NotImplementedError(f"amli_degree={p.amli_degree}: 0..15")
     if p.aggregation_type not in (haznics.VMB, haznics.MIS, haznics.MWM, haznics.HEC, haznics.HEM):
         raise NotImplementedError(f"aggregation_type={p.aggregation_type}")
     if p.smoother not in (haznics.SMOOTHER_JACOBI, haznics.SMOOTHER_GS, haznics.SMOOTHER_SGS,
                           haznics.SMOOTHER_SOR, haznics.SMOOTHER_SSOR, haznics.SMOOTHER_L1DIAG):
         raise NotImplementedError(f"smoother={p.smoother}")
-    if p.coarse_solver != haznics.SOLVER_UMFPACK:
-        raise NotImplementedError("coarse_solver: only 32 (direct) is implemented")
-    if p.Schwarz_levels > 0 and p.Schwarz_blksolver != haznics.SOLVER_UMFPACK:
-        raise NotImplementedError("Schwarz_blksolver: only 32 (direct) is implemented")
+    # 0 = "iterative" upstream (src/amg_parameters.py:14,43): the coarsest operator / the patch blocks are
+    # iterated to tol*1e-4 there; the dense inverses used here are the limit of that iteration
+    if p.coarse_solver not in (haznics.SOLVER_UMFPACK, haznics.SOLVER_DEFAULT):
+        raise NotImplementedError(f"coarse_solver={p.coarse_solver}: 32 (direct) or 0 (iterative)")
+    if p.Schwarz_levels > 0 and p.Schwarz_blksolver not in (haznics.SOLVER_UMFPACK, haznics.SOLVER_DEFAULT):
+        raise NotImplementedError(f"Schwarz_blksolver={p.Schwarz_blksolver}: 32 (direct) or 0 (iterative)")
     return p
 
 

@@ -34,7 +34,7 @@ static int omp_get_thread_num(void) { return 0; }
 static int omp_get_max_threads(void) { return 1; }
 #endif
 
-enum { UA_AMG = 1, V_CYCLE = 1, W_CYCLE = 2, SM_JACOBI = 1, SM_GS = 2, SM_SGS = 3, SM_SOR = 5, SM_SSOR = 6, SM_L1DIAG = 10,
+enum { UA_AMG = 1, V_CYCLE = 1, W_CYCLE = 2, AMLI_CYCLE = 3, NL_AMLI_CYCLE = 4, ADD_CYCLE = 5, SOLVER_GCG = 5, SM_JACOBI = 1, SM_GS = 2, SM_SGS = 3, SM_SOR = 5, SM_SSOR = 6, SM_L1DIAG = 10,
        SW_FORWARD = 1, SW_BACKWARD = 2, SW_SYMMETRIC = 3 };
 
 typedef struct {
@@ -44,6 +44,7 @@ typedef struct {
   int *crow_ptr, *crow, *cpat_ptr, *cpat;
   unsigned char* skip;
   double *a, *invd, *x, *b, *w;
+  double* kw;       /* 4 n work vectors of the AMLI / K-cycle coarse corrections (allocated on first use) */
   /* Schwarz blocks are factorised once at setup, as HAZmath does with UMFPACK
    * (Schwarz_blksolver 32): packed lower Cholesky factors, pfoff[p] = start of patch p */
   double* pfac;
@@ -55,6 +56,8 @@ typedef struct {
 
 typedef struct {
   int cycle_type, maxit, smoother, presmooth, postsmooth, coarse_scaling, schwarz_type;
+  int amli_degree, nl_amli_krylov_type;
+  double amli_coef[16];
   double relaxation;
   int nlevels, cap;
   orc_level* lv;
@@ -64,6 +67,8 @@ typedef struct {
   int threads;      /* > 1 only for the multicolour ordering (bench reference arm) */
   int ordering;
   long visits;      /* level visits of the last apply (for reporting) */
+  double kmargin_all; /* the same since the hierarchy was created */
+  double kmargin;   /* K-cycle: smallest |nr2 / (tol2 nb2) - 1| of the last apply (how close a stopping decision was) */
 } orc_hier;
 
 static double vdot(int n, const double* u, const double* v);
@@ -106,6 +111,7 @@ orc_hier* orc_create(int cycle_type, int maxit, int smoother, double relaxation,
   h->cycle_type = cycle_type; h->maxit = maxit; h->smoother = smoother; h->relaxation = relaxation;
   h->presmooth = presmooth; h->postsmooth = postsmooth; h->coarse_scaling = coarse_scaling;
   h->schwarz_type = schwarz_type; h->ordering = 1; h->threads = 1;
+  h->amli_degree = 3; h->nl_amli_krylov_type = 4; h->kmargin = h->kmargin_all = 1e300;
   return h;
 }
 
@@ -196,7 +202,13 @@ int orc_set_threads(orc_hier* h, int threads) {
   return h->threads;
 }
 void orc_set_cycle(orc_hier* h, int cycle_type) { h->cycle_type = cycle_type; }
+/* amli_degree (src/amg_parameters.py:62,82) and HAZmath's nl_amli_krylov_type (SOLVER_GCG = 5 -> GCG, else GCR) */
+void orc_set_amli(orc_hier* h, int degree, int krylov_type) {
+  h->amli_degree = degree < 0 ? 0 : (degree > 15 ? 15 : degree);
+  h->nl_amli_krylov_type = krylov_type;
+}
 long orc_visits(orc_hier* h) { return h->visits; }
+double orc_kcycle_margin(orc_hier* h, int all) { return all ? h->kmargin_all : h->kmargin; }
 
 void orc_destroy(orc_hier* h) {
   if (!h) return;
@@ -205,7 +217,7 @@ void orc_destroy(orc_hier* h) {
     free(L->ia); free(L->ja); free(L->a); free(L->agg); free(L->color); free(L->skip); free(L->invd);
     free(L->x); free(L->b); free(L->w); free(L->crow_ptr); free(L->crow);
     free(L->pptr); free(L->pdofs); free(L->pcolor); free(L->cpat_ptr); free(L->cpat);
-    free(L->pfac); free(L->pfoff); free(L->pia); free(L->pja); free(L->pa);
+    free(L->pfac); free(L->pfoff); free(L->pia); free(L->pja); free(L->pa); free(L->kw);
   }
   free(h->lv); free(h->coarse_inv); free(h->rhs); free(h);
 }
@@ -335,6 +347,57 @@ static void coarse_solve(orc_hier* h) {
   }
 }
 
+/* b_c = R (b - A x) on level lev, x_c = 0 (aggregate sums for UA, P' for SA) */
+static void restrict_residual(orc_hier* h, int lev) {
+  orc_level* L = &h->lv[lev];
+  orc_level* C = &h->lv[lev + 1];
+  memset(C->b, 0, sizeof(double) * C->n);
+  if (L->pia) {   /* SA_AMG: b_c = P' (b - A x) */
+    for (int i = 0; i < L->n; ++i) {
+      const double w = L->b[i] - row_dot(L, i, L->x);
+      for (int p = L->pia[i]; p < L->pia[i + 1]; ++p) C->b[L->pja[p]] += L->pa[p] * w;
+    }
+  } else if (h->threads > 1) {
+#pragma omp parallel for schedule(static) num_threads(h->threads)
+    for (int i = 0; i < L->n; ++i) L->w[i] = L->b[i] - row_dot(L, i, L->x);
+    for (int i = 0; i < L->n; ++i) { int I = L->agg[i]; if (I >= 0) C->b[I] += L->w[i]; }
+  } else {
+    for (int i = 0; i < L->n; ++i) {
+      int I = L->agg[i];
+      if (I >= 0) C->b[I] += L->b[i] - row_dot(L, i, L->x);
+    }
+  }
+  memset(C->x, 0, sizeof(double) * C->n);
+}
+
+/* coarse scaling: alpha = min(1, e.rhs / e.A_c e) for the correction e = x_c */
+static double coarse_alpha(orc_hier* h, const orc_level* C, const double* rhs) {
+  if (!h->coarse_scaling) return 1.0;
+  double num = 0.0, den = 0.0;
+#pragma omp parallel for schedule(static) reduction(+ : num, den) num_threads(h->threads) if (h->threads > 1)
+  for (int i = 0; i < C->n; ++i) { num += C->x[i] * rhs[i]; den += C->x[i] * row_dot(C, i, C->x); }
+  double alpha = num / den;
+  return (alpha < 1.0) ? alpha : 1.0;  /* MIN(alpha, 1.0); NaN -> 1 */
+}
+
+/* x += alpha P x_c */
+static void prolong_add(orc_hier* h, int lev, double alpha) {
+  orc_level* L = &h->lv[lev];
+  const orc_level* C = &h->lv[lev + 1];
+  if (L->pia) {   /* SA_AMG: x += alpha P e */
+    for (int i = 0; i < L->n; ++i) {
+      double s = 0.0;
+      for (int p = L->pia[i]; p < L->pia[i + 1]; ++p) s += L->pa[p] * C->x[L->pja[p]];
+      L->x[i] += alpha * s;
+    }
+  } else {
+    for (int i = 0; i < L->n; ++i) {
+      int I = L->agg[i];
+      if (I >= 0) L->x[i] += alpha * C->x[I];
+    }
+  }
+}
+
 /* FASP-lineage cycle: level l > 0 is visited cycle_type times per parent visit,
  * re-entering with its current iterate. */
 static void cycle_level(orc_hier* h, int lev) {
@@ -345,56 +408,167 @@ static void cycle_level(orc_hier* h, int lev) {
   for (int rep = 0; rep < reps; ++rep) {
     h->visits++;
     smooth(h, lev, L->b, L->x, 0);
-    memset(C->b, 0, sizeof(double) * C->n);
-    if (L->pia) {   /* SA_AMG: b_c = P' (b - A x) */
-      for (int i = 0; i < L->n; ++i) {
-        const double w = L->b[i] - row_dot(L, i, L->x);
-        for (int p = L->pia[i]; p < L->pia[i + 1]; ++p) C->b[L->pja[p]] += L->pa[p] * w;
-      }
-    } else if (h->threads > 1) {
-#pragma omp parallel for schedule(static) num_threads(h->threads)
-      for (int i = 0; i < L->n; ++i) L->w[i] = L->b[i] - row_dot(L, i, L->x);
-      for (int i = 0; i < L->n; ++i) { int I = L->agg[i]; if (I >= 0) C->b[I] += L->w[i]; }
-    } else {
-      for (int i = 0; i < L->n; ++i) {
-        int I = L->agg[i];
-        if (I >= 0) C->b[I] += L->b[i] - row_dot(L, i, L->x);
-      }
-    }
-    memset(C->x, 0, sizeof(double) * C->n);
+    restrict_residual(h, lev);
     cycle_level(h, lev + 1);
-    double alpha = 1.0;
-    if (h->coarse_scaling) {
-      double num = 0.0, den = 0.0;
-#pragma omp parallel for schedule(static) reduction(+ : num, den) num_threads(h->threads) if (h->threads > 1)
-      for (int i = 0; i < C->n; ++i) { num += C->x[i] * C->b[i]; den += C->x[i] * row_dot(C, i, C->x); }
-      alpha = num / den;
-      alpha = (alpha < 1.0) ? alpha : 1.0;  /* MIN(alpha, 1.0); NaN -> 1 */
-    }
-    if (L->pia) {   /* SA_AMG: x += alpha P e */
-      for (int i = 0; i < L->n; ++i) {
-        double s = 0.0;
-        for (int p = L->pia[i]; p < L->pia[i + 1]; ++p) s += L->pa[p] * C->x[L->pja[p]];
-        L->x[i] += alpha * s;
-      }
-    } else {
-      for (int i = 0; i < L->n; ++i) {
-        int I = L->agg[i];
-        if (I >= 0) L->x[i] += alpha * C->x[I];
-      }
-    }
+    const double alpha = coarse_alpha(h, C, C->b);
+    prolong_add(h, lev, alpha);
     smooth(h, lev, L->b, L->x, 1);
   }
+}
+
+static double* level_work(orc_level* L) {
+  if (!L->kw) L->kw = (double*)calloc((size_t)4 * (L->n ? L->n : 1), sizeof(double));
+  return L->kw;
+}
+
+/* Coefficients of the AMLI polynomial (FASP lineage, fasp_amg_amli_coef): q_k from the three-term recurrence
+ * of the shifted Chebyshev polynomials on [lambda_min, lambda_max]; coef has degree + 1 entries. */
+static void amli_coef(double lambda_max, double lambda_min, int degree, double* coef) {
+  const double mu0 = 1.0 / lambda_max, mu1 = 1.0 / lambda_min;
+  const double c = (sqrt(mu0) + sqrt(mu1)) * (sqrt(mu0) + sqrt(mu1));
+  const double a = (4.0 * mu0 * mu1) / c;
+  const double kappa = lambda_max / lambda_min;
+  const double delta = (sqrt(kappa) - 1.0) / (sqrt(kappa) + 1.0);
+  const double b = delta * delta;
+  if (degree == 0) {
+    coef[0] = 0.5 * (mu0 + mu1);
+  } else if (degree == 1) {
+    coef[0] = 0.5 * c;
+    coef[1] = -1.0 * mu0 * mu1;
+  } else {
+    double ck[16] = {0}, ckm1[16] = {0};
+    amli_coef(lambda_max, lambda_min, degree - 1, ck);
+    amli_coef(lambda_max, lambda_min, degree - 2, ckm1);
+    coef[0] = a - b * ckm1[0] + (1.0 + b) * ck[0];
+    for (int i = 1; i < degree - 1; ++i) coef[i] = -b * ckm1[i] + (1.0 + b) * ck[i] - a * ck[i - 1];
+    coef[degree - 1] = (1.0 + b) * ck[degree - 1] - a * ck[degree - 2];
+    coef[degree] = -a * ck[degree - 1];
+  }
+}
+void orc_amli_coef(int degree, double* coef) { amli_coef(2.0, 0.5, degree, coef); }
+
+/* AMLI-cycle (FASP lineage, amli() of mgcycle.c): the coarse correction is the polynomial
+ * q(B_c A_c) B_c r_c of degree amli_degree in the coarse cycle B_c, evaluated Horner-style:
+ *   e = B_c r_c;  repeat degree times: rhs = A_c e + (coef[degree-i]/coef[degree]) r_c, e = B_c rhs;
+ *   e *= coef[degree];  alpha = min(1, e.r_c / e.A_c e). */
+static void cycle_amli(orc_hier* h, int lev) {
+  if (lev == h->nlevels - 1) { coarse_solve(h); return; }
+  orc_level* L = &h->lv[lev];
+  orc_level* C = &h->lv[lev + 1];
+  const int deg = h->amli_degree;
+  const double* coef = h->amli_coef;
+  h->visits++;
+  smooth(h, lev, L->b, L->x, 0);
+  restrict_residual(h, lev);
+  double* r1 = level_work(C);
+  memcpy(r1, C->b, sizeof(double) * C->n);
+  for (int i = 1; i <= deg; ++i) {
+    memset(C->x, 0, sizeof(double) * C->n);
+    cycle_amli(h, lev + 1);
+    const double s = coef[deg - i] / coef[deg];
+    for (int k = 0; k < C->n; ++k) C->b[k] = row_dot(C, k, C->x);
+    for (int k = 0; k < C->n; ++k) C->b[k] += s * r1[k];
+  }
+  memset(C->x, 0, sizeof(double) * C->n);
+  cycle_amli(h, lev + 1);
+  for (int k = 0; k < C->n; ++k) C->x[k] *= coef[deg];
+  const double alpha = coarse_alpha(h, C, r1);
+  prolong_add(h, lev, alpha);
+  smooth(h, lev, L->b, L->x, 1);
+}
+
+static void cycle_nlamli(orc_hier* h, int lev);
+
+/* K-cycle coarse correction (Notay & Vassilevski 2008; FASP lineage Kcycle_dcsr_pgcg / _pgcr): at most two steps of
+ * a Krylov method on A_c x = b_c preconditioned by the nonlinear AMLI cycle of level lc itself; the second
+ * step is skipped when the first reduced the residual below KCYCLE_TOL.  gcg: inner products with the
+ * directions (flexible CG), otherwise with their images (GCR, HAZmath's default branch). */
+#define KCYCLE_TOL2 0.04   /* relres < 0.2 */
+static void kcycle(orc_hier* h, int lc) {
+  orc_level* C = &h->lv[lc];
+  const int n = C->n;
+  const int gcg = h->nl_amli_krylov_type == SOLVER_GCG;
+  double* bH = level_work(C);
+  double *c1 = bH + n, *v1 = bH + 2 * (size_t)n, *v2 = bH + 3 * (size_t)n;
+  double* r = C->b;   /* the Krylov residual lives in the level's right-hand side: it is what the cycle reads */
+  memcpy(bH, C->b, sizeof(double) * n);
+  const double nb2 = vdot(n, r, r);
+  memset(C->x, 0, sizeof(double) * n);
+  cycle_nlamli(h, lc);
+  memcpy(c1, C->x, sizeof(double) * n);
+  for (int i = 0; i < n; ++i) v1[i] = row_dot(C, i, c1);
+  const double rho1 = vdot(n, gcg ? c1 : v1, v1);
+  const double alpha1 = vdot(n, gcg ? c1 : v1, r);
+  const double beta1 = rho1 != 0.0 ? alpha1 / rho1 : 0.0;
+  for (int i = 0; i < n; ++i) r[i] += -beta1 * v1[i];
+  const double nr2 = vdot(n, r, r);
+  if (nb2 != 0.0) { double m = fabs(nr2 / (KCYCLE_TOL2 * nb2) - 1.0); if (m < h->kmargin) h->kmargin = m; if (m < h->kmargin_all) h->kmargin_all = m; }
+  double beta3 = beta1, beta4 = 0.0;
+  if (!(nr2 < KCYCLE_TOL2 * nb2) && nb2 != 0.0) {
+    memset(C->x, 0, sizeof(double) * n);
+    cycle_nlamli(h, lc);
+    for (int i = 0; i < n; ++i) v2[i] = row_dot(C, i, C->x);
+    const double* q = gcg ? C->x : v2;
+    const double gamma = vdot(n, q, v1), alpha2 = vdot(n, q, v2), rho2 = vdot(n, q, r);
+    const double beta2 = alpha2 - gamma * gamma / rho1;
+    if (beta2 != 0.0 && rho1 != 0.0) {
+      beta3 = (alpha1 - gamma * rho2 / beta2) / rho1;
+      beta4 = rho2 / beta2;
+    }
+  }
+  if (beta4 == 0.0) for (int i = 0; i < n; ++i) C->x[i] = beta3 * c1[i];
+  else for (int i = 0; i < n; ++i) C->x[i] = beta3 * c1[i] + beta4 * C->x[i];
+  memcpy(C->b, bH, sizeof(double) * n);
+}
+
+/* nonlinear AMLI-cycle (FASP lineage, nl_amli() of mgcycle.c): the coarse problem of every level but the
+ * last is "solved" by the K-cycle above; the coarsest level is solved directly. */
+static void cycle_nlamli(orc_hier* h, int lev) {
+  if (lev == h->nlevels - 1) { coarse_solve(h); return; }
+  orc_level* L = &h->lv[lev];
+  orc_level* C = &h->lv[lev + 1];
+  h->visits++;
+  smooth(h, lev, L->b, L->x, 0);
+  restrict_residual(h, lev);
+  if (lev + 1 == h->nlevels - 1) coarse_solve(h);
+  else kcycle(h, lev + 1);
+  const double alpha = coarse_alpha(h, C, C->b);
+  prolong_add(h, lev, alpha);
+  smooth(h, lev, L->b, L->x, 1);
+}
+
+/* additive cycle: z = sum_l P_0..P_{l-1} S_l R_{l-1}..R_0 r with S_l = pre- then post-smoothing from a zero
+ * iterate (a symmetric operator for the symmetric smoothers), the exact solve on the coarsest level and no
+ * coarse scaling.  Frozen choice: HAZmath's additive cycle could not be consulted. */
+static void cycle_add(orc_hier* h) {
+  const int nl = h->nlevels;
+  for (int lev = 0; lev + 1 < nl; ++lev) {
+    orc_level* L = &h->lv[lev];
+    h->visits++;
+    memset(L->x, 0, sizeof(double) * L->n);
+    restrict_residual(h, lev);          /* x = 0: the right-hand side itself is restricted */
+    smooth(h, lev, L->b, L->x, 0);
+    smooth(h, lev, L->b, L->x, 1);
+  }
+  coarse_solve(h);
+  for (int lev = nl - 2; lev >= 0; --lev) prolong_add(h, lev, 1.0);
 }
 
 /* z = B r : haznics.apply_precond as called by cbc.block's Precond.matvec */
 void orc_apply(orc_hier* h, const double* r, double* z) {
   orc_level* L0 = &h->lv[0];
   h->visits = 0;
+  h->kmargin = 1e300;
   memcpy(L0->b, r, sizeof(double) * L0->n);
   if (h->nlevels == 1) { coarse_solve(h); memcpy(z, L0->x, sizeof(double) * L0->n); return; }
   memset(L0->x, 0, sizeof(double) * L0->n);
-  for (int it = 0; it < (h->maxit > 1 ? h->maxit : 1); ++it) cycle_level(h, 0);
+  if (h->cycle_type == ADD_CYCLE) { cycle_add(h); memcpy(z, L0->x, sizeof(double) * L0->n); return; }
+  if (h->cycle_type == AMLI_CYCLE) amli_coef(2.0, 0.5, h->amli_degree, h->amli_coef);   /* lambda_max = 2, lambda_min = lambda_max / 4 */
+  for (int it = 0; it < (h->maxit > 1 ? h->maxit : 1); ++it) {
+    if (h->cycle_type == AMLI_CYCLE) cycle_amli(h, 0);
+    else if (h->cycle_type == NL_AMLI_CYCLE) cycle_nlamli(h, 0);
+    else cycle_level(h, 0);
+  }
   memcpy(z, L0->x, sizeof(double) * L0->n);
 }
 

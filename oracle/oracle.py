@@ -28,10 +28,14 @@ def _load():
     lib.orc_set_prolongator.argtypes = [vp, i32, vp, vp, vp]
     lib.orc_set_ordering.argtypes = [vp, i32]
     lib.orc_set_cycle.argtypes = [vp, i32]
+    lib.orc_set_amli.argtypes = [vp, i32, i32]
+    lib.orc_amli_coef.argtypes = [i32, vp]
     lib.orc_set_threads.restype = i32
     lib.orc_set_threads.argtypes = [vp, i32]
     lib.orc_visits.restype = C.c_long
     lib.orc_visits.argtypes = [vp]
+    lib.orc_kcycle_margin.restype = dbl
+    lib.orc_kcycle_margin.argtypes = [vp, i32]
     lib.orc_destroy.argtypes = [vp]
     lib.orc_apply.argtypes = [vp, vp, vp]
     lib.orc_spmv.argtypes = [vp, i32, vp, vp]
@@ -60,6 +64,7 @@ class Oracle:
         self.h = self.lib.orc_create(P["cycle_type"], P["maxit"], P["smoother"], P["relaxation"],
                                      P["presmooth_iter"], P["postsmooth_iter"], P["coarse_scaling"],
                                      P["Schwarz_type"])
+        self.lib.orc_set_amli(self.h, int(P.get("amli_degree", 3)), int(P.get("nl_amli_krylov_type", 4)))
         self._keep = []
         for L in hier["levels"]:
             arrs = [np.ascontiguousarray(L["indptr"], np.int32), np.ascontiguousarray(L["indices"], np.int32),
@@ -98,6 +103,10 @@ class Oracle:
     def set_cycle(self, cycle_type):
         self.lib.orc_set_cycle(self.h, int(cycle_type))
 
+    def set_amli(self, degree, krylov_type=4):
+        """amli_degree and HAZmath's nl_amli_krylov_type (5 = GCG, anything else GCR)."""
+        self.lib.orc_set_amli(self.h, int(degree), int(krylov_type))
+
     def apply(self, r):
         r = np.ascontiguousarray(r, np.float64)
         z = np.empty(self.n)
@@ -106,6 +115,12 @@ class Oracle:
 
     def visits(self):
         return int(self.lib.orc_visits(self.h))
+
+    def kcycle_margin(self, since_creation=False):
+        """Nonlinear AMLI: how close the closest K-cycle stopping decision of the last apply (or of every apply so
+        far) was to its threshold, relatively; tests use it to make sure rounding cannot flip a decision on the
+        inputs they compare."""
+        return float(self.lib.orc_kcycle_margin(self.h, int(since_creation)))
 
     def spmv(self, x, level=0):
         x = np.ascontiguousarray(x, np.float64)
@@ -143,3 +158,11 @@ class Oracle:
         res = np.zeros(maxiter + 2)
         k = self.lib.orc_gmres(self.h, _p(b), _p(x), tolerance, int(relative), maxiter, int(restart), _p(res))
         return x, {"niters": k, "residuals": res[:k + 1].tolist()}
+
+
+def amli_coefficients(degree):
+    """Coefficients q_0..q_degree of the AMLI polynomial the oracle uses (lambda_max = 2, lambda_min = 1/2)."""
+    lib = _load()
+    coef = np.zeros(16)
+    lib.orc_amli_coef(int(degree), _p(coef))
+    return coef[:degree + 1].copy()

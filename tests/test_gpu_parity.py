@@ -354,3 +354,65 @@ def test_block_diag_precond_matches_exact_block_solves():
     assert np.allclose(inv.residuals[:5], ref.residuals[:5], rtol=1e-6)
     assert rel(np.concatenate(list(xb)), np.concatenate(list(xr))) < 1e-7
     assert all(k < 60 for op in BB.ops for k in op.iterations)
+
+
+# ---- the remaining values of cycle_type (src/amg_parameters.py:6,26,49,69): AMLI, nonlinear AMLI, additive ----
+FURTHER_CYCLES = {
+    "amli3": dict(cycle_type=haznics.AMLI_CYCLE),
+    "amli1": dict(cycle_type=haznics.AMLI_CYCLE, amli_degree=1),
+    "nlamli_gcr": dict(cycle_type=haznics.NL_AMLI_CYCLE),
+    "nlamli_gcg": dict(cycle_type=haznics.NL_AMLI_CYCLE, nl_amli_krylov_type=haznics.SOLVER_GCG),
+    "additive": dict(cycle_type=haznics.ADD_CYCLE),
+}
+
+
+def _check_cycle(system, prm, seed, pcg=True):
+    H, orc = make(system, prm)
+    r = np.random.default_rng(seed).standard_normal(system.ndofs)
+    zo = orc.apply(r)
+    nl = prm["cycle_type"] == haznics.NL_AMLI_CYCLE
+    if nl:   # no K-cycle stopping decision on this input is within rounding of its threshold
+        assert orc.kcycle_margin() > 1e-3
+    z = H.apply(r)
+    assert rel(z, zo) < APPLY_TOL
+    assert np.array_equal(H.apply(r), z)
+    if pcg:
+        b, _ = system.random_rhs(seed)
+        x, info = H.pcg(b, tolerance=1e-8, relative=True, maxiter=300)
+        xo, io = orc.pcg(b, tolerance=1e-8, relative=True, maxiter=300)
+        assert info["residuals"][-1] <= 1e-8 * info["residuals"][0]
+        if not nl or orc.kcycle_margin(since_creation=True) > 1e-6:
+            assert abs(info["niters"] - io["niters"]) <= 1 and rel(x, xo) < 1e-6
+    return H, orc
+
+
+@pytest.mark.parametrize("base", ["parameters_metric", "parameters_metric_schwarz"])
+@pytest.mark.parametrize("name", sorted(FURTHER_CYCLES))
+def test_further_cycle_types_match_oracle(name, base):
+    """2-D bidomain at gamma 1e6: the nonlinear AMLI cycle takes its second Krylov step on most levels here."""
+    system = problems.bidomain_system(2, 32, gamma=1e6)
+    _check_cycle(system, dict(getattr(params, base), **FURTHER_CYCLES[name]), 21)
+
+
+@pytest.mark.parametrize("name", sorted(FURTHER_CYCLES))
+def test_further_cycle_types_3d_emi_and_sa(name):
+    """3-D EMI with the reference's default dict (general Schwarz kernel, wide rows) and smoothed aggregation
+    (stored prolongators) under the further cycle types."""
+    system = problems.emi_system(3, 8, gamma=1e4)
+    _check_cycle(system, dict(params.default_metric_parameters, **FURTHER_CYCLES[name]), 22, pcg=False)
+    s2 = problems.bidomain_system(2, 24, gamma=1e2)
+    prm = dict(params.parameters_metric, AMG_type=haznics.SA_AMG, smoother=haznics.SMOOTHER_GS, **FURTHER_CYCLES[name])
+    _check_cycle(s2, prm, 23, pcg=False)
+
+
+def test_set_cycle_switches_between_all_cycle_types():
+    """mamg_set_cycle on an uploaded hierarchy: every cycle type on the same device arrays, ending where it began."""
+    system = problems.bidomain_system(2, 24, gamma=1e3)
+    H, orc = make(system, dict(params.parameters_metric_schwarz, cycle_type=haznics.V_CYCLE))
+    r = np.random.default_rng(24).standard_normal(system.ndofs)
+    z_v = H.apply(r)
+    for ct in (haznics.AMLI_CYCLE, haznics.W_CYCLE, haznics.NL_AMLI_CYCLE, haznics.ADD_CYCLE, haznics.V_CYCLE):
+        H.set_cycle(ct)
+        orc.set_cycle(ct)
+        assert rel(H.apply(r), orc.apply(r)) < APPLY_TOL, ct
+    assert np.array_equal(H.apply(r), z_v)

@@ -88,7 +88,7 @@ ENV_CASES = [
     {"MAMG_UNROLL": "1"}, {"MAMG_UNROLL": "2"}, {"MAMG_UNROLL": "4"},
     {"MAMG_LANES": "2"}, {"MAMG_LANES": "4"}, {"MAMG_LANES": "8"}, {"MAMG_LANES": "16"}, {"MAMG_LANES": "32"},
     {"MAMG_SCHWARZ_GENERAL": "1"}, {"MAMG_GRAPH": "0"}, {"MAMG_TAIL_ROWS": "0"}, {"MAMG_DROP_ZEROS": "1"},
-    {"MAMG_DROP_ZEROS": "0"}, {"MAMG_SW_DEDUP": "0"}, {"MAMG_ROWS": "csr"}, {"MAMG_ROWS": "sell"},
+    {"MAMG_DROP_ZEROS": "0"}, {"MAMG_SW_DEDUP": "0"}, {"MAMG_ROWS": "csr"}, {"MAMG_ROWS": "sell"}, {"MAMG_NVTX": "1"},
 ]
 
 

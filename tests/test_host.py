@@ -160,14 +160,23 @@ def test_parameter_translation():
     assert d.Schwarz_maxlvl == 2 and d.smoother == haznics.SMOOTHER_SGS
     with pytest.warns(UserWarning):
         params.to_struct({"no_such_key": 1})
+    for ct in (haznics.AMLI_CYCLE, haznics.NL_AMLI_CYCLE, haznics.ADD_CYCLE):   # the whole cycle_type option space
+        assert params.to_struct({"cycle_type": ct}).cycle_type == ct
+    assert params.to_struct(None).nl_amli_krylov_type == haznics.SOLVER_VFGMRES and params.to_struct(None).amli_degree == 3
     with pytest.raises(NotImplementedError):
-        params.to_struct({"cycle_type": haznics.AMLI_CYCLE})
+        params.to_struct({"cycle_type": 6})
+    with pytest.raises(NotImplementedError):
+        params.to_struct({"cycle_type": haznics.ADD_CYCLE, "maxit": 2})
+    with pytest.raises(NotImplementedError):
+        params.to_struct({"cycle_type": haznics.AMLI_CYCLE, "amli_degree": 16})
     with pytest.raises(NotImplementedError):
         params.to_struct({"aggregation_type": 77})
     with pytest.raises(NotImplementedError):
         params.to_struct({"smoother": 4})
+    # 0 = "iterative" upstream: served by the same dense inverses (the limit of that iteration)
+    assert params.to_struct({"coarse_solver": 0, "Schwarz_blksolver": 0}).coarse_solver == 0
     with pytest.raises(NotImplementedError):
-        params.to_struct({"coarse_solver": 0})
+        params.to_struct({"coarse_solver": 7})
 
 
 def test_reference_parameter_file_runs_unchanged():

@@ -262,3 +262,168 @@ def test_dropping_explicit_zeros_is_bit_neutral(monkeypatch):
         h0 = Oracle(full, order).pcg(b, tolerance=1e-10)[1]["residuals"]
         h1 = Oracle(lean, order).pcg(b, tolerance=1e-10)[1]["residuals"]
         assert h0 == h1
+
+
+# ---- AMLI / nonlinear AMLI / additive cycles (the remaining values of cycle_type, src/amg_parameters.py:6) -------
+
+def _smoother_matrices(orc, level, n, post):
+    """The smoother is affine, x' = E x + N b: extract E and N from the oracle's own sweeps."""
+    Z, I = np.zeros(n), np.eye(n)
+    E = np.column_stack([orc.smooth(Z, I[:, k], level, post) for k in range(n)])
+    N = np.column_stack([orc.smooth(I[:, k], Z, level, post) for k in range(n)])
+    return E, N
+
+
+def _dense_hierarchy(ex, orc):
+    lv = []
+    for l, L in enumerate(ex["levels"]):
+        A = level_matrix(L).toarray()
+        d = {"A": A}
+        if l + 1 < len(ex["levels"]):
+            agg = L["agg"]
+            rows = np.flatnonzero(agg >= 0)
+            d["P"] = sp.csr_matrix((np.ones(len(rows)), (rows, agg[rows])), shape=(L["n"], L["n_aggregates"])).toarray()
+            d["pre"] = _smoother_matrices(orc, l, L["n"], False)
+            d["post"] = _smoother_matrices(orc, l, L["n"], True)
+        lv.append(d)
+    return lv
+
+
+def test_amli_coefficients_are_the_best_uniform_approximation_of_the_reciprocal():
+    """q_k (three-term recurrence in the degree, lambda in [1/2, 2]) is the polynomial of best uniform approximation
+    to 1/t: the error 1/t - q_k(t) equioscillates at k + 2 points (Chebyshev's criterion), with magnitude
+    (3/4) 3^-k, i.e. the factor (sqrt(kappa)-1)/(sqrt(kappa)+1) = 1/3 per degree."""
+    from oracle.oracle import amli_coefficients
+    t = np.linspace(0.5, 2.0, 300001)
+    for deg in range(0, 8):
+        q = amli_coefficients(deg)
+        err = 1.0 / t - np.polyval(q[::-1], t)
+        d = np.diff(err)
+        idx = [0] + [i + 1 for i in range(len(d) - 1) if d[i] * d[i + 1] < 0] + [len(t) - 1]
+        ext = err[idx]
+        assert len(ext) == deg + 2
+        assert np.all(ext[:-1] * ext[1:] < 0)
+        assert np.allclose(np.abs(ext), 0.75 * 3.0 ** (-deg), rtol=1e-6)
+
+
+@pytest.mark.parametrize("degree", [0, 1, 2, 3])
+def test_amli_cycle_matches_dense_polynomial_formula(degree):
+    """Without coarse scaling the AMLI cycle is linear: B_l = post(pre + P q(B_c A_c) B_c P'(I - A pre)) with
+    q(t) = sum_i q_i t^i, built here as dense matrices level by level."""
+    from oracle.oracle import amli_coefficients
+    s = problems.bidomain_system(2, 8, gamma=10.0)
+    prm = dict(params.parameters_metric, cycle_type=haznics.AMLI_CYCLE, amli_degree=degree,
+               coarse_scaling=haznics.OFF, coarse_dof=10)
+    ex = mamg.Hierarchy(s.A, prm, s.interface_dofs).export()
+    assert len(ex["levels"]) >= 3
+    orc = Oracle(ex, "multicolor")
+    lv = _dense_hierarchy(ex, orc)
+    q = amli_coefficients(degree)
+    B = np.linalg.inv(lv[-1]["A"])
+    for d in reversed(lv[:-1]):
+        A, P = d["A"], d["P"]
+        Ac = P.T @ A @ P
+        X = B @ Ac
+        Q = sum(q[i] * np.linalg.matrix_power(X, i) for i in range(degree + 1)) @ B
+        (Epre, Npre), (Epost, Npost) = d["pre"], d["post"]
+        x1 = Npre                                          # pre-smoothing from zero
+        x2 = x1 + P @ Q @ P.T @ (np.eye(A.shape[0]) - A @ x1)
+        B = Epost @ x2 + Npost
+    r = np.random.default_rng(5).standard_normal(s.ndofs)
+    z = orc.apply(r)
+    assert np.allclose(z, B @ r, rtol=1e-9, atol=1e-11)
+    # degree 0 with q_0 = 1.25 is a V-cycle whose coarse corrections are over-relaxed by q_0
+    assert orc.visits() == sum((degree + 1) ** l for l in range(len(lv) - 1))
+
+
+def test_nonlinear_amli_two_level_is_a_v_cycle_and_kcycle_formula():
+    """Two levels: the coarse problem is solved directly, so NL-AMLI == V-cycle.  Three levels: the coarse
+    correction of level 0 is the two-step Krylov combination of the level-1 cycle (dense restatement)."""
+    s = problems.bidomain_system(2, 8, gamma=10.0)
+    prm = dict(params.parameters_metric, cycle_type=haznics.NL_AMLI_CYCLE, coarse_scaling=haznics.OFF, max_levels=2)
+    ex = mamg.Hierarchy(s.A, prm, s.interface_dofs).export()
+    orc = Oracle(ex, "multicolor")
+    r = np.random.default_rng(6).standard_normal(s.ndofs)
+    z = orc.apply(r)
+    orc.set_cycle(haznics.V_CYCLE)
+    assert np.array_equal(z, orc.apply(r))
+
+    for krylov in (haznics.SOLVER_GCG, haznics.SOLVER_VFGMRES):
+        prm = dict(params.parameters_metric, cycle_type=haznics.NL_AMLI_CYCLE, coarse_scaling=haznics.OFF,
+                   max_levels=3, coarse_dof=5, nl_amli_krylov_type=krylov)
+        ex = mamg.Hierarchy(s.A, prm, s.interface_dofs).export()
+        assert len(ex["levels"]) == 3
+        orc = Oracle(ex, "multicolor")
+        lv = _dense_hierarchy(ex, orc)
+        A0, P0, A1, P1 = lv[0]["A"], lv[0]["P"], lv[1]["A"], lv[1]["P"]
+        (E1, N1), (E1p, N1p) = lv[1]["pre"], lv[1]["post"]
+        x = N1
+        x = x + P1 @ np.linalg.inv(lv[2]["A"]) @ P1.T @ (np.eye(A1.shape[0]) - A1 @ x)
+        B1 = E1p @ x + N1p                                  # the level-1 cycle (its coarse level is the last)
+        (E0, N0), (E0p, N0p) = lv[0]["pre"], lv[0]["post"]
+        x0 = N0 @ r
+        b1 = P0.T @ (r - A0 @ x0)
+        c1 = B1 @ b1
+        v1 = A1 @ c1
+        w1 = c1 if krylov == haznics.SOLVER_GCG else v1
+        rho1, alpha1 = w1 @ v1, w1 @ b1
+        rt = b1 - alpha1 / rho1 * v1
+        if rt @ rt < 0.04 * (b1 @ b1):
+            e = alpha1 / rho1 * c1
+        else:
+            c2 = B1 @ rt
+            v2 = A1 @ c2
+            w2 = c2 if krylov == haznics.SOLVER_GCG else v2
+            gamma, alpha2, rho2 = w2 @ v1, w2 @ v2, w2 @ rt
+            beta2 = alpha2 - gamma * gamma / rho1
+            e = (alpha1 - gamma * rho2 / beta2) / rho1 * c1 + rho2 / beta2 * c2
+            # the two-step combination minimises the A-norm (GCG) / residual norm (GCR) over span{c1, c2}
+            C = np.column_stack([c1, c2])
+            if krylov == haznics.SOLVER_GCG:
+                best = C @ np.linalg.solve(C.T @ A1 @ C, C.T @ b1)
+            else:
+                best = C @ np.linalg.lstsq(A1 @ C, b1, rcond=None)[0]
+            assert np.allclose(e, best, rtol=1e-8, atol=1e-10)
+        x0 = x0 + P0 @ e
+        z_ref = E0p @ x0 + N0p @ r
+        assert np.allclose(orc.apply(r), z_ref, rtol=1e-9, atol=1e-11)
+
+
+def test_additive_cycle_is_the_sum_of_level_corrections_and_symmetric():
+    s = problems.bidomain_system(2, 8, gamma=10.0)
+    prm = dict(params.parameters_metric, cycle_type=haznics.ADD_CYCLE, coarse_dof=10)
+    ex = mamg.Hierarchy(s.A, prm, s.interface_dofs).export()
+    orc = Oracle(ex, "multicolor")
+    lv = _dense_hierarchy(ex, orc)
+    n = s.ndofs
+    B = np.zeros((n, n))
+    T = np.eye(n)                                           # P_0 ... P_{l-1}
+    for d in lv[:-1]:
+        (Epre, Npre), (Epost, Npost) = d["pre"], d["post"]
+        S = Epost @ Npre + Npost                            # pre- then post-smoothing from zero
+        B += T @ S @ T.T
+        T = T @ d["P"]
+    B += T @ np.linalg.inv(lv[-1]["A"]) @ T.T
+    r = np.random.default_rng(7).standard_normal(n)
+    assert np.allclose(orc.apply(r), B @ r, rtol=1e-9, atol=1e-11)
+    assert np.allclose(B, B.T, rtol=1e-9, atol=1e-11)
+    assert np.linalg.eigvalsh(0.5 * (B + B.T)).min() > 0
+
+
+@pytest.mark.parametrize("cycle", ["AMLI_CYCLE", "NL_AMLI_CYCLE", "ADD_CYCLE"])
+def test_further_cycles_precondition_cg(cycle):
+    """The further cycle types are usable preconditioners of the reference's solve (scaling on, Schwarz patches):
+    AMLI / NL-AMLI need no more iterations than the V-cycle, the additive cycle converges."""
+    s = problems.bidomain_system(2, 32, gamma=1e3)
+    b = np.random.default_rng(8).standard_normal(s.ndofs)
+    its = {}
+    for ct in ("V_CYCLE", cycle):
+        prm = dict(params.parameters_metric_schwarz, cycle_type=getattr(haznics, ct))
+        orc = Oracle(mamg.Hierarchy(s.A, prm, s.interface_dofs).export(), "multicolor")
+        x, info = orc.pcg(b, tolerance=1e-8, relative=True, maxiter=200)
+        assert np.linalg.norm(b - s.A @ x) <= 2e-8 * np.linalg.norm(b) * 10
+        its[ct] = info["niters"]
+    if cycle != "ADD_CYCLE":
+        assert its[cycle] <= its["V_CYCLE"]
+    else:
+        assert its[cycle] < 200
