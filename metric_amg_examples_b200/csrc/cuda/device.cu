@@ -18,6 +18,7 @@
 #include <vector>
 
 #include <nccl.h>
+#include <omp.h>
 #include <nvtx3/nvToolsExt.h>
 
 #include "../host/handle.h"
@@ -85,7 +86,20 @@ enum KClass { K_SPMV = 0, K_GS, K_SCHWARZ, K_RESTRICT, K_SCALE, K_PROLONG, K_COA
 
 struct ProfEvent { cudaEvent_t start, stop; int cls; int lev; };
 
+// pinned bounce buffers of the upload (see Stager::copy below)
+struct Stager {
+  void* buf[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  cudaStream_t stream = nullptr;
+  size_t chunk = 0, min_bytes = 0;
+  bool ok = false;
+  void init();
+  void release();
+  void copy(void* dst, const void* src, size_t bytes);
+};
+
 struct DeviceState {
+  Stager stager;
   bool prof_on = false;
   int cur_level = 0;          // level the cycle is working on (profiling breakdown only)
   std::vector<ProfEvent> prof_events;
@@ -217,11 +231,65 @@ static void dfree(DeviceState& D, T* p, size_t count) {
   cudaFree(p);
   D.dev_bytes -= (int64_t)(count * sizeof(T));
 }
+// Large host -> device copies of the upload (the level matrices: 17 GB at emi_3d n=464) go through two pinned
+// bounce buffers that all cores fill while the previous chunk is on the bus: a plain cudaMemcpy from pageable
+// memory is staged by one driver thread (measured 4.7 GB/s).  MAMG_STAGE_MIN_KB: smallest copy that is staged
+// (default 256 MB; 0 stages everything), MAMG_STAGE_CHUNK_KB: chunk size (default 64 MB; 0 disables staging).
+void Stager::init() {
+  const char* ec = getenv("MAMG_STAGE_CHUNK_KB");
+  const char* em = getenv("MAMG_STAGE_MIN_KB");
+  chunk = (ec ? (size_t)atoll(ec) : (size_t)65536) << 10;
+  min_bytes = (em ? (size_t)atoll(em) : (size_t)262144) << 10;
+  if (chunk == 0) return;
+  for (int k = 0; k < 2; ++k) {
+    if (cudaMallocHost(&buf[k], chunk) != cudaSuccess) { cudaGetLastError(); release(); return; }
+    if (cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); release(); return; }
+  }
+  if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); release(); return; }
+  ok = true;
+}
+void Stager::release() {
+  for (int k = 0; k < 2; ++k) {
+    if (buf[k]) cudaFreeHost(buf[k]);
+    if (ev[k]) cudaEventDestroy(ev[k]);
+    buf[k] = nullptr;
+    ev[k] = nullptr;
+  }
+  if (stream) cudaStreamDestroy(stream);
+  stream = nullptr;
+  ok = false;
+}
+void Stager::copy(void* dst, const void* src, size_t bytes) {
+  size_t off = 0;
+  int k = 0;
+  while (off < bytes) {
+    const size_t len = std::min(chunk, bytes - off);
+    CUDA_OK(cudaEventSynchronize(ev[k]));   // the copy that last read this buffer is done (no-op before its first use)
+    const char* from = (const char*)src + off;
+    char* to = (char*)buf[k];
+    const size_t piece = (size_t)1 << 20;
+    const long long pieces = (long long)((len + piece - 1) / piece);
+#pragma omp parallel for schedule(static)
+    for (long long q = 0; q < pieces; ++q) {
+      const size_t o = (size_t)q * piece;
+      std::memcpy(to + o, from + o, std::min(piece, len - o));
+    }
+    CUDA_OK(cudaMemcpyAsync((char*)dst + off, to, len, cudaMemcpyHostToDevice, stream));
+    CUDA_OK(cudaEventRecord(ev[k], stream));
+    off += len;
+    k ^= 1;
+  }
+  CUDA_OK(cudaStreamSynchronize(stream));
+}
+
 template <class V>
 static typename V::value_type* upload(DeviceState& D, const V& v) {
   using T = typename V::value_type;
   T* p = dalloc<T>(D, v.size());
-  if (!v.empty()) CUDA_OK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  const size_t bytes = v.size() * sizeof(T);
+  if (bytes == 0) return p;
+  if (D.stager.ok && bytes >= D.stager.min_bytes) D.stager.copy(p, v.data(), bytes);
+  else CUDA_OK(cudaMemcpy(p, v.data(), bytes, cudaMemcpyHostToDevice));
   return p;
 }
 
@@ -393,6 +461,8 @@ static void upload_hierarchy(const Hierarchy& H, DeviceState& D) {
     fprintf(stderr, "[mamg upload] level %d %-14s %.3f s\n", lev, what, std::chrono::duration<double>(now - tp).count());
     tp = now;
   };
+  D.stager.init();
+  struct StagerGuard { Stager& s; ~StagerGuard() { s.release(); } } stager_guard{D.stager};
   D.lv.resize(L);
   std::vector<std::vector<int>> perm(L), iperm(L);
   for (int l = 0; l < L; ++l) {
@@ -411,12 +481,31 @@ static void upload_hierarchy(const Hierarchy& H, DeviceState& D) {
       dl.nb = (H.nparts > 1 && !hl.part.empty() && n >= dist_min_rows(D.halo && D.world > 1)) ? H.nparts : 1;
       const int nbc = dl.nb * dl.ncolors;
       auto key = [&](int i) { return (dl.nb > 1 ? hl.part[i] : 0) * dl.ncolors + hl.color[i]; };
+      // stable counting sort by (part, colour) on all cores: every thread counts and later places one contiguous
+      // chunk of rows, the chunks in thread order inside every bucket (the same permutation as a serial pass)
       dl.bc_ptr.assign(nbc + 1, 0);
-      for (int i = 0; i < n; ++i) ++dl.bc_ptr[key(i) + 1];
-      for (int k = 0; k < nbc; ++k) dl.bc_ptr[k + 1] += dl.bc_ptr[k];
-      std::vector<int> fill(dl.bc_ptr.begin(), dl.bc_ptr.end() - 1);
-      for (int i = 0; i < n; ++i) perm[l][fill[key(i)]++] = i;
+      const int tmax = std::max(1, omp_get_max_threads());
+      std::vector<int> cnt((size_t)tmax * nbc, 0);
+#pragma omp parallel num_threads(tmax)
+      {
+        const int nt = omp_get_num_threads(), t = omp_get_thread_num();
+        const int lo = (int)((long long)n * t / nt), hi = (int)((long long)n * (t + 1) / nt);
+        int* c = &cnt[(size_t)t * nbc];
+        for (int i = lo; i < hi; ++i) ++c[key(i)];
+#pragma omp barrier
+#pragma omp single
+        {
+          int run = 0;
+          for (int k = 0; k < nbc; ++k) {
+            dl.bc_ptr[k] = run;
+            for (int u = 0; u < nt; ++u) { const int v = cnt[(size_t)u * nbc + k]; cnt[(size_t)u * nbc + k] = run; run += v; }
+          }
+          dl.bc_ptr[nbc] = run;
+        }
+        for (int i = lo; i < hi; ++i) perm[l][c[key(i)]++] = i;
+      }
     }
+#pragma omp parallel for schedule(static)
     for (int i = 0; i < n; ++i) iperm[l][perm[l][i]] = i;
   }
   lap("permutations", -1);
@@ -498,11 +587,16 @@ static void upload_hierarchy(const Hierarchy& H, DeviceState& D) {
     lap("h2d csr", l);
     if (!hl.gs_skip.empty()) {
       std::vector<uint8_t> sk(n);
+#pragma omp parallel for schedule(static)
       for (int i = 0; i < n; ++i) sk[i] = hl.gs_skip[perm[l][i]];
       dl.skip = upload(D, sk);
       dl.color_active.assign(dl.nb * dl.ncolors, 0);
-      for (int k = 0; k < dl.nb * dl.ncolors; ++k)
-        for (int i = dl.bc_ptr[k]; i < dl.bc_ptr[k + 1]; ++i) dl.color_active[k] += sk[i] == 0;
+      for (int k = 0; k < dl.nb * dl.ncolors; ++k) {
+        int active = 0;
+#pragma omp parallel for schedule(static) reduction(+ : active)
+        for (int i = dl.bc_ptr[k]; i < dl.bc_ptr[k + 1]; ++i) active += sk[i] == 0;
+        dl.color_active[k] = active;
+      }
     }
     if (l + 1 < L && hl.P.n > 0) {
       // SA_AMG: P (fine' x coarse') and R = P' (coarse' x fine') in the permuted numberings
@@ -526,17 +620,31 @@ static void upload_hierarchy(const Hierarchy& H, DeviceState& D) {
       permute(hl.R, perm[l + 1], iperm[l], dl.R);
     }
     if (l + 1 < L) {
+      // members of every aggregate in ascending (permuted) row order -- the order the restriction sums them in:
+      // counted and placed with atomics on all cores, then every (short) member list is sorted
       std::vector<int> agg(n), cptr(hl.nc + 1, 0), cidx;
+#pragma omp parallel for schedule(static)
       for (int i = 0; i < n; ++i) {
-        int I = hl.agg[perm[l][i]];
+        const int I = hl.agg[perm[l][i]];
         agg[i] = I >= 0 ? iperm[l + 1][I] : -1;
-        if (I >= 0) ++cptr[agg[i] + 1];
+        if (I >= 0) {
+#pragma omp atomic
+          ++cptr[agg[i] + 1];
+        }
       }
       for (int I = 0; I < hl.nc; ++I) cptr[I + 1] += cptr[I];
       cidx.resize(cptr[hl.nc]);
       std::vector<int> fill(cptr.begin(), cptr.end() - 1);
+#pragma omp parallel for schedule(static)
       for (int i = 0; i < n; ++i)
-        if (agg[i] >= 0) cidx[fill[agg[i]]++] = i;
+        if (agg[i] >= 0) {
+          int slot;
+#pragma omp atomic capture
+          slot = fill[agg[i]]++;
+          cidx[slot] = i;
+        }
+#pragma omp parallel for schedule(static, 4096)
+      for (int I = 0; I < hl.nc; ++I) std::sort(cidx.begin() + cptr[I], cidx.begin() + cptr[I + 1]);
       dl.agg = upload(D, agg);
       dl.cptr = upload(D, cptr);
       dl.cidx = upload(D, cidx);

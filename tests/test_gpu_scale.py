@@ -89,6 +89,7 @@ ENV_CASES = [
     {"MAMG_LANES": "2"}, {"MAMG_LANES": "4"}, {"MAMG_LANES": "8"}, {"MAMG_LANES": "16"}, {"MAMG_LANES": "32"},
     {"MAMG_SCHWARZ_GENERAL": "1"}, {"MAMG_GRAPH": "0"}, {"MAMG_TAIL_ROWS": "0"}, {"MAMG_DROP_ZEROS": "1"},
     {"MAMG_DROP_ZEROS": "0"}, {"MAMG_SW_DEDUP": "0"}, {"MAMG_ROWS": "csr"}, {"MAMG_ROWS": "sell"}, {"MAMG_NVTX": "1"},
+    {"MAMG_STAGE_MIN_KB": "0", "MAMG_STAGE_CHUNK_KB": "4"},   # every upload through the pinned bounce buffers, 4 KB chunks
 ]
 
 
@@ -98,7 +99,7 @@ def test_env_variants_match_oracle(env, monkeypatch):
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     check_against_oracle(problems.bidomain_system(3, 20, gamma=1e4), params.parameters_metric_schwarz, 1e-8)
-    if "MAMG_SCHWARZ_GENERAL" in env or "MAMG_DROP_ZEROS" in env or "MAMG_ROWS" in env or "MAMG_SW_DEDUP" in env:
+    if "MAMG_SCHWARZ_GENERAL" in env or "MAMG_DROP_ZEROS" in env or "MAMG_ROWS" in env or "MAMG_SW_DEDUP" in env or "MAMG_STAGE_MIN_KB" in env:
         check_against_oracle(problems.emi_system(3, 16, gamma=1e6), params.default_metric_parameters, 1e-10)
 
 
