@@ -7,10 +7,12 @@ A "step" is one complete solve of the hot path: cbc.block-style PCG to rtol 1e-8
   value   DOF/s with b already resident in HBM (CUDA events around K solves)
   e2e     the same solves through the public API (ConjGrad(A, precond=B) * b) with HOST
           vectors: H2D of b and D2H of x inside the timed region
-Default workload at N=1: BASELINE.json configs[2], bidomain_3d on UnitCubeMesh(199) (16.0 M DOFs)
-with src/amg_parameters.py:parameters_metric_schwarz; the headline uses cycle_type V_CYCLE (the
-metric names the V-cycle); the W-cycle that src/amg_parameters.py configures is timed beside it on the
-same hierarchy (`wcycle_ms`, --wcycle K applies; 0 disables).
+Default workload at every N: BASELINE.json configs[3], emi_3d on UnitCubeMesh(464) (100.8 M DOFs, the
+configuration the north-star target is quoted on; it fits one B200) with the reference's default metric
+parameters (src/utils.py:60-82); `--workload bidomain_3d` is configs[2] (n=199, 16.0 M DOFs,
+parameters_metric_schwarz).  The headline uses cycle_type V_CYCLE (the metric names the V-cycle); one apply of
+the W-cycle that src/amg_parameters.py configures is timed beside it on the same hierarchy at N=1
+(`wcycle_ms`, --wcycle K applies; 0 disables).
 `--impl reference` times the CPU restatement (oracle/) on a bounded sample of the same workload.
 """
 import argparse
@@ -323,9 +325,11 @@ def run_mamg(a):
         cycle_ms = c0.elapsed_time(c1) / 5
         # the W-cycle that src/amg_parameters.py:5,25,49,69 configures, on the same hierarchy
         wcycle_ms = None
-        if a.wcycle > 0 and a.cycle == "V":
+        # (one rank only: below the distributed levels every rank runs the same coarse sequence, which is where a
+        # W apply spends its time; no warm-up apply: the W sequence is far above the graph-capture limit, so every
+        # apply launches eagerly, and all of its kernels have already run in the V-cycles above)
+        if a.wcycle > 0 and a.cycle == "V" and world == 1:
             H.set_cycle(hz.W_CYCLE)
-            lib.mamg_apply(H._h, C.c_void_p(r.data_ptr()), C.c_void_p(z.data_ptr()), 1)   # warm
             torch.cuda.synchronize()
             c0.record(stream)
             for _ in range(a.wcycle):
