@@ -480,6 +480,10 @@ extern "C" int mamg_import_hierarchy(const mamg_params* p, int32_t nlevels, cons
                                      const double* coarse_inv, int32_t nparts, mamg_handle* out) {
   MAMG_TRY
   if (!p || !levels || !out || nlevels < 1) { set_error("import_hierarchy: NULL argument or no levels"); return -1; }
+  {
+    std::string perr;
+    if (!validate_params(*p, perr)) { set_error("import_hierarchy: " + perr); return -1; }
+  }
   mamg_handle h = new mamg_handle_s();
   Hierarchy& H = h->H;
   H.prm = *p;

@@ -91,6 +91,7 @@ void schwarz_patches(const Csr& A, const int* seeds, int nseeds, int maxlvl, int
                      SchwarzPatches& out);
 void schwarz_color(const Csr& A, SchwarzPatches& sw);
 bool dense_inverse(const Csr& A, std::vector<double>& inv);
+bool validate_params(const mamg_params& prm, std::string& err);
 bool build_hierarchy(const mamg_params& prm, Csr&& A0, const int* idofs, int n_idofs,
                      const int* part, int nparts, Hierarchy& H, std::string& err);
 

@@ -630,15 +630,8 @@ static void greedy_mis(const Csr& A, std::vector<int>& seeds) {
   }
 }
 
-bool build_hierarchy(const mamg_params& prm, Csr&& A0, const int* idofs, int n_idofs,
-                     const int* part, int nparts, Hierarchy& H, std::string& err) {
-  auto t0 = std::chrono::steady_clock::now();
-  H.prm = prm;
-  H.nparts = part ? std::max(1, nparts) : 1;
-  H.lv.clear();
-  H.lv.emplace_back();
-  H.lv[0].A = std::move(A0);
-  if (part) H.lv[0].part.assign(part, part + H.lv[0].A.n);
+// the option space of the parameter dict (src/amg_parameters.py) that setup, import and the device cycle accept
+bool validate_params(const mamg_params& prm, std::string& err) {
   if (prm.AMG_type != MAMG_UA_AMG && prm.AMG_type != MAMG_SA_AMG) { err = "AMG_type: only UA_AMG and SA_AMG are implemented"; return false; }
   switch (prm.cycle_type) {
     case MAMG_V_CYCLE: case MAMG_W_CYCLE: case MAMG_AMLI_CYCLE: case MAMG_NL_AMLI_CYCLE: break;
@@ -671,6 +664,19 @@ bool build_hierarchy(const mamg_params& prm, Csr&& A0, const int* idofs, int n_i
     err = "Schwarz_blksolver: 32 (direct) or 0 (iterative)";
     return false;
   }
+  return true;
+}
+
+bool build_hierarchy(const mamg_params& prm, Csr&& A0, const int* idofs, int n_idofs,
+                     const int* part, int nparts, Hierarchy& H, std::string& err) {
+  auto t0 = std::chrono::steady_clock::now();
+  H.prm = prm;
+  H.nparts = part ? std::max(1, nparts) : 1;
+  H.lv.clear();
+  H.lv.emplace_back();
+  H.lv[0].A = std::move(A0);
+  if (part) H.lv[0].part.assign(part, part + H.lv[0].A.n);
+  if (!validate_params(prm, err)) return false;
   const int max_levels = std::max(1, prm.max_levels);
   // Store no explicit zeros on any level (MAMG_DROP_ZEROS=0 keeps the caller's full pattern): a +0*x
   // term never changes a sum, aggregation / colouring / patch search ignore zero couplings anyway, and

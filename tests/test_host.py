@@ -391,6 +391,13 @@ def test_import_hierarchy_rejects_bad_input():
     bad["levels"] = bad["levels"][:1] + bad["levels"][2:]
     with pytest.raises(_capi.MamgError, match="aggregates"):
         mamg.Hierarchy.from_export(bad)
+    # the parameter struct is validated on the C side too (a caller that bypasses params.to_struct)
+    prm = params.to_struct(params.parameters_metric)
+    prm.cycle_type = 9
+    recs = (_capi.MamgLevelArrays * 1)()
+    h = C.c_void_p()
+    assert _capi.lib.mamg_import_hierarchy(C.byref(prm), 1, recs, None, 1, C.byref(h)) != 0
+    assert b"cycle_type" in _capi.lib.mamg_last_error()
 
 
 @pytest.mark.parametrize("agg", ["VMB", "MIS", "MWM", "HEC", "HEM"])
